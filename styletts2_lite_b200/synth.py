@@ -1,0 +1,130 @@
+"""Deterministic synthetic weights and inputs (no checkpoint, no dataset).
+
+SURVEY.md §8(d) "Synthetic inputs": random-init weights of the reference
+architecture and seeded asr / F0 / N / style / noise tensors.  Weights are
+drawn by this module (torch CPU generator, reproducible across machines with
+the same torch build) in the reference's own state_dict schema, so the very
+same dict can be `load_state_dict`-ed into the reference Decoder (that is how
+tests/golden/make_golden.py produced the committed fixtures) and into the
+B200 drop-in.
+
+`perturb=True` moves weight_g away from ||v||, alpha away from 1 and scales
+biases, so that the weight-norm fold, the Snake alphas and every bias path
+are actually exercised by parity tests (with the reference's init,
+g == ||v|| and alpha == 1, those bugs would be invisible).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .config import DecoderConfig, param_specs, buffer_specs, HARMONICS
+
+
+def _fan_in(shape):
+    f = 1
+    for d in shape[1:]:
+        f *= d
+    return max(f, 1)
+
+
+def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    specs = param_specs(cfg)
+    # pass 1: everything that does not depend on another tensor
+    for name, shape, kind in specs:
+        if kind == "conv":
+            bound = 1.0 / math.sqrt(_fan_in(shape))
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        elif kind == "linear":
+            bound = 1.0 / math.sqrt(shape[1])
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        elif kind.startswith("linear_bias"):
+            bound = 1.0 / math.sqrt(int(kind.split(":")[1]))
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        elif kind == "alpha":
+            if perturb:
+                sd[name] = 0.6 + 0.8 * torch.rand(shape, generator=g)
+            else:
+                sd[name] = torch.ones(shape)
+    # pass 2: g and conv biases
+    for name, shape, kind in specs:
+        if kind.startswith("g:"):
+            v = sd[kind[2:]]
+            nrm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(shape)
+            if perturb:
+                nrm = nrm * (0.85 + 0.3 * torch.rand(shape, generator=g))
+            sd[name] = nrm
+        elif kind.startswith("bias:"):
+            w = sd[kind[5:]]
+            bound = 1.0 / math.sqrt(_fan_in(w.shape))
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    for name, shape in buffer_specs(cfg):
+        sd[name] = stft_buffers(cfg)[name]
+    return {k: v.float().contiguous() for k, v in sd.items()}
+
+
+def stft_buffers(cfg: DecoderConfig) -> Dict[str, torch.Tensor]:
+    """The five CustomSTFT buffers, built the way istftnet.py:141-203 builds them
+    (periodic Hann, float64 DFT basis rounded to fp32, inverse scaled by 1/n_fft)."""
+    n = cfg.gen_istft_n_fft
+    bins = n // 2 + 1
+    window = torch.hann_window(n, periodic=True, dtype=torch.float32)
+    wn = window.numpy()
+    kk = np.arange(bins)
+    nn_ = np.arange(n)
+    ang = 2 * np.pi * np.outer(kk, nn_) / n
+    fr = torch.from_numpy(np.cos(ang) * wn).float().unsqueeze(1)
+    fi = torch.from_numpy(-np.sin(ang) * wn).float().unsqueeze(1)
+    ang_t = 2 * np.pi * np.outer(nn_, kk) / n
+    inv_w = wn * (1.0 / n)
+    br = torch.from_numpy(np.cos(ang_t).T * inv_w).float().unsqueeze(1)
+    bi = torch.from_numpy(np.sin(ang_t).T * inv_w).float().unsqueeze(1)
+    p = "generator.stft."
+    return {p + "window": window, p + "weight_forward_real": fr, p + "weight_forward_imag": fi,
+            p + "weight_backward_real": br, p + "weight_backward_imag": bi}
+
+
+def make_inputs(B: int, T: int, seed: int = 1000, cfg: DecoderConfig | None = None,
+                with_noise: bool = True) -> Dict[str, torch.Tensor]:
+    """asr [B,512,T], F0_curve [B,2T] (80..280 Hz with ~20 % unvoiced runs set to 0),
+    N [B,2T], s [B,128], noise [B,S,9] (the SineGen `randn_like` draw, hifigan.py:213)."""
+    cfg = cfg or DecoderConfig()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    asr = torch.randn(B, cfg.dim_in, T, generator=g)
+    f0 = 80.0 + 200.0 * torch.rand(B, 2 * T, generator=g)
+    # unvoiced runs: contiguous stretches of 3..12 frames until ~20 % is covered
+    L = 2 * T
+    for b in range(B):
+        target = int(0.2 * L)
+        covered = 0
+        guard = 0
+        while covered < target and guard < 1000:
+            guard += 1
+            ln = int(torch.randint(3, 13, (1,), generator=g))
+            st = int(torch.randint(0, max(L - ln, 1), (1,), generator=g))
+            f0[b, st:st + ln] = 0.0
+            covered += ln
+    n = torch.randn(B, 2 * T, generator=g)
+    s = torch.randn(B, cfg.style_dim, generator=g)
+    out = {"asr": asr, "F0_curve": f0, "N": n, "s": s}
+    if with_noise:
+        S = cfg.samples_per_frame * T
+        out["noise"] = torch.randn(B, S, HARMONICS, generator=g)
+    return out
+
+
+def make_durations(B: int, L: int, F: int, seed: int = 7) -> torch.Tensor:
+    """Seeded integer durations [B,L], each >= 1, each row summing to F
+    (SURVEY.md §8(d) cfg 3: synthetic durations replace pred_dur after inference.py:257)."""
+    assert F >= L
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dur = torch.ones(B, L, dtype=torch.int64)
+    for b in range(B):
+        extra = torch.randint(0, L, (F - L,), generator=g)
+        dur[b] += torch.bincount(extra, minlength=L)
+    return dur

@@ -1,0 +1,124 @@
+"""CPU tests: the numpy oracle against the golden fixtures produced by the unmodified
+reference (tests/golden/make_golden.py).  Tolerances:
+  * SineGen phase, length regulator: bit-exact / torch.equal-style equality;
+  * waveforms and intermediate activations: max-abs <= 5e-5 (the reference's own
+    fp32 self-consistency level, SURVEY.md §0: 2.2e-5 between its fp32 and fp64 runs)."""
+import numpy as np
+import pytest
+
+from styletts2_lite_b200.config import DecoderConfig
+from oracle import decoder_np as O
+from helpers import golden, np_inputs, np_state_dict, sha, rel_l2
+
+WAVE_TOL = 5e-5
+
+
+def test_phase_bit_exact_small():
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B2_T5_w0_i1001.npz")
+    inp = np_inputs(2, 5, 1001, cfg)
+    ph = O.sinegen_phase(inp["F0_curve"], cfg.upsample_scale)
+    assert ph.dtype == np.float32
+    assert np.array_equal(ph, g["phase"])
+
+
+def test_phase_bit_exact_10s_checksum():
+    cfg = DecoderConfig.hifigan()
+    g = golden("sinegen_phase_B2_T400_i1004.npz")
+    inp = np_inputs(2, 400, 1004, cfg, with_noise=False)
+    ph = O.sinegen_phase(inp["F0_curve"], cfg.upsample_scale)
+    assert np.array_equal(ph[:, :1200], g["phase_head"])
+    assert np.array_equal(ph[:, -1200:], g["phase_tail"])
+    assert sha(ph) == str(g["phase_sha256"])
+    assert float(np.abs(ph).max()) > 5e4          # the regime where 1 ulp = 0.004..0.008 rad
+
+
+def test_hifigan_small_waveform_and_taps():
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B2_T5_w0_i1001.npz")
+    sd = np_state_dict(cfg, 0, True)
+    inp = np_inputs(2, 5, 1001, cfg)
+    taps = {}
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"], taps=taps)
+    assert out.shape == (2, 1, 3000)
+    assert np.abs(out - g["out"]).max() <= WAVE_TOL
+    pairs = {"encode": "encode", "decode.0": "decode.0", "decode.3": "decode.3",
+             "generator.noise_res.0": "generator.noise_res.0.iter2",
+             "generator.resblocks.0": "generator.resblocks.0.iter2",
+             "generator.resblocks.5": "generator.resblocks.5.iter2",
+             "generator.noise_res.3": "generator.noise_res.3.iter2",
+             "generator.resblocks.11": "generator.resblocks.11.iter2"}
+    for gname, oname in pairs.items():
+        assert rel_l2(g["tap:" + gname], taps[oname][:1]) <= 2e-5, gname
+    har_ref = g["tap:generator.m_source"].transpose(0, 2, 1)
+    assert np.abs(taps["har_source"][:1] - har_ref).max() <= 1e-6
+
+
+def test_hifigan_reference_init():
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B1_T4_w3_i1002_plain.npz")
+    sd = np_state_dict(cfg, 3, False)
+    inp = np_inputs(1, 4, 1002, cfg)
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"])
+    assert np.abs(out - g["out"]).max() <= WAVE_TOL
+
+
+def test_hifigan_cfg1_3s():
+    """BASELINE.json configs[0]: B=1, ~3 s (T=120)."""
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B1_T120_w0_i1001.npz")
+    sd = np_state_dict(cfg, 0, True)
+    inp = np_inputs(1, 120, 1001, cfg)
+    ph = O.sinegen_phase(inp["F0_curve"], cfg.upsample_scale)
+    assert sha(ph) == str(g["phase_sha256"])
+    taps = {}
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"], taps=taps)
+    assert np.abs(taps["har_source"] - g["har_source"].transpose(0, 2, 1)).max() <= 1e-6
+    assert np.abs(out - g["out"]).max() <= 1e-4
+
+
+def test_istftnet_small():
+    cfg = DecoderConfig.istftnet()
+    g = golden("istftnet_B2_T5_w0_i1005.npz")
+    sd = np_state_dict(cfg, 0, True)
+    inp = np_inputs(2, 5, 1005, cfg)
+    taps = {}
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"], taps=taps)
+    assert out.shape == (2, 1, 3000)
+    assert rel_l2(g["tap:generator.noise_res.0"], taps["generator.noise_res.0.iter2"][:1]) <= 2e-5
+    assert rel_l2(g["tap:generator.noise_res.1"], taps["generator.noise_res.1.iter2"][:1]) <= 2e-5
+    assert np.abs(out - g["out"]).max() <= WAVE_TOL
+
+
+def test_length_regulator_golden():
+    g = golden("length_regulator_L37.npz")
+    pd = O.round_durations(g["duration"][0])
+    assert np.array_equal(pd, g["pred_dur"].astype(np.int64))
+    assert pd[3] == 1 and pd[5] == 2 and pd[6] == 4          # clamp, half-to-even
+    out = O.length_regulate(g["t_en"][0], pd)
+    assert np.array_equal(out, g["asr"][0])
+    # gather restatement == matmul restatement
+    idx = np.repeat(np.arange(len(pd)), pd)
+    assert np.array_equal(out, g["t_en"][0][:, idx])
+
+
+def test_length_regulator_batch_ragged():
+    rng = np.random.default_rng(0)
+    B, C, L = 3, 8, 11
+    src = rng.standard_normal((B, C, L)).astype(np.float32)
+    dur = rng.integers(1, 5, (B, L))
+    dur[1, 7:] = 0                                           # ragged: padded tokens
+    dur[2, :] = 0                                            # empty utterance
+    out = O.length_regulate_batch(src, dur)
+    assert out.shape == (B, C, int(dur.sum(1).max()))
+    for b in range(B):
+        idx = np.repeat(np.arange(L), dur[b])
+        assert np.array_equal(out[b, :, :len(idx)], src[b][:, idx])
+        assert not out[b, :, len(idx):].any()
+
+
+def test_bf16_rounding_helper():
+    x = np.array([1.0, 1.00390625, 1.005859375, -3.1415927, 0.0], np.float32)
+    r = O.round_bf16(x)
+    import torch
+    assert np.array_equal(r, torch.from_numpy(x).bfloat16().float().numpy())
