@@ -1,0 +1,178 @@
+/*
+ * st2_b200.h -- C ABI of the B200-native StyleTTS2-lite waveform Decoder hot path.
+ *
+ * The reference (thewh1teagle/StyleTTS2-lite) has no FFI / plugin API for this path:
+ * the boundary is the nn.Module duck-type `Decoder.forward(asr, F0_curve, N, s)` picked
+ * by name in models.py:538-561 / inference.py:95-118 and called at inference.py:270.
+ * These entry points are what a ctypes binding for that call (and for the length
+ * regulation of inference.py:257-268) binds; styletts2_lite_b200/decoder.py is that
+ * binding, INTEGRATION.md shows the three lines a reference maintainer changes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative st2_status; nothing throws,
+ *     exits or prints.  st2_last_error() returns a thread-local message.
+ *   - all pointers named dev_* / asr / f0 / ... are raw DEVICE pointers owned by the
+ *     caller (PyTorch).  No hidden allocation and no synchronisation happens inside
+ *     st2_decoder_forward: the launches are ordered on the caller's stream and scratch
+ *     comes from the caller-provided workspace.  (st2_decoder_finalize allocates the
+ *     re-packed weights once; st2_decoder_destroy frees them.)
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - internal activations are channels-last fp32 [B][T][C]; the ABI itself speaks the
+ *     reference's layouts (asr [B,512,T], F0_curve [B,2T], N [B,2T], s [B,128],
+ *     out [B,1,600T]).
+ */
+#ifndef ST2_B200_H
+#define ST2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST2_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ST2_API __attribute__((visibility("default")))
+#else
+#define ST2_API
+#endif
+
+typedef enum {
+    ST2_OK = 0,
+    ST2_ERR_INVALID = -1,      /* bad argument / unknown name / shape mismatch */
+    ST2_ERR_STATE = -2,        /* call order (e.g. forward before finalize) */
+    ST2_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed */
+    ST2_ERR_WORKSPACE = -4,    /* workspace too small */
+    ST2_ERR_UNSUPPORTED = -5   /* shape family or device not supported */
+} st2_status;
+
+/* arithmetic of the dense convolutions */
+typedef enum {
+    ST2_PREC_FP32 = 0,         /* SIMT FFMA, fp32 everywhere (parity backbone, <=1e-4) */
+    ST2_PREC_BF16 = 1,         /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+    ST2_PREC_FP16 = 2          /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM */
+} st2_precision;
+
+/* Mirrors the `decoder:` block of Configs/config_example.yaml:57-73 plus the two
+ * constructor arguments Decoder actually uses (dim_in, style_dim; hifigan.py:417-422,
+ * istftnet.py:661-667). */
+typedef struct {
+    int32_t variant;                 /* 0 = hifigan, 1 = istftnet */
+    int32_t dim_in;                  /* 512 */
+    int32_t style_dim;               /* 128 */
+    int32_t upsample_initial_channel;/* 512 */
+    int32_t n_stages;                /* len(upsample_rates): 4 (hifigan) / 2 (istftnet) */
+    int32_t upsample_rates[4];
+    int32_t upsample_kernel_sizes[4];
+    int32_t n_kernels;               /* len(resblock_kernel_sizes) = 3 */
+    int32_t resblock_kernel_sizes[3];
+    int32_t resblock_dilations[3][3];
+    int32_t gen_istft_n_fft;         /* 20 (istftnet only) */
+    int32_t gen_istft_hop_size;      /* 5  (istftnet only) */
+} st2_config;
+
+typedef struct st2_decoder st2_decoder;
+
+ST2_API int st2_abi_version(void);
+ST2_API const char* st2_last_error(void);
+
+/* ---- Decoder: replaces Modules/hifigan.py:416-475 and Modules/istftnet.py:660-721 ---- */
+
+/* Decoder.__init__ */
+ST2_API int st2_decoder_create(const st2_config* cfg, st2_decoder** out);
+ST2_API void st2_decoder_destroy(st2_decoder* d);
+
+/* load_state_dict (inference.py:160): hand over one tensor of the reference state_dict by
+ * its reference key ("generator.ups.0.weight_v", "encode.norm1.fc.bias", ...).  fp32,
+ * contiguous, on the device; only read during st2_decoder_finalize. */
+ST2_API int st2_decoder_set_weight(st2_decoder* d, const char* name, const float* dev_ptr,
+                           const int64_t* shape, int32_t ndim);
+
+/* Fold weight-norm (w = v*g/||v||, norm over all dims but 0), transpose every conv to the
+ * tap-major [k][Cin][Cout] layout, build bf16/fp16 copies for the tensor-core path and
+ * concatenate the 106 (hifigan) AdaIN fc layers into one [R,128] matrix.  Allocates the
+ * packed weights (device) and synchronises `stream` once. */
+ST2_API int st2_decoder_finalize(st2_decoder* d, void* stream);
+
+/* number of parameters handed over (the reference prints it, inference.py:170-171) */
+ST2_API int64_t st2_decoder_num_params(const st2_decoder* d);
+
+/* scratch needed by one forward of B utterances x T asr frames at `precision` */
+ST2_API int64_t st2_decoder_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision);
+
+/* Decoder.forward(asr, F0_curve, N, s) in eval mode.
+ *   asr [B,dim_in,T]  f0 [B,2T]  n [B,2T]  s [B,style_dim]  ->  out [B,1,spf*T]
+ *   (spf = 600 samples per asr frame for both shipped variants).
+ *   noise: the SineGen `randn_like` draw (hifigan.py:213), [B,spf*T,9] fp32, or NULL to
+ *   draw it on the device from Philox4x32-10 keyed by `seed` (the reference uses the
+ *   global torch RNG; the two other draws, hifigan.py:126 and :267, never reach the
+ *   output -- SURVEY.md 8(a)). */
+ST2_API int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const float* n,
+                        const float* s, const float* noise, uint64_t seed, float* out,
+                        int32_t B, int32_t T, int32_t precision,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Debug / per-layer parity: copy the named intermediate of the NEXT forwards into dst as a
+ * dense channels-last fp32 [B][T'][C] (capacity in floats; dst=NULL unregisters).  Names
+ * follow the oracle's taps ("encode", "decode.3", "har_source",
+ * "generator.resblocks.5.iter2", "generator.stage1.out", ...). */
+ST2_API int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t capacity);
+
+/* how many kernels of this library the last forward launched */
+ST2_API int64_t st2_decoder_last_launch_count(const st2_decoder* d);
+
+/* ---- Length regulator: replaces inference.py:257-268 ---- */
+
+/* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);
+ * tokens at or beyond n_tokens[b] get 0.  duration [B,L] fp32 -> dur [B,L] int32,
+ * total_frames [B] int32. */
+ST2_API int st2_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur,
+                        int32_t* total_frames, int32_t B, int32_t L, void* stream);
+
+/* out[b,c,f] = src[b,c,tok_b(f)] for f < sum(dur[b,:]), 0 beyond: the `src @ alignment`
+ * products of inference.py:266 and :268 as a bit-exact gather (the one-hot matmul adds
+ * only zeros).  src [B,C,L], dur [B,L] int32 (>=0), out [B,C,F].  channels_last != 0
+ * writes out as [B,F,C] instead (the decoder's internal layout). */
+ST2_API int st2_length_regulate(const float* src, const int32_t* dur, float* out, int32_t B, int32_t C,
+                        int32_t L, int32_t F, int32_t channels_last, void* stream);
+
+/* ---- unit entry points (per-kernel parity) ---- */
+
+/* SineGen phase argument (hifigan.py:117-157): f0 [B,L2] -> phase [B,L2*scale,9],
+ * bit-exact with the CPU reference.  frames_scratch: [B,L2,9] fp32. */
+ST2_API int st2_sinegen_phase(const float* f0, float* phase, float* frames_scratch, int32_t B, int32_t L2,
+                      int32_t upsample_scale, void* stream);
+
+/* SourceModuleHnNSF.forward (hifigan.py:254-268): f0 [B,L2] -> har_source [B,L2*scale].
+ * lin_w [9], lin_b [1] device pointers; noise as in st2_decoder_forward. */
+ST2_API int st2_har_source(const float* f0, const float* noise, uint64_t seed, const float* lin_w,
+                   const float* lin_b, float* har, float* frames_scratch, int32_t B, int32_t L2,
+                   int32_t upsample_scale, void* stream);
+
+/* AdaIN1d + activation (hifigan.py:14-24 with :68 or LeakyReLU) on channels-last
+ * x [B,T,C] (pitch ld_x): y = act((1+gamma)*IN(x)+beta), gamma|beta = h[b, 0:C | C:2C].
+ * act: 0 none, 1 leaky-relu(slope), 2 snake(alpha[C]).  out_dtype: 0 fp32, 1 bf16, 2 fp16.
+ * scratch: at least st2_adain_scratch_bytes(B,T,C) bytes. */
+ST2_API int64_t st2_adain_scratch_bytes(int32_t B, int32_t T, int32_t C);
+ST2_API int st2_adain_act(const float* x, int32_t ld_x, const float* h, int32_t ld_h, const float* alpha,
+                  int32_t act, float slope, void* y, int32_t ld_y, int32_t out_dtype,
+                  int32_t B, int32_t T, int32_t C, void* scratch, void* stream);
+
+/* Conv1d / ConvTranspose1d on channels-last fp32 x [B,Tin,Cin] with the reference weight
+ * layout (Conv1d [Cout,Cin,k]; ConvTranspose1d [Cin,Cout,k]); y [B,Tout,Cout].
+ * transposed != 0 selects ConvTranspose1d (stride = upsampling factor).  scratch holds the
+ * re-packed weight (and, for 16-bit precisions, the 16-bit operand copies):
+ * st2_conv1d_scratch_bytes(...) bytes. */
+ST2_API int64_t st2_conv1d_scratch_bytes(int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k,
+                                 int32_t precision);
+ST2_API int st2_conv1d(const float* x, const float* w, const float* bias, float* y, void* scratch,
+               int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
+               int32_t padding, int32_t dilation, int32_t output_padding, int32_t transposed,
+               int32_t precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ST2_B200_H */

@@ -245,6 +245,7 @@ def sinegen_phase_frames(f0_curve: np.ndarray, upsample_scale: int, sr: int = 24
     h = np.arange(1, harmonics + 1, dtype=F32)
     fn = (f0[:, :, None] * h[None, None, :]).astype(F32)
     rad = np.fmod((fn / F32(sr)).astype(F32), F32(1)).astype(F32)
+    rad = np.where((rad != 0) & (rad < 0), (rad + F32(1)).astype(F32), rad)   # torch `%` == python modulo
     cs = np.cumsum(rad.astype(F64), axis=1).astype(F32)
     pf = (cs * F32(2)).astype(F32)
     pf = (pf * F32(np.pi)).astype(F32)

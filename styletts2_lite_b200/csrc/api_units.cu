@@ -1,0 +1,128 @@
+// Per-kernel C-ABI entry points (unit parity against the oracle) and the length-regulator ABI.
+#include "common.cuh"
+
+using namespace st2;
+
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" {
+
+int st2_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur, int32_t* total_frames,
+                        int32_t B, int32_t L, void* stream) {
+    ST2_REQUIRE(duration && dur && total_frames && B >= 0 && L >= 0, "round_durations: bad argument");
+    return launch_round_durations(duration, n_tokens, dur, total_frames, B, L, (cudaStream_t)stream);
+}
+
+int st2_length_regulate(const float* src, const int32_t* dur, float* out, int32_t B, int32_t C, int32_t L,
+                        int32_t F, int32_t channels_last, void* stream) {
+    ST2_REQUIRE(B >= 0 && C >= 0 && L >= 0 && F >= 0, "length_regulate: negative size");
+    if (B == 0 || C == 0 || F == 0) return ST2_OK;
+    ST2_REQUIRE(src && dur && out, "length_regulate: null tensor");
+    return launch_length_regulate(src, dur, out, B, C, L, F, channels_last, (cudaStream_t)stream);
+}
+
+int st2_sinegen_phase(const float* f0, float* phase, float* frames_scratch, int32_t B, int32_t L2,
+                      int32_t upsample_scale, void* stream) {
+    ST2_REQUIRE(f0 && phase && frames_scratch && B > 0 && L2 > 0 && upsample_scale > 0, "sinegen_phase: bad argument");
+    int e = launch_sinegen_frames(f0, frames_scratch, B, L2, upsample_scale, (cudaStream_t)stream);
+    if (e != ST2_OK) return e;
+    return launch_sinegen_phase(frames_scratch, phase, B, L2, upsample_scale, (cudaStream_t)stream);
+}
+
+int st2_har_source(const float* f0, const float* noise, uint64_t seed, const float* lin_w, const float* lin_b,
+                   float* har, float* frames_scratch, int32_t B, int32_t L2, int32_t upsample_scale, void* stream) {
+    ST2_REQUIRE(f0 && lin_w && lin_b && har && frames_scratch && B > 0 && L2 > 0 && upsample_scale > 0,
+                "har_source: bad argument");
+    int e = launch_sinegen_frames(f0, frames_scratch, B, L2, upsample_scale, (cudaStream_t)stream);
+    if (e != ST2_OK) return e;
+    return launch_har_source(f0, frames_scratch, noise, seed, lin_w, lin_b, har, B, L2, upsample_scale,
+                             (cudaStream_t)stream);
+}
+
+int64_t st2_adain_scratch_bytes(int32_t B, int32_t T, int32_t C) {
+    if (B <= 0 || T <= 0 || C <= 0) return ST2_ERR_INVALID;
+    const int Cpad = (C + 3) / 4 * 4;
+    return align256(adain_scratch_bytes(B, T, C)) + align256((int64_t)B * 2 * Cpad * sizeof(float));
+}
+
+int st2_adain_act(const float* x, int32_t ld_x, const float* h, int32_t ld_h, const float* alpha, int32_t act,
+                  float slope, void* y, int32_t ld_y, int32_t out_dtype, int32_t B, int32_t T, int32_t C,
+                  void* scratch, void* stream) {
+    ST2_REQUIRE(x && y && scratch && B > 0 && T > 0 && C > 0, "adain_act: bad argument");
+    ST2_REQUIRE(C % 4 == 0, "adain_act: C=%d must be a multiple of 4", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* coef = (float*)((char*)scratch + align256(adain_scratch_bytes(B, T, C)));
+    int e = ST2_OK;
+    if (h != nullptr) {
+        e = launch_in_stats(x, ld_x, B, T, C, scratch, st);
+        if (e != ST2_OK) return e;
+    }
+    e = launch_adain_coef(scratch, h, ld_h, 0, coef, B, T, C, C, st);
+    if (e != ST2_OK) return e;
+    return launch_affine_act(x, ld_x, coef, alpha, act, slope, y, ld_y, out_dtype, B, T, C, st);
+}
+
+int64_t st2_conv1d_scratch_bytes(int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k, int32_t precision) {
+    if (B <= 0 || Tin <= 0 || Cin <= 0 || Cout <= 0 || k <= 0) return ST2_ERR_INVALID;
+    int64_t bytes = align256((int64_t)k * Cin * Cout * sizeof(float));
+    if (precision != ST2_PREC_FP32) {
+        const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 15) / 16 * 16;
+        bytes += align256((int64_t)k * cin_pad * cout_pad * 2);
+        bytes += align256((int64_t)B * Tin * cin_pad * 2);       // 16-bit copy of x
+        bytes += align256((int64_t)B * 2 * cin_pad * sizeof(float));
+    }
+    return bytes;
+}
+
+int st2_conv1d(const float* x, const float* w, const float* bias, float* y, void* scratch, int32_t B, int32_t Tin,
+               int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t padding, int32_t dilation,
+               int32_t output_padding, int32_t transposed, int32_t precision, void* stream) {
+    ST2_REQUIRE(x && w && y && scratch && B > 0 && Tin > 0 && Cin > 0 && Cout > 0 && k > 0 && stride > 0 && dilation > 0,
+                "conv1d: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wp = (float*)scratch;
+    const int d0 = transposed ? Cin : Cout, d1 = transposed ? Cout : Cin;
+    int e = launch_fold_pack(nullptr, w, wp, d0, d1, k, transposed ? 1 : 0, st);
+    if (e != ST2_OK) return e;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.Tin = Tin;
+    a.w = wp; a.bias = bias; a.y = y; a.ld_y = Cout; a.scale = 1.f;
+    if (!transposed) {
+        a.Tout = (Tin + 2 * padding - dilation * (k - 1) - 1) / stride + 1;
+        a.M = a.Tout; a.ntaps = k; a.tap_step = dilation; a.in_off = -padding; a.in_stride = stride;
+        a.phases = 1; a.w_step = 1; a.out_stride = 1; a.out_pad = 0;
+    } else {
+        ST2_REQUIRE(k % stride == 0 && dilation == 1, "conv1d: transposed needs k %% stride == 0 and dilation 1");
+        a.Tout = (Tin - 1) * stride - 2 * padding + (k - 1) + output_padding + 1;
+        a.ntaps = k / stride; a.tap_step = -1; a.in_off = 0; a.in_stride = 1;
+        a.phases = stride; a.w_step = stride; a.out_stride = stride; a.out_pad = padding;
+        a.M = (a.Tout - 1 + padding) / stride + 1;
+    }
+    ST2_REQUIRE(a.Tout > 0, "conv1d: empty output");
+    if (precision == ST2_PREC_FP32) {
+        a.x = x; a.ld_x = Cin;
+        return launch_conv_simt(a, st);
+    }
+    const int dt = precision == ST2_PREC_BF16 ? DT_BF16 : DT_F16;
+    const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 15) / 16 * 16;
+    char* p = (char*)scratch + align256((int64_t)k * Cin * Cout * sizeof(float));
+    void* w16 = p;
+    p += align256((int64_t)k * cin_pad * cout_pad * 2);
+    void* x16 = p;
+    p += align256((int64_t)B * Tin * cin_pad * 2);
+    float* coef = (float*)p;
+    e = launch_pack_w16(wp, w16, k, Cin, Cout, cin_pad, cout_pad, dt, st);
+    if (e != ST2_OK) return e;
+    ST2_REQUIRE(Cin % 4 == 0, "conv1d: tensor-core unit path needs Cin %% 4 == 0");
+    // 16-bit, channel-padded copy of x (identity affine)
+    ST2_CUDA_CHECK(cudaMemsetAsync(x16, 0, (size_t)B * Tin * cin_pad * 2, st));
+    e = launch_adain_coef(nullptr, nullptr, 0, 0, coef, B, Tin, Cin, Cin, st);
+    if (e != ST2_OK) return e;
+    e = launch_affine_act(x, Cin, coef, nullptr, ACT_NONE, 0.f, x16, cin_pad, dt, B, Tin, Cin, st);
+    if (e != ST2_OK) return e;
+    a.x16 = x16; a.ld_x16 = cin_pad; a.w16 = w16; a.w16_cin_pad = cin_pad; a.w16_cout_pad = cout_pad; a.fmt16 = dt;
+    return launch_conv_tc(a, st);
+}
+
+}  // extern "C"

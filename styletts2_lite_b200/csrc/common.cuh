@@ -1,0 +1,127 @@
+// Shared declarations for the st2_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/st2_b200.h"
+
+namespace st2 {
+
+void set_error(const char* fmt, ...);
+extern thread_local int64_t g_launch_count;
+
+#define ST2_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::st2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                         \
+            return ST2_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define ST2_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        ::st2::g_launch_count++;                                                          \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ::st2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                             __FILE__, __LINE__);                                         \
+            return ST2_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define ST2_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            ::st2::set_error(__VA_ARGS__);                                                \
+            return ST2_ERR_INVALID;                                                       \
+        }                                                                                 \
+    } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2 };
+enum OutDtype { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+
+// ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------
+// InstanceNorm statistics of channels-last x[B][T][ld] over T: partial (sum, sumsq) in
+// double per time slab, then mean / rstd folded with the AdaIN affine into y = a*x + b.
+int64_t adain_scratch_bytes(int B, int T, int C);
+int launch_in_stats(const float* x, int ld, int B, int T, int C, void* scratch, cudaStream_t st);
+// coef[b][0][c] = a, coef[b][1][c] = b  (c < Cpad; zero beyond C).  h: [B][ld_h] with
+// gamma at h_off + c and beta at h_off + C + c; h == nullptr -> a = 1, b = 0 (no norm).
+int launch_adain_coef(const void* scratch, const float* h, int ld_h, int h_off, float* coef, int B,
+                      int T, int C, int Cpad, cudaStream_t st);
+// y = act(a*x+b); snake uses alpha[c].  y pitch ld_y, dtype out_dtype; processes Cpad channels.
+int launch_affine_act(const float* x, int ld_x, const float* coef, const float* alpha, int act,
+                      float slope, void* y, int ld_y, int out_dtype, int B, int T, int Cpad,
+                      cudaStream_t st);
+
+// misc elementwise (kernels_misc.cu)
+int launch_cf_to_cl(const float* src, float* dst, int ld_dst, int B, int C, int T, cudaStream_t st);
+int launch_f0n_conv(const float* f0, const float* n, const float* wf, const float* bf, const float* wn,
+                    const float* bn, float* dst0, int ld0, int c0, int pad0_from, float* dst1, int ld1,
+                    int c1, int pad1_from, int B, int T, cudaStream_t st);
+int launch_style_fc(const float* s, const float* W, const float* bias, float* h, int B, int R, int K,
+                    cudaStream_t st);
+int launch_pool_dw(const float* x, int ld_x, const float* w, const float* bias, float* y, int ld_y, int B,
+                   int T, int C, int Cpad, cudaStream_t st);
+int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
+                        float* out, int B, int S, int C, cudaStream_t st);
+int launch_copy_dense(const float* src, int ld, float* dst, int64_t rows, int C, cudaStream_t st);
+int launch_fold_pack(const float* g, const float* v, float* wp, int d0, int d1, int k, int transposed,
+                     cudaStream_t st);
+int launch_cast16(const float* src, void* dst, int64_t n, int out_dtype, cudaStream_t st);
+int launch_pack_w16(const float* wp, void* w16, int k, int Cin, int Cout, int CinPad, int CoutPad, int out_dtype,
+                    cudaStream_t st);
+
+// source / stft (kernels_source.cu; compiled without fast-math)
+int launch_sinegen_frames(const float* f0, float* frames, int B, int L2, int scale, cudaStream_t st);
+int launch_sinegen_phase(const float* frames, float* phase, int B, int L2, int scale, cudaStream_t st);
+int launch_har_source(const float* f0, const float* frames, const float* noise, uint64_t seed,
+                      const float* lin_w, const float* lin_b, float* har, int B, int L2, int scale,
+                      cudaStream_t st);
+int launch_stft_transform(const float* har, const float* wr, const float* wi, float* out, int ld_out, int B,
+                          int S, int n_fft, int hop, cudaStream_t st);
+int launch_istft_head(const float* x, int ld_x, const float* wr, const float* wi, float* out, int B,
+                      int frames, int S, int n_fft, int hop, cudaStream_t st);
+
+// length regulator (length_regulator.cu)
+int launch_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur, int32_t* total,
+                           int B, int L, cudaStream_t st);
+int launch_length_regulate(const float* src, const int32_t* dur, float* out, int B, int C, int L, int F,
+                           int channels_last, cudaStream_t st);
+
+// ---- convolutions ----------------------------------------------------------------------
+// One description for Conv1d and (polyphase) ConvTranspose1d on channels-last tensors:
+//   for output index m in [0,M) and phase p in [0,phases):
+//     t_out = m*out_stride + p - out_pad        (store if 0 <= t_out < Tout)
+//     acc[co] = sum_j sum_ci x[b][m*in_stride + j*tap_step + in_off][ci] * W[widx(p,j)][ci][co]
+//     widx(p,j) = p + j*w_step            (Conv1d: phases=1, w_step=1; ConvT: w_step=stride)
+//   y = (acc + bias + res[b][t_out >> res_shift][co] (+ y_old if accumulate)) * scale
+//   mirror: the row written at t_out == 2 is also written at row 0 (ReflectionPad1d((1,0)))
+struct ConvArgs {
+    const float* x;  int ld_x;  int Tin;
+    const void* x16; int ld_x16;            // 16-bit operand copy (tensor-core path)
+    const float* w;                          // packed fp32 [k][Cin][Cout]
+    const void* w16;                         // packed 16-bit [k][CoutPad][CinPad] (tensor-core path)
+    int w16_cin_pad, w16_cout_pad;
+    const float* bias;
+    const float* res; int ld_res; int res_shift;
+    float* y; int ld_y; int Tout;
+    int B, Cin, Cout, M;
+    int ntaps, tap_step, in_off, in_stride;
+    int phases, w_step, out_stride, out_pad;
+    float scale; int accumulate; int mirror;
+    int fmt16;                               // DT_BF16 / DT_F16 for the tensor-core path
+};
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int launch_conv_tc(const ConvArgs& a, cudaStream_t st);   // tcgen05 + TMA
+bool conv_tc_supported(const ConvArgs& a);
+
+}  // namespace st2

@@ -1,0 +1,718 @@
+// Decoder handle, load-time weight packing and the forward "program" (the sequence of kernel
+// launches that replaces Decoder.forward / Generator.forward, Modules/hifigan.py:446-475,
+// :321-347 and Modules/istftnet.py:692-721, :542-573), plus the C ABI of include/st2_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace st2 {
+
+thread_local char g_err[1024] = "";
+thread_local int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct RawTensor {
+    const float* ptr;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+struct ConvW {
+    float* w32 = nullptr;       // [k][Cin][Cout]
+    void* w16[3] = {nullptr, nullptr, nullptr};   // index by OutDtype: [k][CoutPad][CinPad]
+    float* bias = nullptr;
+    int Cin = 0, Cout = 0, k = 0;
+    int cin_pad = 0, cout_pad = 0;
+    bool transposed = false;
+};
+
+struct AdaINRef { int h_off = 0; int C = 0; };
+
+struct ResBlock1W {           // AdaINResBlock1 (hifigan.py:26-74)
+    ConvW c1[3], c2[3];
+    AdaINRef n1[3], n2[3];
+    float* alpha1[3] = {nullptr, nullptr, nullptr};
+    float* alpha2[3] = {nullptr, nullptr, nullptr};
+    int k = 0, C = 0;
+    int dil[3] = {1, 3, 5};
+    std::string name;
+};
+
+struct ResBlk1dW {            // AdainResBlk1d (hifigan.py:359-403)
+    ConvW conv1, conv2, conv1x1;
+    bool has_sc = false, upsample = false;
+    AdaINRef norm1, norm2;
+    float* pool_w = nullptr;  // [3][ld_in]
+    float* pool_b = nullptr;  // [ld_in]
+    int Cin = 0, Cout = 0;
+    std::string name;
+};
+
+struct Tap { float* dst; int64_t cap; };
+
+}  // namespace st2
+
+using namespace st2;
+
+struct st2_decoder {
+    st2_config cfg;
+    std::map<std::string, RawTensor> raw;
+    bool finalized = false;
+    std::vector<void*> allocs;
+    int64_t num_params = 0;
+    int64_t last_launches = 0;
+    bool tc_ok = false;
+
+    ResBlk1dW encode, decode[4];
+    float *f0_w = nullptr, *f0_b = nullptr, *n_w = nullptr, *n_b = nullptr;
+    ConvW asr_res;
+    float *lin_w = nullptr, *lin_b = nullptr;
+    float* gen_alpha[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ConvW noise_convs[4], ups[4], conv_post;
+    ResBlock1W noise_res[4], resblocks[12];
+    float *fc_w = nullptr, *fc_b = nullptr;
+    int fc_rows = 0;
+    float *stft_fr = nullptr, *stft_fi = nullptr, *stft_br = nullptr, *stft_bi = nullptr;
+    std::map<std::string, Tap> taps;
+
+    int spf() const {    // samples per asr frame
+        int p = 2;
+        for (int i = 0; i < cfg.n_stages; ++i) p *= cfg.upsample_rates[i];
+        return p * (cfg.variant == 1 ? cfg.gen_istft_hop_size : 1);
+    }
+    int stage_channels(int i) const { return cfg.upsample_initial_channel >> (i + 1); }
+};
+
+namespace st2 {
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------
+// load time
+// ------------------------------------------------------------------------------------------
+struct Packer {
+    st2_decoder* d;
+    cudaStream_t st;
+    int err = ST2_OK;
+    std::vector<std::pair<std::string, int>> adain_list;   // (prefix, C) in h_off order
+
+    void* dalloc(size_t bytes) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed while packing weights", bytes);
+            err = ST2_ERR_CUDA;
+            return nullptr;
+        }
+        d->allocs.push_back(p);
+        return p;
+    }
+    const RawTensor* get(const std::string& n, bool required = true) {
+        auto it = d->raw.find(n);
+        if (it == d->raw.end()) {
+            if (required && err == ST2_OK) {
+                set_error("missing weight '%s'", n.c_str());
+                err = ST2_ERR_INVALID;
+            }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    float* copy(const std::string& n, int64_t expect_numel) {
+        const RawTensor* t = get(n);
+        if (!t) return nullptr;
+        if (t->numel() != expect_numel) {
+            set_error("weight '%s' has %lld elements, expected %lld", n.c_str(), (long long)t->numel(),
+                      (long long)expect_numel);
+            err = ST2_ERR_INVALID;
+            return nullptr;
+        }
+        float* p = (float*)dalloc(expect_numel * sizeof(float));
+        if (p && cudaMemcpyAsync(p, t->ptr, expect_numel * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            err = ST2_ERR_CUDA;
+        return p;
+    }
+    void conv(ConvW& c, const std::string& n, int Cin, int Cout, int k, bool transposed, bool bias, bool want16) {
+        c.Cin = Cin; c.Cout = Cout; c.k = k; c.transposed = transposed;
+        const RawTensor* g = get(n + ".weight_g", false);
+        const RawTensor* v = g ? get(n + ".weight_v") : get(n + ".weight");
+        if (!v) return;
+        const int d0 = transposed ? Cin : Cout, d1 = transposed ? Cout : Cin;
+        if (v->shape.size() != 3 || v->shape[0] != d0 || v->shape[1] != d1 || v->shape[2] != k ||
+            (g && g->numel() != d0)) {
+            set_error("weight '%s' has the wrong shape (expected [%d,%d,%d])", n.c_str(), d0, d1, k);
+            err = ST2_ERR_INVALID;
+            return;
+        }
+        c.w32 = (float*)dalloc((size_t)k * Cin * Cout * sizeof(float));
+        if (!c.w32) return;
+        if (launch_fold_pack(g ? g->ptr : nullptr, v->ptr, c.w32, d0, d1, k, transposed ? 1 : 0, st) != ST2_OK)
+            err = ST2_ERR_CUDA;
+        if (bias) c.bias = copy(n + ".bias", Cout);
+        if (want16 && d->tc_ok) {
+            c.cin_pad = round_up(Cin, 64);
+            c.cout_pad = round_up(Cout, 16);
+            for (int dt = DT_BF16; dt <= DT_F16; ++dt) {
+                c.w16[dt] = dalloc((size_t)k * c.cin_pad * c.cout_pad * 2);
+                if (c.w16[dt] &&
+                    launch_pack_w16(c.w32, c.w16[dt], k, Cin, Cout, c.cin_pad, c.cout_pad, dt, st) != ST2_OK)
+                    err = ST2_ERR_CUDA;
+            }
+        }
+    }
+    void adain(AdaINRef& a, const std::string& prefix, int C) {
+        a.C = C;
+        a.h_off = d->fc_rows;
+        d->fc_rows += 2 * C;
+        adain_list.push_back({prefix, C});
+    }
+    void resblk1d(ResBlk1dW& b, const std::string& n, int Cin, int Cout, bool upsample) {
+        b.name = n; b.Cin = Cin; b.Cout = Cout; b.upsample = upsample; b.has_sc = (Cin != Cout);
+        conv(b.conv1, n + ".conv1", Cin, Cout, 3, false, true, true);
+        conv(b.conv2, n + ".conv2", Cout, Cout, 3, false, true, true);
+        if (b.has_sc) conv(b.conv1x1, n + ".conv1x1", Cin, Cout, 1, false, false, true);
+        adain(b.norm1, n + ".norm1", Cin);
+        adain(b.norm2, n + ".norm2", Cout);
+        if (upsample) {
+            // depthwise ConvTranspose1d weight [C,1,3] -> [3][ld] (zero padded), bias [ld]
+            const int ld = round_up(Cin, 64);
+            ConvW tmp;
+            conv(tmp, n + ".pool", Cin, 1, 3, true, false, false);
+            tmp.bias = copy(n + ".pool.bias", Cin);
+            b.pool_w = (float*)dalloc((size_t)3 * ld * sizeof(float));
+            b.pool_b = (float*)dalloc((size_t)ld * sizeof(float));
+            if (err != ST2_OK || !b.pool_w || !b.pool_b) return;
+            cudaMemsetAsync(b.pool_w, 0, (size_t)3 * ld * sizeof(float), st);
+            cudaMemsetAsync(b.pool_b, 0, (size_t)ld * sizeof(float), st);
+            cudaMemcpy2DAsync(b.pool_w, (size_t)ld * sizeof(float), tmp.w32, (size_t)Cin * sizeof(float),
+                              (size_t)Cin * sizeof(float), 3, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(b.pool_b, tmp.bias, (size_t)Cin * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        }
+    }
+    void resblock1(ResBlock1W& b, const std::string& n, int C, int k, const int* dil) {
+        b.name = n; b.C = C; b.k = k;
+        for (int j = 0; j < 3; ++j) {
+            b.dil[j] = dil[j];
+            const std::string js = std::to_string(j);
+            conv(b.c1[j], n + ".convs1." + js, C, C, k, false, true, true);
+            conv(b.c2[j], n + ".convs2." + js, C, C, k, false, true, true);
+            adain(b.n1[j], n + ".adain1." + js, C);
+            adain(b.n2[j], n + ".adain2." + js, C);
+            b.alpha1[j] = copy(n + ".alpha1." + js, C);
+            b.alpha2[j] = copy(n + ".alpha2." + js, C);
+        }
+    }
+};
+
+static int finalize_impl(st2_decoder* d, cudaStream_t st) {
+    const st2_config& c = d->cfg;
+    Packer P{d, st};
+    d->fc_rows = 0;
+    const int dim_in = c.dim_in;
+    P.resblk1d(d->encode, "encode", dim_in + 2, 1024, false);
+    for (int i = 0; i < 3; ++i) P.resblk1d(d->decode[i], "decode." + std::to_string(i), 1024 + 2 + 64, 1024, false);
+    P.resblk1d(d->decode[3], "decode.3", 1024 + 2 + 64, c.upsample_initial_channel, true);
+    {
+        ConvW t;
+        P.conv(t, "F0_conv", 1, 1, 3, false, true, false);
+        d->f0_w = t.w32; d->f0_b = t.bias;
+        ConvW u;
+        P.conv(u, "N_conv", 1, 1, 3, false, true, false);
+        d->n_w = u.w32; d->n_b = u.bias;
+    }
+    P.conv(d->asr_res, "asr_res.0", dim_in, 64, 1, false, true, true);
+    d->lin_w = P.copy("generator.m_source.l_linear.weight", 9);
+    d->lin_b = P.copy("generator.m_source.l_linear.bias", 1);
+    const bool istft = c.variant == 1;
+    const int c0 = c.upsample_initial_channel;
+    if (!istft) d->gen_alpha[0] = P.copy("generator.alphas.0", c0);
+    const int dil135[3] = {1, 3, 5};
+    for (int i = 0; i < c.n_stages; ++i) {
+        const int C = d->stage_channels(i);
+        const std::string is = std::to_string(i);
+        int sf = 1;
+        for (int j = i + 1; j < c.n_stages; ++j) sf *= c.upsample_rates[j];
+        const bool last = (i + 1 == c.n_stages);
+        const int nc_cin = istft ? c.gen_istft_n_fft + 2 : 1;
+        P.conv(d->noise_convs[i], "generator.noise_convs." + is, nc_cin, C, last ? 1 : 2 * sf, false, true, false);
+        P.resblock1(d->noise_res[i], "generator.noise_res." + is, C, last ? 11 : 7, dil135);
+        P.conv(d->ups[i], "generator.ups." + is, 2 * C, C, c.upsample_kernel_sizes[i], true, true, true);
+        if (!istft) d->gen_alpha[i + 1] = P.copy("generator.alphas." + std::to_string(i + 1), C);
+        for (int j = 0; j < c.n_kernels; ++j)
+            P.resblock1(d->resblocks[i * c.n_kernels + j], "generator.resblocks." + std::to_string(i * c.n_kernels + j),
+                        C, c.resblock_kernel_sizes[j], c.resblock_dilations[j]);
+    }
+    {
+        const int Cl = d->stage_channels(c.n_stages - 1);
+        P.conv(d->conv_post, "generator.conv_post", Cl, istft ? c.gen_istft_n_fft + 2 : 1, 7, false, true, istft);
+    }
+    if (istft) {
+        const int n = c.gen_istft_n_fft, bins = n / 2 + 1;
+        d->stft_fr = P.copy("generator.stft.weight_forward_real", (int64_t)bins * n);
+        d->stft_fi = P.copy("generator.stft.weight_forward_imag", (int64_t)bins * n);
+        d->stft_br = P.copy("generator.stft.weight_backward_real", (int64_t)bins * n);
+        d->stft_bi = P.copy("generator.stft.weight_backward_imag", (int64_t)bins * n);
+    }
+    if (P.err != ST2_OK) return P.err;
+    // all AdaIN fc layers -> one [R,style] matrix (rows: gamma(C) | beta(C) per instance)
+    d->fc_w = (float*)P.dalloc((size_t)d->fc_rows * c.style_dim * sizeof(float));
+    d->fc_b = (float*)P.dalloc((size_t)d->fc_rows * sizeof(float));
+    if (!d->fc_w || !d->fc_b) return P.err;
+    int row = 0;
+    for (auto& pr : P.adain_list) {
+        const RawTensor* w = P.get(pr.first + ".fc.weight");
+        const RawTensor* b = P.get(pr.first + ".fc.bias");
+        if (!w || !b) return P.err;
+        const int rows = 2 * pr.second;
+        if (w->numel() != (int64_t)rows * c.style_dim || b->numel() != rows) {
+            set_error("AdaIN fc '%s' has the wrong shape", pr.first.c_str());
+            return ST2_ERR_INVALID;
+        }
+        ST2_CUDA_CHECK(cudaMemcpyAsync(d->fc_w + (size_t)row * c.style_dim, w->ptr,
+                                       (size_t)rows * c.style_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        ST2_CUDA_CHECK(cudaMemcpyAsync(d->fc_b + row, b->ptr, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        row += rows;
+    }
+    ST2_CUDA_CHECK(cudaStreamSynchronize(st));
+    ST2_CUDA_CHECK(cudaGetLastError());
+    d->num_params = 0;
+    for (auto& kv : d->raw)
+        if (kv.first.find("generator.stft.") == std::string::npos) d->num_params += kv.second.numel();
+    d->finalized = true;
+    return ST2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward program
+// ------------------------------------------------------------------------------------------
+struct Exec {
+    st2_decoder* d;
+    cudaStream_t st;
+    bool dry;                 // plan only: compute the workspace high-water mark
+    int prec;                 // st2_precision
+    int B;
+    char* base;
+    int64_t cap, off = 0, peak = 0;
+    int err = ST2_OK;
+    const float* H = nullptr; // style rows [B][fc_rows]
+    float* coef = nullptr;    // [B][2][2048]
+
+    void* alloc(int64_t bytes) {
+        off = (off + 255) / 256 * 256;
+        void* p = dry ? nullptr : base + off;
+        off += bytes;
+        if (off > peak) peak = off;
+        if (!dry && off > cap && err == ST2_OK) {
+            set_error("workspace too small: need at least %lld bytes, have %lld", (long long)off, (long long)cap);
+            err = ST2_ERR_WORKSPACE;
+        }
+        return p;
+    }
+    float* allocf(int64_t n) { return (float*)alloc(n * (int64_t)sizeof(float)); }
+    bool live() const { return !dry && err == ST2_OK; }
+    void chk(int e) { if (e != ST2_OK && err == ST2_OK) err = e; }
+
+    int fmt_for(const std::string& name) const {
+        if (prec == ST2_PREC_FP32) return DT_F32;
+        if (prec == ST2_PREC_FP16) return DT_F16;
+        // bf16 everywhere except generator.noise_res (fp16 operands, same tensor throughput):
+        // bf16 there alone costs ~9 dB of SNR (precision study)
+        return name.find("noise_res") != std::string::npos ? DT_F16 : DT_BF16;
+    }
+
+    void tap(const std::string& name, const float* src, int ld, int64_t rows, int C) {
+        if (!live()) return;
+        auto it = d->taps.find(name);
+        if (it == d->taps.end() || it->second.dst == nullptr) return;
+        if (rows * C > it->second.cap) {
+            set_error("tap '%s' needs %lld floats, buffer has %lld", name.c_str(), (long long)(rows * C),
+                      (long long)it->second.cap);
+            err = ST2_ERR_INVALID;
+            return;
+        }
+        chk(launch_copy_dense(src, ld, it->second.dst, rows, C, st));
+    }
+
+    // y = act(AdaIN(x)) or act(x) when `n` is null.  x fp32 [B,T,ld_x]; y dtype dt, pitch ld_y.
+    void norm_act(const float* x, int ld_x, int T, int C, const AdaINRef* n, int act, float slope, const float* alpha,
+                  void* y, int ld_y, int dt) {
+        const int Cpad = ld_y < ld_x ? ld_y : ld_x;
+        void* scratch = nullptr;
+        const int64_t mark = off;
+        if (n) scratch = alloc(adain_scratch_bytes(B, T, C));
+        if (live()) {
+            if (n) chk(launch_in_stats(x, ld_x, B, T, C, scratch, st));
+            if (err == ST2_OK) chk(launch_adain_coef(scratch, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
+            if (err == ST2_OK) chk(launch_affine_act(x, ld_x, coef, alpha, act, slope, y, ld_y, dt, B, T, Cpad, st));
+        }
+        off = mark;
+    }
+
+    bool use_tc(const ConvW& w, int dt) const { return dt != DT_F32 && w.w16[dt] != nullptr; }
+
+    // Conv1d (stride 1 here except noise_convs) / ConvTranspose1d through the common ConvArgs contract
+    void conv(const ConvW& w, const void* x, int ld_x, int Tin, int dt, float* y, int ld_y, int Tout, int stride,
+              int padding, int dilation, const float* res, int ld_res, int res_shift, float scale, int accumulate,
+              int out_row_shift = 0, int mirror = 0) {
+        if (!live()) return;
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.Cin = w.Cin; a.Cout = w.Cout;
+        a.Tin = Tin; a.Tout = Tout;
+        a.w = w.w32; a.bias = w.bias;
+        a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
+        a.y = y; a.ld_y = ld_y;
+        a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
+        if (!w.transposed) {
+            a.M = Tout; a.ntaps = w.k; a.tap_step = dilation; a.in_off = -padding; a.in_stride = stride;
+            a.phases = 1; a.w_step = 1; a.out_stride = 1; a.out_pad = -out_row_shift;
+        } else {
+            if (w.k % stride != 0) {
+                set_error("ConvTranspose1d k=%d must be a multiple of stride=%d", w.k, stride);
+                err = ST2_ERR_UNSUPPORTED;
+                return;
+            }
+            a.ntaps = w.k / stride; a.tap_step = -1; a.in_off = 0; a.in_stride = 1;
+            a.phases = stride; a.w_step = stride; a.out_stride = stride; a.out_pad = padding - out_row_shift;
+            a.M = (Tout - 1 - out_row_shift + padding) / stride + 1;
+        }
+        if (use_tc(w, dt)) {
+            a.x16 = x; a.ld_x16 = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad;
+            a.fmt16 = dt;
+            chk(launch_conv_tc(a, st));
+        } else {
+            a.x = (const float*)x; a.ld_x = ld_x;
+            chk(launch_conv_simt(a, st));
+        }
+    }
+
+    // AdainResBlk1d.forward (hifigan.py:400-403).  x [B,T,ld_x] (Cin real channels) -> y [B,T or 2T,ld_y]
+    void resblk1d(const ResBlk1dW& w, const float* x, int ld_x, int T, float* y, int ld_y) {
+        const int64_t mark = off;
+        const int dt = fmt_for(w.name);
+        const bool tc1 = use_tc(w.conv1, dt) && !w.upsample;   // pooled input stays fp32 -> SIMT conv1
+        const int dt1 = tc1 ? dt : DT_F32;
+        const int es1 = dt1 == DT_F32 ? 4 : 2;
+        const int Tc = w.upsample ? 2 * T : T;
+        void* xa = alloc((int64_t)B * T * ld_x * es1);
+        norm_act(x, ld_x, T, w.Cin, &w.norm1, ACT_LRELU, 0.2f, nullptr, xa, ld_x, dt1);
+        const void* cin = xa;
+        if (w.upsample) {
+            float* xp = allocf((int64_t)B * Tc * ld_x);
+            if (live()) chk(launch_pool_dw((const float*)xa, ld_x, w.pool_w, w.pool_b, xp, ld_x, B, T, w.Cin, ld_x, st));
+            cin = xp;
+        }
+        float* h1 = allocf((int64_t)B * Tc * w.Cout);
+        conv(w.conv1, cin, ld_x, Tc, dt1, h1, w.Cout, Tc, 1, 1, 1, nullptr, 0, 0, 1.f, 0);
+        tap(w.name + ".conv1", h1, w.Cout, (int64_t)B * Tc, w.Cout);
+        const bool tc2 = use_tc(w.conv2, dt);
+        const int dt2 = tc2 ? dt : DT_F32;
+        void* xa2 = alloc((int64_t)B * Tc * w.Cout * (dt2 == DT_F32 ? 4 : 2));
+        norm_act(h1, w.Cout, Tc, w.Cout, &w.norm2, ACT_LRELU, 0.2f, nullptr, xa2, w.Cout, dt2);
+        const float* res = x;
+        int ld_res = ld_x;
+        if (w.has_sc) {
+            float* sc = allocf((int64_t)B * T * w.Cout);
+            const bool tcs = use_tc(w.conv1x1, dt);
+            const void* xin = x;
+            if (tcs) {   // 16-bit copy of the raw block input for the tensor-core 1x1
+                void* x16 = alloc((int64_t)B * T * ld_x * 2);
+                norm_act(x, ld_x, T, w.Cin, nullptr, ACT_NONE, 0.f, nullptr, x16, ld_x, dt);
+                xin = x16;
+            }
+            conv(w.conv1x1, xin, ld_x, T, tcs ? dt : DT_F32, sc, w.Cout, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
+            res = sc;
+            ld_res = w.Cout;
+        }
+        conv(w.conv2, xa2, w.Cout, Tc, dt2, y, ld_y, Tc, 1, 1, 1, res, ld_res, w.upsample ? 1 : 0,
+             0.70710678118654752f, 0);
+        tap(w.name, y, ld_y, (int64_t)B * Tc, w.Cout);
+        off = mark;
+    }
+
+    // AdaINResBlock1.forward (hifigan.py:65-74) on x_in [B,T,C]; the running tensor lives in `run`
+    // (may alias x_in for an in-place block); the last iteration writes
+    // dest = (dest_old*accumulate + conv2 + run) * scale.
+    void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate) {
+        const int64_t mark = off;
+        const int C = w.C;
+        const int dt = fmt_for(w.name);
+        const bool tc = use_tc(w.c1[0], dt);
+        const int dta = tc ? dt : DT_F32;
+        void* xa = alloc((int64_t)B * T * C * (dta == DT_F32 ? 4 : 2));
+        float* xt = allocf((int64_t)B * T * C);
+        const float* cur = x_in;
+        for (int j = 0; j < 3; ++j) {
+            const int dil = w.dil[j];
+            norm_act(cur, C, T, C, &w.n1[j], ACT_SNAKE, 0.f, w.alpha1[j], xa, C, dta);
+            conv(w.c1[j], xa, C, T, dta, xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr, 0, 0, 1.f, 0);
+            tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
+            norm_act(xt, C, T, C, &w.n2[j], ACT_SNAKE, 0.f, w.alpha2[j], xa, C, dta);
+            const bool last = (j == 2);
+            float* out = last ? dest : run;
+            conv(w.c2[j], xa, C, T, dta, out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0, last ? scale : 1.f,
+                 last ? accumulate : 0);
+            if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
+            cur = out;
+        }
+        off = mark;
+    }
+};
+
+static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const float* nn, const float* s,
+                        const float* noise, uint64_t seed, float* out, int B, int T, int prec, void* ws,
+                        int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
+    const st2_config& c = d->cfg;
+    const bool istft = c.variant == 1;
+    Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    const int spf = d->spf();
+    const int S = spf * T, L2 = 2 * T;
+    const int up_scale = spf / 2;
+    const int C514 = c.dim_in + 2, LD514 = round_up(C514, 64);
+    const int C1090 = 1024 + 2 + 64, LD1090 = round_up(C1090, 64);
+
+    float* H = E.allocf((int64_t)B * d->fc_rows);
+    E.H = H;
+    E.coef = E.allocf((int64_t)B * 2 * 2048);
+    float* frames = E.allocf((int64_t)B * L2 * 9);
+    float* har = E.allocf((int64_t)B * S);
+    float* x514 = E.allocf((int64_t)B * T * LD514);
+    float* x1090 = E.allocf((int64_t)B * T * LD1090);
+    const int C0 = c.upsample_initial_channel;
+    float* xg = E.allocf((int64_t)B * 2 * T * C0);
+    // per-stage outputs (the mean over the three resblocks), allocated up front
+    float* stage_out[4];
+    int stage_T[4];
+    {
+        int Tcur = 2 * T;
+        for (int i = 0; i < c.n_stages; ++i) {
+            Tcur *= c.upsample_rates[i];
+            stage_T[i] = Tcur + ((istft && i + 1 == c.n_stages) ? 1 : 0);
+            stage_out[i] = E.allocf((int64_t)B * stage_T[i] * d->stage_channels(i));
+        }
+    }
+    const int har_frames = S / (istft ? c.gen_istft_hop_size : 1) + 1;
+    const int HLD = 24;
+    float* har22 = istft ? E.allocf((int64_t)B * har_frames * HLD) : nullptr;
+
+    if (E.live()) {
+        E.chk(launch_style_fc(s, d->fc_w, d->fc_b, H, B, d->fc_rows, c.style_dim, st));
+        E.chk(launch_cf_to_cl(asr, x514, LD514, B, c.dim_in, T, st));
+        E.chk(launch_f0n_conv(f0, nn, d->f0_w, d->f0_b, d->n_w, d->n_b, x514, LD514, c.dim_in, C514, x1090, LD1090,
+                              1024 + 64, C1090, B, T, st));
+        E.chk(launch_sinegen_frames(f0, frames, B, L2, up_scale, st));
+        E.chk(launch_har_source(f0, frames, noise, seed, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
+        if (istft)
+            E.chk(launch_stft_transform(har, d->stft_fr, d->stft_fi, har22, HLD, B, S, c.gen_istft_n_fft,
+                                        c.gen_istft_hop_size, st));
+    }
+    E.tap("har_source", har, 1, (int64_t)B * S, 1);
+    if (istft) E.tap("har", har22, HLD, (int64_t)B * har_frames, c.gen_istft_n_fft + 2);
+
+    // ---- front half: encode, asr_res, decode[0..3] (hifigan.py:461-472)
+    E.resblk1d(d->encode, x514, LD514, T, x1090, LD1090);
+    {
+        const int dt = E.fmt_for("asr_res");
+        const bool tc = E.use_tc(d->asr_res, dt);
+        const int64_t mark = E.off;
+        const void* xin = x514;
+        if (tc) {
+            void* x16 = E.alloc((int64_t)B * T * LD514 * 2);
+            E.norm_act(x514, LD514, T, C514, nullptr, ACT_NONE, 0.f, nullptr, x16, LD514, dt);
+            xin = x16;
+        }
+        E.conv(d->asr_res, xin, LD514, T, tc ? dt : DT_F32, x1090 + 1024, LD1090, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
+        E.off = mark;
+    }
+    for (int i = 0; i < 3; ++i) E.resblk1d(d->decode[i], x1090, LD1090, T, x1090, LD1090);
+    E.resblk1d(d->decode[3], x1090, LD1090, T, xg, C0);
+    E.tap("decode.out", xg, C0, (int64_t)B * 2 * T, C0);
+
+    // ---- generator (hifigan.py:328-345 / istftnet.py:552-573)
+    const float* x = xg;
+    int Tin = 2 * T;
+    for (int i = 0; i < c.n_stages; ++i) {
+        const int64_t mark = E.off;
+        const int C = d->stage_channels(i), Cin = 2 * C;
+        const int u = c.upsample_rates[i], ku = c.upsample_kernel_sizes[i];
+        const int Tout = stage_T[i];
+        const bool last = (i + 1 == c.n_stages);
+        const int shift = (istft && last) ? 1 : 0;          // ReflectionPad1d((1,0))
+        const std::string is = std::to_string(i);
+        // x_source = noise_res[i](noise_convs[i](har_source), s)
+        float* nc = E.allocf((int64_t)B * Tout * C);
+        {
+            const ConvW& w = d->noise_convs[i];
+            int sf = 1;
+            for (int j = i + 1; j < c.n_stages; ++j) sf *= c.upsample_rates[j];
+            const int stride = last ? 1 : sf, pad = last ? 0 : (sf + 1) / 2;
+            if (istft) E.conv(w, har22, HLD, har_frames, DT_F32, nc, C, Tout, stride, pad, 1, nullptr, 0, 0, 1.f, 0);
+            else E.conv(w, har, 1, S, DT_F32, nc, C, Tout, stride, pad, 1, nullptr, 0, 0, 1.f, 0);
+        }
+        E.resblock1(d->noise_res[i], nc, nc, Tout, nc, 1.f, 0);
+        // x = ups[i](act(x)) + x_source
+        const int dtu = E.fmt_for("generator.ups");
+        const bool tcu = E.use_tc(d->ups[i], dtu);
+        void* xs = E.alloc((int64_t)B * Tin * Cin * (tcu ? 2 : 4));
+        if (istft) E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_LRELU, 0.1f, nullptr, xs, Cin, tcu ? dtu : DT_F32);
+        else E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_SNAKE, 0.f, d->gen_alpha[i], xs, Cin, tcu ? dtu : DT_F32);
+        float* xu = E.allocf((int64_t)B * Tout * C);
+        const int pu = istft ? (ku - u) / 2 : (u / 2 + u % 2);
+        // istftnet: ReflectionPad1d((1,0)) after the last ups = write at row t+1 and mirror row 2 into row 0
+        E.conv(d->ups[i], xs, Cin, Tin, tcu ? dtu : DT_F32, xu, C, Tout, u, pu, 1, nc, C, 0, 1.f, 0, shift, shift);
+        E.tap("generator.stage" + is + ".in", xu, C, (int64_t)B * Tout, C);
+        float* run = E.allocf((int64_t)B * Tout * C);
+        for (int j = 0; j < c.n_kernels; ++j) {
+            const bool lastk = (j + 1 == c.n_kernels);
+            E.resblock1(d->resblocks[i * c.n_kernels + j], xu, run, Tout, stage_out[i], lastk ? 1.f / (float)c.n_kernels : 1.f,
+                        j > 0 ? 1 : 0);
+        }
+        E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
+        x = stage_out[i];
+        Tin = Tout;
+        E.off = mark;
+    }
+    const int Cl = d->stage_channels(c.n_stages - 1);
+    if (!istft) {
+        if (E.live())
+            E.chk(launch_post_hifigan(x, Cl, d->gen_alpha[c.n_stages], d->conv_post.w32, d->conv_post.bias, out, B, S, Cl, st));
+    } else {
+        const int dt = E.fmt_for("generator.conv_post");
+        const bool tc = E.use_tc(d->conv_post, dt);
+        void* xa = E.alloc((int64_t)B * Tin * Cl * (tc ? 2 : 4));
+        E.norm_act(x, Cl, Tin, Cl, nullptr, ACT_LRELU, 0.01f, nullptr, xa, Cl, tc ? dt : DT_F32);
+        float* y22 = E.allocf((int64_t)B * Tin * HLD);
+        E.conv(d->conv_post, xa, Cl, Tin, tc ? dt : DT_F32, y22, HLD, Tin, 1, 3, 1, nullptr, 0, 0, 1.f, 0);
+        E.tap("generator.conv_post", y22, HLD, (int64_t)B * Tin, c.gen_istft_n_fft + 2);
+        if (E.live())
+            E.chk(launch_istft_head(y22, HLD, d->stft_br, d->stft_bi, out, B, Tin, S, c.gen_istft_n_fft,
+                                    c.gen_istft_hop_size, st));
+    }
+    if (peak_out) *peak_out = E.peak;
+    return E.err;
+}
+
+}  // namespace st2
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int st2_abi_version(void) { return ST2_ABI_VERSION; }
+const char* st2_last_error(void) { return st2::g_err; }
+
+int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
+    ST2_REQUIRE(cfg != nullptr && out != nullptr, "create: null argument");
+    ST2_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "create: variant must be 0 (hifigan) or 1 (istftnet)");
+    ST2_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= 4 && cfg->n_kernels == 3, "create: unsupported stage/kernel count");
+    ST2_REQUIRE(cfg->dim_in == 512 && cfg->style_dim >= 4 && cfg->style_dim <= 1024, "create: dim_in must be 512");
+    ST2_REQUIRE(cfg->upsample_initial_channel % 64 == 0 && (cfg->upsample_initial_channel >> cfg->n_stages) >= 4 &&
+                    ((cfg->upsample_initial_channel >> cfg->n_stages) % 4) == 0,
+                "create: unsupported upsample_initial_channel");
+    for (int i = 0; i < cfg->n_stages; ++i)
+        ST2_REQUIRE(cfg->upsample_rates[i] >= 1 && cfg->upsample_kernel_sizes[i] % cfg->upsample_rates[i] == 0,
+                    "create: upsample kernel must be a multiple of its rate");
+    if (cfg->variant == 1)
+        ST2_REQUIRE(cfg->gen_istft_n_fft == 20 && cfg->gen_istft_hop_size == 5, "create: iSTFT head supports n_fft=20, hop=5");
+    st2_decoder* d = new (std::nothrow) st2_decoder();
+    ST2_REQUIRE(d != nullptr, "create: out of memory");
+    d->cfg = *cfg;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+        d->tc_ok = (prop.major == 10);
+    *out = d;
+    return ST2_OK;
+}
+
+void st2_decoder_destroy(st2_decoder* d) {
+    if (!d) return;
+    for (void* p : d->allocs) cudaFree(p);
+    delete d;
+}
+
+int st2_decoder_set_weight(st2_decoder* d, const char* name, const float* dev_ptr, const int64_t* shape, int32_t ndim) {
+    ST2_REQUIRE(d && name && dev_ptr && (shape || ndim == 0) && ndim >= 0 && ndim <= 4, "set_weight: bad argument");
+    st2::RawTensor t;
+    t.ptr = dev_ptr;
+    for (int i = 0; i < ndim; ++i) t.shape.push_back(shape[i]);
+    d->raw[name] = t;
+    return ST2_OK;
+}
+
+int st2_decoder_finalize(st2_decoder* d, void* stream) {
+    ST2_REQUIRE(d != nullptr, "finalize: null handle");
+    for (void* p : d->allocs) cudaFree(p);
+    d->allocs.clear();
+    d->finalized = false;
+    int e = st2::finalize_impl(d, (cudaStream_t)stream);
+    if (e != ST2_OK) {
+        for (void* p : d->allocs) cudaFree(p);
+        d->allocs.clear();
+    }
+    return e;
+}
+
+int64_t st2_decoder_num_params(const st2_decoder* d) { return d ? d->num_params : 0; }
+
+int64_t st2_decoder_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision) {
+    if (!d || !d->finalized || B <= 0 || T <= 0) {
+        st2::set_error("workspace_bytes: handle not finalized or bad shape");
+        return ST2_ERR_STATE;
+    }
+    int64_t peak = 0;
+    int e = st2::forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, B, T,
+                              precision, nullptr, 0, nullptr, true, &peak);
+    if (e != ST2_OK) return e;
+    return peak + 256;
+}
+
+int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const float* n, const float* s,
+                        const float* noise, uint64_t seed, float* out, int32_t B, int32_t T, int32_t precision,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+    ST2_REQUIRE(d != nullptr, "forward: null handle");
+    if (!d->finalized) {
+        st2::set_error("forward: st2_decoder_finalize has not been called");
+        return ST2_ERR_STATE;
+    }
+    ST2_REQUIRE(asr && f0 && n && s && out && workspace, "forward: null tensor");
+    ST2_REQUIRE(B > 0 && T >= 2, "forward: need B>0 and T>=2 (got B=%d T=%d)", B, T);
+    ST2_REQUIRE(precision >= ST2_PREC_FP32 && precision <= ST2_PREC_FP16, "forward: bad precision %d", precision);
+    if (precision != ST2_PREC_FP32 && !d->tc_ok) {
+        st2::set_error("forward: tensor-core precision requires an sm_100 device");
+        return ST2_ERR_UNSUPPORTED;
+    }
+    ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
+    st2::g_launch_count = 0;
+    int e = st2::forward_impl(d, asr, f0, n, s, noise, seed, out, B, T, precision, workspace, workspace_bytes,
+                              (cudaStream_t)stream, false, nullptr);
+    d->last_launches = st2::g_launch_count;
+    return e;
+}
+
+int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t capacity) {
+    ST2_REQUIRE(d && name, "set_tap: bad argument");
+    if (dst == nullptr) d->taps.erase(name);
+    else d->taps[name] = st2::Tap{dst, capacity};
+    return ST2_OK;
+}
+
+int64_t st2_decoder_last_launch_count(const st2_decoder* d) { return d ? d->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// Small layout / front-end / load-time kernels of the decoder.
+#include "common.cuh"
+
+namespace st2 {
+
+// ---- [B,C,T] (reference layout) -> channels-last [B,T,ld] ------------------------------
+__global__ void cf_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int ld, int C, int T) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? src[((size_t)b * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < T && c < C) dst[((size_t)b * T + t) * ld + c] = tile[threadIdx.x][i];
+    }
+}
+
+int launch_cf_to_cl(const float* src, float* dst, int ld_dst, int B, int C, int T, cudaStream_t st) {
+    dim3 grid(cdiv(T, 32), cdiv(C, 32), B), block(32, 8);
+    cf_to_cl_kernel<<<grid, block, 0, st>>>(src, dst, ld_dst, C, T);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- F0_conv / N_conv: Conv1d(1,1,k=3,stride=2,pad=1) (hifigan.py:434-436,458-459) --------
+// Writes F0,N into the channel slots c0,c0+1 of the 514-wide and c1,c1+1 of the 1090-wide
+// concat buffers (torch.cat of hifigan.py:461,469) and zeroes their padding channels.
+__global__ void f0n_conv_kernel(const float* __restrict__ f0, const float* __restrict__ nn,
+                                const float* __restrict__ wf, const float* __restrict__ bf,
+                                const float* __restrict__ wn, const float* __restrict__ bn,
+                                float* __restrict__ dst0, int ld0, int c0, int pad0_from,
+                                float* __restrict__ dst1, int ld1, int c1, int pad1_from, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= T) return;
+    const int L2 = 2 * T;
+    const float* fb = f0 + (size_t)b * L2;
+    const float* nb = nn + (size_t)b * L2;
+    float af = bf[0], an = bn[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int i = 2 * t + k - 1;
+        if (i >= 0 && i < L2) {
+            af = fmaf(wf[k], fb[i], af);
+            an = fmaf(wn[k], nb[i], an);
+        }
+    }
+    float* r0 = dst0 + ((size_t)b * T + t) * ld0;
+    r0[c0] = af;
+    r0[c0 + 1] = an;
+    for (int c = pad0_from; c < ld0; ++c) r0[c] = 0.f;
+    float* r1 = dst1 + ((size_t)b * T + t) * ld1;
+    r1[c1] = af;
+    r1[c1 + 1] = an;
+    for (int c = pad1_from; c < ld1; ++c) r1[c] = 0.f;
+}
+
+int launch_f0n_conv(const float* f0, const float* n, const float* wf, const float* bf, const float* wn,
+                    const float* bn, float* dst0, int ld0, int c0, int pad0_from, float* dst1, int ld1, int c1,
+                    int pad1_from, int B, int T, cudaStream_t st) {
+    dim3 grid(cdiv(T, 128), B);
+    f0n_conv_kernel<<<grid, 128, 0, st>>>(f0, n, wf, bf, wn, bn, dst0, ld0, c0, pad0_from, dst1, ld1, c1,
+                                          pad1_from, T);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- all AdaIN fc layers at once: h[B][R] = s[B][K] @ W[R][K]^T + bias[R] ------------------
+// (the 106 nn.Linear(style_dim, 2C) of hifigan.py:18,21; one warp per output row)
+__global__ void style_fc_kernel(const float* __restrict__ s, const float* __restrict__ W,
+                                const float* __restrict__ bias, float* __restrict__ h, int B, int R, int K) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= R) return;
+    const float* wr = W + (size_t)warp * K;
+    const float bv = bias[warp];
+    for (int b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(wr[k], s[(size_t)b * K + k], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) h[(size_t)b * R + warp] = acc + bv;
+    }
+}
+
+int launch_style_fc(const float* s, const float* W, const float* bias, float* h, int B, int R, int K,
+                    cudaStream_t st) {
+    const int warps_per_cta = 8;
+    style_fc_kernel<<<cdiv(R, warps_per_cta), warps_per_cta * 32, 0, st>>>(s, W, bias, h, B, R, K);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- AdainResBlk1d.pool: depthwise ConvTranspose1d(k=3,s=2,p=1,op=1) (hifigan.py:373) ------
+// w packed [3][Cpad], bias [Cpad].  y[2q] = b + x[q]*w1 ; y[2q+1] = b + x[q]*w2 + x[q+1]*w0.
+__global__ void pool_dw_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ y, int ld_y, int T, int Cpad) {
+    const int cq = Cpad >> 2;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t total = (size_t)2 * T * cq;
+    if (i >= total) return;
+    const int to = (int)(i / cq);
+    const int c = (int)(i - (size_t)to * cq) * 4;
+    const int q = to >> 1;
+    const float* xb = x + (size_t)b * T * ld_x;
+    float4 bv = *reinterpret_cast<const float4*>(bias + c);
+    float4 x0 = *reinterpret_cast<const float4*>(xb + (size_t)q * ld_x + c);
+    float4 o;
+    if ((to & 1) == 0) {
+        float4 w1 = *reinterpret_cast<const float4*>(w + Cpad + c);
+        o.x = fmaf(x0.x, w1.x, bv.x); o.y = fmaf(x0.y, w1.y, bv.y);
+        o.z = fmaf(x0.z, w1.z, bv.z); o.w = fmaf(x0.w, w1.w, bv.w);
+    } else {
+        float4 w2 = *reinterpret_cast<const float4*>(w + 2 * Cpad + c);
+        o.x = fmaf(x0.x, w2.x, bv.x); o.y = fmaf(x0.y, w2.y, bv.y);
+        o.z = fmaf(x0.z, w2.z, bv.z); o.w = fmaf(x0.w, w2.w, bv.w);
+        if (q + 1 < T) {
+            float4 w0 = *reinterpret_cast<const float4*>(w + c);
+            float4 x1 = *reinterpret_cast<const float4*>(xb + (size_t)(q + 1) * ld_x + c);
+            o.x = fmaf(x1.x, w0.x, o.x); o.y = fmaf(x1.y, w0.y, o.y);
+            o.z = fmaf(x1.z, w0.z, o.z); o.w = fmaf(x1.w, w0.w, o.w);
+        }
+    }
+    *reinterpret_cast<float4*>(y + ((size_t)b * 2 * T + to) * ld_y + c) = o;
+}
+
+int launch_pool_dw(const float* x, int ld_x, const float* w, const float* bias, float* y, int ld_y, int B, int T,
+                   int C, int Cpad, cudaStream_t st) {
+    (void)C;
+    size_t total = (size_t)2 * T * (Cpad / 4);
+    dim3 grid(cdiv(total, 256), B);
+    pool_dw_kernel<<<grid, 256, 0, st>>>(x, ld_x, w, bias, y, ld_y, T, Cpad);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- hifigan tail: Snake(alphas[-1]) -> conv_post(C->1,k=7,p=3) -> tanh (hifigan.py:343-345) --
+static constexpr int kPostTile = 256;
+__global__ void __launch_bounds__(kPostTile)
+post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ alpha,
+                    const float* __restrict__ w /*[7][C]*/, const float* __restrict__ bias,
+                    float* __restrict__ out, int S, int C) {
+    extern __shared__ float sm[];
+    const int pitch = C + 1;
+    float* tile = sm;                                  // [(kPostTile+6)][C+1]
+    float* sw = sm + (kPostTile + 6) * pitch;          // [7][C]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * kPostTile;
+    for (int i = threadIdx.x; i < 7 * C; i += kPostTile) sw[i] = w[i];
+    const int cq = C >> 2;
+    for (int i = threadIdx.x; i < (kPostTile + 6) * cq; i += kPostTile) {
+        int r = i / cq, c = (i - r * cq) * 4;
+        int t = t0 + r - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < S) {
+            v = *reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * ld_x + c);
+            float4 al = *reinterpret_cast<const float4*>(alpha + c);
+            float s0 = sinf(al.x * v.x), s1 = sinf(al.y * v.y), s2 = sinf(al.z * v.z), s3 = sinf(al.w * v.w);
+            v.x = fmaf((1.f / al.x) * s0, s0, v.x);
+            v.y = fmaf((1.f / al.y) * s1, s1, v.y);
+            v.z = fmaf((1.f / al.z) * s2, s2, v.z);
+            v.w = fmaf((1.f / al.w) * s3, s3, v.w);
+        }
+        float* d = tile + r * pitch + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= S) return;
+    float acc = bias[0];
+    for (int k = 0; k < 7; ++k) {
+        const float* row = tile + (threadIdx.x + k) * pitch;
+        const float* wk = sw + k * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(wk[c], row[c], acc);
+    }
+    out[(size_t)b * S + t] = tanhf(acc);
+}
+
+int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
+                        float* out, int B, int S, int C, cudaStream_t st) {
+    ST2_REQUIRE(C % 4 == 0 && C <= 64 && ld_x % 4 == 0, "post_hifigan: C=%d ld=%d unsupported", C, ld_x);
+    size_t smem = ((size_t)(kPostTile + 6) * (C + 1) + 7 * C) * sizeof(float);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(post_hifigan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(cdiv(S, kPostTile), B);
+    post_hifigan_kernel<<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- dense copy of a pitched channels-last tensor (debug taps) ------------------------------
+__global__ void copy_dense_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int64_t rows,
+                                  int C) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    dst[i] = src[r * ld + c];
+}
+
+int launch_copy_dense(const float* src, int ld, float* dst, int64_t rows, int C, cudaStream_t st) {
+    copy_dense_kernel<<<cdiv(rows * C, 256), 256, 0, st>>>(src, ld, dst, rows, C);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- load time: weight-norm fold + repack to tap-major [k][Cin][Cout] ------------------------
+// torch._weight_norm(v, g, 0): w = v * g / ||v|| with the norm over all dims but 0.
+// Conv1d: v [Cout][Cin][k] (d0=Cout,d1=Cin);  ConvTranspose1d: v [Cin][Cout][k] (d0=Cin,d1=Cout).
+__global__ void fold_pack_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ wp,
+                                 int d0, int d1, int k, int transposed) {
+    const int r = blockIdx.x;
+    const int n = d1 * k;
+    const float* vr = v + (size_t)r * n;
+    __shared__ double red[256];
+    __shared__ float s_scale;
+    double ss = 0;
+    if (g != nullptr)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) ss += (double)vr[i] * (double)vr[i];
+    red[threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_scale = (g != nullptr) ? g[r] / (float)sqrt(red[0]) : 1.f;
+    __syncthreads();
+    const float sc = s_scale;
+    const int Cin = transposed ? d0 : d1;
+    const int Cout = transposed ? d1 : d0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int j = i / k, kk = i - j * k;          // j indexes d1
+        int ci = transposed ? r : j;
+        int co = transposed ? j : r;
+        wp[((size_t)kk * Cin + ci) * Cout + co] = vr[i] * sc;
+    }
+}
+
+int launch_fold_pack(const float* g, const float* v, float* wp, int d0, int d1, int k, int transposed,
+                     cudaStream_t st) {
+    fold_pack_kernel<<<d0, 256, 0, st>>>(g, v, wp, d0, d1, k, transposed);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- load time: fp32 [k][Cin][Cout] -> 16-bit [k][CoutPad][CinPad] (K-major B operand) -------
+__global__ void pack_w16_kernel(const float* __restrict__ wp, void* __restrict__ w16, int k, int Cin, int Cout,
+                                int CinPad, int CoutPad, int dt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)k * CoutPad * CinPad;
+    if (i >= total) return;
+    int ci = (int)(i % CinPad);
+    int co = (int)((i / CinPad) % CoutPad);
+    int kk = (int)(i / ((size_t)CinPad * CoutPad));
+    float v = (ci < Cin && co < Cout) ? wp[((size_t)kk * Cin + ci) * Cout + co] : 0.f;
+    if (dt == DT_BF16)
+        reinterpret_cast<__nv_bfloat16*>(w16)[i] = __float2bfloat16_rn(v);
+    else
+        reinterpret_cast<__half*>(w16)[i] = __float2half_rn(v);
+}
+
+int launch_cast16(const float* src, void* dst, int64_t n, int out_dtype, cudaStream_t st) {
+    // contiguous cast == pack with k=1, Cout=1, Cin=n
+    pack_w16_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, dst, 1, (int)n, 1, (int)n, 1, out_dtype);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_pack_w16(const float* wp, void* w16, int k, int Cin, int Cout, int CinPad, int CoutPad, int out_dtype,
+                    cudaStream_t st) {
+    size_t total = (size_t)k * CoutPad * CinPad;
+    pack_w16_kernel<<<cdiv(total, 256), 256, 0, st>>>(wp, w16, k, Cin, Cout, CinPad, CoutPad, out_dtype);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+}  // namespace st2

@@ -1,0 +1,168 @@
+"""Drop-in `Decoder` modules for the StyleTTS2-lite waveform decoder.
+
+Host-side mirror of the reference interface (Modules/hifigan.py:416-475 and
+Modules/istftnet.py:660-721): same constructor keywords, same `state_dict` keys
+(legacy weight-norm pairs, so `load_state_dict` of a reference checkpoint works,
+inference.py:160), same `forward(asr, F0_curve, N, s) -> [B,1,600*T]`.  The
+arithmetic runs in the sm_100a kernels behind include/st2_b200.h; PyTorch only
+owns the tensors, the stream and the workspace.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import DecoderConfig, buffer_specs, param_specs
+from .synth import stft_buffers
+
+
+def _register(root: nn.Module, name: str, tensor: torch.Tensor, buffer: bool = False) -> None:
+    parts = name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    if buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class B200Decoder(nn.Module):
+    """Base of the two drop-in decoders.  `precision`: 'fp32' (SIMT, <=1e-4 of the CPU
+    reference), 'bf16' (tcgen05, bf16 operands; generator.noise_res on fp16 operands) or
+    'fp16' (tcgen05, fp16 operands)."""
+
+    def __init__(self, cfg: DecoderConfig, precision: str = "fp32"):
+        super().__init__()
+        if precision not in _lib.PREC:
+            raise ValueError("precision must be one of %s" % list(_lib.PREC))
+        self.cfg = cfg
+        self.precision = precision
+        for name, shape, kind in param_specs(cfg):
+            init = torch.ones(shape) if kind == "alpha" else torch.zeros(shape)
+            _register(self, name, init)
+        if cfg.is_istft:
+            bufs = stft_buffers(cfg)
+            for name, _ in buffer_specs(cfg):
+                _register(self, name, bufs[name].clone(), buffer=True)
+        self._handle: Optional[C.c_void_p] = None
+        self._dirty = True
+        self._workspace: Optional[torch.Tensor] = None
+        self._taps: Dict[str, torch.Tensor] = {}
+        self.train(False)
+
+    # ---- weights -------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._dirty = True
+        return r
+
+    def load_state_dict(self, state_dict, strict: bool = True, *a, **k):
+        r = super().load_state_dict(state_dict, strict, *a, **k)
+        self._dirty = True
+        return r
+
+    def refresh_weights(self) -> None:
+        """Re-pack after an in-place parameter update."""
+        self._dirty = True
+
+    def _sync(self, device: torch.device) -> None:
+        lib = _lib.load()
+        if self._handle is None:
+            h = C.c_void_p()
+            cc = _lib.St2Config.from_config(self.cfg)
+            _lib.check(lib.st2_decoder_create(C.byref(cc), C.byref(h)), "st2_decoder_create")
+            self._handle = h
+        keep = []
+        for name, t in self.state_dict().items():
+            if t.device != device:
+                raise _lib.St2Error("parameter %s is on %s but inputs are on %s; call .to(device)" % (name, t.device, device))
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            _lib.check(lib.st2_decoder_set_weight(self._handle, name.encode(), _lib.ptr(t), shape, t.dim()),
+                       "st2_decoder_set_weight(%s)" % name)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.st2_decoder_finalize(self._handle, C.c_void_p(stream)), "st2_decoder_finalize")
+        del keep
+        self._dirty = False
+
+    def num_params(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    # ---- forward ---------------------------------------------------------------------------
+    def workspace_bytes(self, B: int, T: int, precision: Optional[str] = None) -> int:
+        lib = _lib.load()
+        n = lib.st2_decoder_workspace_bytes(self._handle, B, T, _lib.PREC[precision or self.precision])
+        return _lib.check(n, "st2_decoder_workspace_bytes")
+
+    def set_tap(self, name: str, B: int, rows: int, C_: int) -> torch.Tensor:
+        """Register a debug tap; returns the [B, rows, C] buffer the next forward fills."""
+        dev = next(self.parameters()).device
+        buf = torch.zeros(B, rows, C_, device=dev, dtype=torch.float32)
+        if self._handle is None:
+            self._sync(dev)
+        _lib.check(_lib.load().st2_decoder_set_tap(self._handle, name.encode(), _lib.ptr(buf), buf.numel()), "set_tap")
+        self._taps[name] = buf
+        return buf
+
+    def clear_taps(self) -> None:
+        for name in list(self._taps):
+            _lib.load().st2_decoder_set_tap(self._handle, name.encode(), None, 0)
+        self._taps.clear()
+
+    def forward(self, asr, F0_curve, N, s, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                precision: Optional[str] = None):
+        if self.training:
+            raise RuntimeError("B200Decoder is inference-only (the reference's training-time F0/N smoothing, "
+                               "hifigan.py:447-455, is out of scope); call .eval()")
+        if not asr.is_cuda:
+            raise _lib.St2Error("B200Decoder has no CPU path: inputs must be CUDA tensors")
+        lib = _lib.load()
+        dev = asr.device
+        B, Cin, T = asr.shape
+        if Cin != self.cfg.dim_in or F0_curve.shape != (B, 2 * T) or N.shape != (B, 2 * T) or s.shape != (B, self.cfg.style_dim):
+            raise ValueError("expected asr [B,%d,T], F0_curve [B,2T], N [B,2T], s [B,%d]; got %s %s %s %s" %
+                             (self.cfg.dim_in, self.cfg.style_dim, tuple(asr.shape), tuple(F0_curve.shape),
+                              tuple(N.shape), tuple(s.shape)))
+        prec = _lib.PREC[precision or self.precision]
+        with torch.cuda.device(dev):
+            if self._dirty or self._handle is None:
+                self._sync(dev)
+            asr_, f0_, n_, s_ = (t.detach().float().contiguous() for t in (asr, F0_curve, N, s))
+            S = self.cfg.samples_per_frame * T
+            noise_ = None
+            if noise is not None:
+                if tuple(noise.shape) != (B, S, 9):
+                    raise ValueError("noise must be [B,%d,9]" % S)
+                noise_ = noise.detach().float().contiguous()
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # global torch RNG, like the reference
+            need = _lib.check(lib.st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty(B, 1, S, dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.st2_decoder_forward(self._handle, _lib.ptr(asr_), _lib.ptr(f0_), _lib.ptr(n_), _lib.ptr(s_),
+                                               _lib.ptr(noise_), C.c_uint64(seed), _lib.ptr(out), B, T, prec,
+                                               _lib.ptr(self._workspace), self._workspace.numel(),
+                                               C.c_void_p(stream)), "st2_decoder_forward")
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().st2_decoder_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass

@@ -1,0 +1,64 @@
+"""Duration -> frame length regulation (inference.py:257-268) on the GPU.
+
+    pred_dur = round(duration).clamp(min=1)          # st2_round_durations
+    asr = t_en @ alignment ; en = d^T @ alignment    # st2_length_regulate (bit-exact gather)
+
+Batched and ragged: utterance b uses its first n_tokens[b] tokens and produces
+sum(pred_dur[b]) frames; outputs are zero beyond that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def round_durations(duration: torch.Tensor, n_tokens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """duration [B,L] fp32 (CUDA) -> (pred_dur [B,L] int32, total_frames [B] int32)."""
+    if not duration.is_cuda:
+        raise _lib.St2Error("length regulator has no CPU path: inputs must be CUDA tensors")
+    lib = _lib.load()
+    duration = duration.detach().float().contiguous()
+    B, L = duration.shape
+    dur = torch.empty(B, L, dtype=torch.int32, device=duration.device)
+    tot = torch.empty(B, dtype=torch.int32, device=duration.device)
+    nt = None if n_tokens is None else n_tokens.to(device=duration.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(duration.device):
+        _lib.check(lib.st2_round_durations(_lib.ptr(duration), _lib.ptr(nt), _lib.ptr(dur), _lib.ptr(tot), B, L,
+                                           _stream(duration.device)), "st2_round_durations")
+    return dur, tot
+
+
+def length_regulate(src: torch.Tensor, pred_dur: torch.Tensor, n_frames: int, channels_last: bool = False) -> torch.Tensor:
+    """src [B,C,L] fp32, pred_dur [B,L] int32 -> [B,C,n_frames] (or [B,n_frames,C])."""
+    if not src.is_cuda:
+        raise _lib.St2Error("length regulator has no CPU path: inputs must be CUDA tensors")
+    lib = _lib.load()
+    src = src.detach().float().contiguous()
+    pred_dur = pred_dur.to(device=src.device, dtype=torch.int32).contiguous()
+    B, Cc, L = src.shape
+    if pred_dur.shape != (B, L):
+        raise ValueError("pred_dur must be [B,L]")
+    shape = (B, n_frames, Cc) if channels_last else (B, Cc, n_frames)
+    out = torch.empty(shape, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.st2_length_regulate(_lib.ptr(src), _lib.ptr(pred_dur), _lib.ptr(out), B, Cc, L, n_frames,
+                                           1 if channels_last else 0, _stream(src.device)), "st2_length_regulate")
+    return out
+
+
+def regulate(duration: torch.Tensor, t_en: torch.Tensor, d: torch.Tensor, n_tokens: Optional[torch.Tensor] = None):
+    """The four lines inference.py:257-268 as one call: duration [B,L], t_en [B,512,L],
+    d [B,L,640] -> (asr [B,512,F], en [B,640,F], pred_dur, total_frames), F = max_b frames."""
+    dur, tot = round_durations(duration, n_tokens)
+    F = int(tot.max().item())
+    asr = length_regulate(t_en, dur, F)
+    en = length_regulate(d.transpose(-1, -2), dur, F)
+    return asr, en, dur, tot

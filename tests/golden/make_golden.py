@@ -101,9 +101,25 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def dump_schema(out_dir):
+    """state_dict keys/shapes of the reference Decoders (the drop-in contract)."""
+    import json
+    schema = {}
+    for cfg in (DecoderConfig.hifigan(), DecoderConfig.istftnet()):
+        sd = synth.make_state_dict(cfg, seed=0, perturb=False)
+        m = build_reference(cfg, sd)
+        schema[cfg.type] = {"num_params": sum(p.numel() for p in m.parameters()),
+                            "state_dict": {k: list(v.shape) for k, v in m.state_dict().items()}}
+    with open(os.path.join(out_dir, "state_dict_schema.json"), "w") as f:
+        json.dump(schema, f, sort_keys=True)
+
+
 def main():
     torch.set_num_threads(8)
     out_dir = HERE
+    dump_schema(out_dir)
+    if "--schema-only" in sys.argv:
+        return
     # ---- hifigan small, with intermediate taps (batch element 0 only for the big ones)
     cfg = DecoderConfig.hifigan()
     tap_names = ["encode", "decode.0", "decode.3", "generator.m_source", "generator.noise_res.0",

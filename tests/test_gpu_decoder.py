@@ -1,0 +1,191 @@
+"""-m gpu: whole-decoder parity through the drop-in module / C ABI.
+
+fp32 path: max-abs <= 1e-4 against the golden waveforms of the unmodified reference
+(BASELINE.json north_star) with the shared noise tape; per-layer taps against the oracle.
+16-bit tensor-core paths: SNR >= 40 dB and per-layer relative L2 <= 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from styletts2_lite_b200.config import DecoderConfig
+from styletts2_lite_b200 import synth
+from oracle import decoder_np as O
+from helpers import golden, np_inputs, np_state_dict, rel_l2, snr_db
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_util as G
+    from styletts2_lite_b200 import _lib, hifigan, istftnet
+    from styletts2_lite_b200.decoder import B200Decoder
+
+_CACHE = {}
+
+
+def _decoder(cfg, wseed=0, perturb=True, precision="fp32"):
+    key = (cfg.type, wseed, perturb)
+    if key not in _CACHE:
+        m = B200Decoder(cfg, precision)
+        m.load_state_dict(synth.make_state_dict(cfg, wseed, perturb))
+        _CACHE[key] = m.to("cuda").eval()
+    return _CACHE[key]
+
+
+def _run(m, inp, precision="fp32", noise=True, seed=None):
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        out = m(t["asr"], t["F0_curve"], t["N"], t["s"], noise=t["noise"] if noise else None, seed=seed,
+                precision=precision)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _tap_table(m, cfg, inp, names_shapes, precision="fp32"):
+    """Run with debug taps and compare each against the oracle's tap; returns {name: rel_l2}."""
+    B = inp["asr"].shape[0]
+    bufs = {n: m.set_tap(n, B, rows, C_) for n, (rows, C_) in names_shapes.items()}
+    out = _run(m, inp, precision)
+    taps = {}
+    sd = np_state_dict(cfg, 0, True)
+    ref = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"], taps=taps)
+    res = {}
+    for n, buf in bufs.items():
+        a = G.cf(buf.cpu().numpy())
+        res[n] = rel_l2(taps[n], a)
+    m.clear_taps()
+    return out, ref, res
+
+
+def test_state_dict_is_drop_in():
+    m = hifigan.Decoder(dim_in=512, style_dim=128, dim_out=80, resblock_kernel_sizes=[3, 7, 11],
+                        upsample_rates=[10, 5, 3, 2], upsample_initial_channel=512,
+                        resblock_dilation_sizes=[[1, 3, 5]] * 3, upsample_kernel_sizes=[20, 10, 6, 4])
+    assert sum(p.numel() for p in m.parameters()) == 54_289_492        # README.md:21
+    assert len(m.state_dict()) == 678
+    m2 = istftnet.Decoder(style_dim=128)
+    assert sum(p.numel() for p in m2.parameters()) == 53_276_190
+    assert len(m2.state_dict()) == 380
+
+
+def test_hifigan_small_fp32_golden_and_taps():
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B2_T5_w0_i1001.npz")
+    inp = np_inputs(2, 5, 1001, cfg)
+    m = _decoder(cfg)
+    T = 5
+    shapes = {"har_source": (600 * T, 1), "encode.conv1": (T, 1024), "encode": (T, 1024), "decode.0": (T, 1024),
+              "decode.3": (2 * T, 512), "generator.noise_res.0.iter2": (20 * T, 256),
+              "generator.stage0.in": (20 * T, 256), "generator.resblocks.0.iter1": (20 * T, 256),
+              "generator.stage0.out": (20 * T, 256), "generator.stage1.out": (100 * T, 128),
+              "generator.stage2.out": (300 * T, 64), "generator.noise_res.3.iter2": (600 * T, 32),
+              "generator.stage3.out": (600 * T, 32)}
+    out, ref, res = _tap_table(m, cfg, inp, shapes)
+    for n, v in res.items():
+        G.log("hifigan_small_tap", tap=n, rel_l2=v)
+    err_g = float(np.abs(out - g["out"]).max())
+    err_o = float(np.abs(out - ref).max())
+    G.log("hifigan_small", maxabs_vs_golden=err_g, maxabs_vs_oracle=err_o, launches=m.last_launch_count())
+    for n, v in res.items():
+        assert v <= 1e-4, (n, v)
+    assert err_g <= 1e-4
+
+
+def test_hifigan_reference_init_fp32_golden():
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B1_T4_w3_i1002_plain.npz")
+    m = _decoder(cfg, 3, False)
+    out = _run(m, np_inputs(1, 4, 1002, cfg))
+    err = float(np.abs(out - g["out"]).max())
+    G.log("hifigan_plain", maxabs_vs_golden=err)
+    assert err <= 1e-4
+
+
+def test_hifigan_cfg1_3s_fp32_golden():
+    """BASELINE.json configs[0] shape: B=1, T=120 (3 s)."""
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B1_T120_w0_i1001.npz")
+    m = _decoder(cfg)
+    inp = np_inputs(1, 120, 1001, cfg)
+    har = m.set_tap("har_source", 1, 72000, 1)
+    out = _run(m, inp)
+    err_h = float(np.abs(har.cpu().numpy()[:, :, 0] - g["har_source"][:, :, 0]).max())
+    m.clear_taps()
+    err = float(np.abs(out - g["out"]).max())
+    G.log("hifigan_cfg1", maxabs_vs_golden=err, har_source_maxabs=err_h, snr_db=snr_db(g["out"], out))
+    assert err_h <= 1e-6
+    assert err <= 1e-4
+
+
+def test_istftnet_small_fp32_golden_and_taps():
+    cfg = DecoderConfig.istftnet()
+    g = golden("istftnet_B2_T5_w0_i1005.npz")
+    inp = np_inputs(2, 5, 1005, cfg)
+    m = _decoder(cfg)
+    T = 5
+    shapes = {"har_source": (600 * T, 1), "har": (120 * T + 1, 22), "decode.3": (2 * T, 512),
+              "generator.noise_res.0.iter2": (20 * T, 256), "generator.stage0.out": (20 * T, 256),
+              "generator.noise_res.1.iter2": (120 * T + 1, 128), "generator.stage1.in": (120 * T + 1, 128),
+              "generator.stage1.out": (120 * T + 1, 128)}
+    out, ref, res = _tap_table(m, cfg, inp, shapes)
+    for n, v in res.items():
+        G.log("istftnet_small_tap", tap=n, rel_l2=v)
+    err_g = float(np.abs(out - g["out"]).max())
+    G.log("istftnet_small", maxabs_vs_golden=err_g, maxabs_vs_oracle=float(np.abs(out - ref).max()))
+    for n, v in res.items():
+        assert v <= 1e-4, (n, v)
+    assert err_g <= 1e-4
+
+
+def test_batch_independence_and_determinism():
+    """Every op is per-utterance: element b of a batch equals the B=1 run."""
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    inp = np_inputs(3, 6, 1010, cfg)
+    full = _run(m, inp)
+    again = _run(m, inp)
+    assert np.array_equal(full, again)
+    one = _run(m, {k: v[1:2] for k, v in inp.items()})
+    assert np.abs(one[0] - full[1]).max() <= 1e-6
+
+
+def test_device_noise_seeded():
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    inp = np_inputs(1, 6, 1011, cfg)
+    a = _run(m, inp, noise=False, seed=123)
+    b = _run(m, inp, noise=False, seed=123)
+    c = _run(m, inp, noise=False, seed=124)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.isfinite(a).all() and np.abs(a).max() <= 1.0
+
+
+def test_error_behaviour():
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    x = torch.zeros(1, 512, 4, device="cuda")
+    f = torch.zeros(1, 8, device="cuda")
+    s = torch.zeros(1, 128, device="cuda")
+    with pytest.raises(ValueError):
+        m(x, f[:, :7], f, s)
+    with pytest.raises(_lib.St2Error):
+        m(x.cpu(), f.cpu(), f.cpu(), s.cpu())
+    m.train(True)
+    with pytest.raises(RuntimeError):
+        m(x, f, f, s)
+    m.train(False)
+    # C ABI: forward before finalize, and too-small workspace
+    import ctypes as C
+    lib = _lib.load()
+    h = C.c_void_p()
+    cc = _lib.St2Config.from_config(cfg)
+    assert lib.st2_decoder_create(C.byref(cc), C.byref(h)) == 0
+    out = torch.zeros(1, 1, 2400, device="cuda")
+    ws = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    rc = lib.st2_decoder_forward(h, _lib.ptr(x), _lib.ptr(f), _lib.ptr(f), _lib.ptr(s), None, 0, _lib.ptr(out), 1, 4, 0,
+                                 _lib.ptr(ws), ws.numel(), None)
+    assert rc == -2 and b"finalize" in lib.st2_last_error()
+    lib.st2_decoder_destroy(h)
+    rc = lib.st2_decoder_forward(m._handle, _lib.ptr(x), _lib.ptr(f), _lib.ptr(f), _lib.ptr(s), None, 0, _lib.ptr(out), 1, 4,
+                                 0, _lib.ptr(ws), ws.numel(), G.stream())
+    assert rc == -4 and b"workspace" in lib.st2_last_error()
+    torch.cuda.synchronize()
