@@ -1,9 +1,367 @@
-// placeholder: replaced by the tcgen05/TMA implicit-GEMM kernel
+// Tensor-core implicit-GEMM Conv1d / ConvTranspose1d for sm_100a: TMA -> shared memory ->
+// tcgen05.mma (kind::f16, bf16 or fp16 operands) with fp32 accumulators in TMEM.
+//
+// Same ConvArgs contract as conv_simt.cu (stride-1 Conv1d and polyphase ConvTranspose1d; the
+// strided 1->C noise_convs stay on the SIMT kernel).  GEMM view per CTA:
+//     D[128 time steps, BN couts] = sum_{tap j} sum_{ci chunk of 64}  A_j[128, 64] * W_j[64, BN]
+//   A: channels-last 16-bit activations x16[B][Tin][ld]; a 3-D tensor map (ci, t, b) lets TMA
+//      fetch the [128 x 64] box at time coordinate m0 + j*tap_step + in_off -- dilation is a
+//      coordinate shift and the conv zero padding is TMA's out-of-bounds fill (per utterance,
+//      because b is its own coordinate).
+//   B: weights packed at load time as [tap][CoutPad][CinPad] (K-major), box [BN x 64].
+//   Both land in the canonical 128-byte-swizzled K-major layout that the UMMA shared-memory
+//   descriptors address (SBO = 1024 B between 8-row groups; K advance = +32 B inside the atom).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2-5 = epilogue (tcgen05.ld 32x32b -> bias/residual/scale -> global).
+// Two CTAs fit per SM (<= 96 KB shared, <= 256 TMEM columns each) so one CTA's epilogue overlaps
+// the other's main loop.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace st2 {
-bool conv_tc_supported(const ConvArgs&) { return false; }
-int launch_conv_tc(const ConvArgs&, cudaStream_t) {
-    set_error("tensor-core conv path not built");
-    return ST2_ERR_UNSUPPORTED;
+
+static constexpr int TC_BM = 128;
+static constexpr int TC_KC = 64;             // K chunk: 64 x 16-bit = one 128-byte swizzle row
+static constexpr int TC_THREADS = 192;
+static constexpr uint32_t A_STAGE_BYTES = TC_BM * TC_KC * 2;   // 16 KB
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a lost TMA / MMA completion traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start>>4 | SBO(1024 B)>>4 @32 | version 1 @46 | layout 2 @61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major), canonical value 1
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16 (1) or fp16 (0), both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int is_bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                 // c_format = F32
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;        // a_format
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;       // b_format
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcParams {
+    const float* bias;
+    const float* res; int ld_res; int res_shift;
+    float* y; int ld_y; int Tout;
+    int Cout, M;
+    int ntaps, tap_step, in_off;
+    int phases, w_step, out_stride, out_pad;
+    int kchunks;                 // CinPad / 64
+    int bn;                      // N tile (multiple of 16, <= 256)
+    int tmem_cols;               // power of two >= bn
+    int stages;
+    float scale; int accumulate; int mirror;
+    int is_bf16;
+};
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned tiles (SWIZZLE_128B atoms)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t b_stage_bytes = (uint32_t)p.bn * TC_KC * 2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
+    uint64_t* full_bar = bars;                     // [stages]
+    uint64_t* empty_bar = bars + p.stages;         // [stages]
+    uint64_t* tmem_full_bar = bars + 2 * p.stages; // [1]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM;
+    const int n0 = blockIdx.y * p.bn;
+    const int b = blockIdx.z / p.phases;
+    const int ph = blockIdx.z - b * p.phases;
+    const int nit = p.ntaps * p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nit; ++it) {
+                const int j = it / p.kchunks;
+                const int kc = it - j * p.kchunks;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + b_stage_bytes);
+                tma_load_3d(smem_a + (size_t)stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kc * TC_KC,
+                            m0 + j * p.tap_step + p.in_off, b);
+                tma_load_3d(smem_b + (size_t)stage * b_stage_bytes, &map_b, &full_bar[stage], kc * TC_KC, n0,
+                            ph + j * p.w_step);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_BM, p.bn, p.is_bf16);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nit; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)stage * b_stage_bytes));
+#pragma unroll
+                for (int k4 = 0; k4 < TC_KC / 16; ++k4)
+                    umma_f16(tmem_base, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc,
+                             (it > 0 || k4 > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full_bar);                  // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int t = m * p.out_stride + ph - p.out_pad;
+        const bool row_ok = (m < p.M) && (t >= 0) && (t < p.Tout);
+        const bool vec = (p.Cout % 4 == 0) && (p.ld_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective
+            const int co = n0 + c0;
+            if (!row_ok || co >= p.Cout) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (p.bias != nullptr && co + i < p.Cout) v[i] += __ldg(p.bias + co + i);
+            const int nrep = (p.mirror && t == 2) ? 2 : 1;
+            for (int rep = 0; rep < nrep; ++rep) {
+                const int tt = rep == 0 ? t : 0;
+                float o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = v[i];
+                if (p.res != nullptr) {
+                    const float* rp = p.res + ((size_t)b * (p.Tout >> p.res_shift) + (tt >> p.res_shift)) * p.ld_res + co;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (co + i < p.Cout) o[i] += rp[i];
+                }
+                float* yp = p.y + ((size_t)b * p.Tout + tt) * p.ld_y + co;
+                if (vec && co + 16 <= p.Cout) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 r = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                        if (p.accumulate) {
+                            float4 old = *reinterpret_cast<const float4*>(yp + i);
+                            r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                        }
+                        r.x *= p.scale; r.y *= p.scale; r.z *= p.scale; r.w *= p.scale;
+                        *reinterpret_cast<float4*>(yp + i) = r;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (co + i < p.Cout) yp[i] = ((p.accumulate ? yp[i] : 0.f) + o[i]) * p.scale;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST2_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u]", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1);
+        return ST2_ERR_CUDA;
+    }
+    return ST2_OK;
+}
+
+bool conv_tc_supported(const ConvArgs& a) {
+    return a.x16 != nullptr && a.w16 != nullptr && a.in_stride == 1 && a.w16_cin_pad % TC_KC == 0 &&
+           a.w16_cout_pad % 16 == 0 && a.ld_x16 % 8 == 0;
+}
+
+int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
+    ST2_REQUIRE(conv_tc_supported(a), "conv_tc: unsupported geometry (in_stride=%d cin_pad=%d cout_pad=%d ld=%d)",
+                a.in_stride, a.w16_cin_pad, a.w16_cout_pad, a.ld_x16);
+    const int is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.bias = a.bias; p.res = a.res; p.ld_res = a.ld_res; p.res_shift = a.res_shift;
+    p.y = a.y; p.ld_y = a.ld_y; p.Tout = a.Tout; p.Cout = a.Cout; p.M = a.M;
+    p.ntaps = a.ntaps; p.tap_step = a.tap_step; p.in_off = a.in_off;
+    p.phases = a.phases; p.w_step = a.w_step; p.out_stride = a.out_stride; p.out_pad = a.out_pad;
+    p.kchunks = a.w16_cin_pad / TC_KC;
+    p.scale = a.scale; p.accumulate = a.accumulate; p.mirror = a.mirror; p.is_bf16 = is_bf16;
+    // N tile: whole CoutPad up to 256, else the largest multiple-of-16 divisor <= 256
+    int bn = a.w16_cout_pad;
+    if (bn > 256) {
+        bn = 256;
+        while (a.w16_cout_pad % bn != 0) bn -= 16;
+    }
+    p.bn = bn;
+    int cols = 32;
+    while (cols < bn) cols <<= 1;
+    p.tmem_cols = cols;
+    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)bn * TC_KC * 2;
+    int stages = (int)((96 * 1024) / stage_bytes);       // <= 96 KB so that two CTAs share an SM
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+
+    CUtensorMap map_a, map_b;
+    const int ktaps_total = a.phases > 1 ? a.ntaps * a.phases : a.ntaps;   // weight taps stored
+    const uint64_t a_d0 = (uint64_t)(a.ld_x16 < a.w16_cin_pad ? a.ld_x16 : a.w16_cin_pad);
+    int e = make_map_3d(&map_a, is_bf16, a.x16, a_d0, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x16 * 2,
+                        (uint64_t)a.Tin * a.ld_x16 * 2, TC_KC, TC_BM);
+    if (e != ST2_OK) return e;
+    e = make_map_3d(&map_b, is_bf16, a.w16, (uint64_t)a.w16_cin_pad, (uint64_t)a.w16_cout_pad, (uint64_t)ktaps_total,
+                    (uint64_t)a.w16_cin_pad * 2, (uint64_t)a.w16_cin_pad * a.w16_cout_pad * 2, TC_KC, (uint32_t)bn);
+    if (e != ST2_OK) return e;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(a.M, TC_BM), a.w16_cout_pad / bn, a.B * a.phases);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
 }  // namespace st2
