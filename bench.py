@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the decoder hot path (BASELINE.json metric: decoder audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = Decoder.forward over one synthetic batch of BASELINE.json configs[1]
+(hifigan, B=64 utterances x 5 s = T 200 frames, random-init weights, bf16 tensor-core path).
+Rank 0 prints ONE JSON line.  For N>1 (torchrun) every rank runs its own batch (utterances
+shard with no cross-rank math, weak scaling) and the waveforms are gathered to rank 0 over NCCL
+inside the timed step.
+
+  value     whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public drop-in module with HOST (pinned) inputs and the
+            waveform copied back to the host inside the timed region
+  roofline  the dominant kernel (tcgen05 conv): algorithmic FLOPs / event-timed duration vs the
+            measured bf16 peak of MEASURED_PEAKS.json; `kernels` lists every category
+  cpu_baseline  the numpy oracle port of the reference decoder on the host cores (rank 0, N=1)
+
+--impl reference times that same CPU port (the reference itself is pure Python/PyTorch and
+cannot travel to the GPU box) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoder audio-sec/sec (RTF^-1)"
+UNIT = "audio-s/s"
+SR = 24000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=200, help="asr frames per utterance (200 = 5 s)")
+    ap.add_argument("--variant", default="hifigan", choices=["hifigan", "istftnet"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: --frames)")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    secs = a.frames * 600 / SR
+    return {
+        "workload": "%s Decoder.forward(asr,F0_curve,N,s): %d utterances x %.1f s (T=%d frames) per GPU, "
+                    "synthetic inputs, random-init weights (BASELINE.json configs[1])" % (a.variant, a.batch, secs, a.frames),
+        "variant": a.variant, "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "frames": a.frames,
+        "audio_seconds_per_step": a.batch * n_gpus * secs,
+        "precision": {"fp32": "fp32 SIMT", "fp16": "tcgen05 fp16 operands, fp32 accumulate",
+                      "bf16": "tcgen05 bf16 operands (generator.noise_res + front half on fp16 operands), fp32 accumulate"}[a.precision],
+        "noise": "SineGen noise drawn on the device (Philox) inside the step",
+        "l2": "L2 flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2",
+        "parallelism": "replicas: utterances sharded per rank, no cross-rank math; NCCL gather of waveforms to rank 0 inside the step" if n_gpus > 1 else "single GPU",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle port of the reference decoder, all host threads (BLAS)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(variant, frames, steps, warmup):
+    import numpy as np
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.config import DecoderConfig
+    from oracle import decoder_np as O      # the CPU baseline leg is one of the places allowed to run the oracle
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    W = O.Weights({k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()})
+    inp = {k: v.numpy() for k, v in synth.make_inputs(1, frames, 1000, cfg).items()}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    assert out.shape == (1, 1, 600 * frames) and np.isfinite(out).all()
+    secs = frames * 600 / SR
+    mean = sum(times) / len(times)
+    return {"value": secs / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 utterance x %.1f s (T=%d) of the workload, numpy oracle port of the reference decoder "
+                      "(reference is pure PyTorch and cannot travel), BLAS on all host threads, %d runs after %d warm-up, "
+                      "mean %.2f s/utterance" % (secs, frames, steps, warmup, mean),
+            "ms_per_step": mean * 1e3}
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    frames = a.cpu_frames or a.frames
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+    r = cpu_port_run(a.variant, frames, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == self.idx:
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.config import DecoderConfig
+    from styletts2_lite_b200.decoder import B200Decoder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = DecoderConfig.hifigan() if a.variant == "hifigan" else DecoderConfig.istftnet()
+    B, T = a.batch, a.frames
+    S = 600 * T
+    m = B200Decoder(cfg, a.precision)
+    m.load_state_dict(synth.make_state_dict(cfg, 0, True))
+    m = m.to(dev).eval()
+    inp = synth.make_inputs(B, T, seed=1000 + 2 + rank, cfg=cfg, with_noise=False)
+    host = {k: v.pin_memory() for k, v in inp.items()}
+    res = {k: v.to(dev) for k, v in inp.items()}
+    out_host = torch.empty(B, 1, S, dtype=torch.float32).pin_memory()
+    gathered = [torch.empty(B, 1, S, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        with torch.no_grad():
+            out = m(res["asr"], res["F0_curve"], res["N"], res["s"], seed=1234 + i)
+        if world > 1:
+            dist.gather(out, gathered, dst=0)
+        return out
+
+    def step_e2e(i):
+        d = {k: host[k].to(dev, non_blocking=True) for k in ("asr", "F0_curve", "N", "s")}
+        with torch.no_grad():
+            out = m(d["asr"], d["F0_curve"], d["N"], d["s"], seed=4321 + i)
+        if world > 1:
+            dist.gather(out, gathered, dst=0)
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_wall = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)                    # L2 flush, outside the event pair
+            evs[i][0].record()
+            fn(warmup + i)
+            evs[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = [s.elapsed_time(e) for s, e in evs]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()), ms, wall
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, per_step, wall = timed(step_resident, a.steps, a.warmup)
+    clocks = sampler.summary()
+    sampler.stop()
+    launches = m.last_launch_count()
+    total_e2e_ms, _, _ = timed(step_e2e, a.steps, max(1, a.warmup // 2 + 1))
+
+    # per-category event profile (same workload, profiling on) -> roofline of the dominant kernel
+    m.set_profiling(True)
+    prof_acc = None
+    for i in range(a.steps):
+        step_resident(10_000 + i)
+        p = m.get_profile()
+        if prof_acc is None:
+            prof_acc = p
+        else:
+            for c in p:
+                for k in p[c]:
+                    prof_acc[c][k] += p[c][k]
+    m.set_profiling(False)
+    torch.cuda.synchronize()
+
+    audio_s = B * world * S / SR
+    ms_per_step = total_ms / a.steps
+    value = audio_s / (ms_per_step / 1e3)
+    e2e_value = audio_s / (total_e2e_ms / a.steps / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_src = "MEASURED_PEAKS.json (sustained bf16, copy HBM)" if peaks else "fallback (B200_PROFILING.md)"
+    kernels = {}
+    prof_ms_step = 0.0
+    for c, v in prof_acc.items():
+        if v["launches"] == 0:
+            continue
+        ms_c = v["ms"] / a.steps
+        prof_ms_step += ms_c
+        kernels[c] = {"ms_per_step": round(ms_c, 4), "launches_per_step": v["launches"] // a.steps,
+                      "tflops": round(v["flops"] / v["ms"] / 1e9, 2) if v["flops"] and v["ms"] else None,
+                      "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["bytes"] and v["ms"] else None}
+    for c in kernels:
+        kernels[c]["share"] = round(kernels[c]["ms_per_step"] / prof_ms_step, 4)
+    dom = max(kernels, key=lambda c: kernels[c]["ms_per_step"])
+    if dom in ("conv_tc", "conv_simt"):
+        v = prof_acc[dom]
+        achieved = v["flops"] / v["ms"] / 1e9
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": achieved / tc_peak, "traffic": None}
+    else:
+        v = prof_acc[dom]
+        achieved = v["bytes"] / v["ms"] / 1e6
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None}
+    roof["avg_launch_ms"] = prof_acc[dom]["ms"] / max(prof_acc[dom]["launches"], 1)
+    roof["peak_source"] = peak_src
+    roof["kernels"] = kernels
+    roof["profiled_ms_per_step"] = round(prof_ms_step, 3)
+    # the HBM-bound half, always reported next to the dominant kernel
+    if "affine_act" in prof_acc and prof_acc["affine_act"]["ms"] > 0:
+        g = prof_acc["affine_act"]["bytes"] / prof_acc["affine_act"]["ms"] / 1e6
+        roof["affine_act_hbm"] = {"achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    h2d = sum(host[k].numel() * 4 for k in ("asr", "F0_curve", "N", "s"))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[a.precision], "data": "synthetic",
+            "config": workload_config(a, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * S * 4,
+                    "ms_per_step": total_e2e_ms / a.steps},
+            "gpu_launches": int(launches * a.steps), "launches_per_step": int(launches),
+            "clocks": clocks, "roofline": roof, "wall_s_timed_region": round(wall, 3),
+            "per_step_ms": [round(x, 3) for x in per_step]}
+    if world == 1 and not a.no_cpu_baseline:
+        r = cpu_port_run(a.variant, a.cpu_frames or a.frames, 2, 1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

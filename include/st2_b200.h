@@ -123,6 +123,17 @@ ST2_API int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, in
 /* how many kernels of this library the last forward launched */
 ST2_API int64_t st2_decoder_last_launch_count(const st2_decoder* d);
 
+/* Per-launch event profile (bench.py's roofline leg).  With profiling enabled every forward
+ * records one CUDA event after each kernel launch on the caller's stream; get_profile waits
+ * for the last one and returns, per kernel category, the summed device time (ms), the launch
+ * count and the ALGORITHMIC flops / bytes (SURVEY.md 8(d) figures) of those launches.
+ * Arrays must hold st2_profile_num_categories() entries. */
+ST2_API int st2_decoder_set_profiling(st2_decoder* d, int32_t enable);
+ST2_API int st2_profile_num_categories(void);
+ST2_API const char* st2_profile_category_name(int32_t cat);
+ST2_API int st2_decoder_get_profile(st2_decoder* d, double* ms, int64_t* launches, double* flops,
+                            double* bytes);
+
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 
 /* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);

@@ -69,6 +69,11 @@ SIGNATURES = {
     "st2_decoder_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint64, _P, _I, _I, _I, _P, _L, _P]),
     "st2_decoder_set_tap": (C.c_int, [_P, C.c_char_p, _P, _L]),
     "st2_decoder_last_launch_count": (_L, [_P]),
+    "st2_decoder_set_profiling": (C.c_int, [_P, _I]),
+    "st2_profile_num_categories": (C.c_int, []),
+    "st2_profile_category_name": (C.c_char_p, [_I]),
+    "st2_decoder_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]),
     "st2_round_durations": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "st2_length_regulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "st2_sinegen_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -47,6 +47,18 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2 };
 enum OutDtype { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+// kernel categories of the per-launch event profile (st2_decoder_get_profile)
+enum ProfCat {
+    PC_CONV_TC = 0,     // tcgen05 implicit-GEMM conv               (bound: tensor)
+    PC_CONV_SIMT = 1,   // fp32 FFMA conv                            (bound: fp32 pipe / hbm)
+    PC_NORM_STATS = 2,  // InstanceNorm statistics                   (bound: hbm, read only)
+    PC_NORM_COEF = 3,   // per-(b,c) affine coefficients             (tiny)
+    PC_AFFINE_ACT = 4,  // AdaIN affine + Snake / LeakyReLU          (bound: hbm)
+    PC_SOURCE = 5,      // SineGen + harmonic source (+ STFT front)  (bound: hbm)
+    PC_POST = 6,        // Snake + conv_post + tanh / iSTFT head     (bound: hbm)
+    PC_MISC = 7,        // layout, style fc, pool, taps
+    PC_COUNT = 8
+};
 
 // ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------
 // InstanceNorm statistics of channels-last x[B][T][ld] over T: partial (sum, sumsq) in

@@ -91,6 +91,12 @@ struct st2_decoder {
     float *stft_fr = nullptr, *stft_fi = nullptr, *stft_br = nullptr, *stft_bi = nullptr;
     std::map<std::string, Tap> taps;
 
+    // per-launch event profile (one boundary event after every launch of a profiled forward)
+    struct ProfRec { int cat; double flops; double bytes; };
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<ProfRec> prof_recs;
+
     int spf() const {    // samples per asr frame
         int p = 2;
         for (int i = 0; i < cfg.n_stages; ++i) p *= cfg.upsample_rates[i];
@@ -327,12 +333,30 @@ struct Exec {
     bool live() const { return !dry && err == ST2_OK; }
     void chk(int e) { if (e != ST2_OK && err == ST2_OK) err = e; }
 
+    // boundary event after the launch(es) just issued; flops / bytes are the ALGORITHMIC figures
+    void prof(int cat, double flops, double bytes) {
+        if (!d->profiling || !live()) return;
+        const size_t idx = d->prof_recs.size() + 1;      // event 0 = start of the forward
+        while (d->prof_events.size() <= idx) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) { chk(ST2_ERR_CUDA); return; }
+            d->prof_events.push_back(ev);
+        }
+        cudaEventRecord(d->prof_events[idx], st);
+        d->prof_recs.push_back({cat, flops, bytes});
+    }
+
     int fmt_for(const std::string& name) const {
         if (prec == ST2_PREC_FP32) return DT_F32;
         if (prec == ST2_PREC_FP16) return DT_F16;
-        // bf16 everywhere except generator.noise_res (fp16 operands, same tensor throughput):
-        // bf16 there alone costs ~9 dB of SNR (precision study)
-        return name.find("noise_res") != std::string::npos ? DT_F16 : DT_BF16;
+        // bf16 for the generator resblocks / ups (96 % of the FLOPs).  fp16 operands (same tensor
+        // throughput) for generator.noise_res -- bf16 there alone costs ~9 dB of SNR -- and for the
+        // front half (encode / decode / asr_res, K up to 3270), whose five chained blocks otherwise
+        // reach 1.2e-2 per-layer relative L2 (precision study).
+        if (name.find("noise_res") != std::string::npos || name.find("encode") != std::string::npos ||
+            name.find("decode") != std::string::npos || name.find("asr_res") != std::string::npos)
+            return DT_F16;
+        return DT_BF16;
     }
 
     void tap(const std::string& name, const float* src, int ld, int64_t rows, int C) {
@@ -346,6 +370,7 @@ struct Exec {
             return;
         }
         chk(launch_copy_dense(src, ld, it->second.dst, rows, C, st));
+        prof(PC_MISC, 0, 8.0 * rows * C);
     }
 
     // y = act(AdaIN(x)) or act(x) when `n` is null.  x fp32 [B,T,ld_x]; y dtype dt, pitch ld_y.
@@ -356,9 +381,15 @@ struct Exec {
         const int64_t mark = off;
         if (n) scratch = alloc(adain_scratch_bytes(B, T, C));
         if (live()) {
-            if (n) chk(launch_in_stats(x, ld_x, B, T, C, scratch, st));
+            const double numel = (double)B * T * C;
+            if (n) {
+                chk(launch_in_stats(x, ld_x, B, T, C, scratch, st));
+                prof(PC_NORM_STATS, 0, numel * 4);
+            }
             if (err == ST2_OK) chk(launch_adain_coef(scratch, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
+            prof(PC_NORM_COEF, 0, 0);
             if (err == ST2_OK) chk(launch_affine_act(x, ld_x, coef, alpha, act, slope, y, ld_y, dt, B, T, Cpad, st));
+            prof(PC_AFFINE_ACT, 0, numel * (4 + (dt == DT_F32 ? 4 : 2)));
         }
         off = mark;
     }
@@ -391,13 +422,21 @@ struct Exec {
             a.phases = stride; a.w_step = stride; a.out_stride = stride; a.out_pad = padding - out_row_shift;
             a.M = (Tout - 1 - out_row_shift + padding) / stride + 1;
         }
-        if (use_tc(w, dt)) {
+        // algorithmic work: Conv1d 2*B*Tout*Cout*Cin*k ; ConvTranspose1d 2*B*Tin*Cin*Cout*k
+        const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
+        const bool tc = use_tc(w, dt);
+        const double bytes = (double)B * ((double)w.Cin * Tin * (tc ? 2 : 4) +
+                                          (double)w.Cout * Tout * 4 * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) +
+                             (double)w.k * w.Cin * w.Cout * (tc ? 2 : 4);
+        if (tc) {
             a.x16 = x; a.ld_x16 = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad;
             a.fmt16 = dt;
             chk(launch_conv_tc(a, st));
+            prof(PC_CONV_TC, flops, bytes);
         } else {
             a.x = (const float*)x; a.ld_x = ld_x;
             chk(launch_conv_simt(a, st));
+            prof(PC_CONV_SIMT, flops, bytes);
         }
     }
 
@@ -415,6 +454,7 @@ struct Exec {
         if (w.upsample) {
             float* xp = allocf((int64_t)B * Tc * ld_x);
             if (live()) chk(launch_pool_dw((const float*)xa, ld_x, w.pool_w, w.pool_b, xp, ld_x, B, T, w.Cin, ld_x, st));
+            prof(PC_MISC, 0, 4.0 * B * w.Cin * 3.0 * T);
             cin = xp;
         }
         float* h1 = allocf((int64_t)B * Tc * w.Cout);
@@ -511,15 +551,29 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     float* har22 = istft ? E.allocf((int64_t)B * har_frames * HLD) : nullptr;
 
     if (E.live()) {
+        if (d->profiling) {
+            d->prof_recs.clear();
+            if (d->prof_events.empty()) {
+                cudaEvent_t ev;
+                if (cudaEventCreate(&ev) == cudaSuccess) d->prof_events.push_back(ev);
+            }
+            if (!d->prof_events.empty()) cudaEventRecord(d->prof_events[0], st);
+        }
         E.chk(launch_style_fc(s, d->fc_w, d->fc_b, H, B, d->fc_rows, c.style_dim, st));
         E.chk(launch_cf_to_cl(asr, x514, LD514, B, c.dim_in, T, st));
         E.chk(launch_f0n_conv(f0, nn, d->f0_w, d->f0_b, d->n_w, d->n_b, x514, LD514, c.dim_in, C514, x1090, LD1090,
                               1024 + 64, C1090, B, T, st));
+        E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim,
+               4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * c.dim_in * T + 4.0 * B * L2));
         E.chk(launch_sinegen_frames(f0, frames, B, L2, up_scale, st));
         E.chk(launch_har_source(f0, frames, noise, seed, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
-        if (istft)
+        // SineGen algorithmic bytes: read 4*B*2T (+ 36*B*S of noise when taped), write 4*B*S
+        E.prof(PC_SOURCE, 0, 4.0 * B * L2 + (noise ? 36.0 * B * S : 0.0) + 4.0 * B * S);
+        if (istft) {
             E.chk(launch_stft_transform(har, d->stft_fr, d->stft_fi, har22, HLD, B, S, c.gen_istft_n_fft,
                                         c.gen_istft_hop_size, st));
+            E.prof(PC_SOURCE, 0, 4.0 * B * S + 4.0 * B * har_frames * (c.gen_istft_n_fft + 2));
+        }
     }
     E.tap("har_source", har, 1, (int64_t)B * S, 1);
     if (istft) E.tap("har", har22, HLD, (int64_t)B * har_frames, c.gen_istft_n_fft + 2);
@@ -591,6 +645,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     if (!istft) {
         if (E.live())
             E.chk(launch_post_hifigan(x, Cl, d->gen_alpha[c.n_stages], d->conv_post.w32, d->conv_post.bias, out, B, S, Cl, st));
+        E.prof(PC_POST, 2.0 * B * S * Cl * 7, 4.0 * B * S * (Cl + 1));
     } else {
         const int dt = E.fmt_for("generator.conv_post");
         const bool tc = E.use_tc(d->conv_post, dt);
@@ -602,6 +657,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         if (E.live())
             E.chk(launch_istft_head(y22, HLD, d->stft_br, d->stft_bi, out, B, Tin, S, c.gen_istft_n_fft,
                                     c.gen_istft_hop_size, st));
+        E.prof(PC_POST, 0, 4.0 * B * Tin * (c.gen_istft_n_fft + 2) + 4.0 * B * S);
     }
     if (peak_out) *peak_out = E.peak;
     return E.err;
@@ -644,6 +700,7 @@ int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
 void st2_decoder_destroy(st2_decoder* d) {
     if (!d) return;
     for (void* p : d->allocs) cudaFree(p);
+    for (cudaEvent_t ev : d->prof_events) cudaEventDestroy(ev);
     delete d;
 }
 
@@ -714,5 +771,39 @@ int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t ca
 }
 
 int64_t st2_decoder_last_launch_count(const st2_decoder* d) { return d ? d->last_launches : 0; }
+
+int st2_decoder_set_profiling(st2_decoder* d, int32_t enable) {
+    ST2_REQUIRE(d != nullptr, "set_profiling: null handle");
+    d->profiling = enable != 0;
+    d->prof_recs.clear();
+    return ST2_OK;
+}
+
+int st2_profile_num_categories(void) { return st2::PC_COUNT; }
+
+const char* st2_profile_category_name(int32_t cat) {
+    static const char* names[st2::PC_COUNT] = {"conv_tc", "conv_simt", "norm_stats", "norm_coef", "affine_act",
+                                               "source", "post", "misc"};
+    return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
+}
+
+int st2_decoder_get_profile(st2_decoder* d, double* ms, int64_t* launches, double* flops, double* bytes) {
+    ST2_REQUIRE(d && ms && launches && flops && bytes, "get_profile: null argument");
+    for (int i = 0; i < st2::PC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; bytes[i] = 0; }
+    const size_t n = d->prof_recs.size();
+    if (n == 0) return ST2_OK;
+    ST2_REQUIRE(d->prof_events.size() > n, "get_profile: event pool inconsistent");
+    ST2_CUDA_CHECK(cudaEventSynchronize(d->prof_events[n]));
+    for (size_t i = 0; i < n; ++i) {
+        float t = 0.f;
+        ST2_CUDA_CHECK(cudaEventElapsedTime(&t, d->prof_events[i], d->prof_events[i + 1]));
+        const auto& r = d->prof_recs[i];
+        ms[r.cat] += t;
+        launches[r.cat] += 1;
+        flops[r.cat] += r.flops;
+        bytes[r.cat] += r.bytes;
+    }
+    return ST2_OK;
+}
 
 }  // extern "C"

@@ -156,6 +156,22 @@ class B200Decoder(nn.Module):
                                                C.c_void_p(stream)), "st2_decoder_forward")
         return out
 
+    def set_profiling(self, enable: bool) -> None:
+        """Per-launch CUDA-event profile of the following forwards (bench.py's roofline leg)."""
+        if self._handle is None:
+            self._sync(next(self.parameters()).device)
+        _lib.check(_lib.load().st2_decoder_set_profiling(self._handle, 1 if enable else 0), "set_profiling")
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """{category: {ms, launches, flops, bytes}} of the last profiled forward (waits for it)."""
+        lib = _lib.load()
+        n = lib.st2_profile_num_categories()
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        ln = (C.c_int64 * n)()
+        _lib.check(lib.st2_decoder_get_profile(self._handle, ms, ln, fl, by), "get_profile")
+        return {lib.st2_profile_category_name(i).decode(): {"ms": ms[i], "launches": int(ln[i]), "flops": fl[i],
+                                                            "bytes": by[i]} for i in range(n)}
+
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0
 

@@ -189,3 +189,48 @@ def test_error_behaviour():
                                  0, _lib.ptr(ws), ws.numel(), G.stream())
     assert rc == -4 and b"workspace" in lib.st2_last_error()
     torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------- tensor-core paths
+TC_SHAPES_T5 = {"encode": (5, 1024), "decode.3": (10, 512), "generator.noise_res.0.iter2": (100, 256),
+                "generator.stage0.in": (100, 256), "generator.stage0.out": (100, 256),
+                "generator.stage1.out": (500, 128), "generator.stage2.out": (1500, 64),
+                "generator.noise_res.3.iter2": (3000, 32), "generator.stage3.out": (3000, 32)}
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_hifigan_small_tensor_core_taps_and_snr(prec):
+    """BASELINE.json north_star: 16-bit tensor-core path SNR >= 40 dB and per-layer relative L2 <= 1e-2."""
+    cfg = DecoderConfig.hifigan()
+    inp = np_inputs(2, 5, 1001, cfg)
+    m = _decoder(cfg)
+    out, ref, res = _tap_table(m, cfg, inp, TC_SHAPES_T5, precision=prec)
+    for n, v in res.items():
+        G.log("hifigan_small_tc_tap", prec=prec, tap=n, rel_l2=v)
+    snr = snr_db(ref, out)
+    G.log("hifigan_small_tc", prec=prec, snr_db=snr, maxabs=float(np.abs(out - ref).max()), launches=m.last_launch_count())
+    for n, v in res.items():
+        assert v <= 1e-2, (n, v)
+    assert snr >= 40.0
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_hifigan_cfg1_3s_tensor_core_snr(prec):
+    cfg = DecoderConfig.hifigan()
+    g = golden("hifigan_B1_T120_w0_i1001.npz")
+    m = _decoder(cfg)
+    out = _run(m, np_inputs(1, 120, 1001, cfg), precision=prec)
+    snr = snr_db(g["out"], out)
+    G.log("hifigan_cfg1_tc", prec=prec, snr_db=snr, maxabs=float(np.abs(out - g["out"]).max()))
+    assert snr >= 40.0
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_istftnet_small_tensor_core_snr(prec):
+    cfg = DecoderConfig.istftnet()
+    g = golden("istftnet_B2_T5_w0_i1005.npz")
+    m = _decoder(cfg)
+    out = _run(m, np_inputs(2, 5, 1005, cfg), precision=prec)
+    snr = snr_db(g["out"], out)
+    G.log("istftnet_small_tc", prec=prec, snr_db=snr, maxabs=float(np.abs(out - g["out"]).max()))
+    assert snr >= 40.0

@@ -235,3 +235,50 @@ def test_conv_transpose1d_fp32_vs_oracle(Cin, Cout, k, stride, pad, opad, T):
     err = _relmax(ref, got)
     G.log("convT_fp32", Cin=Cin, Cout=Cout, k=k, stride=stride, relmax=err)
     assert err <= 2e-5
+
+
+# ---------------------------------------------------------------- convolutions (tcgen05 tensor-core path)
+# Same rounded operands as the oracle's emulation (RN to bf16/fp16), fp32 accumulation in TMEM:
+# only the summation order differs -> same 2e-5 bound as the fp32 kernel.
+TC_CONV_CASES = [
+    (32, 32, 11, 1, 25, 5, 700), (32, 32, 3, 1, 1, 1, 131), (64, 64, 7, 1, 9, 3, 333), (64, 64, 11, 1, 5, 1, 1000),
+    (128, 128, 3, 1, 1, 1, 257), (128, 128, 11, 1, 15, 3, 640), (256, 256, 7, 1, 3, 1, 140),
+    (256, 256, 3, 1, 5, 5, 129), (1088, 512, 3, 1, 1, 1, 12), (1024, 1024, 3, 1, 1, 1, 130),
+    (1088, 1024, 1, 1, 0, 1, 7), (512, 64, 1, 1, 0, 1, 11), (128, 22, 7, 1, 3, 1, 301),
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,dil,T", TC_CONV_CASES)
+def test_conv1d_tensor_core_vs_oracle(Cin, Cout, k, stride, pad, dil, T, prec):
+    rng = np.random.default_rng(Cin * 7 + Cout + k)
+    B = 2
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k)) / np.sqrt(Cin * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = O.conv1d(x, w, b, stride=stride, padding=pad, dilation=dil, operand=prec)
+    got = G.cf(G.conv1d(G.cl(x), w, b, stride=stride, padding=pad, dilation=dil, precision=prec))
+    assert got.shape == ref.shape
+    nan = int(np.isnan(got).sum())
+    err = _relmax(ref, np.nan_to_num(got))
+    G.log("conv1d_tc", prec=prec, Cin=Cin, Cout=Cout, k=k, dil=dil, T=T, relmax=err, nan=nan)
+    assert nan == 0
+    assert err <= 2e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,opad,T", CONVT_CASES)
+def test_conv_transpose1d_tensor_core_vs_oracle(Cin, Cout, k, stride, pad, opad, T, prec):
+    rng = np.random.default_rng(Cin + Cout + k)
+    B = 2
+    x = rng.standard_normal((B, Cin, T)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / stride)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = O.conv_transpose1d(x, w, b, stride=stride, padding=pad, output_padding=opad, operand=prec)
+    got = G.cf(G.conv1d(G.cl(x), w, b, stride=stride, padding=pad, output_padding=opad, transposed=True, precision=prec))
+    assert got.shape == ref.shape
+    nan = int(np.isnan(got).sum())
+    err = _relmax(ref, np.nan_to_num(got))
+    G.log("convT_tc", prec=prec, Cin=Cin, Cout=Cout, k=k, stride=stride, relmax=err, nan=nan)
+    assert nan == 0
+    assert err <= 2e-5
