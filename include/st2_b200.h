@@ -134,6 +134,10 @@ ST2_API const char* st2_profile_category_name(int32_t cat);
 ST2_API int st2_decoder_get_profile(st2_decoder* d, double* ms, int64_t* launches, double* flops,
                             double* bytes);
 
+/* the same profile per launch, in launch order; returns the number of records written */
+ST2_API int64_t st2_decoder_get_profile_launches(st2_decoder* d, int64_t max_n, int32_t* cat, float* ms,
+                                         double* flops, double* bytes);
+
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 
 /* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);

@@ -74,6 +74,8 @@ SIGNATURES = {
     "st2_profile_category_name": (C.c_char_p, [_I]),
     "st2_decoder_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double)]),
+    "st2_decoder_get_profile_launches": (_L, [_P, _L, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                              C.POINTER(C.c_double)]),
     "st2_round_durations": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "st2_length_regulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "st2_sinegen_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -16,8 +16,10 @@
 // Two CTAs fit per SM (<= 96 KB shared, <= 256 TMEM columns each) so one CTA's epilogue overlaps
 // the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace st2 {
 
@@ -25,93 +27,6 @@ static constexpr int TC_BM = 128;
 static constexpr int TC_KC = 64;             // K chunk: 64 x 16-bit = one 128-byte swizzle row
 static constexpr int TC_THREADS = 192;
 static constexpr uint32_t A_STAGE_BYTES = TC_BM * TC_KC * 2;   // 16 KB
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a lost TMA / MMA completion traps instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start>>4 | SBO(1024 B)>>4 @32 | version 1 @46 | layout 2 @61
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major), canonical value 1
-    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
-
-// kind::f16 instruction descriptor: D fp32, A/B bf16 (1) or fp16 (0), both K-major, M x N
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int is_bf16) {
-    uint32_t d = 0;
-    d |= 1u << 4;                                 // c_format = F32
-    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;        // a_format
-    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;       // b_format
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(M >> 4) << 24;
-    return d;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 struct TcParams {
     const float* bias;
@@ -126,6 +41,10 @@ struct TcParams {
     int stages;
     float scale; int accumulate; int mirror;
     int is_bf16;
+    // halo mode (kchunks == 1): the A tile is fetched ONCE with halo_rows = 128 + (ntaps-1)*|tap_step| rows and
+    // every tap reads it through a UMMA descriptor whose start address is shifted by whole 128-byte rows
+    int halo_rows;               // 0 = off
+    int halo_min;                // smallest time offset of any tap relative to m0
 };
 
 __global__ void __launch_bounds__(TC_THREADS)
@@ -135,12 +54,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t b_stage_bytes = (uint32_t)p.bn * TC_KC * 2;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + (size_t)p.stages * A_STAGE_BYTES;
+    const size_t a_region = p.halo_rows ? (size_t)256 * 128 : (size_t)p.stages * A_STAGE_BYTES;
+    uint8_t* smem_b = smem + a_region;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
     uint64_t* full_bar = bars;                     // [stages]
     uint64_t* empty_bar = bars + p.stages;         // [stages]
     uint64_t* tmem_full_bar = bars + 2 * p.stages; // [1]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    uint64_t* a_full_bar = bars + 2 * p.stages + 1; // [1] (halo mode)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -158,6 +79,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(a_full_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -176,13 +98,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (p.halo_rows) {
+                mbar_expect_tx(a_full_bar, (uint32_t)p.halo_rows * 128u);
+                tma_load_3d(smem_a, &map_a, a_full_bar, 0, m0 + p.halo_min, b);
+            }
             for (int it = 0; it < nit; ++it) {
                 const int j = it / p.kchunks;
                 const int kc = it - j * p.kchunks;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + b_stage_bytes);
-                tma_load_3d(smem_a + (size_t)stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kc * TC_KC,
-                            m0 + j * p.tap_step + p.in_off, b);
+                mbar_expect_tx(&full_bar[stage], (p.halo_rows ? 0u : A_STAGE_BYTES) + b_stage_bytes);
+                if (!p.halo_rows)
+                    tma_load_3d(smem_a + (size_t)stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kc * TC_KC,
+                                m0 + j * p.tap_step + p.in_off, b);
                 tma_load_3d(smem_b + (size_t)stage * b_stage_bytes, &map_b, &full_bar[stage], kc * TC_KC, n0,
                             ph + j * p.w_step);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -194,10 +121,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t idesc = umma_idesc(TC_BM, p.bn, p.is_bf16);
             int stage = 0;
             uint32_t phase = 0;
+            if (p.halo_rows) mbar_wait(a_full_bar, 0);
             for (int it = 0; it < nit; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES));
+                const uint64_t adesc = p.halo_rows
+                    ? umma_desc_sw128(smem_u32(smem_a + (size_t)(it * p.tap_step + p.in_off - p.halo_min) * 128))
+                    : umma_desc_sw128(smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES));
                 const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)stage * b_stage_bytes));
 #pragma unroll
                 for (int k4 = 0; k4 < TC_KC / 16; ++k4)
@@ -336,18 +266,25 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < bn) cols <<= 1;
     p.tmem_cols = cols;
-    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)bn * TC_KC * 2;
-    int stages = (int)((96 * 1024) / stage_bytes);       // <= 96 KB so that two CTAs share an SM
+    static const bool want_halo = getenv("ST2_TC_HALO") != nullptr && atoi(getenv("ST2_TC_HALO")) != 0;
+    const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
+    if (want_halo && p.kchunks == 1 && TC_BM + span <= 256) {
+        p.halo_rows = TC_BM + span;
+        p.halo_min = a.in_off + (a.tap_step < 0 ? (a.ntaps - 1) * a.tap_step : 0);
+    }
+    const uint32_t stage_bytes = (p.halo_rows ? 0 : A_STAGE_BYTES) + (uint32_t)bn * TC_KC * 2;
+    int stages = (int)((96 * 1024 - (p.halo_rows ? 32 * 1024 : 0)) / stage_bytes);   // <= 96 KB: two CTAs per SM
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (p.halo_rows ? 32 * 1024 : 0) + (2 * stages + 2) * sizeof(uint64_t) +
+                        16 + 1024;
 
     CUtensorMap map_a, map_b;
     const int ktaps_total = a.phases > 1 ? a.ntaps * a.phases : a.ntaps;   // weight taps stored
     const uint64_t a_d0 = (uint64_t)(a.ld_x16 < a.w16_cin_pad ? a.ld_x16 : a.w16_cin_pad);
     int e = make_map_3d(&map_a, is_bf16, a.x16, a_d0, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x16 * 2,
-                        (uint64_t)a.Tin * a.ld_x16 * 2, TC_KC, TC_BM);
+                        (uint64_t)a.Tin * a.ld_x16 * 2, TC_KC, p.halo_rows ? (uint32_t)p.halo_rows : (uint32_t)TC_BM);
     if (e != ST2_OK) return e;
     e = make_map_3d(&map_b, is_bf16, a.w16, (uint64_t)a.w16_cin_pad, (uint64_t)a.w16_cout_pad, (uint64_t)ktaps_total,
                     (uint64_t)a.w16_cin_pad * 2, (uint64_t)a.w16_cin_pad * a.w16_cout_pad * 2, TC_KC, (uint32_t)bn);

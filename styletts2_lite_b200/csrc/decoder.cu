@@ -787,6 +787,22 @@ const char* st2_profile_category_name(int32_t cat) {
     return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
 }
 
+int64_t st2_decoder_get_profile_launches(st2_decoder* d, int64_t max_n, int32_t* cat, float* ms, double* flops,
+                                         double* bytes) {
+    if (!d || !cat || !ms || !flops || !bytes) { st2::set_error("get_profile_launches: null argument"); return ST2_ERR_INVALID; }
+    const size_t n = d->prof_recs.size();
+    if (n == 0) return 0;
+    if (d->prof_events.size() <= n) { st2::set_error("get_profile_launches: event pool inconsistent"); return ST2_ERR_STATE; }
+    ST2_CUDA_CHECK(cudaEventSynchronize(d->prof_events[n]));
+    const size_t m = n < (size_t)max_n ? n : (size_t)max_n;
+    for (size_t i = 0; i < m; ++i) {
+        float t = 0.f;
+        ST2_CUDA_CHECK(cudaEventElapsedTime(&t, d->prof_events[i], d->prof_events[i + 1]));
+        cat[i] = d->prof_recs[i].cat; ms[i] = t; flops[i] = d->prof_recs[i].flops; bytes[i] = d->prof_recs[i].bytes;
+    }
+    return (int64_t)m;
+}
+
 int st2_decoder_get_profile(st2_decoder* d, double* ms, int64_t* launches, double* flops, double* bytes) {
     ST2_REQUIRE(d && ms && launches && flops && bytes, "get_profile: null argument");
     for (int i = 0; i < st2::PC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; bytes[i] = 0; }

@@ -172,6 +172,14 @@ class B200Decoder(nn.Module):
         return {lib.st2_profile_category_name(i).decode(): {"ms": ms[i], "launches": int(ln[i]), "flops": fl[i],
                                                             "bytes": by[i]} for i in range(n)}
 
+    def get_profile_launches(self, max_n: int = 4096):
+        """[(category, ms, flops, bytes)] per launch of the last profiled forward, in launch order."""
+        lib = _lib.load()
+        cat, ms = (C.c_int32 * max_n)(), (C.c_float * max_n)()
+        fl, by = (C.c_double * max_n)(), (C.c_double * max_n)()
+        n = _lib.check(lib.st2_decoder_get_profile_launches(self._handle, max_n, cat, ms, fl, by), "get_profile_launches")
+        return [(lib.st2_profile_category_name(cat[i]).decode(), ms[i], fl[i], by[i]) for i in range(n)]
+
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0
 

@@ -1,0 +1,42 @@
+"""Per-launch event profile of one decoder forward (run on the GPU box):
+    python tools/profile_layers.py [--batch 64] [--frames 200] [--precision bf16] > gpurun_out/layers.txt
+Groups launches by (category, algorithmic flops, bytes) = layer shape and prints time and throughput."""
+import argparse
+import collections
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from styletts2_lite_b200 import synth  # noqa: E402
+from styletts2_lite_b200.config import DecoderConfig  # noqa: E402
+from styletts2_lite_b200.decoder import B200Decoder  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--frames", type=int, default=200)
+ap.add_argument("--precision", default="bf16")
+ap.add_argument("--variant", default="hifigan")
+a = ap.parse_args()
+cfg = DecoderConfig.hifigan() if a.variant == "hifigan" else DecoderConfig.istftnet()
+m = B200Decoder(cfg, a.precision)
+m.load_state_dict(synth.make_state_dict(cfg, 0, True))
+m = m.cuda().eval()
+inp = {k: v.cuda() for k, v in synth.make_inputs(a.batch, a.frames, 1002, cfg, with_noise=False).items()}
+for _ in range(2):
+    m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], seed=1)
+m.set_profiling(True)
+m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], seed=2)
+recs = m.get_profile_launches()
+groups = collections.OrderedDict()
+for cat, ms, fl, by in recs:
+    g = groups.setdefault((cat, fl, by), [0, 0.0])
+    g[0] += 1
+    g[1] += ms
+tot = sum(r[1] for r in recs)
+print("total %.3f ms, %d launches" % (tot, len(recs)))
+print("%-11s %5s %9s %8s %9s %9s %6s" % ("category", "n", "ms_total", "ms_each", "TFLOP/s", "GB/s", "share"))
+for (cat, fl, by), (n, ms) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+    print("%-11s %5d %9.3f %8.4f %9.1f %9.1f %6.3f   GF=%.1f MB=%.1f" % (cat, n, ms, ms / n, fl * n / ms / 1e9 if ms else 0,
+                                                                  by * n / ms / 1e6 if ms else 0, ms / tot, fl / 1e9, by / 1e6))
