@@ -57,7 +57,8 @@ enum ProfCat {
     PC_SOURCE = 5,      // SineGen + harmonic source (+ STFT front)  (bound: hbm)
     PC_POST = 6,        // Snake + conv_post + tanh / iSTFT head     (bound: hbm)
     PC_MISC = 7,        // layout, style fc, pool, taps
-    PC_COUNT = 8
+    PC_CONV_FUSED = 8,  // fused AdaIN/act -> tcgen05 conv -> residual/stats epilogue (bound: hbm for C <= 128)
+    PC_COUNT = 9
 };
 
 // ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------
@@ -135,5 +136,12 @@ struct ConvArgs {
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);   // tcgen05 + TMA
 bool conv_tc_supported(const ConvArgs& a);
+// fused [affine + act] -> tcgen05 conv -> [bias/res/scale/acc + per-tile (sum,sumsq)] (conv_fused.cu); x fp32
+bool conv_fused_supported(const ConvArgs& a);
+int fused_stats_parts(const ConvArgs& a);
+int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
+                      void* stats_out, cudaStream_t st);
+int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
+                         int C, int Cpad, cudaStream_t st);
 
 }  // namespace st2

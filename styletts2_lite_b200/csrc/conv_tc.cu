@@ -239,6 +239,11 @@ static int make_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t
     return ST2_OK;
 }
 
+int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn) {
+    return make_map_3d(map, is_bf16, w16, (uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)ktaps, (uint64_t)cin_pad * 2,
+                       (uint64_t)cin_pad * cout_pad * 2, TC_KC, (uint32_t)bn);
+}
+
 bool conv_tc_supported(const ConvArgs& a) {
     return a.x16 != nullptr && a.w16 != nullptr && a.in_stride == 1 && a.w16_cin_pad % TC_KC == 0 &&
            a.w16_cout_pad % 16 == 0 && a.ld_x16 % 8 == 0;

@@ -2,6 +2,7 @@
 // launches that replaces Decoder.forward / Generator.forward, Modules/hifigan.py:446-475,
 // :321-347 and Modules/istftnet.py:692-721, :542-573), plus the C ABI of include/st2_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -317,6 +318,7 @@ struct Exec {
     int err = ST2_OK;
     const float* H = nullptr; // style rows [B][fc_rows]
     float* coef = nullptr;    // [B][2][2048]
+    int coef_ld = 0;          // stride the last coefficient kernel wrote with
 
     void* alloc(int64_t bytes) {
         off = (off + 255) / 256 * 256;
@@ -396,19 +398,12 @@ struct Exec {
 
     bool use_tc(const ConvW& w, int dt) const { return dt != DT_F32 && w.w16[dt] != nullptr; }
 
-    // Conv1d (stride 1 here except noise_convs) / ConvTranspose1d through the common ConvArgs contract
-    void conv(const ConvW& w, const void* x, int ld_x, int Tin, int dt, float* y, int ld_y, int Tout, int stride,
-              int padding, int dilation, const float* res, int ld_res, int res_shift, float scale, int accumulate,
-              int out_row_shift = 0, int mirror = 0) {
-        if (!live()) return;
-        ConvArgs a;
+    // geometry of Conv1d / (polyphase) ConvTranspose1d in the common ConvArgs contract
+    bool fill_args(ConvArgs& a, const ConvW& w, int Tin, int Tout, int stride, int padding, int dilation, int out_row_shift) {
         memset(&a, 0, sizeof(a));
         a.B = B; a.Cin = w.Cin; a.Cout = w.Cout;
         a.Tin = Tin; a.Tout = Tout;
         a.w = w.w32; a.bias = w.bias;
-        a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
-        a.y = y; a.ld_y = ld_y;
-        a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
         if (!w.transposed) {
             a.M = Tout; a.ntaps = w.k; a.tap_step = dilation; a.in_off = -padding; a.in_stride = stride;
             a.phases = 1; a.w_step = 1; a.out_stride = 1; a.out_pad = -out_row_shift;
@@ -416,12 +411,25 @@ struct Exec {
             if (w.k % stride != 0) {
                 set_error("ConvTranspose1d k=%d must be a multiple of stride=%d", w.k, stride);
                 err = ST2_ERR_UNSUPPORTED;
-                return;
+                return false;
             }
             a.ntaps = w.k / stride; a.tap_step = -1; a.in_off = 0; a.in_stride = 1;
             a.phases = stride; a.w_step = stride; a.out_stride = stride; a.out_pad = padding - out_row_shift;
             a.M = (Tout - 1 - out_row_shift + padding) / stride + 1;
         }
+        return true;
+    }
+
+    // Conv1d (stride 1 here except noise_convs) / ConvTranspose1d through the common ConvArgs contract
+    void conv(const ConvW& w, const void* x, int ld_x, int Tin, int dt, float* y, int ld_y, int Tout, int stride,
+              int padding, int dilation, const float* res, int ld_res, int res_shift, float scale, int accumulate,
+              int out_row_shift = 0, int mirror = 0) {
+        if (!live()) return;
+        ConvArgs a;
+        if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
+        a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
+        a.y = y; a.ld_y = ld_y;
+        a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
         // algorithmic work: Conv1d 2*B*Tout*Cout*Cin*k ; ConvTranspose1d 2*B*Tin*Cin*Cout*k
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const bool tc = use_tc(w, dt);
@@ -438,6 +446,65 @@ struct Exec {
             chk(launch_conv_simt(a, st));
             prof(PC_CONV_SIMT, flops, bytes);
         }
+    }
+
+    // ---- fused path: statistics references, coefficient kernels, fused conv ---------------------
+    struct StatRef { const void* ptr; int nparts; bool f2; };   // f2: float2 tile partials; else double2 slab partials
+
+    // statistics of a tensor no fused epilogue produced (noise_convs output): standalone pass
+    StatRef stats_standalone(const float* x, int ld_x, int T, int C) {
+        void* scratch = alloc(adain_scratch_bytes(B, T, C));
+        if (live()) {
+            chk(launch_in_stats(x, ld_x, B, T, C, scratch, st));
+            prof(PC_NORM_STATS, 0, (double)B * T * C * 4);
+        }
+        return StatRef{scratch, 0, false};
+    }
+    // coef <- (1+gamma)*rstd, beta - mean*(1+gamma)*rstd  (n == nullptr: identity)
+    void coef_from(const StatRef& sr, const AdaINRef* n, int T, int C, int Cpad) {
+        if (!live()) return;
+        if (n == nullptr || !sr.f2)
+            chk(launch_adain_coef(n ? sr.ptr : nullptr, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
+        else
+            chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
+        prof(PC_NORM_COEF, 0, 0);
+        coef_ld = Cpad;
+    }
+    bool can_fuse(const ConvW& w, int dt, int ld_x, int ld_y, int stride, int dilation) {
+        if (!use_tc(w, dt) || getenv("ST2_NO_FUSED") != nullptr) return false;
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_stride = 1; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad;
+        a.Cin = w.Cin; a.Cout = w.Cout; a.ld_x = ld_x; a.ld_y = ld_y; a.ld_res = 4;
+        a.ntaps = w.transposed ? w.k / stride : w.k;
+        a.tap_step = w.transposed ? -1 : dilation;
+        return conv_fused_supported(a);
+    }
+    int fused_parts(const ConvW& w, int Tout, int stride, int padding, int out_row_shift) {
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.w16_cout_pad = w.cout_pad;
+        a.phases = w.transposed ? stride : 1;
+        a.M = w.transposed ? (Tout - 1 - out_row_shift + padding) / stride + 1 : Tout;
+        return fused_stats_parts(a);
+    }
+    // y = epilogue( conv( act(coef.a * x + coef.b) ) ), statistics of y -> stats_out (float2 partials)
+    void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
+                    float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
+                    int res_shift, float scale, int accumulate, void* stats_out, int out_row_shift = 0, int mirror = 0) {
+        if (!live()) return;
+        ConvArgs a;
+        if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
+        a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
+        a.y = y; a.ld_y = ld_y;
+        a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
+        a.x = x; a.ld_x = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
+        chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
+        const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
+        const double bytes = (double)B * ((double)w.Cin * Tin * 4 +
+                                          (double)w.Cout * Tout * 4 * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) +
+                             (double)w.k * w.Cin * w.Cout * 2;
+        prof(PC_CONV_FUSED, flops, bytes);
     }
 
     // AdainResBlk1d.forward (hifigan.py:400-403).  x [B,T,ld_x] (Cin real channels) -> y [B,T or 2T,ld_y]
@@ -488,10 +555,38 @@ struct Exec {
     // AdaINResBlock1.forward (hifigan.py:65-74) on x_in [B,T,C]; the running tensor lives in `run`
     // (may alias x_in for an in-place block); the last iteration writes
     // dest = (dest_old*accumulate + conv2 + run) * scale.
-    void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate) {
+    void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate,
+                   const StatRef* in_stats = nullptr) {
         const int64_t mark = off;
         const int C = w.C;
         const int dt = fmt_for(w.name);
+        if (can_fuse(w.c1[0], dt, C, C, 1, 5)) {
+            // fused: 2 tiny coefficient kernels + 2 fused convs per iteration; AdaIN statistics come from the
+            // producing conv's epilogue (or from in_stats for the block input)
+            const int nparts = fused_parts(w.c1[0], T, 1, 0, 0);
+            void* st_xt = alloc((int64_t)B * nparts * C * 8);
+            void* st_run = alloc((int64_t)B * nparts * C * 8);
+            float* xt = allocf((int64_t)B * T * C);
+            StatRef cur_st = in_stats ? *in_stats : stats_standalone(x_in, C, T, C);
+            const float* cur = x_in;
+            for (int j = 0; j < 3; ++j) {
+                const int dil = w.dil[j];
+                coef_from(cur_st, &w.n1[j], T, C, C);
+                conv_fused(w.c1[j], cur, C, T, dt, ACT_SNAKE, 0.f, w.alpha1[j], xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr,
+                           0, 0, 1.f, 0, st_xt);
+                tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
+                coef_from(StatRef{st_xt, nparts, true}, &w.n2[j], T, C, C);
+                const bool last = (j == 2);
+                float* out = last ? dest : run;
+                conv_fused(w.c2[j], xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
+                           last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run);
+                if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
+                cur = out;
+                cur_st = StatRef{st_run, nparts, true};
+            }
+            off = mark;
+            return;
+        }
         const bool tc = use_tc(w.c1[0], dt);
         const int dta = tc ? dt : DT_F32;
         void* xa = alloc((int64_t)B * T * C * (dta == DT_F32 ? 4 : 2));
@@ -622,19 +717,31 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         // x = ups[i](act(x)) + x_source
         const int dtu = E.fmt_for("generator.ups");
         const bool tcu = E.use_tc(d->ups[i], dtu);
-        void* xs = E.alloc((int64_t)B * Tin * Cin * (tcu ? 2 : 4));
-        if (istft) E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_LRELU, 0.1f, nullptr, xs, Cin, tcu ? dtu : DT_F32);
-        else E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_SNAKE, 0.f, d->gen_alpha[i], xs, Cin, tcu ? dtu : DT_F32);
-        float* xu = E.allocf((int64_t)B * Tout * C);
         const int pu = istft ? (ku - u) / 2 : (u / 2 + u % 2);
-        // istftnet: ReflectionPad1d((1,0)) after the last ups = write at row t+1 and mirror row 2 into row 0
-        E.conv(d->ups[i], xs, Cin, Tin, tcu ? dtu : DT_F32, xu, C, Tout, u, pu, 1, nc, C, 0, 1.f, 0, shift, shift);
+        float* xu = E.allocf((int64_t)B * Tout * C);
+        Exec::StatRef xu_stats{nullptr, 0, true};
+        const bool fuse_u = E.can_fuse(d->ups[i], dtu, Cin, C, u, 1);
+        if (fuse_u) {
+            // Snake / LeakyReLU applied on the A-operand path; InstanceNorm statistics of xu from the epilogue
+            xu_stats.nparts = E.fused_parts(d->ups[i], Tout, u, pu, shift);
+            void* st_xu = E.alloc((int64_t)B * xu_stats.nparts * C * 8);
+            xu_stats.ptr = st_xu;
+            E.coef_from(Exec::StatRef{nullptr, 0, false}, nullptr, Tin, Cin, Cin);
+            E.conv_fused(d->ups[i], x, Cin, Tin, dtu, istft ? ACT_LRELU : ACT_SNAKE, 0.1f, istft ? nullptr : d->gen_alpha[i], xu, C,
+                         Tout, u, pu, 1, nc, C, 0, 1.f, 0, st_xu, shift, shift);
+        } else {
+            void* xs = E.alloc((int64_t)B * Tin * Cin * (tcu ? 2 : 4));
+            if (istft) E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_LRELU, 0.1f, nullptr, xs, Cin, tcu ? dtu : DT_F32);
+            else E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_SNAKE, 0.f, d->gen_alpha[i], xs, Cin, tcu ? dtu : DT_F32);
+            // istftnet: ReflectionPad1d((1,0)) after the last ups = write at row t+1 and mirror row 2 into row 0
+            E.conv(d->ups[i], xs, Cin, Tin, tcu ? dtu : DT_F32, xu, C, Tout, u, pu, 1, nc, C, 0, 1.f, 0, shift, shift);
+        }
         E.tap("generator.stage" + is + ".in", xu, C, (int64_t)B * Tout, C);
         float* run = E.allocf((int64_t)B * Tout * C);
         for (int j = 0; j < c.n_kernels; ++j) {
             const bool lastk = (j + 1 == c.n_kernels);
             E.resblock1(d->resblocks[i * c.n_kernels + j], xu, run, Tout, stage_out[i], lastk ? 1.f / (float)c.n_kernels : 1.f,
-                        j > 0 ? 1 : 0);
+                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr);
         }
         E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
         x = stage_out[i];
@@ -783,7 +890,7 @@ int st2_profile_num_categories(void) { return st2::PC_COUNT; }
 
 const char* st2_profile_category_name(int32_t cat) {
     static const char* names[st2::PC_COUNT] = {"conv_tc", "conv_simt", "norm_stats", "norm_coef", "affine_act",
-                                               "source", "post", "misc"};
+                                               "source", "post", "misc", "conv_fused"};
     return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
 }
 
