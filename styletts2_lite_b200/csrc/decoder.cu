@@ -511,16 +511,20 @@ struct Exec {
     void resblk1d(const ResBlk1dW& w, const float* x, int ld_x, int T, float* y, int ld_y) {
         const int64_t mark = off;
         const int dt = fmt_for(w.name);
-        const bool tc1 = use_tc(w.conv1, dt) && !w.upsample;   // pooled input stays fp32 -> SIMT conv1
+        const bool tc1 = use_tc(w.conv1, dt);
         const int dt1 = tc1 ? dt : DT_F32;
-        const int es1 = dt1 == DT_F32 ? 4 : 2;
+        const int dta = (tc1 && !w.upsample) ? dt : DT_F32;     // the depthwise pool reads fp32, writes the 16-bit operand
+        const int es1 = dta == DT_F32 ? 4 : 2;
         const int Tc = w.upsample ? 2 * T : T;
         void* xa = alloc((int64_t)B * T * ld_x * es1);
-        norm_act(x, ld_x, T, w.Cin, &w.norm1, ACT_LRELU, 0.2f, nullptr, xa, ld_x, dt1);
+        norm_act(x, ld_x, T, w.Cin, &w.norm1, ACT_LRELU, 0.2f, nullptr, xa, ld_x, dta);
         const void* cin = xa;
         if (w.upsample) {
-            float* xp = allocf((int64_t)B * Tc * ld_x);
-            if (live()) chk(launch_pool_dw((const float*)xa, ld_x, w.pool_w, w.pool_b, xp, ld_x, B, T, w.Cin, ld_x, st));
+            void* xp = alloc((int64_t)B * Tc * ld_x * (tc1 ? 2 : 4));
+            if (live()) {
+                if (tc1) chk(launch_pool_dw16((const float*)xa, ld_x, w.pool_w, w.pool_b, xp, ld_x, dt, B, T, ld_x, st));
+                else chk(launch_pool_dw((const float*)xa, ld_x, w.pool_w, w.pool_b, (float*)xp, ld_x, B, T, w.Cin, ld_x, st));
+            }
             prof(PC_MISC, 0, 4.0 * B * w.Cin * 3.0 * T);
             cin = xp;
         }
@@ -705,15 +709,29 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         const std::string is = std::to_string(i);
         // x_source = noise_res[i](noise_convs[i](har_source), s)
         float* nc = E.allocf((int64_t)B * Tout * C);
+        Exec::StatRef nc_stats{nullptr, 0, true};
+        bool nc_have_stats = false;
         {
             const ConvW& w = d->noise_convs[i];
             int sf = 1;
             for (int j = i + 1; j < c.n_stages; ++j) sf *= c.upsample_rates[j];
             const int stride = last ? 1 : sf, pad = last ? 0 : (sf + 1) / 2;
-            if (istft) E.conv(w, har22, HLD, har_frames, DT_F32, nc, C, Tout, stride, pad, 1, nullptr, 0, 0, 1.f, 0);
-            else E.conv(w, har, 1, S, DT_F32, nc, C, Tout, stride, pad, 1, nullptr, 0, 0, 1.f, 0);
+            if (istft) {
+                E.conv(w, har22, HLD, har_frames, DT_F32, nc, C, Tout, stride, pad, 1, nullptr, 0, 0, 1.f, 0);
+            } else {
+                // Conv1d(1 -> C) of the harmonic source: dedicated HBM-bound kernel that also emits the InstanceNorm
+                // partials of its output (consumed by noise_res[i].adain1[0])
+                nc_stats.nparts = noise_conv_parts(Tout);
+                void* stp = E.alloc((int64_t)B * nc_stats.nparts * C * 8);
+                nc_stats.ptr = stp;
+                nc_have_stats = true;
+                if (E.live()) {
+                    E.chk(launch_noise_conv(har, w.w32, w.bias, nc, stp, B, S, Tout, C, w.k, stride, pad, st));
+                    E.prof(PC_SOURCE, 2.0 * B * Tout * C * w.k, 4.0 * B * ((double)S + (double)Tout * C));
+                }
+            }
         }
-        E.resblock1(d->noise_res[i], nc, nc, Tout, nc, 1.f, 0);
+        E.resblock1(d->noise_res[i], nc, nc, Tout, nc, 1.f, 0, nc_have_stats ? &nc_stats : nullptr);
         // x = ups[i](act(x)) + x_source
         const int dtu = E.fmt_for("generator.ups");
         const bool tcu = E.use_tc(d->ups[i], dtu);

@@ -280,3 +280,141 @@ int launch_pack_w16(const float* wp, void* w16, int k, int Cin, int Cout, int Ci
 }
 
 }  // namespace st2
+
+namespace st2 {
+
+// ---- generator.noise_convs[i] (hifigan.py:296-303,330): Conv1d(1 -> C, kernel k, stride s, padding p) of the
+// harmonic source har[B][S] -> y[B][Tout][C] channels-last, plus per-tile (sum, sumsq) per channel for the AdaIN
+// that follows (noise_res[i].adain1[0]).  HBM-bound on its output (4*C bytes per output step); weights and the
+// har segment of the tile live in shared memory.
+static constexpr int kNcTile = 64;      // output time steps per CTA
+__global__ void __launch_bounds__(256)
+noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[k][C]*/, const float* __restrict__ bias,
+                  float* __restrict__ y, float2* __restrict__ stats, int S, int Tout, int C, int k, int stride, int pad,
+                  int ntile) {
+    extern __shared__ float sm[];
+    float* sw = sm;                                   // [k][C]
+    float* sh = sm + (size_t)k * C;                   // [(kNcTile-1)*stride + k]
+    float* sred = sh + (kNcTile - 1) * stride + k;    // [rows_per_pass][C][2]
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int t0 = tile * kNcTile;
+    for (int i = threadIdx.x; i < k * C; i += 256) sw[i] = w[i];
+    const int seg = (kNcTile - 1) * stride + k;
+    const int h0 = t0 * stride - pad;
+    for (int i = threadIdx.x; i < seg; i += 256) {
+        const int hi = h0 + i;
+        sh[i] = (hi >= 0 && hi < S) ? har[(size_t)b * S + hi] : 0.f;
+    }
+    __syncthreads();
+    const int cq = C >> 2;                            // channel quads
+    const int rpp = 256 / cq;                         // rows per pass
+    const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+    const float4 bv = *reinterpret_cast<const float4*>(bias + q * 4);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = rl; r < kNcTile; r += rpp) {
+        const int t = t0 + r;
+        if (t >= Tout) break;
+        float4 acc = bv;
+        const float* hp = sh + r * stride;
+        for (int j = 0; j < k; ++j) {
+            const float hv = hp[j];
+            const float4 wv = *reinterpret_cast<const float4*>(sw + (size_t)j * C + q * 4);
+            acc.x = fmaf(hv, wv.x, acc.x); acc.y = fmaf(hv, wv.y, acc.y);
+            acc.z = fmaf(hv, wv.z, acc.z); acc.w = fmaf(hv, wv.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(y + ((size_t)b * Tout + t) * C + q * 4) = acc;
+        s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
+        s2[0] = fmaf(acc.x, acc.x, s2[0]); s2[1] = fmaf(acc.y, acc.y, s2[1]);
+        s2[2] = fmaf(acc.z, acc.z, s2[2]); s2[3] = fmaf(acc.w, acc.w, s2[3]);
+    }
+    if (stats == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sred[((size_t)rl * C + q * 4 + i) * 2 + 0] = s1[i];
+        sred[((size_t)rl * C + q * 4 + i) * 2 + 1] = s2[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, s = 0.f;
+        for (int r = 0; r < rpp; ++r) {               // fixed order: deterministic
+            a += sred[((size_t)r * C + c) * 2 + 0];
+            s += sred[((size_t)r * C + c) * 2 + 1];
+        }
+        stats[((size_t)b * ntile + tile) * C + c] = make_float2(a, s);
+    }
+}
+
+int noise_conv_parts(int Tout) { return cdiv(Tout, kNcTile); }
+
+int launch_noise_conv(const float* har, const float* w, const float* bias, float* y, void* stats, int B, int S, int Tout,
+                      int C, int k, int stride, int pad, cudaStream_t st) {
+    ST2_REQUIRE(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0 && bias != nullptr, "noise_conv: unsupported C=%d", C);
+    const int ntile = cdiv(Tout, kNcTile);
+    const int rpp = 256 / (C / 4);
+    size_t smem = ((size_t)k * C + (kNcTile - 1) * stride + k + (size_t)rpp * C * 2) * sizeof(float);
+    static size_t max_set = 0;
+    if (smem > 48 * 1024 && smem > max_set) {
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    dim3 grid(ntile, B);
+    noise_conv_kernel<<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- depthwise pool with a 16-bit output (operand of the tensor-core conv1 of the upsampling AdainResBlk1d)
+template <int DT>
+__global__ void pool_dw16_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, void* __restrict__ y, int ld_y, int T, int Cpad) {
+    const int cq = Cpad >> 2;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t total = (size_t)2 * T * cq;
+    if (i >= total) return;
+    const int to = (int)(i / cq);
+    const int c = (int)(i - (size_t)to * cq) * 4;
+    const int q = to >> 1;
+    const float* xb = x + (size_t)b * T * ld_x;
+    const float4 bv = *reinterpret_cast<const float4*>(bias + c);
+    const float4 x0 = *reinterpret_cast<const float4*>(xb + (size_t)q * ld_x + c);
+    float4 o;
+    if ((to & 1) == 0) {
+        const float4 w1 = *reinterpret_cast<const float4*>(w + Cpad + c);
+        o.x = fmaf(x0.x, w1.x, bv.x); o.y = fmaf(x0.y, w1.y, bv.y);
+        o.z = fmaf(x0.z, w1.z, bv.z); o.w = fmaf(x0.w, w1.w, bv.w);
+    } else {
+        const float4 w2 = *reinterpret_cast<const float4*>(w + 2 * Cpad + c);
+        o.x = fmaf(x0.x, w2.x, bv.x); o.y = fmaf(x0.y, w2.y, bv.y);
+        o.z = fmaf(x0.z, w2.z, bv.z); o.w = fmaf(x0.w, w2.w, bv.w);
+        if (q + 1 < T) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w + c);
+            const float4 x1 = *reinterpret_cast<const float4*>(xb + (size_t)(q + 1) * ld_x + c);
+            o.x = fmaf(x1.x, w0.x, o.x); o.y = fmaf(x1.y, w0.y, o.y);
+            o.z = fmaf(x1.z, w0.z, o.z); o.w = fmaf(x1.w, w0.w, o.w);
+        }
+    }
+    const size_t idx = ((size_t)b * 2 * T + to) * ld_y + c;
+    uint2 u;
+    if (DT == DT_BF16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + idx) = u;
+    } else {
+        __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+        u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + idx) = u;
+    }
+}
+
+int launch_pool_dw16(const float* x, int ld_x, const float* w, const float* bias, void* y, int ld_y, int out_dtype, int B,
+                     int T, int Cpad, cudaStream_t st) {
+    size_t total = (size_t)2 * T * (Cpad / 4);
+    dim3 grid(cdiv(total, 256), B);
+    if (out_dtype == DT_BF16) pool_dw16_kernel<DT_BF16><<<grid, 256, 0, st>>>(x, ld_x, w, bias, y, ld_y, T, Cpad);
+    else pool_dw16_kernel<DT_F16><<<grid, 256, 0, st>>>(x, ld_x, w, bias, y, ld_y, T, Cpad);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+}  // namespace st2
