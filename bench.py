@@ -14,7 +14,7 @@ inside the timed step.
             waveform copied back to the host inside the timed region
   roofline  the dominant kernel (tcgen05 conv): algorithmic FLOPs / event-timed duration vs the
             measured bf16 peak of MEASURED_PEAKS.json; `kernels` lists every category
-  cpu_baseline  the numpy oracle port of the reference decoder on the host cores (rank 0, N=1)
+  cpu_baseline  the torch-CPU port of the reference decoder (oracle/decoder_torch.py) on the host cores (rank 0, N=1)
 
 --impl reference times that same CPU port (the reference itself is pure Python/PyTorch and
 cannot travel to the GPU box) on a bounded sample of the workload.
@@ -68,16 +68,19 @@ def workload_config(a, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the numpy oracle port of the reference decoder, all host threads (BLAS)
+# CPU arm: the reference decoder restated on torch CPU kernels (oracle/decoder_torch.py), all host threads
 # ------------------------------------------------------------------------------------------------
 def cpu_port_run(variant, frames, steps, warmup):
-    import numpy as np
+    import torch
     from styletts2_lite_b200 import synth
     from styletts2_lite_b200.config import DecoderConfig
-    from oracle import decoder_np as O      # the CPU baseline leg is one of the places allowed to run the oracle
+    # the CPU baseline leg is one of the places allowed to run the oracle: decoder_torch is the reference decoder
+    # restated on the very ATen CPU kernels the reference dispatches to (oneDNN conv, native_batch_norm, ...)
+    from oracle import decoder_torch as O
+    torch.set_num_threads(os.cpu_count() or 1)
     cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
-    W = O.Weights({k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()})
-    inp = {k: v.numpy() for k, v in synth.make_inputs(1, frames, 1000, cfg).items()}
+    W = O.TorchWeights(synth.make_state_dict(cfg, 0, True))
+    inp = synth.make_inputs(1, frames, 1000, cfg)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -85,13 +88,14 @@ def cpu_port_run(variant, frames, steps, warmup):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    assert out.shape == (1, 1, 600 * frames) and np.isfinite(out).all()
+    assert tuple(out.shape) == (1, 1, 600 * frames) and bool(torch.isfinite(out).all())
     secs = frames * 600 / SR
     mean = sum(times) / len(times)
     return {"value": secs / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": "1 utterance x %.1f s (T=%d) of the workload, numpy oracle port of the reference decoder "
-                      "(reference is pure PyTorch and cannot travel), BLAS on all host threads, %d runs after %d warm-up, "
-                      "mean %.2f s/utterance" % (secs, frames, steps, warmup, mean),
+            "sample": "1 utterance x %.1f s (T=%d) of the workload; torch-CPU port of the reference decoder (same ATen/oneDNN "
+                      "kernels the reference dispatches to; the reference itself is pure PyTorch and cannot travel), "
+                      "%d threads, %d runs after %d warm-up, mean %.2f s/utterance" % (secs, frames, torch.get_num_threads(),
+                                                                                     steps, warmup, mean),
             "ms_per_step": mean * 1e3}
 
 
@@ -166,6 +170,7 @@ def run_b200(a, rank, local_rank, world):
     from styletts2_lite_b200 import synth
     from styletts2_lite_b200.config import DecoderConfig
     from styletts2_lite_b200.decoder import B200Decoder
+    from styletts2_lite_b200.parallel import gather_waveforms
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
@@ -183,7 +188,6 @@ def run_b200(a, rank, local_rank, world):
     host = {k: v.pin_memory() for k, v in inp.items()}
     res = {k: v.to(dev) for k, v in inp.items()}
     out_host = torch.empty(B, 1, S, dtype=torch.float32).pin_memory()
-    gathered = [torch.empty(B, 1, S, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -195,7 +199,7 @@ def run_b200(a, rank, local_rank, world):
         with torch.no_grad():
             out = m(res["asr"], res["F0_curve"], res["N"], res["s"], seed=1234 + i)
         if world > 1:
-            dist.gather(out, gathered, dst=0)
+            gather_waveforms(out)
         return out
 
     def step_e2e(i):
@@ -203,7 +207,7 @@ def run_b200(a, rank, local_rank, world):
         with torch.no_grad():
             out = m(d["asr"], d["F0_curve"], d["N"], d["s"], seed=4321 + i)
         if world > 1:
-            dist.gather(out, gathered, dst=0)
+            gather_waveforms(out)
         out_host.copy_(out, non_blocking=True)
         return out
 

@@ -122,3 +122,17 @@ def test_bf16_rounding_helper():
     r = O.round_bf16(x)
     import torch
     assert np.array_equal(r, torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_torch_cpu_port_matches_golden():
+    """oracle/decoder_torch.py (the CPU speed baseline of bench.py) is pinned to the same reference outputs."""
+    import torch
+    from oracle import decoder_torch as OT
+    from styletts2_lite_b200 import synth
+    for cfg, name, B, T, seed in ((DecoderConfig.hifigan(), "hifigan_B2_T5_w0_i1001.npz", 2, 5, 1001),
+                                  (DecoderConfig.istftnet(), "istftnet_B2_T5_w0_i1005.npz", 2, 5, 1005)):
+        g = golden(name)
+        W = OT.TorchWeights(synth.make_state_dict(cfg, 0, True))
+        inp = synth.make_inputs(B, T, seed, cfg)
+        out = OT.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"]).numpy()
+        assert np.abs(out - g["out"]).max() <= WAVE_TOL, name
