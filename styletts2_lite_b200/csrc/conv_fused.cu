@@ -52,6 +52,9 @@ struct FusedParams {
     float slope;              // ACT_LRELU
     int Cin;                  // real input channels
     int kchunks;              // CinPad / 64
+    int x16in;                // input tensor is 16-bit (is_bf16 selects bf16 / fp16)
+    int y16out;               // output tensor is written as 16-bit
+    int k32;                  // 1: Cin == 32 -> 64-byte operand rows (K = 32, SWIZZLE_64B) instead of zero-padding K to 64
     int xstage;               // 1: activations arrive by TMA into the fp32 staging ring (kchunks == 1)
     // geometry (ConvArgs contract, in_stride == 1)
     int B, M, Tout, Cout;
@@ -215,6 +218,23 @@ __device__ __forceinline__ float4 ldg_stream(const float* ptr) {
     return v;
 }
 
+__device__ __forceinline__ float4 unpack16x4(uint2 u, int is_bf16) {
+    float4 v;
+    if (is_bf16) {
+        v.x = __uint_as_float(u.x << 16); v.y = __uint_as_float(u.x & 0xffff0000u);
+        v.z = __uint_as_float(u.y << 16); v.w = __uint_as_float(u.y & 0xffff0000u);
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        v = make_float4(a.x, a.y, b.x, b.y);
+    }
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
 // per-thread transform constants: y = act(a*x + b) for 4 consecutive channels, packed as two float2
 struct XfCoef { float2 a01, a23, b01, b23, al01, al23, ia01, ia23; };
 
@@ -239,9 +259,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = ((uint32_t)p.rows * 128u + 1023u) & ~1023u;
-    const uint32_t b_stage_bytes = (uint32_t)p.bn * 128u;
-    const uint32_t x_row_bytes = (uint32_t)p.Cin * 4u;                                   // staging row (xstage only)
+    const uint32_t arow = p.k32 ? 64u : 128u;                     // bytes per operand row (K = 32 or 64 16-bit values)
+    const uint32_t a_bytes = ((uint32_t)p.rows * arow + 1023u) & ~1023u;
+    const uint32_t b_stage_bytes = (uint32_t)p.bn * arow;
+    const uint32_t xes = p.x16in ? 2u : 4u;                      // bytes per input element
+    const uint32_t x_row_bytes = (uint32_t)p.Cin * xes;                                  // staging row (xstage only)
     const uint32_t x_bytes = p.xstage ? (((uint32_t)p.rows * x_row_bytes + 1023u) & ~1023u) : 0u;
     uint8_t* smem_a = smem;                                       // 2 x [rows][64] 16-bit, SWIZZLE_128B
     uint8_t* smem_b = smem_a + 2 * a_bytes;                       // resident taps or ring of [bn][64]
@@ -336,8 +358,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
             const uint32_t a_buf_step = a_bytes >> 4;
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
             const uint32_t b_step = b_stage_bytes >> 4;
-            const int row0 = (p.in_off - p.halo_min) * 8;            // (rows * 128 B) >> 4
-            const int row_step = p.tap_step * 8;
+            const int row_u = (int)(arow >> 4);                      // descriptor units (16 B) per operand row
+            const int row0 = (p.in_off - p.halo_min) * row_u;
+            const int row_step = p.tap_step * row_u;
+            // K-major descriptor hi word: SBO = 8 rows (>>4) | version 1 @ bit 46 | SWIZZLE_128B (2) or SWIZZLE_64B (4) @ bit 61
+            const uint32_t dhi = p.k32 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : kDescHi;
             const uint32_t b_res_step = (uint32_t)(p.w_step * p.kchunks) * b_step;
             int stage = 0;
             uint32_t phase = 0;
@@ -361,24 +386,41 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                     tc_fence_after();
                     if (kc == 0) TRACE(1, tcnt, 2);
                     uint32_t a_lo = a_lo0 + buf * a_buf_step + (uint32_t)row0;
-                    uint32_t b_res = b_lo0 + (uint32_t)(ti.ph * p.kchunks + kc) * b_step;    // resident: widx = ph + j*w_step
-                    for (int j = 0; j < p.ntaps; ++j) {
-                        uint32_t b_lo;
-                        if (p.resident) {
-                            b_lo = b_res;
-                            b_res += b_res_step;
+                    if (p.resident) {
+                        // resident weights: no barrier inside the tap loop -> branch-free, unrolled issue
+                        uint32_t b_lo = b_lo0 + (uint32_t)(ti.ph * p.kchunks + kc) * b_step;     // widx = ph + j*w_step
+                        if (p.k32) {
+#pragma unroll 4
+                            for (int j = 0; j < p.ntaps; ++j) {
+                                umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                                accum = 1u;
+                                a_lo += (uint32_t)row_step;
+                                b_lo += b_res_step;
+                            }
                         } else {
+#pragma unroll 2
+                            for (int j = 0; j < p.ntaps; ++j) {
+                                umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                                accum = 1u;
+                                a_lo += (uint32_t)row_step;
+                                b_lo += b_res_step;
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < p.ntaps; ++j) {
                             mbar_wait(&b_full[stage], phase);
                             tc_fence_after();
-                            b_lo = b_lo0 + (uint32_t)stage * b_step;
-                        }
-                        umma_f16_lohi(d_tmem, a_lo, b_lo, kDescHi, idesc, accum);
-                        umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
-                        umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, kDescHi, idesc, 1u);
-                        umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, kDescHi, idesc, 1u);
-                        accum = 1u;
-                        a_lo += (uint32_t)row_step;
-                        if (!p.resident) {
+                            const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_step;
+                            umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                            umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                            umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                            umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                            accum = 1u;
+                            a_lo += (uint32_t)row_step;
                             umma_commit(&b_empty[stage]);
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
@@ -427,10 +469,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                     }
                     cached_b = ti.b;
                 }
-                // A-tile byte address of (row r, this thread's 8-byte slot): r*128 + ((chunk ^ (r & 7)) << 4) + sub
+                // A-tile byte address of (row r, this thread's 8-byte slot):
+                //   SWIZZLE_128B: r*128 + ((chunk ^ (r & 7)) << 4) + sub      SWIZZLE_64B: r*64 + ((chunk ^ ((r >> 1) & 3)) << 4) + sub
                 const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
                 const uint32_t abase = smem_a_u32 + buf * a_bytes + sub;
-#define A_ADDR(r) (abase + (uint32_t)(r) * 128u + ((cidx ^ ((uint32_t)(r) & 7u)) << 4))
+                const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
+#define A_ADDR(r) (abase + (uint32_t)(r) * arow + ((cidx ^ (((uint32_t)(r) >> sw_shift) & sw_mask)) << 4))
                 if (p.xstage) {
                     // ---- staged path: fp32 rows already in shared memory (TMA), no global latency exposed
                     const uint32_t s = cc % NSTG;                           // kchunks == 1: one staging tile per tile
@@ -438,14 +482,19 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                     if (lt == 0) TRACE(0, lseq, 1);
                     mbar_wait_warp(&a_empty[buf], ((cc >> 1) & 1) ^ 1);
                     if (lt == 0) TRACE(0, lseq, 2);
-                    uint32_t xaddr = smem_x_u32 + s * x_bytes + (uint32_t)rl * x_row_bytes + (uint32_t)c4 * 4u;
+                    uint32_t xaddr = smem_x_u32 + s * x_bytes + (uint32_t)rl * x_row_bytes + (uint32_t)c4 * xes;
                     const uint32_t xstep = (uint32_t)rpp * x_row_bytes;
                     int t = t_base + rl;
                     for (int r = rl; r < p.rows; r += 2 * rpp) {            // two independent rows per iteration (ILP)
                         const bool has1 = (r + rpp) < p.rows;
-                        const float4 v0 = lds128(xaddr);
-                        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (has1) v1 = lds128(xaddr + xstep);
+                        float4 v0, v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.x16in) {
+                            v0 = unpack16x4(lds64(xaddr), p.is_bf16);
+                            if (has1) v1 = unpack16x4(lds64(xaddr + xstep), p.is_bf16);
+                        } else {
+                            v0 = lds128(xaddr);
+                            if (has1) v1 = lds128(xaddr + xstep);
+                        }
                         uint2 o0 = transform4<ACT>(v0, cf, p.is_bf16);
                         uint2 o1 = transform4<ACT>(v1, cf, p.is_bf16);
                         if (t < 0 || t >= p.Tin) o0 = make_uint2(0u, 0u);   // conv zero padding
@@ -459,8 +508,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                     if (lane == 0) mbar_arrive(&x_empty[s]);                // staging tile consumed
                 } else {
                     // ---- direct path: batched 128-bit global loads (whole tile in flight), then transform
-                    const float* xp = p.x + ((size_t)ti.b * p.Tin + t_base + rl) * p.ld_x + cg;
-                    const size_t xstep = (size_t)rpp * p.ld_x;
+                    const char* xp = reinterpret_cast<const char*>(p.x) + (((size_t)ti.b * p.Tin + t_base + rl) * p.ld_x + cg) * xes;
+                    const size_t xstep = (size_t)rpp * p.ld_x * xes;
                     constexpr int U = 16;                                   // 16 x 12 rows >= 128 + 64
                     float4 v[U];
 #pragma unroll
@@ -468,7 +517,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                         const int r = rl + u * rpp;
                         const int t = t_base + r;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < p.rows && t >= 0 && t < p.Tin) v[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+                        if (r < p.rows && t >= 0 && t < p.Tin) {
+                            if (p.x16in) v[u] = unpack16x4(__ldg(reinterpret_cast<const uint2*>(xp + u * xstep)), p.is_bf16);
+                            else v[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+                        }
                     }
                     if (lt == 0 && kc == 0) TRACE(0, lseq, 1);
                     mbar_wait_warp(&a_empty[buf], ((cc >> 1) & 1) ^ 1);     // loads are in flight while we wait for the buffer
@@ -591,7 +643,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
                         o01 = fmul2(o01, sc2);
                         o23 = fmul2(o23, sc2);
                     }
-                    *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                    if (p.y16out)
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.y) + (yo - p.y) + it * ystep) =
+                            make_uint2(pack16(o01.x, o01.y, p.is_bf16), pack16(o23.x, o23.y, p.is_bf16));
+                    else
+                        *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
                     s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
                     s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
                     if (p.mirror && t_first + it * 4 * p.out_stride == 2) {
@@ -705,6 +761,9 @@ int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld
 
 // ---------------------------------------------------------------- host side
 int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_act16_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1);
 int make_f32_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                     uint64_t stride2_bytes, uint32_t b0, uint32_t b1);
 
@@ -726,6 +785,8 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.x = a.x; p.ld_x = a.ld_x; p.Tin = a.Tin;
+    p.x16in = a.x16in; p.y16out = a.y16out;
+    ST2_REQUIRE(!(a.y16out && (a.accumulate || a.mirror)), "conv_fused: 16-bit output cannot accumulate / mirror");
     p.coef = coef; p.coef_ld = coef_ld; p.alpha = alpha; p.slope = slope;
     p.Cin = a.Cin; p.kchunks = a.w16_cin_pad / F_KC;
     p.B = a.B; p.M = a.M; p.Tout = a.Tout; p.Cout = a.Cout;
@@ -752,12 +813,14 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     p.stats = (float2*)stats_out;
     // shared-memory plan (one persistent CTA per SM, <= ~224 KB)
     const int64_t budget = 224 * 1024;
-    const int64_t a_bytes = ((int64_t)p.rows * 128 + 1023) & ~(int64_t)1023;
-    const int64_t b_stage = (int64_t)bn * 128;
+    p.k32 = (a.Cin == 32 && a.w16_cin_pad == 64 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
+    const int64_t arow = p.k32 ? 64 : 128;
+    const int64_t a_bytes = ((int64_t)p.rows * arow + 1023) & ~(int64_t)1023;
+    const int64_t b_stage = (int64_t)bn * arow;
     const int64_t base_fixed = 2 * a_bytes + EW * 32 * 32 * 4 + (int64_t)EG * 4 * bn * 8 + 160 * 8 + 1024;
     // activations by TMA into an fp32 staging ring for single-chunk layers (C <= 64), when the ring fits
-    const int64_t x_bytes = (((int64_t)p.rows * a.Cin * 4) + 1023) & ~(int64_t)1023;
-    p.xstage = (p.kchunks == 1 && a.ld_x * 4 % 16 == 0 && getenv("ST2_NO_XSTAGE") == nullptr) ? 1 : 0;
+    const int64_t x_bytes = (((int64_t)p.rows * a.Cin * (a.x16in ? 2 : 4)) + 1023) & ~(int64_t)1023;
+    p.xstage = (p.kchunks == 1 && a.ld_x * (a.x16in ? 2 : 4) % 16 == 0 && getenv("ST2_NO_XSTAGE") == nullptr) ? 1 : 0;
     int64_t fixed = base_fixed + (p.xstage ? NSTG * x_bytes : 0);
     const int ktaps_total = a.phases > 1 ? a.ntaps * a.phases : a.ntaps;
     p.ktaps_total = ktaps_total;
@@ -765,7 +828,10 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     // weights resident when every tap of every phase fits, else a ring with what is left (>= 4 stages; drop the
     // staging ring first if it would starve the weight ring)
     p.resident = (p.ntile_n == 1 && fixed + resident_tiles * b_stage <= budget && resident_tiles * b_stage < (1 << 20)) ? 1 : 0;
-    if (!p.resident && p.xstage && (budget - fixed) / b_stage < 6) {
+    const bool resident_without_stage = (p.ntile_n == 1 && base_fixed + resident_tiles * b_stage <= budget &&
+                                         resident_tiles * b_stage < (1 << 20));
+    // resident weights beat the staging ring: a ring shallower than two tiles of taps starves the tensor core
+    if (!p.resident && p.xstage && (resident_without_stage || (budget - fixed) / b_stage < 6)) {
         p.xstage = 0;
         fixed = base_fixed;
         p.resident = (p.ntile_n == 1 && fixed + resident_tiles * b_stage <= budget && resident_tiles * b_stage < (1 << 20)) ? 1 : 0;
@@ -782,11 +848,16 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     const size_t smem = (size_t)fixed + (size_t)stages * b_stage;
     ST2_REQUIRE(smem <= 227 * 1024, "conv_fused: shared-memory plan %zu exceeds 227 KB", smem);
     CUtensorMap map_b, map_x;
-    int e = make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, ktaps_total, bn);
+    int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, ktaps_total, bn)
+                  : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, ktaps_total, bn);
     if (e != ST2_OK) return e;
     if (p.xstage) {
-        e = make_f32_map_3d(&map_x, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * 4,
-                            (uint64_t)a.Tin * a.ld_x * 4, (uint32_t)a.Cin, (uint32_t)p.rows);
+        if (a.x16in)
+            e = make_act16_map_3d(&map_x, p.is_bf16, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * 2,
+                                  (uint64_t)a.Tin * a.ld_x * 2, (uint32_t)a.Cin, (uint32_t)p.rows);
+        else
+            e = make_f32_map_3d(&map_x, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * 4,
+                                (uint64_t)a.Tin * a.ld_x * 4, (uint32_t)a.Cin, (uint32_t)p.rows);
         if (e != ST2_OK) return e;
     } else {
         map_x = map_b;

@@ -217,7 +217,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int sw64 = 0) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -229,11 +229,34 @@ static int make_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u]", (int)r,
                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
                   (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1);
+        return ST2_ERR_CUDA;
+    }
+    return ST2_OK;
+}
+
+// 16-bit, no swizzle: staging tiles of a 16-bit activation tensor
+int make_act16_map_3d(CUtensorMap* map, int is_bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST2_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(act16) failed (%d)", (int)r);
         return ST2_ERR_CUDA;
     }
     return ST2_OK;
@@ -266,6 +289,11 @@ int make_f32_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1
 int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn) {
     return make_map_3d(map, is_bf16, w16, (uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)ktaps, (uint64_t)cin_pad * 2,
                        (uint64_t)cin_pad * cout_pad * 2, TC_KC, (uint32_t)bn);
+}
+// K = 32 tiles (64-byte rows, SWIZZLE_64B): the first 32 input channels of every [CoutPad][CinPad] tap
+int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn) {
+    return make_map_3d(map, is_bf16, w16, (uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)ktaps, (uint64_t)cin_pad * 2,
+                       (uint64_t)cin_pad * cout_pad * 2, 32, (uint32_t)bn, 1);
 }
 
 bool conv_tc_supported(const ConvArgs& a) {
