@@ -187,6 +187,19 @@ ST2_API int st2_conv1d(const float* x, const float* w, const float* bias, float*
                int32_t padding, int32_t dilation, int32_t output_padding, int32_t transposed,
                int32_t precision, void* stream);
 
+/* One fused half-step of AdaINResBlock1 (Modules/hifigan.py:67-73) on channels-last fp32 tensors, through the
+ * tensor-core fused kernels (16-bit operands, fp32 accumulate):
+ *   y = (conv1d(act(AdaIN(x; h)), w) + bias + res (+ y_old if accumulate)) * scale
+ * h [B,2*Cin] (NULL: no normalisation), alpha [Cin] for snake, w [Cout,Cin,k] (2*padding == dilation*(k-1)),
+ * res [B,T,Cout] or NULL.  If h_next [B,2*Cout] is given, coef_next [B,2,Cout] receives the AdaIN coefficients
+ * (a = (1+gamma)*rstd, b = beta - mean*a) of y computed from the epilogue's statistics partials. */
+ST2_API int64_t st2_adain_conv1d_fused_scratch_bytes(int32_t B, int32_t T, int32_t Cin, int32_t Cout, int32_t k);
+ST2_API int st2_adain_conv1d_fused(const float* x, const float* h, const float* alpha, int32_t act, float slope,
+                           const float* w, const float* bias, const float* res, float* y, const float* h_next,
+                           float* coef_next, void* scratch, int32_t B, int32_t T, int32_t Cin, int32_t Cout,
+                           int32_t k, int32_t padding, int32_t dilation, float scale, int32_t accumulate,
+                           int32_t precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libst2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["decoder.cu", "api_units.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_source.cu",
-           "length_regulator.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu"]
+           "length_regulator.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "conv_pipe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-I", INCLUDE]
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(10, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                   "-Xcompiler", "-fPIC"]

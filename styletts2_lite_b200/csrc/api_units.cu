@@ -125,4 +125,69 @@ int st2_conv1d(const float* x, const float* w, const float* bias, float* y, void
     return launch_conv_tc(a, st);
 }
 
+// One fused half-step of AdaINResBlock1 (hifigan.py:67-73) through the tensor-core fused kernels:
+//   y = (conv1d(act(AdaIN(x; h)), w) + bias + res (+ y_old)) * scale,   coef_next = AdaIN coefficients of y for style h_next
+static int64_t fused_unit_offsets(int B, int T, int Cin, int Cout, int k, int64_t off[6]) {
+    const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 31) / 32 * 32;
+    int64_t o = 0;
+    off[0] = o; o += align256((int64_t)k * Cin * Cout * sizeof(float));          // packed fp32 weight
+    off[1] = o; o += align256((int64_t)k * cin_pad * cout_pad * 2);              // 16-bit weight
+    off[2] = o; o += align256(adain_scratch_bytes(B, T, Cin));                   // input statistics
+    off[3] = o; o += align256((int64_t)B * 2 * cin_pad * sizeof(float));         // input coefficients
+    off[4] = o; o += align256((int64_t)B * (cdiv(T, 128) * 4) * Cout * 8);       // output partials
+    off[5] = o;
+    return o;
+}
+
+int64_t st2_adain_conv1d_fused_scratch_bytes(int32_t B, int32_t T, int32_t Cin, int32_t Cout, int32_t k) {
+    if (B <= 0 || T <= 0 || Cin <= 0 || Cout <= 0 || k <= 0) return ST2_ERR_INVALID;
+    int64_t off[6];
+    return fused_unit_offsets(B, T, Cin, Cout, k, off);
+}
+
+int st2_adain_conv1d_fused(const float* x, const float* h, const float* alpha, int32_t act, float slope, const float* w,
+                           const float* bias, const float* res, float* y, const float* h_next, float* coef_next,
+                           void* scratch, int32_t B, int32_t T, int32_t Cin, int32_t Cout, int32_t k, int32_t padding,
+                           int32_t dilation, float scale, int32_t accumulate, int32_t precision, void* stream) {
+    ST2_REQUIRE(x && w && y && scratch && B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0 && dilation > 0,
+                "adain_conv1d_fused: bad argument");
+    ST2_REQUIRE(precision == ST2_PREC_BF16 || precision == ST2_PREC_FP16, "adain_conv1d_fused: 16-bit precisions only");
+    ST2_REQUIRE(2 * padding == dilation * (k - 1), "adain_conv1d_fused: length-preserving convolutions only");
+    ST2_REQUIRE((h_next == nullptr) == (coef_next == nullptr), "adain_conv1d_fused: h_next and coef_next go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t off[6];
+    fused_unit_offsets(B, T, Cin, Cout, k, off);
+    char* base = (char*)scratch;
+    float* wp = (float*)(base + off[0]);
+    void* w16 = base + off[1];
+    void* xstats = base + off[2];
+    float* coef = (float*)(base + off[3]);
+    void* parts = base + off[4];
+    const int dt = precision == ST2_PREC_BF16 ? DT_BF16 : DT_F16;
+    const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 31) / 32 * 32;
+    int e = launch_fold_pack(nullptr, w, wp, Cout, Cin, k, 0, st);
+    if (e != ST2_OK) return e;
+    e = launch_pack_w16(wp, w16, k, Cin, Cout, cin_pad, cout_pad, dt, st);
+    if (e != ST2_OK) return e;
+    if (h != nullptr) {
+        e = launch_in_stats(x, Cin, B, T, Cin, xstats, st);
+        if (e != ST2_OK) return e;
+    }
+    e = launch_adain_coef(xstats, h, 2 * Cin, 0, coef, B, T, Cin, Cin, st);
+    if (e != ST2_OK) return e;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.Tin = T; a.Tout = T; a.M = T;
+    a.x = x; a.ld_x = Cin; a.w = wp; a.w16 = w16; a.w16_cin_pad = cin_pad; a.w16_cout_pad = cout_pad; a.fmt16 = dt;
+    a.bias = bias; a.res = res; a.ld_res = Cout; a.y = y; a.ld_y = Cout;
+    a.ntaps = k; a.tap_step = dilation; a.in_off = -padding; a.in_stride = 1;
+    a.phases = 1; a.w_step = 1; a.out_stride = 1; a.out_pad = 0;
+    a.scale = scale; a.accumulate = accumulate;
+    ST2_REQUIRE(conv_fused_supported(a), "adain_conv1d_fused: geometry not supported by the fused kernels");
+    e = launch_conv_fused(a, coef, Cin, act, slope, alpha, h_next ? parts : nullptr, st);
+    if (e != ST2_OK) return e;
+    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, T, Cout, Cout, st);
+    return e;
+}
+
 }  // extern "C"

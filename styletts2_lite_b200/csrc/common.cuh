@@ -148,6 +148,10 @@ bool conv_fused_supported(const ConvArgs& a);
 int fused_stats_parts(const ConvArgs& a);
 int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
                       void* stats_out, cudaStream_t st);
+// stride-1 convs: fully TMA-fed pipeline (conv_pipe.cu); launch_conv_fused dispatches to it when supported
+bool conv_pipe_supported(const ConvArgs& a);
+int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
+                     void* stats_out, cudaStream_t st);
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
                          int C, int Cpad, cudaStream_t st);
 

@@ -1,0 +1,717 @@
+// Fully TMA-fed variant of the fused  [AdaIN affine + Snake / LeakyReLU] -> Conv1d (tcgen05) ->
+// [bias + residual + accumulate + scale + InstanceNorm partial statistics]  kernel for stride-1 convolutions
+// (every conv of AdaINResBlock1, Modules/hifigan.py:65-74): 96 of the 100 fused launches of a hifigan forward.
+//
+// conv_fused.cu left three latency chains exposed (measured with its role timeline): the transform warps waited
+// for whole-tile loads, the epilogue warps waited ~1.5 us for their residual rows, and one producer thread
+// serialised weight and activation loads.  Here no compute warp ever touches global memory for input:
+//   * activations arrive by TMA in 8 KB blocks (32 rows x 64 ch or 64 rows x 32 ch, fp32 or 16-bit) through a ring
+//     of `nx` slots that is independent of the tile geometry; each transform warp owns one block at a time
+//     (16 independent 4-channel groups per thread -> the Snake chain is hidden by ILP, not by occupancy);
+//   * residual (+ accumulate) rows arrive by TMA as 128-byte-swizzled [128 rows x 32 ch] fp32 boxes through a ring
+//     of `nr` stages; the epilogue adds them in the TMEM-drain layout and reuses the very same stage as its
+//     transposition buffer, so the only global accesses of the epilogue are full-line stores;
+//   * one producer thread multiplexes three independent queues (weights, activation blocks, residual boxes) with
+//     non-blocking mbarrier tests, so a full weight ring never delays an activation prefetch.
+// The activation and residual rings are plain FIFOs shared by several consumer warps.  An mbarrier parity wait only
+// tells adjacent phases apart and a consumer can be two fills ahead of a slot it does not own, so the producer
+// publishes the sequence number of every fill in a shared-memory word before issuing it; a consumer first sees
+// "its" sequence number (the previous fill has then landed and been consumed) and only then waits on the barrier.
+// Roles (16 warps, one persistent CTA per SM): warp 0 producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2-7 transform, warps 8-15 epilogue (2 groups x 4 TMEM lane quarters, one accumulator each).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "fused_ptx.cuh"
+
+namespace st2 {
+
+static constexpr int P_LW = 6;                           // transform warps
+static constexpr int P_EW = 8;                           // epilogue warps
+static constexpr int P_W_X0 = 2;                         // first transform warp
+static constexpr int P_W_EPI0 = P_W_X0 + P_LW;           // first epilogue warp (8)
+static constexpr int P_THREADS = (P_W_EPI0 + P_EW) * 32; // 512
+static constexpr int P_MT = 128;                         // rows per tile
+static constexpr int P_XSLOT_MAX = 12288;                 // largest activation ring slot
+static constexpr int P_RBOX = P_MT * 32 * 4;             // one residual box: 128 rows x 32 fp32
+
+struct PipeParams {
+    // transform
+    const float* coef; int coef_ld;
+    const float* alpha; float slope;
+    int Cin, kchunks, cch;      // cch: channels per K chunk (64, or 32 for 32-channel layers)
+    int x16in, is_bf16, k32;
+    // geometry
+    int B, M, Tin, Cout;
+    int ntaps, tap_step, halo_min, rows;
+    int xr, nblk, tail_rows;    // activation blocks: xr rows each, nblk per (tile, chunk), the last one tail_rows
+    int xslot;                  // bytes per activation ring slot (xr rows)
+    int lw;                     // active transform warps = min(6, na * nblk): a warp's consecutive blocks are then at most
+                                // na operand fills apart, so its a_empty parity wait is never more than one phase behind
+    int bn, mtiles, num_tiles;
+    int wstages, resident, tmem_cols;
+    int na, nacc, nacc_log2;    // operand (A) buffers 2..4, TMEM accumulators 2 or 4
+    int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
+    // epilogue
+    const float* bias;
+    float* y; int ld_y; float scale; int y16out;
+    float2* stats;              // [B][mtiles*4][Cout] (sum, sumsq) per (tile, 32-row quarter) or nullptr
+};
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// tile = blockIdx.x + i*gridDim.x  ->  (b, mt), advanced without divisions
+struct PTile {
+    int tile, b, mt, d_b, d_mt;
+    __device__ __forceinline__ void init(const PipeParams& p) {
+        tile = blockIdx.x;
+        b = tile / p.mtiles; mt = tile - b * p.mtiles;
+        d_b = gridDim.x / p.mtiles; d_mt = gridDim.x - d_b * p.mtiles;
+    }
+    __device__ __forceinline__ bool valid(const PipeParams& p) const { return tile < p.num_tiles; }
+    __device__ __forceinline__ void next(const PipeParams& p) {
+        tile += gridDim.x;
+        mt += d_mt; if (mt >= p.mtiles) { mt -= p.mtiles; ++b; }
+        b += d_b;
+    }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(P_THREADS, 1)
+conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
+                 const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ CUtensorMap map_o, const PipeParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t arow = p.k32 ? 64u : 128u;                      // bytes per operand row
+    const uint32_t a_bytes = ((uint32_t)p.rows * arow + 1023u) & ~1023u;
+    const uint32_t b_stage_bytes = (uint32_t)p.bn * arow;
+    const uint32_t r_stage_bytes = p.nres ? (uint32_t)p.nres * P_RBOX : 0u;
+    const uint32_t r_bytes = p.nres ? (uint32_t)p.nr * r_stage_bytes : (uint32_t)P_EW * 4096u;   // ring or per-warp staging
+    uint8_t* smem_a = smem;                                        // na x [rows][K] 16-bit, swizzled
+    uint8_t* smem_b = smem_a + (size_t)p.na * a_bytes;             // resident taps or ring of [bn][K]
+    uint8_t* smem_r = smem_b + (size_t)p.wstages * b_stage_bytes;  // residual ring / transposition buffers
+    uint8_t* smem_x = smem_r + r_bytes;                            // nx activation slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_x + (size_t)p.nx * p.xslot);
+    uint64_t* b_full = bars;                    // [wstages]
+    uint64_t* b_empty = b_full + p.wstages;     // [wstages]
+    uint64_t* a_full = b_empty + p.wstages;     // [4]
+    uint64_t* a_empty = a_full + 4;             // [4]
+    uint64_t* acc_full = a_full + 8;            // [4]
+    uint64_t* acc_empty = a_full + 12;          // [4]
+    uint64_t* x_full = a_full + 16;             // [nx]
+    uint64_t* x_empty = x_full + p.nx;          // [nx]
+    uint64_t* r_full = x_empty + p.nx;          // [nr]
+    uint64_t* r_empty = r_full + p.nr;          // [nr]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(r_empty + p.nr);
+    volatile uint32_t* x_seq = tmem_ptr_smem + 2;   // [nx] sequence number of the fill in flight / landed in each slot
+    volatile uint32_t* r_seq = x_seq + p.nx;        // [nr]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t xes = p.x16in ? 2u : 4u;
+    const uint32_t xrow = (uint32_t)p.cch * xes;                   // bytes per slot row
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_b);
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_xt);
+        if (p.nres >= 1) prefetch_tmap(&map_r);
+        if (p.nres >= 2) prefetch_tmap(&map_o);
+        const int nb = p.resident ? 1 : p.wstages;
+        for (int s = 0; s < nb; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&a_full[i], (uint32_t)p.nblk);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        for (int i = 0; i < p.nx; ++i) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 1);
+            x_seq[i] = 0xffffffffu;
+        }
+        for (int i = 0; i < p.nr; ++i) {
+            mbar_init(&r_full[i], 1);
+            mbar_init(&r_empty[i], 4);
+            r_seq[i] = 0xffffffffu;
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // K columns the transform never writes (32-channel layer in a 64-wide operand) stay zero for the whole kernel
+    for (uint32_t i = threadIdx.x; i < (uint32_t)p.na * a_bytes / 16; i += P_THREADS)
+        reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== producer: three independent queues served by one thread with non-blocking barrier tests =====
+        if (elect_one_sync()) {
+            if (p.resident) {
+                mbar_expect_tx(&b_full[0], (uint32_t)p.ntaps * p.kchunks * b_stage_bytes);
+                for (int w = 0; w < p.ntaps; ++w)
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        tma_load_3d(smem_b + (size_t)(w * p.kchunks + kc) * b_stage_bytes, &map_b, &b_full[0], kc * 64, 0, w);
+            }
+            // activation queue: block g = (tile, kc, blk) -> slot g % nx
+            PTile xt; xt.init(p);
+            int x_kc = 0, x_blk = 0; uint32_t x_slot = 0, x_par = 0, x_g = 0;
+            bool x_done = !xt.valid(p);
+            // weight queue: (tile, kc, tap)
+            PTile wt; wt.init(p);
+            int w_kc = 0, w_j = 0; uint32_t w_stage = 0, w_par = 0;
+            bool w_done = p.resident || !wt.valid(p);
+            // residual queue: box set c = (tile, chunk) -> stage c % nr
+            const int nchunks = p.bn >> 5;
+            PTile rt; rt.init(p);
+            int r_ch = 0; uint32_t r_stage = 0, r_par = 0, r_c = 0;
+            bool r_done = p.nres == 0 || !rt.valid(p);
+            while (!(x_done && w_done && r_done)) {
+                if (!w_done && mbar_test(&b_empty[w_stage], w_par ^ 1)) {
+                    mbar_expect_tx(&b_full[w_stage], b_stage_bytes);
+                    tma_load_3d(smem_b + (size_t)w_stage * b_stage_bytes, &map_b, &b_full[w_stage], w_kc * 64, 0, w_j);
+                    if (++w_stage == (uint32_t)p.wstages) { w_stage = 0; w_par ^= 1; }
+                    if (++w_j == p.ntaps) {
+                        w_j = 0;
+                        if (++w_kc == p.kchunks) { w_kc = 0; wt.next(p); w_done = !wt.valid(p); }
+                    }
+                }
+                if (!x_done && mbar_test(&x_empty[x_slot], x_par ^ 1)) {
+                    const bool tail = (x_blk == p.nblk - 1);
+                    const uint32_t nrows = tail ? (uint32_t)p.tail_rows : (uint32_t)p.xr;
+                    x_seq[x_slot] = x_g;                               // published before the fill is issued
+                    mbar_expect_tx(&x_full[x_slot], nrows * xrow);
+                    tma_load_3d(smem_x + (size_t)x_slot * p.xslot, tail ? &map_xt : &map_x, &x_full[x_slot], x_kc * 64,
+                                xt.mt * P_MT + p.halo_min + x_blk * p.xr, xt.b);
+                    ++x_g;
+                    if (++x_slot == (uint32_t)p.nx) { x_slot = 0; x_par ^= 1; }
+                    if (++x_blk == p.nblk) {
+                        x_blk = 0;
+                        if (++x_kc == p.kchunks) { x_kc = 0; xt.next(p); x_done = !xt.valid(p); }
+                    }
+                }
+                if (!r_done && mbar_test(&r_empty[r_stage], r_par ^ 1)) {
+                    r_seq[r_stage] = r_c;
+                    mbar_expect_tx(&r_full[r_stage], r_stage_bytes);
+                    uint8_t* dst = smem_r + (size_t)r_stage * r_stage_bytes;
+                    tma_load_3d(dst, &map_r, &r_full[r_stage], r_ch * 32, rt.mt * P_MT, rt.b);
+                    if (p.nres == 2) tma_load_3d(dst + P_RBOX, &map_o, &r_full[r_stage], r_ch * 32, rt.mt * P_MT, rt.b);
+                    ++r_c;
+                    if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1; }
+                    if (++r_ch == nchunks) { r_ch = 0; rt.next(p); r_done = !rt.valid(p); }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(128, p.bn, p.is_bf16);
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+            const uint32_t a_buf_step = a_bytes >> 4;
+            const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
+            const uint32_t b_step = b_stage_bytes >> 4;
+            const uint32_t row_step = (uint32_t)p.tap_step * (arow >> 4);   // 16-byte units per tap
+            // K-major descriptor hi word: SBO = 8 rows (>>4) | version 1 @ bit 46 | SWIZZLE_128B (2) or SWIZZLE_64B (4) @ bit 61
+            const uint32_t dhi = p.k32 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : kDescHi;
+            const uint32_t b_res_step = (uint32_t)p.kchunks * b_step;
+            uint32_t stage = 0, phase = 0, tcnt = 0;
+            uint32_t buf = 0, buf_par = 0;              // operand buffer cursor (cc % na, (cc / na) & 1)
+            if (p.resident) {
+                mbar_wait(&b_full[0], 0);
+                tc_fence_after();
+            }
+            PTile ti;
+            for (ti.init(p); ti.valid(p); ti.next(p), ++tcnt) {
+                const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
+                mbar_wait(&acc_empty[acc], ((tcnt >> p.nacc_log2) & 1) ^ 1);   // epilogue drained this accumulator
+                tc_fence_after();
+                uint32_t accum = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&a_full[buf], buf_par);
+                    tc_fence_after();
+                    uint32_t a_lo = a_lo0 + buf * a_buf_step;
+                    if (p.resident) {
+                        uint32_t b_lo = b_lo0 + (uint32_t)kc * b_step;
+                        if (p.k32) {
+#pragma unroll 4
+                            for (int j = 0; j < p.ntaps; ++j) {
+                                umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                                accum = 1u;
+                                a_lo += row_step;
+                                b_lo += b_res_step;
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int j = 0; j < p.ntaps; ++j) {
+                                umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                                accum = 1u;
+                                a_lo += row_step;
+                                b_lo += b_res_step;
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < p.ntaps; ++j) {
+                            mbar_wait(&b_full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + stage * b_step;
+                            umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                            umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                            umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                            umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                            accum = 1u;
+                            a_lo += row_step;
+                            umma_commit(&b_empty[stage]);
+                            if (++stage == (uint32_t)p.wstages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    umma_commit(&a_empty[buf]);          // A tile consumed
+                    if (++buf == (uint32_t)p.na) { buf = 0; buf_par ^= 1u; }
+                }
+                umma_commit(&acc_full[acc]);             // accumulator complete
+            }
+        }
+    } else if (warp < P_W_EPI0) {
+        // ===== transform: one warp = one activation block at a time, blocks dealt round-robin =====
+        const int tw = warp - P_W_X0;
+        const int lpr_shift = (p.cch == 64) ? 4 : 3;            // lanes per row: 16 or 8
+        const int rpp = 32 >> lpr_shift;                        // rows per pass: 2 or 4
+        const int rl = lane >> lpr_shift;
+        const int c4 = (lane & ((1 << lpr_shift) - 1)) * 4;
+        const uint32_t smem_a_u32 = smem_u32(smem_a);
+        const uint32_t smem_x_u32 = smem_u32(smem_x);
+        const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
+        const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
+        const uint32_t pass_bytes = (uint32_t)rpp * xrow;
+        PTile ti;
+        ti.init(p);
+        int seq = 0, kc = 0, blk = tw;
+        if (tw >= p.lw) ti.tile = p.num_tiles;                  // idle warp
+        while (blk >= p.nblk && ti.valid(p)) {
+            blk -= p.nblk;
+            if (++kc == p.kchunks) { kc = 0; ti.next(p); ++seq; }
+        }
+        uint32_t g = (uint32_t)tw;                              // global block number -> slot g % nx, fill g / nx
+        uint32_t slot = g % (uint32_t)p.nx, xpar = (g / (uint32_t)p.nx) & 1u;
+        int cached_b = -1, cached_kc = -1;
+        XfCoef cf;
+        while (ti.valid(p)) {
+            const uint32_t cc = (uint32_t)(seq * p.kchunks + kc);
+            const uint32_t fill = cc / (uint32_t)p.na;          // this block's operand buffer and which fill of it
+            const uint32_t buf = cc - fill * (uint32_t)p.na;
+            if (ti.b != cached_b || kc != cached_kc) {          // per-(b,c) coefficients: reload only when they change
+                const int cg = kc * 64 + c4;
+                const float* ca = p.coef + (size_t)ti.b * 2 * p.coef_ld;
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ca + cg));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ca + p.coef_ld + cg));
+                cf.a01 = make_float2(a4.x, a4.y); cf.a23 = make_float2(a4.z, a4.w);
+                cf.b01 = make_float2(b4.x, b4.y); cf.b23 = make_float2(b4.z, b4.w);
+                if (ACT == ACT_SNAKE) {
+                    const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + cg));
+                    cf.al01 = make_float2(al.x, al.y); cf.al23 = make_float2(al.z, al.w);
+                    cf.ia01 = make_float2(__fdividef(1.f, al.x), __fdividef(1.f, al.y));
+                    cf.ia23 = make_float2(__fdividef(1.f, al.z), __fdividef(1.f, al.w));
+                } else {
+                    cf.al01 = make_float2(p.slope, p.slope); cf.al23 = cf.al01; cf.ia01 = cf.al01; cf.ia23 = cf.al01;
+                }
+                cached_b = ti.b; cached_kc = kc;
+            }
+            const int r0 = blk * p.xr;                                       // first A row of this block
+            const int nrows = (blk == p.nblk - 1) ? p.tail_rows : p.xr;
+            const int t0 = ti.mt * P_MT + p.halo_min + r0;                   // time index of that row
+            const bool interior = (t0 >= 0) && (t0 + nrows <= p.Tin);
+            while (x_seq[slot] != g) { }                                     // fill g has been issued into this slot ...
+            mbar_wait_warp(&x_full[slot], xpar);                             // ... and has landed
+            mbar_wait_warp(&a_empty[buf], (fill & 1) ^ 1);
+            const uint32_t xaddr = smem_x_u32 + slot * (uint32_t)p.xslot + (uint32_t)rl * xrow + (uint32_t)c4 * xes;
+            const uint32_t abase = smem_a_u32 + buf * a_bytes + sub;
+#define A_ADDR(r) (abase + (uint32_t)(r) * arow + ((cidx ^ (((uint32_t)(r) >> sw_shift) & sw_mask)) << 4))
+            for (int rb = 0; rb < nrows; rb += 8 * rpp) {       // 8 passes at a time: 8 independent loads, then 8 Snake chains
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = rb + rl + u * rpp;            // row within the block
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nrows) {
+                        const uint32_t ad = xaddr + (uint32_t)(rb + u * rpp) * xrow;
+                        if (p.x16in) v[u] = unpack16x4(lds64(ad), p.is_bf16);
+                        else v[u] = lds128(ad);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = rb + rl + u * rpp;
+                    uint2 o = transform4<ACT>(v[u], cf, p.is_bf16);
+                    if (!interior) {
+                        const int t = t0 + r;
+                        if (t < 0 || t >= p.Tin) o = make_uint2(0u, 0u);   // conv zero padding (after the activation)
+                    }
+                    if (r < nrows) sts64(A_ADDR(r0 + r), o.x, o.y);
+                }
+            }
+#undef A_ADDR
+            fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&x_empty[slot]);
+                mbar_arrive(&a_full[buf]);
+            }
+            blk += p.lw;
+            while (blk >= p.nblk && ti.valid(p)) {
+                blk -= p.nblk;
+                if (++kc == p.kchunks) { kc = 0; ti.next(p); ++seq; }
+            }
+            g += (uint32_t)p.lw;
+            slot += (uint32_t)p.lw;
+            while (slot >= (uint32_t)p.nx) { slot -= (uint32_t)p.nx; xpar ^= 1u; }
+        }
+    } else {
+        // ===== epilogue: TMEM -> (+ residual in the drain layout) -> transposition -> bias/scale -> global, statistics =====
+        const int ew = warp - P_W_EPI0;                   // 0..7
+        const int grp = ew >> 2;                          // accumulator / tile parity this group owns
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int rr = lane >> 3;                         // 0..3: row within a 4-row pass
+        const uint32_t l7 = (uint32_t)lane & 7u;
+        const int c4o = (int)l7 * 4;                      // column within the 32-column chunk
+        const int nchunks = p.bn >> 5;
+        const uint32_t smem_r_u32 = smem_u32(smem_r);
+        const int ystep = 4 * p.ld_y;                     // element distance between consecutive row passes
+        const bool do_scale = p.scale != 1.f;
+        const float2 sc2 = make_float2(p.scale, p.scale);
+        uint32_t rs = 0, rpar = 0, rc = 0;                // residual ring cursor: stage, parity, box-set number
+        auto r_advance = [&](int n) {
+            rc += (uint32_t)n;
+            rs += (uint32_t)n;
+            while (rs >= (uint32_t)p.nr) { rs -= (uint32_t)p.nr; rpar ^= 1u; }
+        };
+        uint32_t tcnt = 0;
+        PTile ti;
+        for (ti.init(p); ti.valid(p); ti.next(p), ++tcnt) {
+            if ((int)(tcnt & 1) != grp) {
+                if (p.nres) r_advance(nchunks);           // the other group's tile
+                continue;
+            }
+            const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
+            const int m_first = ti.mt * P_MT + q * 32 + rr;                  // rows of this lane: m_first + 4*it
+            uint32_t vmask = 0;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                if (m_first + it * 4 < p.M) vmask |= 1u << it;
+            float* ytile = p.y + ((size_t)ti.b * p.M + m_first) * p.ld_y;
+            mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
+            tc_fence_after();
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int co = ch * 32 + c4o;
+                const uint32_t cmask = (co < p.Cout) ? vmask : 0u;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr && cmask) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                const float2 bias01 = make_float2(bias4.x, bias4.y), bias23 = make_float2(bias4.z, bias4.w);
+                // [32 rows][32 cols] fp32 region of this warp, 16-byte slots XOR-swizzled by (row & 7) -- the TMA
+                // SWIZZLE_128B layout of the residual box, and conflict-free for both access directions
+                uint32_t tile_u32;
+                if (p.nres) {
+                    while (r_seq[rs] != rc) { }           // box set rc has been issued into this stage ...
+                    mbar_wait_warp(&r_full[rs], rpar);    // ... and has landed
+                    tile_u32 = smem_r_u32 + rs * r_stage_bytes + (uint32_t)(q * 32) * 128u;
+                } else {
+                    tile_u32 = smem_r_u32 + (uint32_t)ew * 4096u;
+                }
+                const uint32_t st_w = tile_u32 + (uint32_t)lane * 128u;      // row = lane (TMEM drain layout)
+                {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)(ch * 32), v);
+                    if (p.nres) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 r = lds128(st_w + (((uint32_t)i ^ l7) << 4));
+                            v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                        }
+                        if (p.nres == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 r = lds128(st_w + (uint32_t)P_RBOX + (((uint32_t)i ^ l7) << 4));
+                                v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        sts128(st_w + (((uint32_t)i ^ l7) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                __syncwarp();
+                const uint32_t st_r0 = tile_u32 + (uint32_t)rr * 128u + ((l7 ^ (uint32_t)rr) << 4);               // rows rr, rr+8, ...
+                const uint32_t st_r1 = tile_u32 + (uint32_t)(rr + 4) * 128u + ((l7 ^ (uint32_t)(rr + 4)) << 4);   // rows rr+4, rr+12, ...
+                float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
+                float* yo = ytile + co;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const float4 a = lds128(((it & 1) ? st_r1 : st_r0) + (uint32_t)(it >> 1) * 1024u);
+                    if (!((cmask >> it) & 1u)) continue;
+                    float2 o01 = fadd2(make_float2(a.x, a.y), bias01);
+                    float2 o23 = fadd2(make_float2(a.z, a.w), bias23);
+                    if (do_scale) {
+                        o01 = fmul2(o01, sc2);
+                        o23 = fmul2(o23, sc2);
+                    }
+                    if (p.y16out)
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.y) + (yo - p.y) + it * ystep) =
+                            make_uint2(pack16(o01.x, o01.y, p.is_bf16), pack16(o23.x, o23.y, p.is_bf16));
+                    else
+                        *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                    s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
+                    s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
+                }
+                if (p.stats != nullptr) {
+                    float s1[4] = {s1a.x, s1a.y, s1b.x, s1b.y}, s2[4] = {s2a.x, s2a.y, s2b.x, s2b.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 8);
+                        s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 8);
+                        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 16);
+                        s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 16);
+                    }
+                    // one partial per (tile, TMEM lane quarter): written straight to global, no cross-warp barrier
+                    if (lane < 8 && co < p.Cout) {
+                        float2* sp = p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + co;
+                        *reinterpret_cast<float4*>(sp) = make_float4(s1[0], s2[0], s1[1], s2[1]);
+                        *reinterpret_cast<float4*>(sp + 2) = make_float4(s1[2], s2[2], s1[3], s2[3]);
+                    }
+                }
+                if (p.nres) {
+                    fence_proxy_async();                  // our generic writes to the stage precede the next TMA fill
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&r_empty[rs]);
+                    r_advance(1);
+                } else {
+                    __syncwarp();
+                }
+            }
+            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_map_3d_any(CUtensorMap* map, int dtype /*0 f32, 1 bf16, 2 f16*/, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle128);
+
+static bool pipe_geometry_ok(const ConvArgs& a) {
+    if (getenv("ST2_NO_PIPE") != nullptr) return false;
+    if (a.in_stride != 1 || a.phases != 1 || a.out_stride != 1 || a.out_pad != 0 || a.mirror || a.res_shift != 0) return false;
+    if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
+    if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
+    if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
+    const int xes = a.x16in ? 2 : 4;
+    if ((a.ld_x * xes) % 16 != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
+    if (a.y16out && a.accumulate) return false;
+    if (a.accumulate && a.res == nullptr) return false;
+    if (a.tap_step <= 0 || a.M != a.Tout) return false;
+    if (a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
+    const int span = (a.ntaps - 1) * a.tap_step;
+    return span <= 64 && a.in_off <= 0 && a.in_off + span >= 0;
+}
+
+// geometry + shared-memory plan; false if the rings do not fit next to the operand tiles and weights
+static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
+    memset(&p, 0, sizeof(p));
+    p.Cin = a.Cin; p.kchunks = a.w16_cin_pad / 64; p.cch = a.Cin == 32 ? 32 : 64;
+    p.x16in = a.x16in; p.is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
+    p.k32 = (a.Cin == 32 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
+    p.B = a.B; p.M = a.M; p.Tin = a.Tin; p.Cout = a.Cout;
+    p.ntaps = a.ntaps; p.tap_step = a.tap_step; p.halo_min = a.in_off;
+    const int span = (a.ntaps - 1) * a.tap_step;
+    p.rows = P_MT + span;
+    {
+        // activation blocks: the fewest equal blocks (whole passes of the owning warp) that fit a 12 KB slot
+        const int xes = a.x16in ? 2 : 4;
+        const int rowb = p.cch * xes, rpp = 32 / (p.cch / 4);
+        int xmax = P_XSLOT_MAX;
+        if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
+        int nblk = 1;
+        for (;; ++nblk) {
+            p.xr = (cdiv(p.rows, nblk) + rpp - 1) / rpp * rpp;
+            if (p.xr * rowb <= xmax) break;
+        }
+        p.nblk = cdiv(p.rows, p.xr);
+        p.tail_rows = p.rows - (p.nblk - 1) * p.xr;
+        p.xslot = (p.xr * rowb + 127) / 128 * 128;
+    }
+    p.bn = a.w16_cout_pad;
+    p.mtiles = cdiv(a.M, P_MT);
+    p.num_tiles = a.B * p.mtiles;
+    p.nacc = p.bn <= 128 ? 4 : 2;
+    if (const char* e = getenv("ST2_PIPE_NACC")) { const int v = atoi(e); if (v == 2 || (v == 4 && p.bn <= 128)) p.nacc = v; }
+    p.nacc_log2 = p.nacc == 4 ? 2 : 1;
+    int cols = 32;
+    while (cols < p.nacc * p.bn) cols <<= 1;
+    p.tmem_cols = cols;
+    p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+    p.bias = a.bias; p.y = a.y; p.ld_y = a.ld_y; p.scale = a.scale; p.y16out = a.y16out;
+
+    // ---- shared-memory plan (one persistent CTA per SM)
+    const int64_t budget = 225 * 1024;
+    const int64_t arow = p.k32 ? 64 : 128;
+    const int64_t a_bytes = ((int64_t)p.rows * arow + 1023) & ~(int64_t)1023;
+    const int64_t b_stage = (int64_t)p.bn * arow;
+    const int64_t r_stage = (int64_t)p.nres * P_RBOX;
+    int na = 2;
+    int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)P_EW * 4096);
+    const int64_t w_resident = (int64_t)a.ntaps * p.kchunks * b_stage;
+    const int nchunks = p.bn / 32;
+    // rings: nx activation slots and nr residual stages (FIFO); minimum 3 slots / 2 stages
+    const int64_t xslot = p.xslot;
+    int nx = 3, nr = p.nres ? 2 : 0;
+    auto rings = [&](int nx_, int nr_) { return (int64_t)nx_ * xslot + (int64_t)nr_ * r_stage; };
+    p.resident = (base + w_resident + rings(nx, nr) <= budget) ? 1 : 0;
+    int64_t left;
+    if (p.resident) {
+        p.wstages = a.ntaps * p.kchunks;
+        left = budget - base - w_resident;
+    } else {
+        p.wstages = 4;                       // weight ring: at least 4 stages
+        left = budget - base - p.wstages * b_stage;
+        if (left < rings(nx, nr)) return false;
+    }
+    // what is left goes to the two rings in turn (bytes in flight are what hides the HBM latency), then to the weight ring
+    left -= rings(nx, nr);
+    const int nr_goal = p.nres ? (2 * nchunks + 2 > 8 ? 8 : 2 * nchunks + 2) : 0;
+    const int nx_goal = 10;
+    int na_goal = 4;
+    if (const char* e = getenv("ST2_PIPE_NA")) { const int v = atoi(e); if (v >= 2 && v <= 4) na_goal = v; }
+    for (bool grew = true; grew;) {
+        grew = false;
+        // a third / fourth operand buffer as soon as the rings hold ~32 KB / ~48 KB each (or all they are allowed to)
+        const int64_t want = na == 2 ? 32 * 1024 : 48 * 1024;
+        const bool x_ok = (int64_t)nx * xslot >= want || nx >= nx_goal;
+        const bool r_ok = nr_goal == 0 || (int64_t)nr * r_stage >= want || nr >= nr_goal;
+        if (na < na_goal && x_ok && r_ok && left >= a_bytes) { ++na; left -= a_bytes; grew = true; continue; }
+        const bool r_first = (int64_t)nr * r_stage <= (int64_t)nx * xslot;
+        if (nr < nr_goal && left >= r_stage && (r_first || nx >= nx_goal)) { ++nr; left -= r_stage; grew = true; continue; }
+        if (nx < nx_goal && left >= xslot) { ++nx; left -= xslot; grew = true; continue; }
+        if (nr < nr_goal && left >= r_stage) { ++nr; left -= r_stage; grew = true; }
+    }
+    if (!p.resident)
+        while (p.wstages < 8 && left >= b_stage) { ++p.wstages; left -= b_stage; }
+    if (const char* e = getenv("ST2_PIPE_NX")) { const int v = atoi(e); if (v >= 2 && v <= nx) nx = v; }
+    if (const char* e = getenv("ST2_PIPE_NR")) { const int v = atoi(e); if (p.nres && v >= 1 && v <= nr) nr = v; }
+    p.nx = nx; p.nr = nr;
+    p.na = na;
+    p.lw = na * p.nblk < P_LW ? na * p.nblk : P_LW;
+    const size_t smem = (size_t)(na * a_bytes + (int64_t)p.wstages * b_stage + (p.nres ? (int64_t)p.nr * r_stage : (int64_t)P_EW * 4096) +
+                                 (int64_t)p.nx * p.xslot + 2048 + 1024);
+    if (smem > 227 * 1024) return false;
+    if ((2 * p.wstages + 16 + 2 * p.nx + 2 * p.nr) * 8 + 16 + (p.nx + p.nr) * 4 > 2048) return false;
+    *smem_out = smem;
+    return true;
+}
+
+bool conv_pipe_supported(const ConvArgs& a) {
+    if (!pipe_geometry_ok(a)) return false;
+    PipeParams p;
+    size_t smem;
+    return pipe_plan(a, p, &smem);
+}
+
+int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
+                     void* stats_out, cudaStream_t st) {
+    PipeParams p;
+    size_t smem = 0;
+    ST2_REQUIRE(pipe_geometry_ok(a) && pipe_plan(a, p, &smem), "conv_pipe: unsupported geometry");
+    p.coef = coef; p.coef_ld = coef_ld; p.alpha = alpha; p.slope = slope;
+    p.stats = (float2*)stats_out;
+
+    // ---- tensor maps
+    CUtensorMap map_b, map_x, map_xt, map_r, map_o;
+    int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn)
+                  : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn);
+    if (e != ST2_OK) return e;
+    const int xdt = a.x16in ? (p.is_bf16 ? 1 : 2) : 0;
+    const uint64_t xes = a.x16in ? 2 : 4;
+    e = make_map_3d_any(&map_x, xdt, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
+                        (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)p.cch, (uint32_t)p.xr, 0);
+    if (e != ST2_OK) return e;
+    e = make_map_3d_any(&map_xt, xdt, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
+                        (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)p.cch, (uint32_t)p.tail_rows, 0);
+    if (e != ST2_OK) return e;
+    map_r = map_x;
+    map_o = map_x;
+    if (a.res != nullptr) {
+        e = make_map_3d_any(&map_r, 0, a.res, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_res * 4,
+                            (uint64_t)a.Tout * a.ld_res * 4, 32, P_MT, 1);
+        if (e != ST2_OK) return e;
+    }
+    if (a.accumulate) {
+        e = make_map_3d_any(&map_o, 0, a.y, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 4,
+                            (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT, 1);
+        if (e != ST2_OK) return e;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    int grid = num_sms;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    if (getenv("ST2_PIPE_VERBOSE") != nullptr)
+        fprintf(stderr, "conv_pipe: Cin=%d Cout=%d taps=%d step=%d rows=%d nblk=%d tail=%d xr=%d resident=%d wstages=%d na=%d nacc=%d lw=%d nx=%d nr=%d nres=%d smem=%zu tiles=%d\n",
+                p.Cin, p.Cout, p.ntaps, p.tap_step, p.rows, p.nblk, p.tail_rows, p.xr, p.resident, p.wstages, p.na, p.nacc, p.lw, p.nx, p.nr, p.nres, smem,
+                p.num_tiles);
+    switch (act) {
+        case ACT_NONE: conv_pipe_kernel<ACT_NONE><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p); break;
+        case ACT_LRELU: conv_pipe_kernel<ACT_LRELU><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p); break;
+        case ACT_SNAKE:
+            ST2_REQUIRE(alpha != nullptr, "conv_pipe: snake needs alpha");
+            conv_pipe_kernel<ACT_SNAKE><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);
+            break;
+        default: set_error("conv_pipe: bad act %d", act); return ST2_ERR_INVALID;
+    }
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+}  // namespace st2

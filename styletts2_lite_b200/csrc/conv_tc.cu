@@ -286,6 +286,32 @@ int make_f32_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1
     return ST2_OK;
 }
 
+// generic 3-D map: dtype 0 = fp32, 1 = bf16, 2 = fp16; no swizzle or SWIZZLE_128B (conv_pipe.cu rings)
+int make_map_3d_any(CUtensorMap* map, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                    uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST2_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                              : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(any) failed (%d) dtype=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u] sw=%d", (int)r,
+                  dtype, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, swizzle128);
+        return ST2_ERR_CUDA;
+    }
+    return ST2_OK;
+}
+
 int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn) {
     return make_map_3d(map, is_bf16, w16, (uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)ktaps, (uint64_t)cin_pad * 2,
                        (uint64_t)cin_pad * cout_pad * 2, TC_KC, (uint32_t)bn);

@@ -109,3 +109,31 @@ def conv1d(x_btc, w, bias, stride=1, padding=0, dilation=1, output_padding=0, tr
                               stride, padding, dilation, output_padding, 1 if transposed else 0, prec, stream()), "conv1d")
     torch.cuda.synchronize()
     return y.cpu().numpy()
+
+
+def adain_conv1d_fused(x_btc, h, alpha, act, w, bias, res_btc, y_old_btc, h_next, padding, dilation, scale=1.0,
+                       slope=0.0, precision="bf16"):
+    """Fused half-step of AdaINResBlock1 on channels-last tensors; returns (y [B,T,Cout], coef_next [B,2,Cout] or None)."""
+    lib = _lib.load()
+    B, T, Cin = x_btc.shape
+    Cout, _, k = w.shape
+    xd, wd = to_dev(x_btc), to_dev(w)
+    hd = None if h is None else to_dev(h)
+    ad = None if alpha is None else to_dev(alpha.reshape(-1))
+    bd = None if bias is None else to_dev(bias)
+    rd = None if res_btc is None else to_dev(res_btc)
+    hn = None if h_next is None else to_dev(h_next)
+    cn = None if h_next is None else torch.full((B, 2, Cout), float("nan"), device=dev())
+    if y_old_btc is None:
+        y = torch.full((B, T, Cout), float("nan"), device=dev())
+    else:
+        y = to_dev(y_old_btc)
+    nbytes = _lib.check(lib.st2_adain_conv1d_fused_scratch_bytes(B, T, Cin, Cout, k), "fused_scratch_bytes")
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    _lib.check(lib.st2_adain_conv1d_fused(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(ad), _lib.ACT[act], C.c_float(slope),
+                                          _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(rd), _lib.ptr(y), _lib.ptr(hn), _lib.ptr(cn),
+                                          _lib.ptr(scratch), B, T, Cin, Cout, k, padding, dilation, C.c_float(scale),
+                                          0 if y_old_btc is None else 1, _lib.PREC[precision], stream()),
+               "adain_conv1d_fused")
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), (None if cn is None else cn.cpu().numpy())

@@ -1,0 +1,123 @@
+"""-m gpu parity of the fused AdaIN/activation -> tcgen05 conv -> residual/statistics kernels (conv_pipe.cu for
+stride-1 convolutions, conv_fused.cu otherwise) against the numpy oracle, through the C ABI.
+
+Reference: one half-step of AdaINResBlock1.forward, Modules/hifigan.py:67-73.
+Tolerance: operands are rounded to bf16/fp16 exactly as the oracle's emulation does, but the kernel evaluates Snake with
+sin.approx, so an operand can land on the neighbouring 16-bit value (1 ulp = 2^-8 / 2^-11 relative): bound the
+error relative to the output scale at 4e-3 (bf16) / 6e-4 (fp16); the per-layer bar of BASELINE.json is 1e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_np as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_util as G
+
+TOL = {"bf16": 4e-3, "fp16": 6e-4}
+
+
+def _ref(x, h, alpha, act, slope, w, b, res, y_old, pad, dil, scale, prec):
+    C_ = x.shape[1]
+    v = x
+    if h is not None:
+        gamma, beta = h[:, :C_, None], h[:, C_:, None]
+        v = ((1 + gamma) * O.instance_norm(x) + beta).astype(np.float32)
+    if act == "snake":
+        v = O.snake(v, alpha)
+    elif act == "lrelu":
+        v = np.where(v >= 0, v, v * np.float32(slope)).astype(np.float32)
+    y = O.conv1d(v, w, b, padding=pad, dilation=dil, operand=prec)
+    if res is not None:
+        y = y + res
+    if y_old is not None:
+        y = y + y_old
+    return (y * np.float32(scale)).astype(np.float32)
+
+
+def _coef(y, h_next):
+    C_ = y.shape[1]
+    y64 = y.astype(np.float64)
+    mean = y64.mean(axis=2)
+    var = y64.var(axis=2)
+    a = (1.0 + h_next[:, :C_].astype(np.float64)) / np.sqrt(var + 1e-5)
+    b = h_next[:, C_:].astype(np.float64) - mean * a
+    return np.stack([a, b], axis=1)
+
+
+FUSED_CASES = [
+    # C, k, dil, T, res, acc, scale, act
+    (32, 3, 1, 1000, True, False, 1.0, "snake"), (32, 11, 5, 777, False, False, 1.0, "snake"),
+    (32, 7, 3, 100, False, False, 1.0, "snake"), (32, 11, 1, 640, True, True, 1.0 / 3.0, "snake"),
+    (64, 3, 5, 515, False, False, 1.0, "snake"), (64, 11, 1, 900, True, False, 1.0, "snake"),
+    (64, 7, 1, 385, True, True, 1.0, "snake"), (64, 11, 5, 400, False, False, 1.0, "lrelu"),
+    (128, 3, 1, 300, True, False, 1.0, "snake"), (128, 11, 3, 517, False, False, 1.0, "snake"),
+    (128, 7, 1, 260, True, True, 1.0 / 3.0, "snake"), (256, 3, 3, 200, False, False, 1.0, "snake"),
+    (256, 7, 1, 129, True, False, 1.0, "snake"), (256, 11, 1, 131, True, True, 1.0, "none"),
+]
+
+
+@pytest.mark.parametrize("path", ["pipe", "tile"])
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("C_,k,dil,T,use_res,acc,scale,act", FUSED_CASES)
+def test_adain_conv1d_fused_vs_oracle(C_, k, dil, T, use_res, acc, scale, act, prec, path):
+    rng = np.random.default_rng(C_ * 131 + k * 17 + dil + T)
+    B = 3
+    x = (rng.standard_normal((B, C_, T)) * 1.5 + 0.3).astype(np.float32)
+    h = (rng.standard_normal((B, 2 * C_)) * 0.3).astype(np.float32)
+    h_next = (rng.standard_normal((B, 2 * C_)) * 0.3).astype(np.float32)
+    alpha = (0.6 + 0.8 * rng.random((1, C_, 1))).astype(np.float32)
+    w = (rng.standard_normal((C_, C_, k)) / np.sqrt(C_ * k)).astype(np.float32)
+    b = rng.standard_normal(C_).astype(np.float32)
+    res = rng.standard_normal((B, C_, T)).astype(np.float32) if use_res else None
+    y_old = rng.standard_normal((B, C_, T)).astype(np.float32) if acc else None
+    pad = dil * (k - 1) // 2
+    ref = _ref(x, h, alpha, act, 0.1, w, b, res, y_old, pad, dil, scale, prec)
+    if path == "tile":
+        os.environ["ST2_NO_PIPE"] = "1"
+    try:
+        got, coef = G.adain_conv1d_fused(G.cl(x), h, alpha if act == "snake" else None, act, w, b,
+                                         None if res is None else G.cl(res), None if y_old is None else G.cl(y_old),
+                                         h_next, pad, dil, scale=scale, slope=0.1, precision=prec)
+    finally:
+        os.environ.pop("ST2_NO_PIPE", None)
+    got = G.cf(got)
+    nan = int(np.isnan(got).sum())
+    err = float(np.abs(np.nan_to_num(got) - ref).max() / np.abs(ref).max())
+    cref = _coef(ref, h_next)
+    cerr = float(np.abs(np.nan_to_num(coef) - cref).max() / np.abs(cref).max())
+    G.log("adain_conv1d_fused", path=path, prec=prec, C=C_, k=k, dil=dil, T=T, res=use_res, acc=acc, relmax=err,
+          coef_relmax=cerr, nan=nan)
+    assert nan == 0
+    assert err <= TOL[prec]
+    assert cerr <= 2 * TOL[prec]
+
+
+def test_fused_residual_in_place_and_batch_edges():
+    """res aliases y (the running tensor of AdaINResBlock1 is updated in place) and T is far from a tile multiple."""
+    rng = np.random.default_rng(5)
+    B, C_, k, T = 5, 64, 7, 130
+    x = rng.standard_normal((B, C_, T)).astype(np.float32)
+    h = (rng.standard_normal((B, 2 * C_)) * 0.3).astype(np.float32)
+    alpha = (0.6 + 0.8 * rng.random((1, C_, 1))).astype(np.float32)
+    w = (rng.standard_normal((C_, C_, k)) / np.sqrt(C_ * k)).astype(np.float32)
+    res = rng.standard_normal((B, C_, T)).astype(np.float32)
+    ref = _ref(x, h, alpha, "snake", 0.0, w, None, res, None, 3, 1, 1.0, "bf16")
+    lib = G._lib.load()
+    xd, hd, ad, wd = G.to_dev(G.cl(x)), G.to_dev(h), G.to_dev(alpha.reshape(-1)), G.to_dev(w)
+    y = G.to_dev(G.cl(res))           # residual and output are the same buffer
+    nbytes = G._lib.check(lib.st2_adain_conv1d_fused_scratch_bytes(B, T, C_, C_, k))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=G.dev())
+    import ctypes as C
+    G._lib.check(lib.st2_adain_conv1d_fused(G._lib.ptr(xd), G._lib.ptr(hd), G._lib.ptr(ad), 2, C.c_float(0.0), G._lib.ptr(wd),
+                                            None, G._lib.ptr(y), G._lib.ptr(y), None, None, G._lib.ptr(scratch), B, T, C_, C_, k,
+                                            3, 1, C.c_float(1.0), 0, 1, G.stream()), "fused in place")
+    torch.cuda.synchronize()
+    got = G.cf(y.cpu().numpy())
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    G.log("adain_conv1d_fused_inplace", relmax=err)
+    assert err <= TOL["bf16"]
