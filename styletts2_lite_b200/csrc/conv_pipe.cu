@@ -89,7 +89,29 @@ struct PTile {
     }
 };
 
-template <int ACT>
+// per-thread transform constants for 4 consecutive channels (two packed pairs each).
+// Snake: y + sin^2(alpha*y)/alpha with y = a*x + b  ==  (a*x + b + c) - c*cos(2*alpha*(a*x + b)),  c = 1/(2*alpha)
+//   -> yb = a*x + (b + c);  t = (2*alpha*a)*x + 2*alpha*b;  out = yb + nc*cos(t)        (3 packed FMAs + 2 MUFU per pair)
+struct PXf { float2 a01, a23, b01, b23, ta01, ta23, tb01, tb23, nc01, nc23; };
+
+template <int ACT, bool BF16>
+__device__ __forceinline__ uint2 pipe_transform4(const float4 v, const PXf& c) {
+    const float2 x01 = make_float2(v.x, v.y), x23 = make_float2(v.z, v.w);
+    float2 y01 = ffma2(c.a01, x01, c.b01), y23 = ffma2(c.a23, x23, c.b23);
+    if (ACT == ACT_SNAKE) {
+        const float2 t01 = ffma2(c.ta01, x01, c.tb01), t23 = ffma2(c.ta23, x23, c.tb23);
+        const float2 s01 = make_float2(__cosf(t01.x), __cosf(t01.y)), s23 = make_float2(__cosf(t23.x), __cosf(t23.y));
+        y01 = ffma2(c.nc01, s01, y01);
+        y23 = ffma2(c.nc23, s23, y23);
+    } else if (ACT == ACT_LRELU) {
+        const float2 z01 = fmul2(y01, c.ta01), z23 = fmul2(y23, c.ta23);    // slope < 1: lrelu(y) = max(y, slope*y)
+        y01 = make_float2(fmaxf(y01.x, z01.x), fmaxf(y01.y, z01.y));
+        y23 = make_float2(fmaxf(y23.x, z23.x), fmaxf(y23.y, z23.y));
+    }
+    return make_uint2(pack16(y01.x, y01.y, BF16 ? 1 : 0), pack16(y23.x, y23.y, BF16 ? 1 : 0));
+}
+
+template <int ACT, bool BF16>
 __global__ void __launch_bounds__(P_THREADS, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
@@ -122,7 +144,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t xes = p.x16in ? 2u : 4u;
+    constexpr uint32_t xes = 4u;                                   // fp32 activations
     const uint32_t xrow = (uint32_t)p.cch * xes;                   // bytes per slot row
 
     if (warp == 0 && lane == 0) {
@@ -230,7 +252,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one_sync()) {
-            const uint32_t idesc = umma_idesc(128, p.bn, p.is_bf16);
+            const uint32_t idesc = umma_idesc(128, p.bn, BF16 ? 1 : 0);
             const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
             const uint32_t a_buf_step = a_bytes >> 4;
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
@@ -304,14 +326,25 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         // ===== transform: one warp = one activation block at a time, blocks dealt round-robin =====
         const int tw = warp - P_W_X0;
         const int lpr_shift = (p.cch == 64) ? 4 : 3;            // lanes per row: 16 or 8
-        const int rpp = 32 >> lpr_shift;                        // rows per pass: 2 or 4
+        const int rpp = 32 >> lpr_shift;                        // rows per pass: 2 or 4  (one pass = 512 bytes of the slot)
         const int rl = lane >> lpr_shift;
         const int c4 = (lane & ((1 << lpr_shift) - 1)) * 4;
         const uint32_t smem_a_u32 = smem_u32(smem_a);
         const uint32_t smem_x_u32 = smem_u32(smem_x);
-        const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
-        const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
-        const uint32_t pass_bytes = (uint32_t)rpp * xrow;
+        // operand-tile offsets of this thread's 8 rows of a batch, relative to the batch's first row (a multiple of 8, so
+        // the swizzle term only depends on the row within the batch):
+        //   SWIZZLE_128B: R*128 + ((chunk ^ (R & 7)) << 4)      SWIZZLE_64B: R*64 + ((chunk ^ ((R >> 1) & 3)) << 4)
+        uint32_t aoff[8];
+        {
+            const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
+            const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t R = (uint32_t)(rl + u * rpp);
+                aoff[u] = R * arow + ((cidx ^ ((R >> sw_shift) & sw_mask)) << 4) + sub;
+            }
+        }
+        const uint32_t batch_a = (uint32_t)(8 * rpp) * arow;    // operand bytes per batch of 8 passes
         PTile ti;
         ti.init(p);
         int seq = 0, kc = 0, blk = tw;
@@ -323,7 +356,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         uint32_t g = (uint32_t)tw;                              // global block number -> slot g % nx, fill g / nx
         uint32_t slot = g % (uint32_t)p.nx, xpar = (g / (uint32_t)p.nx) & 1u;
         int cached_b = -1, cached_kc = -1;
-        XfCoef cf;
+        PXf cf;
         while (ti.valid(p)) {
             const uint32_t cc = (uint32_t)(seq * p.kchunks + kc);
             const uint32_t fill = cc / (uint32_t)p.na;          // this block's operand buffer and which fill of it
@@ -337,48 +370,63 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 cf.b01 = make_float2(b4.x, b4.y); cf.b23 = make_float2(b4.z, b4.w);
                 if (ACT == ACT_SNAKE) {
                     const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + cg));
-                    cf.al01 = make_float2(al.x, al.y); cf.al23 = make_float2(al.z, al.w);
-                    cf.ia01 = make_float2(__fdividef(1.f, al.x), __fdividef(1.f, al.y));
-                    cf.ia23 = make_float2(__fdividef(1.f, al.z), __fdividef(1.f, al.w));
+                    const float4 c = make_float4(__fdividef(0.5f, al.x), __fdividef(0.5f, al.y), __fdividef(0.5f, al.z), __fdividef(0.5f, al.w));
+                    cf.ta01 = make_float2(2.f * al.x * a4.x, 2.f * al.y * a4.y); cf.ta23 = make_float2(2.f * al.z * a4.z, 2.f * al.w * a4.w);
+                    cf.tb01 = make_float2(2.f * al.x * b4.x, 2.f * al.y * b4.y); cf.tb23 = make_float2(2.f * al.z * b4.z, 2.f * al.w * b4.w);
+                    cf.b01 = make_float2(b4.x + c.x, b4.y + c.y); cf.b23 = make_float2(b4.z + c.z, b4.w + c.w);
+                    cf.nc01 = make_float2(-c.x, -c.y); cf.nc23 = make_float2(-c.z, -c.w);
                 } else {
-                    cf.al01 = make_float2(p.slope, p.slope); cf.al23 = cf.al01; cf.ia01 = cf.al01; cf.ia23 = cf.al01;
+                    cf.ta01 = make_float2(p.slope, p.slope); cf.ta23 = cf.ta01;
+                    cf.tb01 = cf.ta01; cf.tb23 = cf.ta01; cf.nc01 = cf.ta01; cf.nc23 = cf.ta01;
                 }
                 cached_b = ti.b; cached_kc = kc;
             }
-            const int r0 = blk * p.xr;                                       // first A row of this block
+            const int r0 = blk * p.xr;                                       // first A row of this block (multiple of 8)
             const int nrows = (blk == p.nblk - 1) ? p.tail_rows : p.xr;
             const int t0 = ti.mt * P_MT + p.halo_min + r0;                   // time index of that row
             const bool interior = (t0 >= 0) && (t0 + nrows <= p.Tin);
             while (x_seq[slot] != g) { }                                     // fill g has been issued into this slot ...
             mbar_wait_warp(&x_full[slot], xpar);                             // ... and has landed
             mbar_wait_warp(&a_empty[buf], (fill & 1) ^ 1);
-            const uint32_t xaddr = smem_x_u32 + slot * (uint32_t)p.xslot + (uint32_t)rl * xrow + (uint32_t)c4 * xes;
-            const uint32_t abase = smem_a_u32 + buf * a_bytes + sub;
-#define A_ADDR(r) (abase + (uint32_t)(r) * arow + ((cidx ^ (((uint32_t)(r) >> sw_shift) & sw_mask)) << 4))
-            for (int rb = 0; rb < nrows; rb += 8 * rpp) {       // 8 passes at a time: 8 independent loads, then 8 Snake chains
-                float4 v[8];
+            uint32_t xaddr = smem_x_u32 + slot * (uint32_t)p.xslot + (uint32_t)rl * xrow + (uint32_t)c4 * xes;
+            uint32_t abase = smem_a_u32 + buf * a_bytes + (uint32_t)r0 * arow;
+            int rb = 0;
+            if (interior) {
+                // full batches: 8 independent loads, then 8 independent activation chains, no per-row checks
+                for (; rb + 8 * rpp <= nrows; rb += 8 * rpp, xaddr += 8 * 512, abase += batch_a) {
+                    float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int r = rb + rl + u * rpp;            // row within the block
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nrows) {
-                        const uint32_t ad = xaddr + (uint32_t)(rb + u * rpp) * xrow;
-                        if (p.x16in) v[u] = unpack16x4(lds64(ad), p.is_bf16);
-                        else v[u] = lds128(ad);
-                    }
-                }
+                    for (int u = 0; u < 8; ++u) v[u] = lds128(xaddr + (uint32_t)u * 512u);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int r = rb + rl + u * rpp;
-                    uint2 o = transform4<ACT>(v[u], cf, p.is_bf16);
-                    if (!interior) {
-                        const int t = t0 + r;
-                        if (t < 0 || t >= p.Tin) o = make_uint2(0u, 0u);   // conv zero padding (after the activation)
+                    for (int u = 0; u < 8; ++u) {
+                        const uint2 o = pipe_transform4<ACT, BF16>(v[u], cf);
+                        sts64(abase + aoff[u], o.x, o.y);
                     }
-                    if (r < nrows) sts64(A_ADDR(r0 + r), o.x, o.y);
                 }
             }
-#undef A_ADDR
+            // ragged end of the block, and blocks that touch the zero padding of the convolution: two passes at a time
+            {
+                const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
+                const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
+                const uint32_t abuf = smem_a_u32 + buf * a_bytes + sub;
+                for (; rb < nrows; rb += 2 * rpp, xaddr += 2 * 512) {
+                    float4 v[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rb + rl + u * rpp < nrows) v[u] = lds128(xaddr + (uint32_t)u * 512u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int r = rb + rl + u * rpp;
+                        uint2 o = pipe_transform4<ACT, BF16>(v[u], cf);
+                        const int t = t0 + r;
+                        if (t < 0 || t >= p.Tin) o = make_uint2(0u, 0u);   // conv zero padding (after the activation)
+                        const uint32_t R = (uint32_t)(r0 + r);
+                        if (r < nrows) sts64(abuf + R * arow + ((cidx ^ ((R >> sw_shift) & sw_mask)) << 4), o.x, o.y);
+                    }
+                }
+            }
             fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) {
@@ -482,11 +530,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         o01 = fmul2(o01, sc2);
                         o23 = fmul2(o23, sc2);
                     }
-                    if (p.y16out)
-                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.y) + (yo - p.y) + it * ystep) =
-                            make_uint2(pack16(o01.x, o01.y, p.is_bf16), pack16(o23.x, o23.y, p.is_bf16));
-                    else
-                        *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                    *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
                     s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
                     s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
                 }
@@ -542,9 +586,8 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
     if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
-    const int xes = a.x16in ? 2 : 4;
-    if ((a.ld_x * xes) % 16 != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
-    if (a.y16out && a.accumulate) return false;
+    if (a.x16in || a.y16out) return false;                 // 16-bit intra-block tensors: conv_fused.cu only
+    if (a.ld_x % 4 != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
     if (a.tap_step <= 0 || a.M != a.Tout) return false;
     if (a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
@@ -564,8 +607,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.rows = P_MT + span;
     {
         // activation blocks: the fewest equal blocks (whole passes of the owning warp) that fit a 12 KB slot
-        const int xes = a.x16in ? 2 : 4;
-        const int rowb = p.cch * xes, rpp = 32 / (p.cch / 4);
+        const int rowb = p.cch * 4, rpp = 8;                // blocks are whole multiples of 8 rows (swizzle period)
         int xmax = P_XSLOT_MAX;
         if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
         int nblk = 1;
@@ -666,8 +708,8 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn)
                   : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn);
     if (e != ST2_OK) return e;
-    const int xdt = a.x16in ? (p.is_bf16 ? 1 : 2) : 0;
-    const uint64_t xes = a.x16in ? 2 : 4;
+    const int xdt = 0;
+    const uint64_t xes = 4;
     e = make_map_3d_any(&map_x, xdt, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
                         (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)p.cch, (uint32_t)p.xr, 0);
     if (e != ST2_OK) return e;
@@ -691,9 +733,12 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     int grid = num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
@@ -701,15 +746,16 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         fprintf(stderr, "conv_pipe: Cin=%d Cout=%d taps=%d step=%d rows=%d nblk=%d tail=%d xr=%d resident=%d wstages=%d na=%d nacc=%d lw=%d nx=%d nr=%d nres=%d smem=%zu tiles=%d\n",
                 p.Cin, p.Cout, p.ntaps, p.tap_step, p.rows, p.nblk, p.tail_rows, p.xr, p.resident, p.wstages, p.na, p.nacc, p.lw, p.nx, p.nr, p.nres, smem,
                 p.num_tiles);
+    ST2_REQUIRE(act != ACT_SNAKE || alpha != nullptr, "conv_pipe: snake needs alpha");
+#define PIPE_LAUNCH(A, BF) conv_pipe_kernel<A, BF><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
+    const bool bf = p.is_bf16 != 0;
     switch (act) {
-        case ACT_NONE: conv_pipe_kernel<ACT_NONE><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p); break;
-        case ACT_LRELU: conv_pipe_kernel<ACT_LRELU><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p); break;
-        case ACT_SNAKE:
-            ST2_REQUIRE(alpha != nullptr, "conv_pipe: snake needs alpha");
-            conv_pipe_kernel<ACT_SNAKE><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);
-            break;
+        case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true); else PIPE_LAUNCH(ACT_NONE, false); break;
+        case ACT_LRELU: if (bf) PIPE_LAUNCH(ACT_LRELU, true); else PIPE_LAUNCH(ACT_LRELU, false); break;
+        case ACT_SNAKE: if (bf) PIPE_LAUNCH(ACT_SNAKE, true); else PIPE_LAUNCH(ACT_SNAKE, false); break;
         default: set_error("conv_pipe: bad act %d", act); return ST2_ERR_INVALID;
     }
+#undef PIPE_LAUNCH
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
