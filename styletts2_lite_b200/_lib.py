@@ -12,7 +12,8 @@ import os
 from .config import DecoderConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libst2_b200.so")
+# ST2_B200_LIB selects another build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("ST2_B200_LIB") or os.path.join(_HERE, "lib", "libst2_b200.so")
 
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
 DTYPE = {"fp32": 0, "bf16": 1, "fp16": 2}

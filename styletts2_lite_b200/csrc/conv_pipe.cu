@@ -111,6 +111,23 @@ __device__ __forceinline__ uint2 pipe_transform4(const float4 v, const PXf& c) {
     return make_uint2(pack16(y01.x, y01.y, BF16 ? 1 : 0), pack16(y23.x, y23.y, BF16 ? 1 : 0));
 }
 
+// Epilogue rows of one 32x32 chunk in the transposed layout: this lane owns 4 channels of rows rr + 4*it.
+// o = a*scale + bias*scale, 128-byte row segments to global, running (sum, sum of squares) per channel.
+template <bool FULL>
+__device__ __forceinline__ void pipe_store_rows(uint32_t st_r0, uint32_t st_r1, float* yo, int ystep, uint32_t vmask, float2 sc2,
+                                                float2 bs01, float2 bs23, float2& s1a, float2& s1b, float2& s2a, float2& s2b) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const float4 a = lds128(((it & 1) ? st_r1 : st_r0) + (uint32_t)(it >> 1) * 1024u);
+        if (!FULL && !((vmask >> it) & 1u)) continue;
+        const float2 o01 = ffma2(make_float2(a.x, a.y), sc2, bs01);
+        const float2 o23 = ffma2(make_float2(a.z, a.w), sc2, bs23);
+        *reinterpret_cast<float4*>(yo + (size_t)it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
+        s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
+        s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
+    }
+}
+
 template <int ACT, bool BF16>
 __global__ void __launch_bounds__(P_THREADS, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
@@ -453,7 +470,6 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         const int nchunks = p.bn >> 5;
         const uint32_t smem_r_u32 = smem_u32(smem_r);
         const int ystep = 4 * p.ld_y;                     // element distance between consecutive row passes
-        const bool do_scale = p.scale != 1.f;
         const float2 sc2 = make_float2(p.scale, p.scale);
         uint32_t rs = 0, rpar = 0, rc = 0;                // residual ring cursor: stage, parity, box-set number
         auto r_advance = [&](int n) {
@@ -470,19 +486,22 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             }
             const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
             const int m_first = ti.mt * P_MT + q * 32 + rr;                  // rows of this lane: m_first + 4*it
-            uint32_t vmask = 0;
+            const bool full = ti.mt * P_MT + q * 32 + 32 <= p.M;             // warp-uniform: every row of this quarter exists
+            uint32_t vmask = 0xffu;
+            if (!full) {
+                vmask = 0;
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-                if (m_first + it * 4 < p.M) vmask |= 1u << it;
-            float* ytile = p.y + ((size_t)ti.b * p.M + m_first) * p.ld_y;
+                for (int it = 0; it < 8; ++it)
+                    if (m_first + it * 4 < p.M) vmask |= 1u << it;
+            }
+            float* ytile = p.y + ((size_t)ti.b * p.M + m_first) * p.ld_y + c4o;
+            float2* stile = p.stats ? p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + c4o : nullptr;
             mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
             tc_fence_after();
             for (int ch = 0; ch < nchunks; ++ch) {
-                const int co = ch * 32 + c4o;
-                const uint32_t cmask = (co < p.Cout) ? vmask : 0u;
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr && cmask) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                const float2 bias01 = make_float2(bias4.x, bias4.y), bias23 = make_float2(bias4.z, bias4.w);
+                if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 + c4o));
+                const float2 bs01 = fmul2(make_float2(bias4.x, bias4.y), sc2), bs23 = fmul2(make_float2(bias4.z, bias4.w), sc2);
                 // [32 rows][32 cols] fp32 region of this warp, 16-byte slots XOR-swizzled by (row & 7) -- the TMA
                 // SWIZZLE_128B layout of the residual box, and conflict-free for both access directions
                 uint32_t tile_u32;
@@ -497,17 +516,33 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)(ch * 32), v);
+#ifndef PIPE_NO_EARLY
+                    if (ch == nchunks - 1) {
+                        // the accumulator is in registers: hand it back to the MMA warp before the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+#endif
                     if (p.nres) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 r = lds128(st_w + (((uint32_t)i ^ l7) << 4));
+#ifdef PIPE_SCALAR_RES
                             v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                            continue;
+#endif
+                            const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(r.x, r.y));
+                            const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
+                            v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
                         }
                         if (p.nres == 2) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 r = lds128(st_w + (uint32_t)P_RBOX + (((uint32_t)i ^ l7) << 4));
-                                v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                                const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(r.x, r.y));
+                                const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
+                                v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
                             }
                         }
                     }
@@ -519,22 +554,14 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 const uint32_t st_r0 = tile_u32 + (uint32_t)rr * 128u + ((l7 ^ (uint32_t)rr) << 4);               // rows rr, rr+8, ...
                 const uint32_t st_r1 = tile_u32 + (uint32_t)(rr + 4) * 128u + ((l7 ^ (uint32_t)(rr + 4)) << 4);   // rows rr+4, rr+12, ...
                 float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
-                float* yo = ytile + co;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const float4 a = lds128(((it & 1) ? st_r1 : st_r0) + (uint32_t)(it >> 1) * 1024u);
-                    if (!((cmask >> it) & 1u)) continue;
-                    float2 o01 = fadd2(make_float2(a.x, a.y), bias01);
-                    float2 o23 = fadd2(make_float2(a.z, a.w), bias23);
-                    if (do_scale) {
-                        o01 = fmul2(o01, sc2);
-                        o23 = fmul2(o23, sc2);
-                    }
-                    *reinterpret_cast<float4*>(yo + it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
-                    s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
-                    s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
-                }
-                if (p.stats != nullptr) {
+                float* yo = ytile + ch * 32;
+#ifdef PIPE_NO_FULL
+                if (false) pipe_store_rows<true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+#else
+                if (full) pipe_store_rows<true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+#endif
+                else pipe_store_rows<false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                if (stile != nullptr) {
                     float s1[4] = {s1a.x, s1a.y, s1b.x, s1b.y}, s2[4] = {s2a.x, s2a.y, s2b.x, s2b.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -544,8 +571,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 16);
                     }
                     // one partial per (tile, TMEM lane quarter): written straight to global, no cross-warp barrier
-                    if (lane < 8 && co < p.Cout) {
-                        float2* sp = p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + co;
+                    if (lane < 8) {
+                        float2* sp = stile + ch * 32;
                         *reinterpret_cast<float4*>(sp) = make_float4(s1[0], s2[0], s1[1], s2[1]);
                         *reinterpret_cast<float4*>(sp + 2) = make_float4(s1[2], s2[2], s1[3], s2[3]);
                     }
@@ -559,10 +586,11 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     __syncwarp();
                 }
             }
-            // accumulator drained: hand it back to the MMA warp
+#ifdef PIPE_NO_EARLY
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#endif
         }
     }
     tc_fence_before();

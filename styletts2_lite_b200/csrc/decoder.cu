@@ -774,7 +774,8 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     const int Cl = d->stage_channels(c.n_stages - 1);
     if (!istft) {
         if (E.live())
-            E.chk(launch_post_hifigan(x, Cl, d->gen_alpha[c.n_stages], d->conv_post.w32, d->conv_post.bias, out, B, S, Cl, st));
+            E.chk(launch_post_hifigan(x, Cl, d->gen_alpha[c.n_stages], d->conv_post.w32, d->conv_post.bias, out, B, S, Cl,
+                                       prec != ST2_PREC_FP32 ? 1 : 0, st));
         E.prof(PC_POST, 2.0 * B * S * Cl * 7, 4.0 * B * S * (Cl + 1));
     } else {
         const int dt = E.fmt_for("generator.conv_post");

@@ -140,14 +140,18 @@ int launch_pool_dw(const float* x, int ld_x, const float* w, const float* bias, 
 }
 
 // ---- hifigan tail: Snake(alphas[-1]) -> conv_post(C->1,k=7,p=3) -> tanh (hifigan.py:343-345) --
+// HBM-bound on its input (4*C bytes per sample).  The Snake'd tile lives in shared memory with a pitch of C+4 floats
+// (16-byte aligned rows, conflict-free 128-bit reads for consecutive rows); FAST selects sin.approx / approximate
+// reciprocal for the 16-bit precisions (the fp32 parity path keeps sinf).
 static constexpr int kPostTile = 256;
+template <bool FAST>
 __global__ void __launch_bounds__(kPostTile)
 post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ alpha,
                     const float* __restrict__ w /*[7][C]*/, const float* __restrict__ bias,
                     float* __restrict__ out, int S, int C) {
-    extern __shared__ float sm[];
-    const int pitch = C + 1;
-    float* tile = sm;                                  // [(kPostTile+6)][C+1]
+    extern __shared__ __align__(16) float sm[];
+    const int pitch = C + 4;
+    float* tile = sm;                                  // [(kPostTile+6)][C+4]
     float* sw = sm + (kPostTile + 6) * pitch;          // [7][C]
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kPostTile;
@@ -158,37 +162,51 @@ post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restri
         int t = t0 + r - 3;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < S) {
-            v = *reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * ld_x + c);
+            v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * ld_x + c));
             float4 al = *reinterpret_cast<const float4*>(alpha + c);
-            float s0 = sinf(al.x * v.x), s1 = sinf(al.y * v.y), s2 = sinf(al.z * v.z), s3 = sinf(al.w * v.w);
-            v.x = fmaf((1.f / al.x) * s0, s0, v.x);
-            v.y = fmaf((1.f / al.y) * s1, s1, v.y);
-            v.z = fmaf((1.f / al.z) * s2, s2, v.z);
-            v.w = fmaf((1.f / al.w) * s3, s3, v.w);
+            if (FAST) {
+                float s0 = __sinf(al.x * v.x), s1 = __sinf(al.y * v.y), s2 = __sinf(al.z * v.z), s3 = __sinf(al.w * v.w);
+                v.x = fmaf(__fdividef(1.f, al.x) * s0, s0, v.x);
+                v.y = fmaf(__fdividef(1.f, al.y) * s1, s1, v.y);
+                v.z = fmaf(__fdividef(1.f, al.z) * s2, s2, v.z);
+                v.w = fmaf(__fdividef(1.f, al.w) * s3, s3, v.w);
+            } else {
+                float s0 = sinf(al.x * v.x), s1 = sinf(al.y * v.y), s2 = sinf(al.z * v.z), s3 = sinf(al.w * v.w);
+                v.x = fmaf((1.f / al.x) * s0, s0, v.x);
+                v.y = fmaf((1.f / al.y) * s1, s1, v.y);
+                v.z = fmaf((1.f / al.z) * s2, s2, v.z);
+                v.w = fmaf((1.f / al.w) * s3, s3, v.w);
+            }
         }
-        float* d = tile + r * pitch + c;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        *reinterpret_cast<float4*>(tile + r * pitch + c) = v;
     }
     __syncthreads();
     const int t = t0 + threadIdx.x;
     if (t >= S) return;
     float acc = bias[0];
     for (int k = 0; k < 7; ++k) {
-        const float* row = tile + (threadIdx.x + k) * pitch;
-        const float* wk = sw + k * C;
-        for (int c = 0; c < C; ++c) acc = fmaf(wk[c], row[c], acc);
+        const float4* row = reinterpret_cast<const float4*>(tile + (threadIdx.x + k) * pitch);
+        const float4* wk = reinterpret_cast<const float4*>(sw + k * C);
+        for (int c = 0; c < cq; ++c) {                 // same summation order as the scalar loop
+            const float4 rv = row[c], wv = wk[c];
+            acc = fmaf(wv.x, rv.x, acc); acc = fmaf(wv.y, rv.y, acc);
+            acc = fmaf(wv.z, rv.z, acc); acc = fmaf(wv.w, rv.w, acc);
+        }
     }
     out[(size_t)b * S + t] = tanhf(acc);
 }
 
 int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
-                        float* out, int B, int S, int C, cudaStream_t st) {
+                        float* out, int B, int S, int C, int fast, cudaStream_t st) {
     ST2_REQUIRE(C % 4 == 0 && C <= 64 && ld_x % 4 == 0, "post_hifigan: C=%d ld=%d unsupported", C, ld_x);
-    size_t smem = ((size_t)(kPostTile + 6) * (C + 1) + 7 * C) * sizeof(float);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(post_hifigan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = ((size_t)(kPostTile + 6) * (C + 4) + 7 * C) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(post_hifigan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(post_hifigan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     dim3 grid(cdiv(S, kPostTile), B);
-    post_hifigan_kernel<<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    if (fast) post_hifigan_kernel<true><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    else post_hifigan_kernel<false><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
@@ -287,7 +305,7 @@ namespace st2 {
 // harmonic source har[B][S] -> y[B][Tout][C] channels-last, plus per-tile (sum, sumsq) per channel for the AdaIN
 // that follows (noise_res[i].adain1[0]).  HBM-bound on its output (4*C bytes per output step); weights and the
 // har segment of the tile live in shared memory.
-static constexpr int kNcTile = 64;      // output time steps per CTA
+static constexpr int kNcTile = 256;     // output time steps per CTA (weights + har segment are staged once per tile)
 __global__ void __launch_bounds__(256)
 noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[k][C]*/, const float* __restrict__ bias,
                   float* __restrict__ y, float2* __restrict__ stats, int S, int Tout, int C, int k, int stride, int pad,
@@ -311,21 +329,30 @@ noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[
     const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
     const float4 bv = *reinterpret_cast<const float4*>(bias + q * 4);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = rl; r < kNcTile; r += rpp) {
-        const int t = t0 + r;
-        if (t >= Tout) break;
-        float4 acc = bv;
+    // 4 rows x 4 channels per thread: one 128-bit weight read per tap feeds 16 FMAs
+    for (int r = rl; r < kNcTile; r += 4 * rpp) {
+        if (t0 + r >= Tout) break;
+        float4 acc[4] = {bv, bv, bv, bv};
         const float* hp = sh + r * stride;
+        const int hstep = rpp * stride;
         for (int j = 0; j < k; ++j) {
-            const float hv = hp[j];
             const float4 wv = *reinterpret_cast<const float4*>(sw + (size_t)j * C + q * 4);
-            acc.x = fmaf(hv, wv.x, acc.x); acc.y = fmaf(hv, wv.y, acc.y);
-            acc.z = fmaf(hv, wv.z, acc.z); acc.w = fmaf(hv, wv.w, acc.w);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float hv = (r + u * rpp < kNcTile) ? hp[u * hstep + j] : 0.f;
+                acc[u].x = fmaf(hv, wv.x, acc[u].x); acc[u].y = fmaf(hv, wv.y, acc[u].y);
+                acc[u].z = fmaf(hv, wv.z, acc[u].z); acc[u].w = fmaf(hv, wv.w, acc[u].w);
+            }
         }
-        *reinterpret_cast<float4*>(y + ((size_t)b * Tout + t) * C + q * 4) = acc;
-        s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
-        s2[0] = fmaf(acc.x, acc.x, s2[0]); s2[1] = fmaf(acc.y, acc.y, s2[1]);
-        s2[2] = fmaf(acc.z, acc.z, s2[2]); s2[3] = fmaf(acc.w, acc.w, s2[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ru = r + u * rpp, t = t0 + ru;
+            if (ru >= kNcTile || t >= Tout) break;
+            *reinterpret_cast<float4*>(y + ((size_t)b * Tout + t) * C + q * 4) = acc[u];
+            s1[0] += acc[u].x; s1[1] += acc[u].y; s1[2] += acc[u].z; s1[3] += acc[u].w;
+            s2[0] = fmaf(acc[u].x, acc[u].x, s2[0]); s2[1] = fmaf(acc[u].y, acc[u].y, s2[1]);
+            s2[2] = fmaf(acc[u].z, acc[u].z, s2[2]); s2[3] = fmaf(acc[u].w, acc[u].w, s2[3]);
+        }
     }
     if (stats == nullptr) return;
 #pragma unroll
