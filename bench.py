@@ -161,6 +161,29 @@ class ClockSampler:
                 "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
+# DRAM bytes per launch of a kernel category, from the committed ncu launch list (profiles/<tag>_traffic.json,
+# written by tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)
+CATEGORY_KERNELS = {"conv_fused": ("conv_pipe_kernel", "conv_fused_kernel"), "conv_tc": ("conv_tc_kernel",),
+                    "conv_simt": ("conv_simt_kernel",)}
+
+
+def ncu_traffic(category):
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files or category not in CATEGORY_KERNELS:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        n = b = 0.0
+        for name, k in d["kernels"].items():
+            if any(t in name for t in CATEGORY_KERNELS[category]):
+                n += k["launches"]
+                b += k["launches"] * k["dram_bytes_per_launch"]
+        return (b / n if n else None), os.path.relpath(files[-1], ROOT) + ": " + d.get("source", "")
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -288,6 +311,8 @@ def run_b200(a, rank, local_rank, world):
         achieved = v["bytes"] / v["ms"] / 1e6
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None}
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(dom)
+    roof["algorithmic_bytes_per_launch"] = prof_acc[dom]["bytes"] / max(prof_acc[dom]["launches"], 1)
     roof["avg_launch_ms"] = prof_acc[dom]["ms"] / max(prof_acc[dom]["launches"], 1)
     roof["peak_source"] = peak_src
     roof["kernels"] = kernels

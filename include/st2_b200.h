@@ -200,6 +200,18 @@ ST2_API int st2_adain_conv1d_fused(const float* x, const float* h, const float* 
                            int32_t k, int32_t padding, int32_t dilation, float scale, int32_t accumulate,
                            int32_t precision, void* stream);
 
+/* Generator upsampling step (Modules/hifigan.py:329-334) through the fused tensor-core kernels:
+ *   y = conv_transpose1d(act(x), w) + bias + res        x [B,Tin,Cin], w [Cin,Cout,k] (k a multiple of stride),
+ * res / y [B,Tout,Cout], Tout = (Tin-1)*stride - 2*padding + k + output_padding.  alpha [Cin] for snake.
+ * If h_next [B,2*Cout] is given, coef_next [B,2,Cout] receives the AdaIN coefficients of y. */
+ST2_API int64_t st2_act_conv_transpose1d_fused_scratch_bytes(int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k,
+                                                     int32_t stride);
+ST2_API int st2_act_conv_transpose1d_fused(const float* x, const float* alpha, int32_t act, float slope, const float* w,
+                                   const float* bias, const float* res, float* y, const float* h_next,
+                                   float* coef_next, void* scratch, int32_t B, int32_t Tin, int32_t Cin, int32_t Cout,
+                                   int32_t k, int32_t stride, int32_t padding, int32_t output_padding,
+                                   int32_t precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

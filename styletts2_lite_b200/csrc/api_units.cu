@@ -190,4 +190,68 @@ int st2_adain_conv1d_fused(const float* x, const float* h, const float* alpha, i
     return e;
 }
 
+// Generator upsampling step (hifigan.py:329-334): y = conv_transpose1d(act(x), w) + bias + res, plus the AdaIN
+// coefficients of y for style h_next, through the fused tensor-core kernels.
+static int64_t fused_t_offsets(int B, int Tin, int Cin, int Cout, int k, int stride, int64_t off[5]) {
+    const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 31) / 32 * 32;
+    const int M = Tin + k / stride;                                                    // >= rows of any phase
+    int64_t o = 0;
+    off[0] = o; o += align256((int64_t)k * Cin * Cout * sizeof(float));               // packed fp32 weight
+    off[1] = o; o += align256((int64_t)k * cin_pad * cout_pad * 2);                   // 16-bit weight
+    off[2] = o; o += align256((int64_t)B * 2 * cin_pad * sizeof(float));              // identity coefficients
+    off[3] = o; o += align256((int64_t)B * ((int64_t)stride * cdiv(M, 128) * 4) * Cout * 8);   // output partials
+    off[4] = o;
+    return o;
+}
+
+int64_t st2_act_conv_transpose1d_fused_scratch_bytes(int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k,
+                                                     int32_t stride) {
+    if (B <= 0 || Tin <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0) return ST2_ERR_INVALID;
+    int64_t off[5];
+    return fused_t_offsets(B, Tin, Cin, Cout, k, stride, off);
+}
+
+int st2_act_conv_transpose1d_fused(const float* x, const float* alpha, int32_t act, float slope, const float* w,
+                                   const float* bias, const float* res, float* y, const float* h_next, float* coef_next,
+                                   void* scratch, int32_t B, int32_t Tin, int32_t Cin, int32_t Cout, int32_t k,
+                                   int32_t stride, int32_t padding, int32_t output_padding, int32_t precision, void* stream) {
+    ST2_REQUIRE(x && w && y && scratch && B > 0 && Tin > 0 && Cin > 0 && Cout > 0 && k > 0 && stride > 0,
+                "act_conv_transpose1d_fused: bad argument");
+    ST2_REQUIRE(precision == ST2_PREC_BF16 || precision == ST2_PREC_FP16, "act_conv_transpose1d_fused: 16-bit precisions only");
+    ST2_REQUIRE(k % stride == 0, "act_conv_transpose1d_fused: k must be a multiple of stride");
+    ST2_REQUIRE((h_next == nullptr) == (coef_next == nullptr), "act_conv_transpose1d_fused: h_next and coef_next go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t off[5];
+    fused_t_offsets(B, Tin, Cin, Cout, k, stride, off);
+    char* base = (char*)scratch;
+    float* wp = (float*)(base + off[0]);
+    void* w16 = base + off[1];
+    float* coef = (float*)(base + off[2]);
+    void* parts = base + off[3];
+    const int dt = precision == ST2_PREC_BF16 ? DT_BF16 : DT_F16;
+    const int cin_pad = (Cin + 63) / 64 * 64, cout_pad = (Cout + 31) / 32 * 32;
+    int e = launch_fold_pack(nullptr, w, wp, Cin, Cout, k, 1, st);
+    if (e != ST2_OK) return e;
+    e = launch_pack_w16(wp, w16, k, Cin, Cout, cin_pad, cout_pad, dt, st);
+    if (e != ST2_OK) return e;
+    e = launch_adain_coef(nullptr, nullptr, 0, 0, coef, B, Tin, Cin, Cin, st);
+    if (e != ST2_OK) return e;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = Cin; a.Cout = Cout; a.Tin = Tin;
+    a.Tout = (Tin - 1) * stride - 2 * padding + (k - 1) + output_padding + 1;
+    ST2_REQUIRE(a.Tout > 0, "act_conv_transpose1d_fused: empty output");
+    a.x = x; a.ld_x = Cin; a.w = wp; a.w16 = w16; a.w16_cin_pad = cin_pad; a.w16_cout_pad = cout_pad; a.fmt16 = dt;
+    a.bias = bias; a.res = res; a.ld_res = Cout; a.y = y; a.ld_y = Cout;
+    a.ntaps = k / stride; a.tap_step = -1; a.in_off = 0; a.in_stride = 1;
+    a.phases = stride; a.w_step = stride; a.out_stride = stride; a.out_pad = padding;
+    a.M = (a.Tout - 1 + padding) / stride + 1;
+    a.scale = 1.f;
+    ST2_REQUIRE(conv_fused_supported(a), "act_conv_transpose1d_fused: geometry not supported by the fused kernels");
+    e = launch_conv_fused(a, coef, Cin, act, slope, alpha, h_next ? parts : nullptr, st);
+    if (e != ST2_OK) return e;
+    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, a.Tout, Cout, Cout, st);
+    return e;
+}
+
 }  // extern "C"

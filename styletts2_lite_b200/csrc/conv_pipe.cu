@@ -17,6 +17,10 @@
 // tells adjacent phases apart and a consumer can be two fills ahead of a slot it does not own, so the producer
 // publishes the sequence number of every fill in a shared-memory word before issuing it; a consumer first sees
 // "its" sequence number (the previous fill has then landed and been consumed) and only then waits on the barrier.
+// ConvTranspose1d(k = taps*stride, stride) runs here too: its `stride` polyphase sub-convolutions read the same
+// input rows, so their weights are stacked along N (N = stride*Cout) and row m of the accumulator is exactly the
+// `stride` consecutive output rows m*stride - pad ... of the channels-last tensor, i.e. a dense [M][stride*Cout] matrix
+// at a constant element offset (Modules/hifigan.py:292-294 `ups`, 329-334).
 // Roles (16 warps, one persistent CTA per SM): warp 0 producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2-7 transform, warps 8-15 epilogue (2 groups x 4 TMEM lane quarters, one accumulator each).
 #include <cuda.h>
@@ -57,7 +61,10 @@ struct PipeParams {
     int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
     // epilogue
     const float* bias;
-    float* y; int ld_y; float scale; int y16out;
+    float* y; int ld_y; float scale; int y16out;   // y already shifted by -out_pad*cdiv rows for a transposed conv
+    int ostride, opad, Tout, cdiv;                  // output row of (m, column c): t = m*ostride + c/cdiv - opad, valid in [0,Tout)
+    int a_row0;                                     // operand row of tap 0 for output row 0 of the tile
+    long long ybatch;                               // elements between consecutive utterances of y
     float2* stats;              // [B][mtiles*4][Cout] (sum, sumsq) per (tile, 32-row quarter) or nullptr
 };
 
@@ -258,8 +265,13 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     r_seq[r_stage] = r_c;
                     mbar_expect_tx(&r_full[r_stage], r_stage_bytes);
                     uint8_t* dst = smem_r + (size_t)r_stage * r_stage_bytes;
-                    tma_load_3d(dst, &map_r, &r_full[r_stage], r_ch * 32, rt.mt * P_MT, rt.b);
-                    if (p.nres == 2) tma_load_3d(dst + P_RBOX, &map_o, &r_full[r_stage], r_ch * 32, rt.mt * P_MT, rt.b);
+                    // columns [32*r_ch, +32) of accumulator row m are channels co0.. of output row m*ostride + phs - opad
+                    //   = phase (phs - opad) mod ostride of row m + floor((phs - opad) / ostride) in the (c, phase, m, b) view
+                    const int phs = (r_ch * 32) / p.cdiv, co0 = r_ch * 32 - phs * p.cdiv;
+                    int u = phs - p.opad, moff = 0;
+                    while (u < 0) { u += p.ostride; --moff; }
+                    tma_load_4d(dst, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
+                    if (p.nres == 2) tma_load_4d(dst + P_RBOX, &map_o, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
                     ++r_c;
                     if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1; }
                     if (++r_ch == nchunks) { r_ch = 0; rt.next(p); r_done = !rt.valid(p); }
@@ -274,7 +286,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             const uint32_t a_buf_step = a_bytes >> 4;
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
             const uint32_t b_step = b_stage_bytes >> 4;
-            const uint32_t row_step = (uint32_t)p.tap_step * (arow >> 4);   // 16-byte units per tap
+            const uint32_t row_step = (uint32_t)(p.tap_step * (int)(arow >> 4));   // 16-byte units per tap (wraps when negative)
+            const uint32_t row0 = (uint32_t)p.a_row0 * (arow >> 4);
             // K-major descriptor hi word: SBO = 8 rows (>>4) | version 1 @ bit 46 | SWIZZLE_128B (2) or SWIZZLE_64B (4) @ bit 61
             const uint32_t dhi = p.k32 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : kDescHi;
             const uint32_t b_res_step = (uint32_t)p.kchunks * b_step;
@@ -294,7 +307,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&a_full[buf], buf_par);
                     tc_fence_after();
-                    uint32_t a_lo = a_lo0 + buf * a_buf_step;
+                    uint32_t a_lo = a_lo0 + buf * a_buf_step + row0;
                     if (p.resident) {
                         uint32_t b_lo = b_lo0 + (uint32_t)kc * b_step;
                         if (p.k32) {
@@ -486,21 +499,27 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             }
             const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
             const int m_first = ti.mt * P_MT + q * 32 + rr;                  // rows of this lane: m_first + 4*it
-            const bool full = ti.mt * P_MT + q * 32 + 32 <= p.M;             // warp-uniform: every row of this quarter exists
+            // warp-uniform: every (row, column) of this quarter maps to an output row inside [0, Tout)
+            const int m_lo = ti.mt * P_MT + q * 32;
+            const bool full = m_lo + 32 <= p.M && m_lo * p.ostride - p.opad >= 0 &&
+                              (m_lo + 31) * p.ostride + (p.ostride - 1) - p.opad < p.Tout;
             uint32_t vmask = 0xffu;
-            if (!full) {
-                vmask = 0;
-#pragma unroll
-                for (int it = 0; it < 8; ++it)
-                    if (m_first + it * 4 < p.M) vmask |= 1u << it;
-            }
-            float* ytile = p.y + ((size_t)ti.b * p.M + m_first) * p.ld_y + c4o;
+            float* ytile = p.y + (size_t)ti.b * (size_t)p.ybatch + (size_t)m_first * p.ld_y + c4o;
             float2* stile = p.stats ? p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + c4o : nullptr;
             mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
             tc_fence_after();
             for (int ch = 0; ch < nchunks; ++ch) {
+                const int phs = (ch * 32) / p.cdiv;            // polyphase index of this column chunk (0 for a plain conv)
+                if (!full) {
+                    vmask = 0;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int m = m_first + it * 4, t = m * p.ostride + phs - p.opad;
+                        if (m < p.M && t >= 0 && t < p.Tout) vmask |= 1u << it;
+                    }
+                }
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 + c4o));
+                if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 - phs * p.cdiv + c4o));
                 const float2 bs01 = fmul2(make_float2(bias4.x, bias4.y), sc2), bs23 = fmul2(make_float2(bias4.z, bias4.w), sc2);
                 // [32 rows][32 cols] fp32 region of this warp, 16-byte slots XOR-swizzled by (row & 7) -- the TMA
                 // SWIZZLE_128B layout of the residual box, and conflict-free for both access directions
@@ -605,22 +624,32 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
 // ---------------------------------------------------------------- host side
 int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
 int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_map_4d_f32_sw128(CUtensorMap* map, const void* base, uint64_t C, uint64_t phases, uint64_t rows, uint64_t B,
+                          uint64_t ld_bytes, uint64_t batch_bytes, uint32_t b0, uint32_t b2);
 int make_map_3d_any(CUtensorMap* map, int dtype /*0 f32, 1 bf16, 2 f16*/, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle128);
 
 static bool pipe_geometry_ok(const ConvArgs& a) {
     if (getenv("ST2_NO_PIPE") != nullptr) return false;
-    if (a.in_stride != 1 || a.phases != 1 || a.out_stride != 1 || a.out_pad != 0 || a.mirror || a.res_shift != 0) return false;
+    if (a.in_stride != 1 || a.mirror || a.res_shift != 0) return false;
+    const bool tr = a.phases > 1;          // polyphase ConvTranspose1d -> dense conv with N = phases * Cout
+    if (tr) {
+        if (a.out_stride != a.phases || a.w_step != a.phases || a.tap_step != -1 || a.in_off != 0 || a.accumulate) return false;
+        if (a.ld_y != a.Cout || (a.res != nullptr && a.ld_res != a.Cout) || a.phases * a.Cout > 256) return false;
+        if (a.Tout % a.phases != 0 || a.out_pad < 0 || a.out_pad > a.phases) return false;
+        if (getenv("ST2_NO_PIPE_UPS") != nullptr) return false;
+    } else if (a.out_stride != 1 || a.out_pad != 0 || a.tap_step <= 0 || a.M != a.Tout) {
+        return false;
+    }
     if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
     if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
     if (a.x16in || a.y16out) return false;                 // 16-bit intra-block tensors: conv_fused.cu only
     if (a.ld_x % 4 != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
-    if (a.tap_step <= 0 || a.M != a.Tout) return false;
-    if (a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
-    const int span = (a.ntaps - 1) * a.tap_step;
-    return span <= 64 && a.in_off <= 0 && a.in_off + span >= 0;
+    if (!tr && a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
+    const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
+    return span <= 64 && (tr || (a.in_off <= 0 && a.in_off + span >= 0));
 }
 
 // geometry + shared-memory plan; false if the rings do not fit next to the operand tiles and weights
@@ -629,14 +658,20 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.Cin = a.Cin; p.kchunks = a.w16_cin_pad / 64; p.cch = a.Cin == 32 ? 32 : 64;
     p.x16in = a.x16in; p.is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
     p.k32 = (a.Cin == 32 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
-    p.B = a.B; p.M = a.M; p.Tin = a.Tin; p.Cout = a.Cout;
-    p.ntaps = a.ntaps; p.tap_step = a.tap_step; p.halo_min = a.in_off;
-    const int span = (a.ntaps - 1) * a.tap_step;
+    const int ph = a.phases;               // 1, or the stride of a transposed conv (columns = ph * Cout)
+    p.B = a.B; p.M = a.M; p.Tin = a.Tin; p.Cout = ph * a.Cout;
+    p.ntaps = a.ntaps; p.tap_step = a.tap_step;
+    const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
+    p.halo_min = a.in_off + (a.tap_step < 0 ? (a.ntaps - 1) * a.tap_step : 0);
+    p.a_row0 = a.in_off - p.halo_min;
     p.rows = P_MT + span;
+    p.ostride = a.out_stride; p.opad = a.out_pad; p.Tout = a.Tout; p.cdiv = a.Cout;
     {
         // activation blocks: the fewest equal blocks (whole passes of the owning warp) that fit a 12 KB slot
         const int rowb = p.cch * 4, rpp = 8;                // blocks are whole multiples of 8 rows (swizzle period)
-        int xmax = P_XSLOT_MAX;
+        // 12 KB blocks by default; 8 KB when every residual stage holds two boxes (residual + accumulate), where the
+        // smaller blocks leave room for one more stage (measured: 0.75 -> 0.60 ms on the 32-channel k=11 layer)
+        int xmax = (a.res != nullptr && a.accumulate) ? 8192 : P_XSLOT_MAX;
         if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
         int nblk = 1;
         for (;; ++nblk) {
@@ -647,7 +682,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
         p.tail_rows = p.rows - (p.nblk - 1) * p.xr;
         p.xslot = (p.xr * rowb + 127) / 128 * 128;
     }
-    p.bn = a.w16_cout_pad;
+    p.bn = ph * a.w16_cout_pad;
     p.mtiles = cdiv(a.M, P_MT);
     p.num_tiles = a.B * p.mtiles;
     p.nacc = p.bn <= 128 ? 4 : 2;
@@ -657,7 +692,10 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     while (cols < p.nacc * p.bn) cols <<= 1;
     p.tmem_cols = cols;
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
-    p.bias = a.bias; p.y = a.y; p.ld_y = a.ld_y; p.scale = a.scale; p.y16out = a.y16out;
+    p.bias = a.bias; p.scale = a.scale; p.y16out = a.y16out;
+    p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout])
+    p.ld_y = ph * a.ld_y;
+    p.ybatch = (long long)a.Tout * a.ld_y;
 
     // ---- shared-memory plan (one persistent CTA per SM)
     const int64_t budget = 225 * 1024;
@@ -733,8 +771,10 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
 
     // ---- tensor maps
     CUtensorMap map_b, map_x, map_xt, map_r, map_o;
-    int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn)
-                  : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, p.bn);
+    // transposed conv: taps are stored phase-major (widx = phase + j*stride), so tap j of the stacked weight is the
+    // [phases*Cout][Cin] slab starting at stored tap j*stride -- the same memory viewed with phases*Cout rows per tap
+    int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.phases * a.w16_cout_pad, a.ntaps, p.bn)
+                  : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.phases * a.w16_cout_pad, a.ntaps, p.bn);
     if (e != ST2_OK) return e;
     const int xdt = 0;
     const uint64_t xes = 4;
@@ -747,13 +787,13 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     map_r = map_x;
     map_o = map_x;
     if (a.res != nullptr) {
-        e = make_map_3d_any(&map_r, 0, a.res, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_res * 4,
-                            (uint64_t)a.Tout * a.ld_res * 4, 32, P_MT, 1);
+        e = make_map_4d_f32_sw128(&map_r, a.res, (uint64_t)a.Cout, (uint64_t)a.phases, (uint64_t)(a.Tout / a.phases), (uint64_t)a.B,
+                                  (uint64_t)a.ld_res * 4, (uint64_t)a.Tout * a.ld_res * 4, 32, P_MT);
         if (e != ST2_OK) return e;
     }
     if (a.accumulate) {
-        e = make_map_3d_any(&map_o, 0, a.y, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 4,
-                            (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT, 1);
+        e = make_map_4d_f32_sw128(&map_o, a.y, (uint64_t)a.Cout, 1, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 4,
+                                  (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT);
         if (e != ST2_OK) return e;
     }
     static int num_sms = 0;

@@ -137,3 +137,28 @@ def adain_conv1d_fused(x_btc, h, alpha, act, w, bias, res_btc, y_old_btc, h_next
                "adain_conv1d_fused")
     torch.cuda.synchronize()
     return y.cpu().numpy(), (None if cn is None else cn.cpu().numpy())
+
+
+def act_conv_transpose1d_fused(x_btc, alpha, act, w, bias, res_btc, h_next, stride, padding, output_padding, slope=0.0,
+                               precision="bf16"):
+    """Fused upsampling step on channels-last tensors; returns (y [B,Tout,Cout], coef_next [B,2,Cout] or None)."""
+    lib = _lib.load()
+    B, T, Cin = x_btc.shape
+    _, Cout, k = w.shape
+    Tout = (T - 1) * stride - 2 * padding + (k - 1) + output_padding + 1
+    xd, wd = to_dev(x_btc), to_dev(w)
+    ad = None if alpha is None else to_dev(alpha.reshape(-1))
+    bd = None if bias is None else to_dev(bias)
+    rd = None if res_btc is None else to_dev(res_btc)
+    hn = None if h_next is None else to_dev(h_next)
+    cn = None if h_next is None else torch.full((B, 2, Cout), float("nan"), device=dev())
+    y = torch.full((B, Tout, Cout), float("nan"), device=dev())
+    nbytes = _lib.check(lib.st2_act_conv_transpose1d_fused_scratch_bytes(B, T, Cin, Cout, k, stride), "fused_t_scratch_bytes")
+    # the residual view of the kernel may read (never use) a few rows before / after the tensor: keep it inside one arena
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    _lib.check(lib.st2_act_conv_transpose1d_fused(_lib.ptr(xd), _lib.ptr(ad), _lib.ACT[act], C.c_float(slope), _lib.ptr(wd),
+                                                  _lib.ptr(bd), _lib.ptr(rd), _lib.ptr(y), _lib.ptr(hn), _lib.ptr(cn),
+                                                  _lib.ptr(scratch), B, T, Cin, Cout, k, stride, padding, output_padding,
+                                                  _lib.PREC[precision], stream()), "act_conv_transpose1d_fused")
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), (None if cn is None else cn.cpu().numpy())

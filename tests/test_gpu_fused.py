@@ -121,3 +121,47 @@ def test_fused_residual_in_place_and_batch_edges():
     err = float(np.abs(got - ref).max() / np.abs(ref).max())
     G.log("adain_conv1d_fused_inplace", relmax=err)
     assert err <= TOL["bf16"]
+
+
+# ConvTranspose1d of the generator (`ups`): polyphase sub-convolutions stacked along N in conv_pipe.cu (stride*Cout <= 256),
+# one launch per phase group in conv_fused.cu otherwise
+UPS_CASES = [
+    # Cin, Cout, k, stride, pad, out_pad, T, act
+    (64, 32, 4, 2, 1, 0, 700, "snake"), (128, 64, 6, 3, 2, 1, 333, "snake"), (256, 128, 10, 5, 3, 1, 150, "snake"),
+    (512, 256, 20, 10, 5, 0, 40, "snake"), (64, 32, 4, 2, 1, 0, 129, "lrelu"), (256, 128, 12, 6, 3, 0, 100, "lrelu"),
+]
+
+
+@pytest.mark.parametrize("path", ["pipe", "tile"])
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,opad,T,act", UPS_CASES)
+def test_act_conv_transpose1d_fused_vs_oracle(Cin, Cout, k, stride, pad, opad, T, act, prec, path):
+    rng = np.random.default_rng(Cin + 3 * Cout + k + T)
+    B = 3
+    x = (rng.standard_normal((B, Cin, T)) * 1.2).astype(np.float32)
+    alpha = (0.6 + 0.8 * rng.random((1, Cin, 1))).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(Cin * k / stride)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    h_next = (rng.standard_normal((B, 2 * Cout)) * 0.3).astype(np.float32)
+    v = O.snake(x, alpha) if act == "snake" else np.where(x >= 0, x, x * np.float32(0.1)).astype(np.float32)
+    ref = O.conv_transpose1d(v, w, b, stride=stride, padding=pad, output_padding=opad, operand=prec)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    ref = (ref + res).astype(np.float32)
+    if path == "tile":
+        os.environ["ST2_NO_PIPE"] = "1"
+    try:
+        got, coef = G.act_conv_transpose1d_fused(G.cl(x), alpha if act == "snake" else None, act, w, b, G.cl(res), h_next,
+                                                 stride, pad, opad, slope=0.1, precision=prec)
+    finally:
+        os.environ.pop("ST2_NO_PIPE", None)
+    got = G.cf(got)
+    assert got.shape == ref.shape
+    nan = int(np.isnan(got).sum())
+    err = float(np.abs(np.nan_to_num(got) - ref).max() / np.abs(ref).max())
+    cref = _coef(ref, h_next)
+    cerr = float(np.abs(np.nan_to_num(coef) - cref).max() / np.abs(cref).max())
+    G.log("act_conv_transpose1d_fused", path=path, prec=prec, Cin=Cin, Cout=Cout, k=k, stride=stride, T=T, relmax=err,
+          coef_relmax=cerr, nan=nan)
+    assert nan == 0
+    assert err <= TOL[prec]
+    assert cerr <= 2 * TOL[prec]
