@@ -92,6 +92,7 @@ int launch_noise_conv(const float* har, const float* w, const float* bias, float
 int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
                         float* out, int B, int S, int C, int fast, cudaStream_t st);
 int launch_copy_dense(const float* src, int ld, float* dst, int64_t rows, int C, cudaStream_t st);
+int launch_half_to_float(const void* src, float* dst, int64_t n, cudaStream_t st);
 int launch_fold_pack(const float* g, const float* v, float* wp, int d0, int d1, int k, int transposed,
                      cudaStream_t st);
 int launch_cast16(const float* src, void* dst, int64_t n, int out_dtype, cudaStream_t st);

@@ -120,7 +120,7 @@ __device__ __forceinline__ uint2 pipe_transform4(const float4 v, const PXf& c) {
 
 // Epilogue rows of one 32x32 chunk in the transposed layout: this lane owns 4 channels of rows rr + 4*it.
 // o = a*scale + bias*scale, 128-byte row segments to global, running (sum, sum of squares) per channel.
-template <bool FULL>
+template <bool FULL, bool Y16>
 __device__ __forceinline__ void pipe_store_rows(uint32_t st_r0, uint32_t st_r1, float* yo, int ystep, uint32_t vmask, float2 sc2,
                                                 float2 bs01, float2 bs23, float2& s1a, float2& s1b, float2& s2a, float2& s2b) {
 #pragma unroll
@@ -129,13 +129,17 @@ __device__ __forceinline__ void pipe_store_rows(uint32_t st_r0, uint32_t st_r1, 
         if (!FULL && !((vmask >> it) & 1u)) continue;
         const float2 o01 = ffma2(make_float2(a.x, a.y), sc2, bs01);
         const float2 o23 = ffma2(make_float2(a.z, a.w), sc2, bs23);
-        *reinterpret_cast<float4*>(yo + (size_t)it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
+        if (Y16)   // fp16 storage of the intra-block tensor: yo is a half pointer in disguise (element offsets are the same)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(yo) + (size_t)it * ystep) =
+                make_uint2(pack16(o01.x, o01.y, 0), pack16(o23.x, o23.y, 0));
+        else
+            *reinterpret_cast<float4*>(yo + (size_t)it * ystep) = make_float4(o01.x, o01.y, o23.x, o23.y);
         s1a = fadd2(s1a, o01); s1b = fadd2(s1b, o23);
         s2a = ffma2(o01, o01, s2a); s2b = ffma2(o23, o23, s2b);
     }
 }
 
-template <int ACT, bool BF16>
+template <int ACT, bool BF16, bool X16>
 __global__ void __launch_bounds__(P_THREADS, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
@@ -168,7 +172,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr uint32_t xes = 4u;                                   // fp32 activations
+    constexpr uint32_t xes = X16 ? 2u : 4u;                        // fp32 activations, or the fp16 intra-block tensor
+    constexpr uint32_t PASS = X16 ? 256u : 512u;                   // slot bytes one warp pass covers
     const uint32_t xrow = (uint32_t)p.cch * xes;                   // bytes per slot row
 
     if (warp == 0 && lane == 0) {
@@ -356,7 +361,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         // ===== transform: one warp = one activation block at a time, blocks dealt round-robin =====
         const int tw = warp - P_W_X0;
         const int lpr_shift = (p.cch == 64) ? 4 : 3;            // lanes per row: 16 or 8
-        const int rpp = 32 >> lpr_shift;                        // rows per pass: 2 or 4  (one pass = 512 bytes of the slot)
+        const int rpp = 32 >> lpr_shift;                        // rows per pass: 2 or 4  (one pass = PASS bytes of the slot)
         const int rl = lane >> lpr_shift;
         const int c4 = (lane & ((1 << lpr_shift) - 1)) * 4;
         const uint32_t smem_a_u32 = smem_u32(smem_a);
@@ -423,10 +428,13 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             int rb = 0;
             if (interior) {
                 // full batches: 8 independent loads, then 8 independent activation chains, no per-row checks
-                for (; rb + 8 * rpp <= nrows; rb += 8 * rpp, xaddr += 8 * 512, abase += batch_a) {
+                for (; rb + 8 * rpp <= nrows; rb += 8 * rpp, xaddr += 8 * PASS, abase += batch_a) {
                     float4 v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = lds128(xaddr + (uint32_t)u * 512u);
+                    for (int u = 0; u < 8; ++u) {
+                        if (X16) v[u] = unpack16x4(lds64(xaddr + (uint32_t)u * PASS), 0);
+                        else v[u] = lds128(xaddr + (uint32_t)u * PASS);
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const uint2 o = pipe_transform4<ACT, BF16>(v[u], cf);
@@ -439,12 +447,15 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 const uint32_t cidx = (uint32_t)(c4 >> 3), sub = (uint32_t)(c4 & 4) * 2u;
                 const uint32_t sw_shift = p.k32 ? 1u : 0u, sw_mask = p.k32 ? 3u : 7u;
                 const uint32_t abuf = smem_a_u32 + buf * a_bytes + sub;
-                for (; rb < nrows; rb += 2 * rpp, xaddr += 2 * 512) {
+                for (; rb < nrows; rb += 2 * rpp, xaddr += 2 * PASS) {
                     float4 v[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rb + rl + u * rpp < nrows) v[u] = lds128(xaddr + (uint32_t)u * 512u);
+                        if (rb + rl + u * rpp < nrows) {
+                            if (X16) v[u] = unpack16x4(lds64(xaddr + (uint32_t)u * PASS), 0);
+                            else v[u] = lds128(xaddr + (uint32_t)u * PASS);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -504,7 +515,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             const bool full = m_lo + 32 <= p.M && m_lo * p.ostride - p.opad >= 0 &&
                               (m_lo + 31) * p.ostride + (p.ostride - 1) - p.opad < p.Tout;
             uint32_t vmask = 0xffu;
-            float* ytile = p.y + (size_t)ti.b * (size_t)p.ybatch + (size_t)m_first * p.ld_y + c4o;
+            const size_t yoff = (size_t)ti.b * (size_t)p.ybatch + (size_t)m_first * p.ld_y + c4o;
+            float* ytile = p.y16out ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.y) + yoff) : p.y + yoff;
             float2* stile = p.stats ? p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + c4o : nullptr;
             mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
             tc_fence_after();
@@ -573,13 +585,14 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 const uint32_t st_r0 = tile_u32 + (uint32_t)rr * 128u + ((l7 ^ (uint32_t)rr) << 4);               // rows rr, rr+8, ...
                 const uint32_t st_r1 = tile_u32 + (uint32_t)(rr + 4) * 128u + ((l7 ^ (uint32_t)(rr + 4)) << 4);   // rows rr+4, rr+12, ...
                 float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
-                float* yo = ytile + ch * 32;
-#ifdef PIPE_NO_FULL
-                if (false) pipe_store_rows<true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-#else
-                if (full) pipe_store_rows<true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-#endif
-                else pipe_store_rows<false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                float* yo = p.y16out ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ytile) + ch * 32) : ytile + ch * 32;
+                if (p.y16out) {
+                    if (full) pipe_store_rows<true, true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                    else pipe_store_rows<false, true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                } else {
+                    if (full) pipe_store_rows<true, false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                    else pipe_store_rows<false, false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                }
                 if (stile != nullptr) {
                     float s1[4] = {s1a.x, s1a.y, s1b.x, s1b.y}, s2[4] = {s2a.x, s2a.y, s2b.x, s2b.y};
 #pragma unroll
@@ -644,8 +657,11 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
     if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
-    if (a.x16in || a.y16out) return false;                 // 16-bit intra-block tensors: conv_fused.cu only
-    if (a.ld_x % 4 != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
+    // x16in / y16out: the intra-block tensor of AdaINResBlock1 stored as fp16 (plain stride-1 convs only)
+    if ((a.x16in || a.y16out) && tr) return false;
+    if (a.y16out && a.accumulate) return false;
+    if (a.x16in && a.y16out) return false;
+    if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
     if (!tr && a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
     const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
@@ -668,7 +684,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.ostride = a.out_stride; p.opad = a.out_pad; p.Tout = a.Tout; p.cdiv = a.Cout;
     {
         // activation blocks: the fewest equal blocks (whole passes of the owning warp) that fit a 12 KB slot
-        const int rowb = p.cch * 4, rpp = 8;                // blocks are whole multiples of 8 rows (swizzle period)
+        const int rowb = p.cch * (a.x16in ? 2 : 4), rpp = 8;   // blocks are whole multiples of 8 rows (swizzle period)
         // 12 KB blocks by default; 8 KB when every residual stage holds two boxes (residual + accumulate), where the
         // smaller blocks leave room for one more stage (measured: 0.75 -> 0.60 ms on the 32-channel k=11 layer)
         int xmax = (a.res != nullptr && a.accumulate) ? 8192 : P_XSLOT_MAX;
@@ -693,7 +709,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.tmem_cols = cols;
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
     p.bias = a.bias; p.scale = a.scale; p.y16out = a.y16out;
-    p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout])
+    p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout]); out_pad = 0 when y16out
     p.ld_y = ph * a.ld_y;
     p.ybatch = (long long)a.Tout * a.ld_y;
 
@@ -776,8 +792,8 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     int e = p.k32 ? make_weight_map_k32(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.phases * a.w16_cout_pad, a.ntaps, p.bn)
                   : make_weight_map(&map_b, p.is_bf16, a.w16, a.w16_cin_pad, a.phases * a.w16_cout_pad, a.ntaps, p.bn);
     if (e != ST2_OK) return e;
-    const int xdt = 0;
-    const uint64_t xes = 4;
+    const int xdt = a.x16in ? 2 : 0;
+    const uint64_t xes = a.x16in ? 2 : 4;
     e = make_map_3d_any(&map_x, xdt, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
                         (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)p.cch, (uint32_t)p.xr, 0);
     if (e != ST2_OK) return e;
@@ -801,12 +817,12 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_LRELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<ACT_SNAKE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define PIPE_ATTR(A, BF, X) ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<A, BF, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        PIPE_ATTR(ACT_NONE, true, false); PIPE_ATTR(ACT_NONE, false, false);
+        PIPE_ATTR(ACT_LRELU, true, false); PIPE_ATTR(ACT_LRELU, false, false);
+        PIPE_ATTR(ACT_SNAKE, true, false); PIPE_ATTR(ACT_SNAKE, false, false);
+        PIPE_ATTR(ACT_SNAKE, true, true); PIPE_ATTR(ACT_SNAKE, false, true);
+#undef PIPE_ATTR
     }
     int grid = num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
@@ -815,12 +831,16 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
                 p.Cin, p.Cout, p.ntaps, p.tap_step, p.rows, p.nblk, p.tail_rows, p.xr, p.resident, p.wstages, p.na, p.nacc, p.lw, p.nx, p.nr, p.nres, smem,
                 p.num_tiles);
     ST2_REQUIRE(act != ACT_SNAKE || alpha != nullptr, "conv_pipe: snake needs alpha");
-#define PIPE_LAUNCH(A, BF) conv_pipe_kernel<A, BF><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
+    ST2_REQUIRE(!a.x16in || act == ACT_SNAKE, "conv_pipe: 16-bit input is only built for the Snake transform");
+#define PIPE_LAUNCH(A, BF, X) conv_pipe_kernel<A, BF, X><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
     const bool bf = p.is_bf16 != 0;
     switch (act) {
-        case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true); else PIPE_LAUNCH(ACT_NONE, false); break;
-        case ACT_LRELU: if (bf) PIPE_LAUNCH(ACT_LRELU, true); else PIPE_LAUNCH(ACT_LRELU, false); break;
-        case ACT_SNAKE: if (bf) PIPE_LAUNCH(ACT_SNAKE, true); else PIPE_LAUNCH(ACT_SNAKE, false); break;
+        case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true, false); else PIPE_LAUNCH(ACT_NONE, false, false); break;
+        case ACT_LRELU: if (bf) PIPE_LAUNCH(ACT_LRELU, true, false); else PIPE_LAUNCH(ACT_LRELU, false, false); break;
+        case ACT_SNAKE:
+            if (a.x16in) { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, true); else PIPE_LAUNCH(ACT_SNAKE, false, true); }
+            else { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, false); else PIPE_LAUNCH(ACT_SNAKE, false, false); }
+            break;
         default: set_error("conv_pipe: bad act %d", act); return ST2_ERR_INVALID;
     }
 #undef PIPE_LAUNCH

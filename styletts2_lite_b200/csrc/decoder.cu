@@ -375,6 +375,20 @@ struct Exec {
         prof(PC_MISC, 0, 8.0 * rows * C);
     }
 
+    // tap of a dense fp16 tensor (the intra-block tensor of the fused resblocks)
+    void tap16(const std::string& name, const void* src, int64_t n) {
+        if (!live()) return;
+        auto it = d->taps.find(name);
+        if (it == d->taps.end() || it->second.dst == nullptr) return;
+        if (n > it->second.cap) {
+            set_error("tap '%s' needs %lld floats, buffer has %lld", name.c_str(), (long long)n, (long long)it->second.cap);
+            err = ST2_ERR_INVALID;
+            return;
+        }
+        chk(launch_half_to_float(src, it->second.dst, n, st));
+        prof(PC_MISC, 0, 6.0 * n);
+    }
+
     // y = act(AdaIN(x)) or act(x) when `n` is null.  x fp32 [B,T,ld_x]; y dtype dt, pitch ld_y.
     void norm_act(const float* x, int ld_x, int T, int C, const AdaINRef* n, int act, float slope, const float* alpha,
                   void* y, int ld_y, int dt) {
@@ -488,6 +502,17 @@ struct Exec {
         a.M = w.transposed ? (Tout - 1 - out_row_shift + padding) / stride + 1 : Tout;
         return fused_stats_parts(a);
     }
+    // would launch_conv_fused run this stride-1 conv on the TMA pipeline kernel (conv_pipe.cu) with these storage types?
+    bool pipe_ok(const ConvW& w, int ld_x, int ld_y, int T, int padding, int dilation, bool has_res, int accumulate, int dt,
+                 int x16in, int y16out) {
+        ConvArgs a;
+        if (!fill_args(a, w, T, T, 1, padding, dilation, 0)) return false;
+        a.accumulate = accumulate;
+        a.ld_x = ld_x; a.ld_y = ld_y; a.ld_res = ld_y; a.res = has_res ? (const float*)this : nullptr;   // only null-ness matters
+        a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
+        a.x16in = x16in; a.y16out = y16out; a.scale = 1.f;
+        return conv_pipe_supported(a);
+    }
     // y = epilogue( conv( act(coef.a * x + coef.b) ) ), statistics of y -> stats_out (float2 partials)
     void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
                     float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
@@ -572,10 +597,17 @@ struct Exec {
             const int nparts = fused_parts(w.c1[0], T, 1, 0, 0);
             void* st_xt = alloc((int64_t)B * nparts * C * 8);
             void* st_run = alloc((int64_t)B * nparts * C * 8);
-            // the intra-block tensor xt (conv1 output, only consumed by conv2's transform) is stored in 16 bits:
-            // -0.9 dB of SNR for 20 % fewer HBM bytes per iteration (optional: ST2_XT16=1)
-            const int xt16 = getenv("ST2_XT16") != nullptr ? 1 : 0;   // measured: fewer bytes but more instructions -> slower; off by default
-            float* xt = (float*)alloc((int64_t)B * T * C * (xt16 ? 2 : 4));
+            // the intra-block tensor xt (conv1 output, only consumed by conv2's transform) is stored as fp16 when both convs
+            // run on the TMA pipeline kernel: 20 % fewer HBM bytes per iteration for -0.1 dB of SNR (its statistics still come
+            // from the fp32 values in the epilogue).  ST2_NO_XT16=1 keeps it fp32.
+            int xt16 = getenv("ST2_NO_XT16") == nullptr ? 1 : 0;
+            for (int j = 0; j < 3 && xt16; ++j) {
+                const int dil = w.dil[j];
+                if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 0, 1) ||
+                    !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, j == 2 ? accumulate : 0, dt, 1, 0))
+                    xt16 = 0;
+            }
+            float* xt = (float*)alloc((int64_t)B * T * C * 4);      // sized for fp32 (the dry run must not depend on the device)
             StatRef cur_st = in_stats ? *in_stats : stats_standalone(x_in, C, T, C);
             const float* cur = x_in;
             for (int j = 0; j < 3; ++j) {
@@ -584,6 +616,7 @@ struct Exec {
                 conv_fused(w.c1[j], cur, C, T, dt, ACT_SNAKE, 0.f, w.alpha1[j], xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr,
                            0, 0, 1.f, 0, st_xt, 0, 0, 0, xt16);
                 if (!xt16) tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
+                else tap16(w.name + ".convs1." + std::to_string(j), xt, (int64_t)B * T * C);
                 coef_from(StatRef{st_xt, nparts, true}, &w.n2[j], T, C, C);
                 const bool last = (j == 2);
                 float* out = last ? dest : run;

@@ -211,6 +211,18 @@ int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const floa
     return ST2_OK;
 }
 
+// ---- fp16 -> fp32 (debug taps of the fp16 intra-block tensor)
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __half2float(src[i]);
+}
+
+int launch_half_to_float(const void* src, float* dst, int64_t n, cudaStream_t st) {
+    half_to_float_kernel<<<cdiv(n, 256), 256, 0, st>>>((const __half*)src, dst, n);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
 // ---- dense copy of a pitched channels-last tensor (debug taps) ------------------------------
 __global__ void copy_dense_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int64_t rows,
                                   int C) {
