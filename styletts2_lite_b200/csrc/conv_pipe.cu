@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "fused_ptx.cuh"
@@ -62,7 +64,7 @@ struct PipeParams {
     // epilogue
     const float* bias;
     float* y; int ld_y; float scale; int y16out;   // y already shifted by -out_pad*cdiv rows for a transposed conv
-    int ostride, opad, Tout, cdiv;                  // output row of (m, column c): t = m*ostride + c/cdiv - opad, valid in [0,Tout)
+    int ostride, opad, Tout, cdiv, cshift;          // output row of (m, column c): t = m*ostride + c/cdiv - opad, valid in [0,Tout); cdiv = 1 << cshift
     int a_row0;                                     // operand row of tap 0 for output row 0 of the tile
     long long ybatch;                               // elements between consecutive utterances of y
     float2* stats;              // [B][mtiles*4][Cout] (sum, sumsq) per (tile, 32-row quarter) or nullptr
@@ -272,7 +274,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     uint8_t* dst = smem_r + (size_t)r_stage * r_stage_bytes;
                     // columns [32*r_ch, +32) of accumulator row m are channels co0.. of output row m*ostride + phs - opad
                     //   = phase (phs - opad) mod ostride of row m + floor((phs - opad) / ostride) in the (c, phase, m, b) view
-                    const int phs = (r_ch * 32) / p.cdiv, co0 = r_ch * 32 - phs * p.cdiv;
+                    const int phs = (r_ch * 32) >> p.cshift, co0 = r_ch * 32 - phs * p.cdiv;
                     int u = phs - p.opad, moff = 0;
                     while (u < 0) { u += p.ostride; --moff; }
                     tma_load_4d(dst, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
@@ -520,8 +522,11 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             float2* stile = p.stats ? p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + c4o : nullptr;
             mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
             tc_fence_after();
+            auto run_chunks = [&](auto nres_c, auto y16_c) {
+            constexpr int NRES = decltype(nres_c)::value;
+            constexpr bool Y16 = decltype(y16_c)::value;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const int phs = (ch * 32) / p.cdiv;            // polyphase index of this column chunk (0 for a plain conv)
+                const int phs = (ch * 32) >> p.cshift;         // polyphase index of this column chunk (0 for a plain conv)
                 if (!full) {
                     vmask = 0;
 #pragma unroll
@@ -536,7 +541,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 // [32 rows][32 cols] fp32 region of this warp, 16-byte slots XOR-swizzled by (row & 7) -- the TMA
                 // SWIZZLE_128B layout of the residual box, and conflict-free for both access directions
                 uint32_t tile_u32;
-                if (p.nres) {
+                if (NRES) {
                     while (r_seq[rs] != rc) { }           // box set rc has been issued into this stage ...
                     mbar_wait_warp(&r_full[rs], rpar);    // ... and has landed
                     tile_u32 = smem_r_u32 + rs * r_stage_bytes + (uint32_t)(q * 32) * 128u;
@@ -555,7 +560,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         if (lane == 0) mbar_arrive(&acc_empty[acc]);
                     }
 #endif
-                    if (p.nres) {
+                    if (NRES) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 r = lds128(st_w + (((uint32_t)i ^ l7) << 4));
@@ -567,7 +572,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                             const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
                             v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
                         }
-                        if (p.nres == 2) {
+                        if (NRES == 2) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 r = lds128(st_w + (uint32_t)P_RBOX + (((uint32_t)i ^ l7) << 4));
@@ -585,14 +590,9 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 const uint32_t st_r0 = tile_u32 + (uint32_t)rr * 128u + ((l7 ^ (uint32_t)rr) << 4);               // rows rr, rr+8, ...
                 const uint32_t st_r1 = tile_u32 + (uint32_t)(rr + 4) * 128u + ((l7 ^ (uint32_t)(rr + 4)) << 4);   // rows rr+4, rr+12, ...
                 float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
-                float* yo = p.y16out ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ytile) + ch * 32) : ytile + ch * 32;
-                if (p.y16out) {
-                    if (full) pipe_store_rows<true, true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-                    else pipe_store_rows<false, true>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-                } else {
-                    if (full) pipe_store_rows<true, false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-                    else pipe_store_rows<false, false>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
-                }
+                float* yo = Y16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ytile) + ch * 32) : ytile + ch * 32;
+                if (full) pipe_store_rows<true, Y16>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
+                else pipe_store_rows<false, Y16>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
                 if (stile != nullptr) {
                     float s1[4] = {s1a.x, s1a.y, s1b.x, s1b.y}, s2[4] = {s2a.x, s2a.y, s2b.x, s2b.y};
 #pragma unroll
@@ -609,7 +609,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         *reinterpret_cast<float4*>(sp + 2) = make_float4(s1[2], s2[2], s1[3], s2[3]);
                     }
                 }
-                if (p.nres) {
+                if (NRES) {
                     fence_proxy_async();                  // our generic writes to the stage precede the next TMA fill
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&r_empty[rs]);
@@ -617,6 +617,16 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 } else {
                     __syncwarp();
                 }
+            }
+            };
+            // one specialisation per launch configuration (uniform over the grid): no per-chunk branches on kernel parameters
+            if (p.nres == 0) {
+                if (p.y16out) run_chunks(std::integral_constant<int, 0>{}, std::true_type{});
+                else run_chunks(std::integral_constant<int, 0>{}, std::false_type{});
+            } else if (p.nres == 1) {
+                run_chunks(std::integral_constant<int, 1>{}, std::false_type{});
+            } else {
+                run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
             }
 #ifdef PIPE_NO_EARLY
             tc_fence_before();
@@ -656,6 +666,7 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     }
     if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
     if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
+    if ((a.Cout & (a.Cout - 1)) != 0) return false;        // column -> phase is a shift
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
     // x16in / y16out: the intra-block tensor of AdaINResBlock1 stored as fp16 (plain stride-1 convs only)
     if ((a.x16in || a.y16out) && tr) return false;
@@ -682,6 +693,8 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.a_row0 = a.in_off - p.halo_min;
     p.rows = P_MT + span;
     p.ostride = a.out_stride; p.opad = a.out_pad; p.Tout = a.Tout; p.cdiv = a.Cout;
+    p.cshift = 0;
+    while ((1 << p.cshift) < a.Cout) ++p.cshift;
     {
         // activation blocks: the fewest equal blocks (whole passes of the owning warp) that fit a 12 KB slot
         const int rowb = p.cch * (a.x16in ? 2 : 4), rpp = 8;   // blocks are whole multiples of 8 rows (swizzle period)
