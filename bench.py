@@ -12,8 +12,9 @@ inside the timed step.
   value     whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the public drop-in module with HOST (pinned) inputs and the
             waveform copied back to the host inside the timed region
-  roofline  the dominant kernel (tcgen05 conv): algorithmic FLOPs / event-timed duration vs the
-            measured bf16 peak of MEASURED_PEAKS.json; `kernels` lists every category
+  roofline  the dominant kernel (conv_pipe_kernel: fused AdaIN/Snake -> tcgen05 conv -> residual/stats): algorithmic
+            bytes / event-timed duration vs the measured HBM copy peak of MEASURED_PEAKS.json; `kernels` lists
+            every kernel category with its time share, TFLOP/s and GB/s
   cpu_baseline  the torch-CPU port of the reference decoder (oracle/decoder_torch.py) on the host cores (rank 0, N=1)
 
 --impl reference times that same CPU port (the reference itself is pure Python/PyTorch and
@@ -163,7 +164,7 @@ class ClockSampler:
 
 # DRAM bytes per launch of a kernel category, from the committed ncu launch list (profiles/<tag>_traffic.json,
 # written by tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)
-CATEGORY_KERNELS = {"conv_fused": ("conv_pipe_kernel", "conv_fused_kernel"), "conv_tc": ("conv_tc_kernel",),
+CATEGORY_KERNELS = {"conv_pipe": ("conv_pipe_kernel",), "conv_fused": ("conv_fused_kernel",), "conv_tc": ("conv_tc_kernel",),
                     "conv_simt": ("conv_simt_kernel",)}
 
 
@@ -301,7 +302,7 @@ def run_b200(a, rank, local_rank, world):
     for c in kernels:
         kernels[c]["share"] = round(kernels[c]["ms_per_step"] / prof_ms_step, 4)
     dom = max(kernels, key=lambda c: kernels[c]["ms_per_step"])
-    if dom in ("conv_tc", "conv_simt"):
+    if dom in ("conv_tc", "conv_simt", "conv_fused"):
         v = prof_acc[dom]
         achieved = v["flops"] / v["ms"] / 1e9
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",

@@ -57,8 +57,9 @@ enum ProfCat {
     PC_SOURCE = 5,      // SineGen + harmonic source (+ STFT front)  (bound: hbm)
     PC_POST = 6,        // Snake + conv_post + tanh / iSTFT head     (bound: hbm)
     PC_MISC = 7,        // layout, style fc, pool, taps
-    PC_CONV_FUSED = 8,  // fused AdaIN/act -> tcgen05 conv -> residual/stats epilogue (bound: hbm for C <= 128)
-    PC_COUNT = 9
+    PC_CONV_FUSED = 8,  // conv_fused_kernel: fused AdaIN/act -> tcgen05 conv -> residual/stats, register-staged (256-ch: tensor)
+    PC_CONV_PIPE = 9,   // conv_pipe_kernel: the same fusion fully TMA-fed (C <= 128, ups; bound: hbm / shared memory)
+    PC_COUNT = 10
 };
 
 // ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------

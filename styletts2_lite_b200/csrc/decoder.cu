@@ -531,7 +531,7 @@ struct Exec {
         const double bytes = (double)B * ((double)w.Cin * Tin * (x16in ? 2 : 4) +
                                           (double)w.Cout * Tout * ((y16out ? 2 : 4) + 4 * ((res ? 1 : 0) + (accumulate ? 1 : 0)))) +
                              (double)w.k * w.Cin * w.Cout * 2;
-        prof(PC_CONV_FUSED, flops, bytes);
+        prof(conv_pipe_supported(a) ? PC_CONV_PIPE : PC_CONV_FUSED, flops, bytes);
     }
 
     // AdainResBlk1d.forward (hifigan.py:400-403).  x [B,T,ld_x] (Cin real channels) -> y [B,T or 2T,ld_y]
@@ -947,7 +947,7 @@ int st2_profile_num_categories(void) { return st2::PC_COUNT; }
 
 const char* st2_profile_category_name(int32_t cat) {
     static const char* names[st2::PC_COUNT] = {"conv_tc", "conv_simt", "norm_stats", "norm_coef", "affine_act",
-                                               "source", "post", "misc", "conv_fused"};
+                                               "source", "post", "misc", "conv_fused", "conv_pipe"};
     return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
 }
 
