@@ -120,6 +120,11 @@ ST2_API int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f
  * "generator.resblocks.5.iter2", "generator.stage1.out", ...). */
 ST2_API int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t capacity);
 
+/* Optional device-resident Philox seed: when set (non-NULL), the harmonic source reads its noise seed from *dev_seed
+ * at run time instead of the `seed` argument of st2_decoder_forward, so a forward captured in a CUDA graph
+ * (the forward allocates nothing and never synchronises) draws new noise on every replay.  NULL restores `seed`. */
+ST2_API int st2_decoder_set_seed_buffer(st2_decoder* d, const uint64_t* dev_seed);
+
 /* how many kernels of this library the last forward launched */
 ST2_API int64_t st2_decoder_last_launch_count(const st2_decoder* d);
 

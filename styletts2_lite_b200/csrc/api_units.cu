@@ -35,7 +35,7 @@ int st2_har_source(const float* f0, const float* noise, uint64_t seed, const flo
                 "har_source: bad argument");
     int e = launch_sinegen_frames(f0, frames_scratch, B, L2, upsample_scale, (cudaStream_t)stream);
     if (e != ST2_OK) return e;
-    return launch_har_source(f0, frames_scratch, noise, seed, lin_w, lin_b, har, B, L2, upsample_scale,
+    return launch_har_source(f0, frames_scratch, noise, seed, nullptr, lin_w, lin_b, har, B, L2, upsample_scale,
                              (cudaStream_t)stream);
 }
 

@@ -103,7 +103,7 @@ int launch_pack_w16(const float* wp, void* w16, int k, int Cin, int Cout, int Ci
 // source / stft (kernels_source.cu; compiled without fast-math)
 int launch_sinegen_frames(const float* f0, float* frames, int B, int L2, int scale, cudaStream_t st);
 int launch_sinegen_phase(const float* frames, float* phase, int B, int L2, int scale, cudaStream_t st);
-int launch_har_source(const float* f0, const float* frames, const float* noise, uint64_t seed,
+int launch_har_source(const float* f0, const float* frames, const float* noise, uint64_t seed, const uint64_t* seed_dev,
                       const float* lin_w, const float* lin_b, float* har, int B, int L2, int scale,
                       cudaStream_t st);
 int launch_stft_transform(const float* har, const float* wr, const float* wi, float* out, int ld_out, int B,

@@ -78,6 +78,7 @@ struct st2_decoder {
     std::vector<void*> allocs;
     int64_t num_params = 0;
     int64_t last_launches = 0;
+    const uint64_t* seed_dev = nullptr;     // optional device-resident Philox seed (st2_decoder_set_seed_buffer)
     bool tc_ok = false;
 
     ResBlk1dW encode, decode[4];
@@ -703,7 +704,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim,
                4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * c.dim_in * T + 4.0 * B * L2));
         E.chk(launch_sinegen_frames(f0, frames, B, L2, up_scale, st));
-        E.chk(launch_har_source(f0, frames, noise, seed, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
+        E.chk(launch_har_source(f0, frames, noise, seed, d->seed_dev, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
         // SineGen algorithmic bytes: read 4*B*2T (+ 36*B*S of noise when taped), write 4*B*S
         E.prof(PC_SOURCE, 0, 4.0 * B * L2 + (noise ? 36.0 * B * S : 0.0) + 4.0 * B * S);
         if (istft) {
@@ -931,6 +932,12 @@ int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t ca
     ST2_REQUIRE(d && name, "set_tap: bad argument");
     if (dst == nullptr) d->taps.erase(name);
     else d->taps[name] = st2::Tap{dst, capacity};
+    return ST2_OK;
+}
+
+int st2_decoder_set_seed_buffer(st2_decoder* d, const uint64_t* dev_seed) {
+    ST2_REQUIRE(d != nullptr, "set_seed_buffer: null handle");
+    d->seed_dev = dev_seed;
     return ST2_OK;
 }
 

@@ -116,8 +116,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 static constexpr int kSrcTile = 256;
 __global__ void __launch_bounds__(kSrcTile)
 har_source_kernel(const float* __restrict__ f0, const float* __restrict__ frames, const float* __restrict__ noise,
-                  uint64_t seed, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
-                  float* __restrict__ har, int L2, int S, int scale, float inv_scale) {
+                  uint64_t seed, const uint64_t* __restrict__ seed_dev, const float* __restrict__ lin_w,
+                  const float* __restrict__ lin_b, float* __restrict__ har, int L2, int S, int scale, float inv_scale) {
     __shared__ float snz[kSrcTile * kH];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * kSrcTile;
@@ -135,6 +135,7 @@ har_source_kernel(const float* __restrict__ f0, const float* __restrict__ frames
         for (int h = 0; h < kH; ++h) nz[h] = snz[threadIdx.x * kH + h];
     } else {
         const uint64_t idx = (uint64_t)b * (uint64_t)S + (uint64_t)n;
+        if (seed_dev != nullptr) seed = __ldg(seed_dev);         // seed in device memory: a captured CUDA graph replays with new noise
         const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -164,11 +165,11 @@ har_source_kernel(const float* __restrict__ f0, const float* __restrict__ frames
     har[(size_t)b * S + n] = tanhf(acc);
 }
 
-int launch_har_source(const float* f0, const float* frames, const float* noise, uint64_t seed, const float* lin_w,
-                      const float* lin_b, float* har, int B, int L2, int scale, cudaStream_t st) {
+int launch_har_source(const float* f0, const float* frames, const float* noise, uint64_t seed, const uint64_t* seed_dev,
+                      const float* lin_w, const float* lin_b, float* har, int B, int L2, int scale, cudaStream_t st) {
     const int S = L2 * scale;
     dim3 grid(cdiv(S, kSrcTile), B);
-    har_source_kernel<<<grid, kSrcTile, 0, st>>>(f0, frames, noise, seed, lin_w, lin_b, har, L2, S, scale,
+    har_source_kernel<<<grid, kSrcTile, 0, st>>>(f0, frames, noise, seed, seed_dev, lin_w, lin_b, har, L2, S, scale,
                                                  (float)(1.0 / (double)scale));
     ST2_LAUNCH_CHECK();
     return ST2_OK;

@@ -55,12 +55,14 @@ class B200Decoder(nn.Module):
         self._dirty = True
         self._workspace: Optional[torch.Tensor] = None
         self._taps: Dict[str, torch.Tensor] = {}
+        self._graphs: Dict[tuple, dict] = {}
         self.train(False)
 
     # ---- weights -------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self._dirty = True
+        self._graphs.clear()
         return r
 
     def load_state_dict(self, state_dict, strict: bool = True, *a, **k):
@@ -71,6 +73,7 @@ class B200Decoder(nn.Module):
     def refresh_weights(self) -> None:
         """Re-pack after an in-place parameter update."""
         self._dirty = True
+        self._graphs.clear()
 
     def _sync(self, device: torch.device) -> None:
         lib = _lib.load()
@@ -117,8 +120,56 @@ class B200Decoder(nn.Module):
             _lib.load().st2_decoder_set_tap(self._handle, name.encode(), None, 0)
         self._taps.clear()
 
+    # ---- CUDA-graph replay for small batches ------------------------------------------------
+    def _forward_graph(self, asr, F0_curve, N, s, seed, prec_name):
+        """One captured graph per (B, T, precision, device): the ~270 launches of a forward replay as one graph launch.
+        Inputs are copied into the graph's static buffers, the Philox seed lives in device memory
+        (st2_decoder_set_seed_buffer), the returned waveform is a copy of the static output."""
+        lib = _lib.load()
+        dev = asr.device
+        B, _, T = asr.shape
+        prec = _lib.PREC[prec_name]
+        key = (B, T, prec, dev.index)
+        g = self._graphs.get(key)
+        if g is None:
+            S = self.cfg.samples_per_frame * T
+            need = _lib.check(lib.st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
+            g = {"asr": torch.empty(B, self.cfg.dim_in, T, device=dev), "f0": torch.empty(B, 2 * T, device=dev),
+                 "n": torch.empty(B, 2 * T, device=dev), "s": torch.empty(B, self.cfg.style_dim, device=dev),
+                 "seed": torch.zeros(1, dtype=torch.int64, device=dev), "out": torch.empty(B, 1, S, device=dev),
+                 "ws": torch.empty(need, dtype=torch.uint8, device=dev)}
+            for k_, t in (("asr", asr), ("f0", F0_curve), ("n", N), ("s", s)):
+                g[k_].copy_(t)
+
+            def launch():
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                _lib.check(lib.st2_decoder_forward(self._handle, _lib.ptr(g["asr"]), _lib.ptr(g["f0"]), _lib.ptr(g["n"]),
+                                                   _lib.ptr(g["s"]), None, C.c_uint64(0), _lib.ptr(g["out"]), B, T, prec,
+                                                   _lib.ptr(g["ws"]), g["ws"].numel(), C.c_void_p(stream)),
+                           "st2_decoder_forward (graph capture)")
+
+            _lib.check(lib.st2_decoder_set_seed_buffer(self._handle, _lib.ptr(g["seed"])), "set_seed_buffer")
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    launch()                                    # eager warm-up (function attributes, tensor-map driver entry)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch()
+            finally:
+                lib.st2_decoder_set_seed_buffer(self._handle, None)
+            g["graph"] = graph
+            self._graphs[key] = g
+        for k_, t in (("asr", asr), ("f0", F0_curve), ("n", N), ("s", s)):
+            g[k_].copy_(t, non_blocking=True)
+        g["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+        g["graph"].replay()
+        return g["out"].clone()
+
     def forward(self, asr, F0_curve, N, s, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
-                precision: Optional[str] = None):
+                precision: Optional[str] = None, cuda_graph: bool = False):
         if self.training:
             raise RuntimeError("B200Decoder is inference-only (the reference's training-time F0/N smoothing, "
                                "hifigan.py:447-455, is out of scope); call .eval()")
@@ -144,6 +195,8 @@ class B200Decoder(nn.Module):
                 noise_ = noise.detach().float().contiguous()
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # global torch RNG, like the reference
+            if cuda_graph and noise_ is None and not self._taps:
+                return self._forward_graph(asr_, f0_, n_, s_, seed, precision or self.precision)
             need = _lib.check(lib.st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None

@@ -275,3 +275,23 @@ def test_full_size_tensor_core_path_tracks_fp32_path(variant, B, T):
     snr = snr_db(ref, out)
     G.log("full_size_tc_vs_fp32", variant=variant, B=B, T=T, snr_db=snr)
     assert snr >= 40.0
+
+
+@pytest.mark.parametrize("variant", ["hifigan", "istftnet"])
+def test_cuda_graph_replay_matches_eager(variant):
+    """forward(..., cuda_graph=True) captures the launches once per shape and replays them; the Philox seed is read from
+    device memory, so a replay with another seed must equal the eager forward with that seed bit for bit."""
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    m = _decoder(cfg)
+    for B, T in ((1, 30), (2, 12)):
+        a = {k: v.cuda() for k, v in synth.make_inputs(B, T, seed=50 + T, cfg=cfg, with_noise=False).items()}
+        b = {k: v.cuda() for k, v in synth.make_inputs(B, T, seed=60 + T, cfg=cfg, with_noise=False).items()}
+        with torch.no_grad():
+            for inp, seed in ((a, 11), (b, 2 ** 63 + 5), (a, 12)):
+                eager = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], seed=seed, precision="bf16")
+                graph = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], seed=seed, precision="bf16", cuda_graph=True)
+                torch.cuda.synchronize()
+                assert torch.equal(eager, graph), (variant, B, T, seed)
+            e1 = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=11, precision="bf16")
+            e2 = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=12, precision="bf16")
+            assert not torch.equal(e1, e2)       # the seed really changes the noise
