@@ -36,10 +36,12 @@
 namespace st2 {
 
 static constexpr int P_LW = 6;                           // transform warps
-static constexpr int P_EW = 8;                           // epilogue warps
+static constexpr int P_EW = 8;                           // epilogue warps of the 2-group kernel (staging buffers of non-residual layers)
 static constexpr int P_W_X0 = 2;                         // first transform warp
 static constexpr int P_W_EPI0 = P_W_X0 + P_LW;           // first epilogue warp (8)
-static constexpr int P_THREADS = (P_W_EPI0 + P_EW) * 32; // 512
+// threads: (8 + 4*EG) warps.  EG = 2 epilogue groups (512 threads, 128 registers) is the default; the 32-channel layers with
+// a residual are epilogue-bound and run EG = 3 (640 threads, 96 registers): 0.53 -> 0.47 ms on the k=3 layer, while
+// transform-bound layers lose with the smaller register budget.
 static constexpr int P_MT = 128;                         // rows per tile
 static constexpr int P_XSLOT_MAX = 12288;                 // largest activation ring slot
 static constexpr int P_RBOX = P_MT * 32 * 4;             // one residual box: 128 rows x 32 fp32
@@ -60,6 +62,7 @@ struct PipeParams {
     int bn, mtiles, num_tiles;
     int wstages, resident, tmem_cols;
     int na, nacc, nacc_log2;    // operand (A) buffers 2..4, TMEM accumulators 2 or 4
+    int eg;                     // epilogue groups of the kernel variant launched (2 or 3)
     int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
     // epilogue
     const float* bias;
@@ -141,8 +144,8 @@ __device__ __forceinline__ void pipe_store_rows(uint32_t st_r0, uint32_t st_r1, 
     }
 }
 
-template <int ACT, bool BF16, bool X16>
-__global__ void __launch_bounds__(P_THREADS, 1)
+template <int ACT, bool BF16, bool X16, int EG>
+__global__ void __launch_bounds__((P_W_EPI0 + 4 * EG) * 32, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
                  const __grid_constant__ CUtensorMap map_o, const PipeParams p) {
@@ -214,7 +217,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // K columns the transform never writes (32-channel layer in a 64-wide operand) stay zero for the whole kernel
-    for (uint32_t i = threadIdx.x; i < (uint32_t)p.na * a_bytes / 16; i += P_THREADS)
+    for (uint32_t i = threadIdx.x; i < (uint32_t)p.na * a_bytes / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
@@ -487,7 +490,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         }
     } else {
         // ===== epilogue: TMEM -> (+ residual in the drain layout) -> transposition -> bias/scale -> global, statistics =====
-        const int ew = warp - P_W_EPI0;                   // 0..7
+        const int ew = warp - P_W_EPI0;                   // 0 .. 4*EG-1
         const int grp = ew >> 2;                          // accumulator / tile parity this group owns
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
         const int rr = lane >> 3;                         // 0..3: row within a 4-row pass
@@ -506,7 +509,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
         uint32_t tcnt = 0;
         PTile ti;
         for (ti.init(p); ti.valid(p); ti.next(p), ++tcnt) {
-            if ((int)(tcnt & 1) != grp) {
+            if ((int)(tcnt % (uint32_t)EG) != grp) {
                 if (p.nres) r_advance(nchunks);           // the other group's tile
                 continue;
             }
@@ -686,6 +689,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.x16in = a.x16in; p.is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
     p.k32 = (a.Cin == 32 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
     const int ph = a.phases;               // 1, or the stride of a transposed conv (columns = ph * Cout)
+    const bool tr_ = a.phases > 1;
     p.B = a.B; p.M = a.M; p.Tin = a.Tin; p.Cout = ph * a.Cout;
     p.ntaps = a.ntaps; p.tap_step = a.tap_step;
     const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
@@ -721,6 +725,8 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     while (cols < p.nacc * p.bn) cols <<= 1;
     p.tmem_cols = cols;
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+    p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
+    if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && p.nres > 0 && !tr_)) p.eg = v; }
     p.bias = a.bias; p.scale = a.scale; p.y16out = a.y16out;
     p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout]); out_pad = 0 when y16out
     p.ld_y = ph * a.ld_y;
@@ -830,11 +836,13 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-#define PIPE_ATTR(A, BF, X) ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<A, BF, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
-        PIPE_ATTR(ACT_NONE, true, false); PIPE_ATTR(ACT_NONE, false, false);
-        PIPE_ATTR(ACT_LRELU, true, false); PIPE_ATTR(ACT_LRELU, false, false);
-        PIPE_ATTR(ACT_SNAKE, true, false); PIPE_ATTR(ACT_SNAKE, false, false);
-        PIPE_ATTR(ACT_SNAKE, true, true); PIPE_ATTR(ACT_SNAKE, false, true);
+#define PIPE_ATTR(A, BF, X, G) ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<A, BF, X, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        PIPE_ATTR(ACT_NONE, true, false, 2); PIPE_ATTR(ACT_NONE, false, false, 2);
+        PIPE_ATTR(ACT_LRELU, true, false, 2); PIPE_ATTR(ACT_LRELU, false, false, 2);
+        PIPE_ATTR(ACT_SNAKE, true, false, 2); PIPE_ATTR(ACT_SNAKE, false, false, 2);
+        PIPE_ATTR(ACT_SNAKE, true, true, 2); PIPE_ATTR(ACT_SNAKE, false, true, 2);
+        PIPE_ATTR(ACT_SNAKE, true, false, 3); PIPE_ATTR(ACT_SNAKE, false, false, 3);
+        PIPE_ATTR(ACT_SNAKE, true, true, 3); PIPE_ATTR(ACT_SNAKE, false, true, 3);
 #undef PIPE_ATTR
     }
     int grid = num_sms;
@@ -845,14 +853,20 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
                 p.num_tiles);
     ST2_REQUIRE(act != ACT_SNAKE || alpha != nullptr, "conv_pipe: snake needs alpha");
     ST2_REQUIRE(!a.x16in || act == ACT_SNAKE, "conv_pipe: 16-bit input is only built for the Snake transform");
-#define PIPE_LAUNCH(A, BF, X) conv_pipe_kernel<A, BF, X><<<grid, P_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
+    if (act != ACT_SNAKE) p.eg = 2;                          // the 3-group variant is only built for Snake
+#define PIPE_LAUNCH(A, BF, X, G) conv_pipe_kernel<A, BF, X, G><<<grid, (P_W_EPI0 + 4 * G) * 32, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
     const bool bf = p.is_bf16 != 0;
     switch (act) {
-        case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true, false); else PIPE_LAUNCH(ACT_NONE, false, false); break;
-        case ACT_LRELU: if (bf) PIPE_LAUNCH(ACT_LRELU, true, false); else PIPE_LAUNCH(ACT_LRELU, false, false); break;
+        case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true, false, 2); else PIPE_LAUNCH(ACT_NONE, false, false, 2); break;
+        case ACT_LRELU: if (bf) PIPE_LAUNCH(ACT_LRELU, true, false, 2); else PIPE_LAUNCH(ACT_LRELU, false, false, 2); break;
         case ACT_SNAKE:
-            if (a.x16in) { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, true); else PIPE_LAUNCH(ACT_SNAKE, false, true); }
-            else { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, false); else PIPE_LAUNCH(ACT_SNAKE, false, false); }
+            if (p.eg == 3) {
+                if (a.x16in) { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, true, 3); else PIPE_LAUNCH(ACT_SNAKE, false, true, 3); }
+                else { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, false, 3); else PIPE_LAUNCH(ACT_SNAKE, false, false, 3); }
+            } else {
+                if (a.x16in) { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, true, 2); else PIPE_LAUNCH(ACT_SNAKE, false, true, 2); }
+                else { if (bf) PIPE_LAUNCH(ACT_SNAKE, true, false, 2); else PIPE_LAUNCH(ACT_SNAKE, false, false, 2); }
+            }
             break;
         default: set_error("conv_pipe: bad act %d", act); return ST2_ERR_INVALID;
     }
