@@ -186,7 +186,7 @@ int st2_adain_conv1d_fused(const float* x, const float* h, const float* alpha, i
     ST2_REQUIRE(conv_fused_supported(a), "adain_conv1d_fused: geometry not supported by the fused kernels");
     e = launch_conv_fused(a, coef, Cin, act, slope, alpha, h_next ? parts : nullptr, st);
     if (e != ST2_OK) return e;
-    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, T, Cout, Cout, nullptr, st);
+    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, T, Cout, Cout, st);
     return e;
 }
 
@@ -250,7 +250,7 @@ int st2_act_conv_transpose1d_fused(const float* x, const float* alpha, int32_t a
     ST2_REQUIRE(conv_fused_supported(a), "act_conv_transpose1d_fused: geometry not supported by the fused kernels");
     e = launch_conv_fused(a, coef, Cin, act, slope, alpha, h_next ? parts : nullptr, st);
     if (e != ST2_OK) return e;
-    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, a.Tout, Cout, Cout, nullptr, st);
+    if (h_next != nullptr) e = launch_adain_coef_f2(parts, fused_stats_parts(a), h_next, 2 * Cout, 0, coef_next, B, a.Tout, Cout, Cout, st);
     return e;
 }
 

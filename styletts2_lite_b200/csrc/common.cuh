@@ -154,9 +154,7 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
 bool conv_pipe_supported(const ConvArgs& a);
 int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
                      void* stats_out, cudaStream_t st);
-int64_t adain_coef_f2_scratch_bytes(int B);     // scratch of launch_adain_coef_f2 (tickets first, zeroed once per forward)
-int64_t adain_coef_f2_ticket_bytes(int B);
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
-                         int C, int Cpad, void* scratch, cudaStream_t st);
+                         int C, int Cpad, cudaStream_t st);
 
 }  // namespace st2

@@ -570,28 +570,20 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 }
 
 // ---------------------------------------------------------------- coefficients from float2 tile partials
-// grid (ceil(Cpad/32), B, split), block (32 channels x 32 slices of the partial list): CTA z sums the z-th contiguous
-// range of the list, each thread every 32nd partial of it (8 independent loads in flight), then a fixed-order tree over
-// the 32 slices.  With split > 1 the range sums go to a scratch array and the last CTA to arrive (ticket counter, reset by
-// that CTA) adds them in the order z = 0, 1, ... -> deterministic whatever the arrival order.  The 32/64-channel layers
-// have 3752 / 1876 partials per (b, c) and were latency-bound with one CTA per (b, 32 channels).
+// grid (ceil(Cpad/32), B), block (32 channels x 32 slices of the partial list): each thread sums every 32nd partial
+// (8 independent loads in flight), then a fixed-order tree over the 32 slices -> deterministic.
 __global__ void __launch_bounds__(1024)
 adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float* __restrict__ h, int ld_h, int h_off,
-                     float* __restrict__ coef, int T, int C, int Cpad, double2* __restrict__ split_sums,
-                     unsigned int* __restrict__ tickets) {
+                     float* __restrict__ coef, int T, int C, int Cpad) {
     __shared__ double ssum[32][33], ssq[32][33];
-    __shared__ unsigned int s_ticket;
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     const int b = blockIdx.y;
-    const int split = gridDim.z, z = blockIdx.z;
-    const int per = (nparts + split - 1) / split;
-    const int i0 = z * per, i1 = min(nparts, i0 + per);
     double s = 0, ss = 0;
     if (c < C) {
         const float2* pp = partial + (size_t)b * nparts * C + c;
-        int i = i0 + py;
-        for (; i + 7 * 32 < i1; i += 8 * 32) {
+        int i = py;
+        for (; i + 7 * 32 < nparts; i += 8 * 32) {
             float2 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = __ldg(pp + (size_t)(i + u * 32) * C);
@@ -601,7 +593,7 @@ adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float
                 ss += (double)v[u].y;
             }
         }
-        for (; i < i1; i += 32) {
+        for (; i < nparts; i += 32) {
             const float2 v = __ldg(pp + (size_t)i * C);
             s += (double)v.x;
             ss += (double)v.y;
@@ -610,36 +602,13 @@ adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float
     ssum[py][cx] = s;
     ssq[py][cx] = ss;
     __syncthreads();
-    if (py == 0) {
+    if (py != 0 || c >= Cpad) return;
+    float a = 0.f, bb = 0.f;
+    if (c < C) {
         for (int i = 1; i < 32; ++i) {
             s += ssum[i][cx];
             ss += ssq[i][cx];
         }
-    }
-    if (split > 1) {
-        // range sums -> scratch; the last CTA of this (b, channel block) finishes
-        const size_t slot = ((size_t)b * gridDim.x + blockIdx.x) * split;
-        if (py == 0) split_sums[(slot + z) * 32 + cx] = make_double2(s, ss);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[(size_t)b * gridDim.x + blockIdx.x], 1u);
-        __syncthreads();
-        if (s_ticket != (unsigned int)(split - 1)) return;
-        __threadfence();
-        if (py == 0) {
-            s = 0;
-            ss = 0;
-            for (int k = 0; k < split; ++k) {
-                const double2 v = __ldcg(&split_sums[(slot + k) * 32 + cx]);
-                s += v.x;
-                ss += v.y;
-            }
-        }
-        if (threadIdx.x == 0) tickets[(size_t)b * gridDim.x + blockIdx.x] = 0u;     // ready for the next launch
-    }
-    if (py != 0 || c >= Cpad) return;
-    float a = 0.f, bb = 0.f;
-    if (c < C) {
         const double mean = s / (double)T;
         double var = ss / (double)T - mean * mean;
         if (var < 0) var = 0;
@@ -654,26 +623,10 @@ adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float
     coef[((size_t)b * 2 + 1) * Cpad + c] = bb;
 }
 
-// scratch: adain_coef_f2_scratch_bytes(B) bytes whose first 4*B*kCoefMaxBlocks bytes (the tickets) are zero before the
-// first launch (every launch leaves them zero again); nullptr = one CTA per (b, 32 channels)
-static constexpr int kCoefMaxSplit = 8, kCoefMaxBlocks = 8;          // channel blocks: C <= 256
-int64_t adain_coef_f2_scratch_bytes(int B) {
-    return (int64_t)B * kCoefMaxBlocks * 4 + 256 + (int64_t)B * kCoefMaxBlocks * kCoefMaxSplit * 32 * sizeof(double2);
-}
-int64_t adain_coef_f2_ticket_bytes(int B) { return (int64_t)B * kCoefMaxBlocks * 4; }
-
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
-                         int C, int Cpad, void* scratch, cudaStream_t st) {
-    int split = 1;
-    if (scratch != nullptr && cdiv(Cpad, 32) <= kCoefMaxBlocks) {
-        split = nparts / 384;                                            // >= ~12 partials per thread and range
-        if (split > kCoefMaxSplit) split = kCoefMaxSplit;
-        if (split < 1) split = 1;
-    }
-    dim3 grid(cdiv(Cpad, 32), B, split);
-    unsigned int* tickets = (unsigned int*)scratch;
-    double2* sums = scratch ? (double2*)((char*)scratch + ((adain_coef_f2_ticket_bytes(B) + 255) / 256 * 256)) : nullptr;
-    adain_coef_f2_kernel<<<grid, 1024, 0, st>>>((const float2*)partial, nparts, h, ld_h, h_off, coef, T, C, Cpad, sums, tickets);
+                         int C, int Cpad, cudaStream_t st) {
+    dim3 grid(cdiv(Cpad, 32), B);
+    adain_coef_f2_kernel<<<grid, 1024, 0, st>>>((const float2*)partial, nparts, h, ld_h, h_off, coef, T, C, Cpad);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

@@ -319,7 +319,6 @@ struct Exec {
     int err = ST2_OK;
     const float* H = nullptr; // style rows [B][fc_rows]
     float* coef = nullptr;    // [B][2][2048]
-    void* coef_scratch = nullptr;   // tickets + range sums of adain_coef_f2_kernel
     int coef_ld = 0;          // stride the last coefficient kernel wrote with
 
     void* alloc(int64_t bytes) {
@@ -482,7 +481,7 @@ struct Exec {
         if (n == nullptr || !sr.f2)
             chk(launch_adain_coef(n ? sr.ptr : nullptr, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
         else
-            chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, coef_scratch, st));
+            chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
         prof(PC_NORM_COEF, 0, 0);
         coef_ld = Cpad;
     }
@@ -668,8 +667,6 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     float* H = E.allocf((int64_t)B * d->fc_rows);
     E.H = H;
     E.coef = E.allocf((int64_t)B * 2 * 2048);
-    E.coef_scratch = E.alloc(adain_coef_f2_scratch_bytes(B));
-    if (E.live()) E.chk(cudaMemsetAsync(E.coef_scratch, 0, (size_t)adain_coef_f2_ticket_bytes(B), st) == cudaSuccess ? ST2_OK : ST2_ERR_CUDA);
     float* frames = E.allocf((int64_t)B * L2 * 9);
     float* har = E.allocf((int64_t)B * S);
     float* x514 = E.allocf((int64_t)B * T * LD514);
