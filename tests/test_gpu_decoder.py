@@ -295,3 +295,25 @@ def test_cuda_graph_replay_matches_eager(variant):
             e1 = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=11, precision="bf16")
             e2 = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=12, precision="bf16")
             assert not torch.equal(e1, e2)       # the seed really changes the noise
+
+
+def test_pipelined_serving_loop_matches_direct_forward():
+    """streaming.PipelinedDecoder (pinned H2D / forward / pinned D2H on three streams) returns, batch by batch and in order,
+    exactly what the module returns for the same inputs and seeds -- including a change of shape between batches."""
+    from styletts2_lite_b200.streaming import PipelinedDecoder
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    shapes = [(2, 9), (2, 9), (3, 14), (2, 9), (1, 30)]
+    batches = [{k: v.pin_memory() for k, v in synth.make_inputs(B, T, seed=300 + i, cfg=cfg, with_noise=False).items()}
+               for i, (B, T) in enumerate(shapes)]
+    direct = []
+    with torch.no_grad():
+        for i, b in enumerate(batches):
+            direct.append(m(b["asr"].cuda(), b["F0_curve"].cuda(), b["N"].cuda(), b["s"].cuda(), seed=900 + i,
+                            precision="bf16").cpu())
+    pipe = PipelinedDecoder(m, precision="bf16")
+    got = [w.clone() for w in pipe.decode(batches, iter(range(900, 900 + len(batches))))]
+    assert len(got) == len(direct)
+    for i, (a, b) in enumerate(zip(direct, got)):
+        assert a.shape == b.shape and torch.equal(a, b), i
+    assert list(pipe.decode([])) == []
