@@ -103,7 +103,7 @@ def cpu_port_run(variant, frames, steps, warmup):
 
 def run_reference(a, rank, world):
     if rank != 0:
-        return
+        return None
     frames = a.cpu_frames or a.frames
     steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
     r = cpu_port_run(a.variant, frames, steps, warmup)
@@ -113,7 +113,7 @@ def run_reference(a, rank, world):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -343,7 +343,7 @@ def run_b200(a, rank, local_rank, world):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
     h2d = sum(host[k].numel() * 4 for k in ("asr", "F0_curve", "N", "s"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -359,9 +359,24 @@ def run_b200(a, rank, local_rank, world):
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_port_run(a.variant, a.cpu_frames or a.frames, 2, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+class _StdoutToStderr:
+    """Library banners (e.g. "NCCL version ..." on stdout) must not mix with the one JSON line: while active, file descriptor 1
+    points at stderr; the JSON line is printed after restore()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -369,10 +384,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.impl == "reference":
-        run_reference(a, rank, world)
-    else:
-        run_b200(a, rank, local_rank, world)
+    guard = _StdoutToStderr()
+    line = run_reference(a, rank, world) if a.impl == "reference" else run_b200(a, rank, local_rank, world)
+    guard.restore()
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

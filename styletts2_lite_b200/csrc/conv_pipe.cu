@@ -555,22 +555,16 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)(ch * 32), v);
-#ifndef PIPE_NO_EARLY
                     if (ch == nchunks - 1) {
                         // the accumulator is in registers: hand it back to the MMA warp before the stores
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[acc]);
                     }
-#endif
                     if (NRES) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 r = lds128(st_w + (((uint32_t)i ^ l7) << 4));
-#ifdef PIPE_SCALAR_RES
-                            v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-                            continue;
-#endif
                             const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(r.x, r.y));
                             const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
                             v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
@@ -631,11 +625,6 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             } else {
                 run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
             }
-#ifdef PIPE_NO_EARLY
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
-#endif
         }
     }
     tc_fence_before();
