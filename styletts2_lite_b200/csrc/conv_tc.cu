@@ -148,14 +148,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int t = m * p.out_stride + ph - p.out_pad;
         const bool row_ok = (m < p.M) && (t >= 0) && (t < p.Tout);
         const bool vec = (p.Cout % 4 == 0) && (p.ld_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool vres = vec && p.res != nullptr && (p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+        const bool vbias = p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (n0 % 4 == 0);
         for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            const int co = n0 + c0;
+            const bool full16 = vec && co + 16 <= p.Cout;
+            // residual rows of this chunk: 128-bit loads issued before the accumulator is drained
+            float4 rv[4];
+            if (row_ok && full16 && vres && !(p.mirror && t == 2)) {
+                const float* rp = p.res + ((size_t)b * (p.Tout >> p.res_shift) + (t >> p.res_shift)) * p.ld_res + co;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
+            }
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective
-            const int co = n0 + c0;
             if (!row_ok || co >= p.Cout) continue;
+            if (full16 && vbias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (p.bias != nullptr && co + i < p.Cout) v[i] += __ldg(p.bias + co + i);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co) + i);
+                    v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (p.bias != nullptr && co + i < p.Cout) v[i] += __ldg(p.bias + co + i);
+            }
             const int nrep = (p.mirror && t == 2) ? 2 : 1;
             for (int rep = 0; rep < nrep; ++rep) {
                 const int tt = rep == 0 ? t : 0;
@@ -163,13 +181,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) o[i] = v[i];
                 if (p.res != nullptr) {
-                    const float* rp = p.res + ((size_t)b * (p.Tout >> p.res_shift) + (tt >> p.res_shift)) * p.ld_res + co;
+                    if (full16 && vres && nrep == 1) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (co + i < p.Cout) o[i] += rp[i];
+                        for (int i = 0; i < 4; ++i) {
+                            o[4 * i] += rv[i].x; o[4 * i + 1] += rv[i].y; o[4 * i + 2] += rv[i].z; o[4 * i + 3] += rv[i].w;
+                        }
+                    } else {
+                        const float* rp = p.res + ((size_t)b * (p.Tout >> p.res_shift) + (tt >> p.res_shift)) * p.ld_res + co;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (co + i < p.Cout) o[i] += rp[i];
+                    }
                 }
                 float* yp = p.y + ((size_t)b * p.Tout + tt) * p.ld_y + co;
-                if (vec && co + 16 <= p.Cout) {
+                if (full16) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         float4 r = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
