@@ -70,27 +70,52 @@ int launch_f0n_conv(const float* f0, const float* n, const float* wf, const floa
 }
 
 // ---- all AdaIN fc layers at once: h[B][R] = s[B][K] @ W[R][K]^T + bias[R] ------------------
-// (the 106 nn.Linear(style_dim, 2C) of hifigan.py:18,21; one warp per output row)
-__global__ void style_fc_kernel(const float* __restrict__ s, const float* __restrict__ W,
-                                const float* __restrict__ bias, float* __restrict__ h, int B, int R, int K) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= R) return;
-    const float* wr = W + (size_t)warp * K;
-    const float bv = bias[warp];
-    for (int b = 0; b < B; ++b) {
-        float acc = 0.f;
-        for (int k = lane; k < K; k += 32) acc = fmaf(wr[k], s[(size_t)b * K + k], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) h[(size_t)b * R + warp] = acc + bv;
+// (the 106 nn.Linear(style_dim, 2C) of hifigan.py:18,21).  CTA = 64 utterances x 4 row quads: the style vectors of up to
+// 64 utterances sit in shared memory as [k][b] (conflict-free for consecutive b), every thread owns 4 consecutive output
+// rows of one utterance, reads their weight rows with warp-uniform 128-bit loads and writes one float4.
+static constexpr int kFcB = 64, kFcRq = 4;
+__global__ void __launch_bounds__(kFcB * kFcRq)
+style_fc_kernel(const float* __restrict__ s, const float* __restrict__ W, const float* __restrict__ bias,
+                float* __restrict__ h, int B, int R, int K) {
+    extern __shared__ float ssm[];                    // [K][kFcB]
+    const int b0 = blockIdx.y * kFcB;
+    for (int i = threadIdx.x; i < K * kFcB; i += kFcB * kFcRq) {
+        const int bb = i / K, k = i - bb * K;         // coalesced read of s, transposed write
+        ssm[k * kFcB + bb] = (b0 + bb < B) ? s[(size_t)(b0 + bb) * K + k] : 0.f;
     }
+    __syncthreads();
+    const int bb = threadIdx.x % kFcB, rq = threadIdx.x / kFcB;
+    const int r = (blockIdx.x * kFcRq + rq) * 4;
+    if (r >= R || b0 + bb >= B) return;
+    const int nr = min(4, R - r);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; k += 4) {
+        const float s0 = ssm[(k + 0) * kFcB + bb], s1 = ssm[(k + 1) * kFcB + bb], s2 = ssm[(k + 2) * kFcB + bb],
+                    s3 = ssm[(k + 3) * kFcB + bb];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nr) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)(r + j) * K + k));   // same order as k = 0..K-1
+                acc[j] = fmaf(w.x, s0, acc[j]); acc[j] = fmaf(w.y, s1, acc[j]);
+                acc[j] = fmaf(w.z, s2, acc[j]); acc[j] = fmaf(w.w, s3, acc[j]);
+            }
+        }
+    }
+    float* hp = h + (size_t)(b0 + bb) * R + r;
+    for (int j = 0; j < nr; ++j) hp[j] = acc[j] + bias[r + j];
 }
 
 int launch_style_fc(const float* s, const float* W, const float* bias, float* h, int B, int R, int K,
                     cudaStream_t st) {
-    const int warps_per_cta = 8;
-    style_fc_kernel<<<cdiv(R, warps_per_cta), warps_per_cta * 32, 0, st>>>(s, W, bias, h, B, R, K);
+    ST2_REQUIRE(K % 4 == 0 && K <= 1024, "style_fc: style_dim %d must be a multiple of 4 and <= 1024", K);
+    dim3 grid(cdiv(R, 4 * kFcRq), cdiv(B, kFcB));
+    const size_t smem = (size_t)K * kFcB * sizeof(float);
+    static size_t max_set = 0;
+    if (smem > 48 * 1024 && smem > max_set) {
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(style_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    style_fc_kernel<<<grid, kFcB * kFcRq, smem, st>>>(s, W, bias, h, B, R, K);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
