@@ -63,6 +63,8 @@ struct PipeParams {
     int wstages, resident, tmem_cols;
     int na, nacc, nacc_log2;    // operand (A) buffers 2..4, TMEM accumulators 2 or 4
     int eg;                     // epilogue groups of the kernel variant launched (2 or 3)
+    int pair;                   // 1: the MMA warp runs two consecutive tiles against every weight stage (streamed weights,
+                                //    2 K chunks, 4 operand buffers, 4 accumulators): half the weight traffic into shared memory
     int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
     // epilogue
     const float* bias;
@@ -254,7 +256,12 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     if (++w_stage == (uint32_t)p.wstages) { w_stage = 0; w_par ^= 1; }
                     if (++w_j == p.ntaps) {
                         w_j = 0;
-                        if (++w_kc == p.kchunks) { w_kc = 0; wt.next(p); w_done = !wt.valid(p); }
+                        if (++w_kc == p.kchunks) {
+                            w_kc = 0;
+                            wt.next(p);
+                            if (p.pair && wt.valid(p)) wt.next(p);       // the MMA warp covers two tiles per pass
+                            w_done = !wt.valid(p);
+                        }
                     }
                 }
                 if (!x_done && mbar_test(&x_empty[x_slot], x_par ^ 1)) {
@@ -308,7 +315,59 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 tc_fence_after();
             }
             PTile ti;
-            for (ti.init(p); ti.valid(p); ti.next(p), ++tcnt) {
+            ti.init(p);
+            if (p.pair) {
+                // two tiles per pass over the weight ring: operand buffers (cc & 3) of tile 0 and tile 1, accumulators
+                // tcnt & 3 and (tcnt + 1) & 3; every weight stage feeds 8 MMAs instead of 4
+                while (ti.valid(p)) {
+                    PTile t1 = ti;
+                    t1.next(p);
+                    const bool two = t1.valid(p);
+                    const uint32_t acc0 = tcnt & 3u, acc1 = (tcnt + 1u) & 3u;
+                    const uint32_t d0 = tmem_base + acc0 * (uint32_t)p.bn, d1 = tmem_base + acc1 * (uint32_t)p.bn;
+                    mbar_wait(&acc_empty[acc0], ((tcnt >> 2) & 1) ^ 1);
+                    if (two) mbar_wait(&acc_empty[acc1], (((tcnt + 1u) >> 2) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t cc0 = tcnt * (uint32_t)p.kchunks;
+                    uint32_t accum = 0;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        const uint32_t ca = cc0 + (uint32_t)kc, cb = ca + (uint32_t)p.kchunks;
+                        const uint32_t ba = ca & 3u, bb = cb & 3u;
+                        mbar_wait(&a_full[ba], (ca >> 2) & 1);
+                        if (two) mbar_wait(&a_full[bb], (cb >> 2) & 1);
+                        tc_fence_after();
+                        uint32_t a0 = a_lo0 + ba * a_buf_step + row0, a1 = a_lo0 + bb * a_buf_step + row0;
+                        for (int j = 0; j < p.ntaps; ++j) {
+                            mbar_wait(&b_full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + stage * b_step;
+                            umma_f16_lohi(d0, a0, b_lo, dhi, idesc, accum);
+                            umma_f16_lohi(d0, a0 + 2, b_lo + 2, dhi, idesc, 1u);
+                            umma_f16_lohi(d0, a0 + 4, b_lo + 4, dhi, idesc, 1u);
+                            umma_f16_lohi(d0, a0 + 6, b_lo + 6, dhi, idesc, 1u);
+                            if (two) {
+                                umma_f16_lohi(d1, a1, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d1, a1 + 2, b_lo + 2, dhi, idesc, 1u);
+                                umma_f16_lohi(d1, a1 + 4, b_lo + 4, dhi, idesc, 1u);
+                                umma_f16_lohi(d1, a1 + 6, b_lo + 6, dhi, idesc, 1u);
+                            }
+                            accum = 1u;
+                            a0 += row_step;
+                            a1 += row_step;
+                            umma_commit(&b_empty[stage]);
+                            if (++stage == (uint32_t)p.wstages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(&a_empty[ba]);
+                        if (two) umma_commit(&a_empty[bb]);
+                    }
+                    umma_commit(&acc_full[acc0]);
+                    if (two) umma_commit(&acc_full[acc1]);
+                    tcnt += two ? 2u : 1u;
+                    ti = t1;
+                    if (two) ti.next(p);
+                }
+            }
+            for (; ti.valid(p); ti.next(p), ++tcnt) {
                 const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
                 mbar_wait(&acc_empty[acc], ((tcnt >> p.nacc_log2) & 1) ^ 1);   // epilogue drained this accumulator
@@ -727,7 +786,12 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     const int64_t a_bytes = ((int64_t)p.rows * arow + 1023) & ~(int64_t)1023;
     const int64_t b_stage = (int64_t)p.bn * arow;
     const int64_t r_stage = (int64_t)p.nres * P_RBOX;
-    int na = 2;
+    // tile pairs: streamed weights with exactly 2 K chunks (the 128-channel layers) -> 4 operand buffers up front
+    // (measured on the 128-channel layers: conv2 with one residual 0.405 -> 0.36 ms (k=7), 0.535 -> 0.507 (k=11); layers without
+    // a residual, whose epilogue staging leaves less room for the rings, and the accumulate layers lose, so only nres == 1)
+    const bool pair_ok = p.kchunks == 2 && p.bn <= 128 && p.nacc == 4 && p.nres == 1 &&
+                         (int64_t)a.ntaps * p.kchunks * b_stage > 96 * 1024 && getenv("ST2_NO_PIPE_PAIR") == nullptr;
+    int na = pair_ok ? 4 : 2;
     int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)P_EW * 4096);
     const int64_t w_resident = (int64_t)a.ntaps * p.kchunks * b_stage;
     const int nchunks = p.bn / 32;
@@ -769,6 +833,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     if (const char* e = getenv("ST2_PIPE_NR")) { const int v = atoi(e); if (p.nres && v >= 1 && v <= nr) nr = v; }
     p.nx = nx; p.nr = nr;
     p.na = na;
+    p.pair = (pair_ok && !p.resident && na == 4) ? 1 : 0;
     p.lw = na * p.nblk < P_LW ? na * p.nblk : P_LW;
     const size_t smem = (size_t)(na * a_bytes + (int64_t)p.wstages * b_stage + (p.nres ? (int64_t)p.nr * r_stage : (int64_t)P_EW * 4096) +
                                  (int64_t)p.nx * p.xslot + 2048 + 1024);
