@@ -1,28 +1,33 @@
-// Fully TMA-fed variant of the fused  [AdaIN affine + Snake / LeakyReLU] -> Conv1d (tcgen05) ->
-// [bias + residual + accumulate + scale + InstanceNorm partial statistics]  kernel for stride-1 convolutions
-// (every conv of AdaINResBlock1, Modules/hifigan.py:65-74): 96 of the 100 fused launches of a hifigan forward.
+// Fully TMA-fed fused  [AdaIN affine + Snake / LeakyReLU] -> Conv1d / ConvTranspose1d (tcgen05) ->
+// [bias + residual + accumulate + scale + InstanceNorm partial statistics]  kernel for sm_100a: every conv of
+// AdaINResBlock1 (Modules/hifigan.py:65-74) with up to 128 channels and the generator `ups` with stride*Cout <= 256
+// (:292-294, :329-334) -- 92 of the 100 fused launches of a hifigan forward; conv_fused.cu runs the rest.
 //
 // conv_fused.cu left three latency chains exposed (measured with its role timeline): the transform warps waited
 // for whole-tile loads, the epilogue warps waited ~1.5 us for their residual rows, and one producer thread
 // serialised weight and activation loads.  Here no compute warp ever touches global memory for input:
-//   * activations arrive by TMA in 8 KB blocks (32 rows x 64 ch or 64 rows x 32 ch, fp32 or 16-bit) through a ring
-//     of `nx` slots that is independent of the tile geometry; each transform warp owns one block at a time
-//     (16 independent 4-channel groups per thread -> the Snake chain is hidden by ILP, not by occupancy);
+//   * activations arrive by TMA in blocks of <= 12 KB (a few equal blocks per tile, multiples of 8 rows; fp32, or fp16 for
+//     the intra-block tensor of the resblocks) through a ring of `nx` slots that is independent of the tile geometry;
+//     blocks are dealt round-robin to the transform warps, which work in batches of 8 row passes (8 independent 128-bit
+//     loads, then 8 independent activation chains -> the Snake chain is hidden by ILP, not by occupancy);
 //   * residual (+ accumulate) rows arrive by TMA as 128-byte-swizzled [128 rows x 32 ch] fp32 boxes through a ring
 //     of `nr` stages; the epilogue adds them in the TMEM-drain layout and reuses the very same stage as its
 //     transposition buffer, so the only global accesses of the epilogue are full-line stores;
 //   * one producer thread multiplexes three independent queues (weights, activation blocks, residual boxes) with
-//     non-blocking mbarrier tests, so a full weight ring never delays an activation prefetch.
+//     non-blocking mbarrier tests, so a full weight ring never delays an activation prefetch;
+//   * 2-4 operand buffers and 4 TMEM accumulators (2 for N > 128) decouple transform, MMA and epilogue; pipe_plan()
+//     splits the 227 KB of shared memory between operand buffers, weights (resident or ring) and the two rings;
+//   * layers that stream their weights (128 channels) run two consecutive tiles against every weight stage (p.pair).
 // The activation and residual rings are plain FIFOs shared by several consumer warps.  An mbarrier parity wait only
 // tells adjacent phases apart and a consumer can be two fills ahead of a slot it does not own, so the producer
 // publishes the sequence number of every fill in a shared-memory word before issuing it; a consumer first sees
 // "its" sequence number (the previous fill has then landed and been consumed) and only then waits on the barrier.
-// ConvTranspose1d(k = taps*stride, stride) runs here too: its `stride` polyphase sub-convolutions read the same
-// input rows, so their weights are stacked along N (N = stride*Cout) and row m of the accumulator is exactly the
-// `stride` consecutive output rows m*stride - pad ... of the channels-last tensor, i.e. a dense [M][stride*Cout] matrix
-// at a constant element offset (Modules/hifigan.py:292-294 `ups`, 329-334).
-// Roles (16 warps, one persistent CTA per SM): warp 0 producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2-7 transform, warps 8-15 epilogue (2 groups x 4 TMEM lane quarters, one accumulator each).
+// ConvTranspose1d(k = taps*stride, stride): its `stride` polyphase sub-convolutions read the same input rows, so their
+// weights are stacked along N (N = stride*Cout) and row m of the accumulator is exactly the `stride` consecutive output
+// rows m*stride - pad ... of the channels-last tensor, i.e. a dense [M][stride*Cout] matrix at a constant element offset.
+// Roles (one persistent CTA per SM): warp 0 producer, warp 1 TMEM allocator + MMA issuer, warps 2-7 transform,
+// warps 8.. epilogue in groups of 4 (one TMEM lane quarter per warp): 2 groups (512 threads, 128 registers) or 3 groups
+// (640 threads, 96 registers; the 32-channel layers with a residual, which are epilogue-bound).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
