@@ -758,6 +758,12 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
         // 12 KB blocks by default; 8 KB when every residual stage holds two boxes (residual + accumulate), where the
         // smaller blocks leave room for one more stage (measured: 0.75 -> 0.60 ms on the 32-channel k=11 layer)
         int xmax = (a.res != nullptr && a.accumulate) ? 8192 : P_XSLOT_MAX;
+        // measured per layer class on the B200 (tools/sweep_pipe.sh, ST2_PIPE_XMAX): 8 KB blocks win by 3-14 % where the 12 KB
+        // split leaves a short last block per tile -- 64 channels k=7 (0.435 -> 0.398 ms), 128 channels k=3 without residual
+        // (0.362 -> 0.312) and k=7 with one residual (0.350 -> 0.338); every 32-channel layer loses 5-14 % with them
+        const int nres_ = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+        if ((a.Cin == 64 && a.ntaps == 7) || (a.Cin == 128 && a.ntaps == 3 && nres_ == 0) || (a.Cin == 128 && a.ntaps == 7 && nres_ == 1))
+            xmax = 8192;
         if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
         int nblk = 1;
         for (;; ++nblk) {
