@@ -786,6 +786,9 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
     p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
     if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && p.nres > 0 && !tr_)) p.eg = v; }
+    // 3 groups need 4 accumulators: a group's previous tile is tcnt-3, so MMA(tcnt-4) -- the previous use of its accumulator
+    // -- has completed when it waits; with 2 accumulators the previous use is tile tcnt-2 and the parity wait could pass early
+    if (p.nacc < 4) p.eg = 2;
     p.bias = a.bias; p.scale = a.scale; p.y16out = a.y16out;
     p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout]); out_pad = 0 when y16out
     p.ld_y = ph * a.ld_y;
@@ -824,7 +827,9 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     left -= rings(nx, nr);
     const int nr_goal = p.nres ? (2 * nchunks + 2 > 8 ? 8 : 2 * nchunks + 2) : 0;
     const int nx_goal = 10;
-    int na_goal = 4;
+    // resident weights of a 2-chunk layer (128 channels, k = 3: 96 KB) leave little for the rings: two operand buffers and
+    // deeper rings measured 0.319 -> 0.264 ms (no residual), 0.356 -> 0.310 (residual), 0.546 -> 0.478 (accumulate)
+    int na_goal = (p.resident && p.kchunks >= 2) ? 2 : 4;
     if (const char* e = getenv("ST2_PIPE_NA")) { const int v = atoi(e); if (v >= 2 && v <= 4) na_goal = v; }
     for (bool grew = true; grew;) {
         grew = false;
