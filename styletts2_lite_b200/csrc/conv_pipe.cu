@@ -825,8 +825,10 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     }
     // what is left goes to the two rings in turn (bytes in flight are what hides the HBM latency), then to the weight ring
     left -= rings(nx, nr);
-    const int nr_goal = p.nres ? (2 * nchunks + 2 > 8 ? 8 : 2 * nchunks + 2) : 0;
-    const int nx_goal = 10;
+    int nr_goal = p.nres ? (2 * nchunks + 2 > 8 ? 8 : 2 * nchunks + 2) : 0;
+    int nx_goal = 10;
+    if (const char* e = getenv("ST2_PIPE_NXG")) { const int v = atoi(e); if (v >= 3 && v <= 16) nx_goal = v; }
+    if (const char* e = getenv("ST2_PIPE_NRG")) { const int v = atoi(e); if (p.nres && v >= 2 && v <= 12) nr_goal = v; }
     // resident weights of a 2-chunk layer (128 channels, k = 3: 96 KB) leave little for the rings: two operand buffers and
     // deeper rings measured 0.319 -> 0.264 ms (no residual), 0.356 -> 0.310 (residual), 0.546 -> 0.478 (accumulate)
     int na_goal = (p.resident && p.kchunks >= 2) ? 2 : 4;
