@@ -449,7 +449,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
             for (int it = 0; it < 8; ++it) {
                 const int m = m_first + it * 4;
                 const int t = t_first + it * 4 * p.out_stride;
-                if (m < p.M && t >= 0 && t < p.Tout) vmask |= 1u << it;
+                if (m < p.M && t >= (p.mirror ? 1 : 0) && t < p.Tout) vmask |= 1u << it;   // mirror: row 0 is written by the row-2 thread only
             }
             if (et == 0) TRACE(2 + grp, tcnt, 4);
             float* ytile = p.y + ((size_t)ti.b * p.Tout + t_first) * p.ld_y;

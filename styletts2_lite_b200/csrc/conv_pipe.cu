@@ -64,7 +64,7 @@ struct PipeParams {
     int xslot;                  // bytes per activation ring slot (xr rows)
     int lw;                     // active transform warps = min(6, na * nblk): a warp's consecutive blocks are then at most
                                 // na operand fills apart, so its a_empty parity wait is never more than one phase behind
-    int bn, mtiles, num_tiles;
+    int bn, nt, mtiles, num_tiles;   // bn columns per accumulator; nt > 1: N passes over the operand tile (Cout = nt * bn)
     int wstages, resident, tmem_cols;
     int na, nacc, nacc_log2;    // operand (A) buffers 2..4, TMEM accumulators 2 or 4
     int eg;                     // epilogue groups of the kernel variant launched (2 or 3)
@@ -247,22 +247,22 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             bool x_done = !xt.valid(p);
             // weight queue: (tile, kc, tap)
             PTile wt; wt.init(p);
-            int w_kc = 0, w_j = 0; uint32_t w_stage = 0, w_par = 0;
+            int w_kc = 0, w_j = 0, w_nt = 0; uint32_t w_stage = 0, w_par = 0;
             bool w_done = p.resident || !wt.valid(p);
             // residual queue: box set c = (tile, chunk) -> stage c % nr
-            const int nchunks = p.bn >> 5;
+            const int nchunks = p.Cout >> 5;             // residual boxes per tile: every 32-column chunk of the row
             PTile rt; rt.init(p);
             int r_ch = 0; uint32_t r_stage = 0, r_par = 0, r_c = 0;
             bool r_done = p.nres == 0 || !rt.valid(p);
             while (!(x_done && w_done && r_done)) {
                 if (!w_done && mbar_test(&b_empty[w_stage], w_par ^ 1)) {
                     mbar_expect_tx(&b_full[w_stage], b_stage_bytes);
-                    tma_load_3d(smem_b + (size_t)w_stage * b_stage_bytes, &map_b, &b_full[w_stage], w_kc * 64, 0, w_j);
+                    tma_load_3d(smem_b + (size_t)w_stage * b_stage_bytes, &map_b, &b_full[w_stage], w_kc * 64, w_nt * p.bn, w_j);
                     if (++w_stage == (uint32_t)p.wstages) { w_stage = 0; w_par ^= 1; }
                     if (++w_j == p.ntaps) {
                         w_j = 0;
-                        if (++w_kc == p.kchunks) {
-                            w_kc = 0;
+                        if (++w_kc == p.kchunks && (w_kc = 0, ++w_nt == p.nt)) {
+                            w_nt = 0;
                             wt.next(p);
                             if (p.pair && wt.valid(p)) wt.next(p);       // the MMA warp covers two tiles per pass
                             w_done = !wt.valid(p);
@@ -370,6 +370,44 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     tcnt += two ? 2u : 1u;
                     ti = t1;
                     if (two) ti.next(p);
+                }
+            }
+            if (p.nt > 1) {
+                // N passes: Cout = nt * bn columns, one accumulator per pass; the tile's operand buffers (cc & 3, all K chunks)
+                // stay valid for every pass and are released in the last one; weights stream per (pass, chunk, tap)
+                uint32_t au = 0;                        // accumulator use = tile * nt + pass
+                for (; ti.valid(p); ti.next(p), ++tcnt) {
+                    const uint32_t cc0 = tcnt * (uint32_t)p.kchunks;
+                    for (int nt = 0; nt < p.nt; ++nt, ++au) {
+                        const uint32_t acc = au & (uint32_t)(p.nacc - 1);
+                        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.bn;
+                        mbar_wait(&acc_empty[acc], ((au >> p.nacc_log2) & 1) ^ 1);
+                        tc_fence_after();
+                        uint32_t accum = 0;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            const uint32_t c = cc0 + (uint32_t)kc, ab = c & 3u;
+                            if (nt == 0) {
+                                mbar_wait(&a_full[ab], (c >> 2) & 1);
+                                tc_fence_after();
+                            }
+                            uint32_t a_lo = a_lo0 + ab * a_buf_step + row0;
+                            for (int j = 0; j < p.ntaps; ++j) {
+                                mbar_wait(&b_full[stage], phase);
+                                tc_fence_after();
+                                const uint32_t b_lo = b_lo0 + stage * b_step;
+                                umma_f16_lohi(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+                                umma_f16_lohi(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                                umma_f16_lohi(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                                accum = 1u;
+                                a_lo += row_step;
+                                umma_commit(&b_empty[stage]);
+                                if (++stage == (uint32_t)p.wstages) { stage = 0; phase ^= 1; }
+                            }
+                            if (nt == p.nt - 1) umma_commit(&a_empty[ab]);
+                        }
+                        umma_commit(&acc_full[acc]);
+                    }
                 }
             }
             for (; ti.valid(p); ti.next(p), ++tcnt) {
@@ -570,14 +608,16 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             rs += (uint32_t)n;
             while (rs >= (uint32_t)p.nr) { rs -= (uint32_t)p.nr; rpar ^= 1u; }
         };
-        uint32_t tcnt = 0;
+        uint32_t tcnt = 0, au = 0;                        // accumulator use = tile * nt + pass; groups take uses in turn
         PTile ti;
         for (ti.init(p); ti.valid(p); ti.next(p), ++tcnt) {
-            if ((int)(tcnt % (uint32_t)EG) != grp) {
-                if (p.nres) r_advance(nchunks);           // the other group's tile
+          for (int nt = 0; nt < p.nt; ++nt, ++au) {
+            if ((int)(au % (uint32_t)EG) != grp) {
+                if (p.nres) r_advance(nchunks);           // another group's accumulator
                 continue;
             }
-            const uint32_t acc = tcnt & (uint32_t)(p.nacc - 1);
+            const uint32_t acc = au & (uint32_t)(p.nacc - 1);
+            const int cb = nt * p.bn;                     // first column of this pass
             const int m_first = ti.mt * P_MT + q * 32 + rr;                  // rows of this lane: m_first + 4*it
             // warp-uniform: every (row, column) of this quarter maps to an output row inside [0, Tout)
             const int m_lo = ti.mt * P_MT + q * 32;
@@ -587,13 +627,14 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             const size_t yoff = (size_t)ti.b * (size_t)p.ybatch + (size_t)m_first * p.ld_y + c4o;
             float* ytile = p.y16out ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.y) + yoff) : p.y + yoff;
             float2* stile = p.stats ? p.stats + (((size_t)ti.b * p.mtiles + ti.mt) * 4 + q) * p.Cout + c4o : nullptr;
-            mbar_wait_warp(&acc_full[acc], (tcnt >> p.nacc_log2) & 1);
+            mbar_wait_warp(&acc_full[acc], (au >> p.nacc_log2) & 1);
             tc_fence_after();
             auto run_chunks = [&](auto nres_c, auto y16_c) {
             constexpr int NRES = decltype(nres_c)::value;
             constexpr bool Y16 = decltype(y16_c)::value;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const int phs = (ch * 32) >> p.cshift;         // polyphase index of this column chunk (0 for a plain conv)
+                const int gcol = cb + ch * 32;                 // column of the row this chunk starts at
+                const int phs = gcol >> p.cshift;              // polyphase index of this column chunk (0 for a plain conv)
                 if (!full) {
                     vmask = 0;
 #pragma unroll
@@ -603,7 +644,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     }
                 }
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 32 - phs * p.cdiv + c4o));
+                if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol - phs * p.cdiv + c4o));
                 const float2 bs01 = fmul2(make_float2(bias4.x, bias4.y), sc2), bs23 = fmul2(make_float2(bias4.z, bias4.w), sc2);
                 // [32 rows][32 cols] fp32 region of this warp, 16-byte slots XOR-swizzled by (row & 7) -- the TMA
                 // SWIZZLE_128B layout of the residual box, and conflict-free for both access directions
@@ -651,7 +692,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 const uint32_t st_r0 = tile_u32 + (uint32_t)rr * 128u + ((l7 ^ (uint32_t)rr) << 4);               // rows rr, rr+8, ...
                 const uint32_t st_r1 = tile_u32 + (uint32_t)(rr + 4) * 128u + ((l7 ^ (uint32_t)(rr + 4)) << 4);   // rows rr+4, rr+12, ...
                 float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
-                float* yo = Y16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ytile) + ch * 32) : ytile + ch * 32;
+                float* yo = Y16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(ytile) + gcol) : ytile + gcol;
                 if (full) pipe_store_rows<true, Y16>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
                 else pipe_store_rows<false, Y16>(st_r0, st_r1, yo, ystep, vmask, sc2, bs01, bs23, s1a, s1b, s2a, s2b);
                 if (stile != nullptr) {
@@ -665,7 +706,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     }
                     // one partial per (tile, TMEM lane quarter): written straight to global, no cross-warp barrier
                     if (lane < 8) {
-                        float2* sp = stile + ch * 32;
+                        float2* sp = stile + gcol;
                         *reinterpret_cast<float4*>(sp) = make_float4(s1[0], s2[0], s1[1], s2[1]);
                         *reinterpret_cast<float4*>(sp + 2) = make_float4(s1[2], s2[2], s1[3], s2[3]);
                     }
@@ -689,6 +730,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
             } else {
                 run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
             }
+          }
         }
     }
     tc_fence_before();
@@ -714,13 +756,28 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     const bool tr = a.phases > 1;          // polyphase ConvTranspose1d -> dense conv with N = phases * Cout
     if (tr) {
         if (a.out_stride != a.phases || a.w_step != a.phases || a.tap_step != -1 || a.in_off != 0 || a.accumulate) return false;
-        if (a.ld_y != a.Cout || (a.res != nullptr && a.ld_res != a.Cout) || a.phases * a.Cout > 256) return false;
+        if (a.ld_y != a.Cout || (a.res != nullptr && a.ld_res != a.Cout)) return false;
         if (a.Tout % a.phases != 0 || a.out_pad < 0 || a.out_pad > a.phases) return false;
         if (getenv("ST2_NO_PIPE_UPS") != nullptr) return false;
     } else if (a.out_stride != 1 || a.out_pad != 0 || a.tap_step <= 0 || a.M != a.Tout) {
         return false;
     }
-    if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0 || a.w16_cout_pad > 256) return false;
+    if (a.w16 == nullptr || a.w16_cin_pad % 64 != 0 || a.w16_cout_pad % 32 != 0) return false;
+    {
+        // columns of one accumulator row: <= 256 in one pass (192 at most in practice), else passes of 128 over an operand
+        // tile that stays resident in the 4 operand buffers (<= 4 K chunks)
+        const int ntot = a.phases * a.w16_cout_pad, kch = a.w16_cin_pad / 64;
+        const bool one_pass = ntot <= 192;
+        const bool n_pass = ntot % 128 == 0 && ntot <= 1024 && (kch == 1 || kch == 2 || kch == 4) && getenv("ST2_NO_PIPE_NT") == nullptr;
+        if (!one_pass && !n_pass) return false;
+        // measured on the 256-channel layers (N passes here vs conv_fused.cu): k=3 0.278 -> 0.165 ms, k=7 0.293 -> 0.276
+        // (no residual) and 0.337 -> 0.313 (accumulate), ups 256->128 1.14 -> 0.37; k=7 with one residual and k=11 are
+        // tensor-bound over there (up to 1250 TFLOP/s) and lose here, so they stay
+        if (!one_pass && a.phases == 1) {
+            const int nres_ = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+            if (a.ntaps > 7 || (a.ntaps == 7 && nres_ == 1)) return false;
+        }
+    }
     if (!(a.Cin == 32 || a.Cin % 64 == 0) || a.Cout % 32 != 0 || a.Cout != a.w16_cout_pad) return false;
     if ((a.Cout & (a.Cout - 1)) != 0) return false;        // column -> phase is a shift
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
@@ -730,7 +787,6 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if (a.x16in && a.y16out) return false;
     if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
-    if (!tr && a.w16_cout_pad > 128 && getenv("ST2_PIPE_256") == nullptr) return false;   // 256-wide layers: tensor-bound, conv_fused.cu
     const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
     return span <= 64 && (tr || (a.in_off <= 0 && a.in_off + span >= 0));
 }
@@ -774,7 +830,11 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
         p.tail_rows = p.rows - (p.nblk - 1) * p.xr;
         p.xslot = (p.xr * rowb + 127) / 128 * 128;
     }
-    p.bn = ph * a.w16_cout_pad;
+    {
+        const int ntot = ph * a.w16_cout_pad;
+        p.nt = ntot <= 192 ? 1 : ntot / 128;
+        p.bn = ntot / p.nt;
+    }
     p.mtiles = cdiv(a.M, P_MT);
     p.num_tiles = a.B * p.mtiles;
     p.nacc = p.bn <= 128 ? 4 : 2;
@@ -803,9 +863,9 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     // tile pairs: streamed weights with exactly 2 K chunks (the 128-channel layers) -> 4 operand buffers up front
     // (measured on the 128-channel layers: conv2 with one residual 0.405 -> 0.36 ms (k=7), 0.535 -> 0.507 (k=11); layers without
     // a residual, whose epilogue staging leaves less room for the rings, and the accumulate layers lose, so only nres == 1)
-    const bool pair_ok = p.kchunks == 2 && p.bn <= 128 && p.nacc == 4 && p.nres == 1 &&
+    const bool pair_ok = p.nt == 1 && p.kchunks == 2 && p.bn <= 128 && p.nacc == 4 && p.nres == 1 &&
                          (int64_t)a.ntaps * p.kchunks * b_stage > 96 * 1024 && getenv("ST2_NO_PIPE_PAIR") == nullptr;
-    int na = pair_ok ? 4 : 2;
+    int na = (pair_ok || p.nt > 1) ? 4 : 2;
     int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)P_EW * 4096);
     const int64_t w_resident = (int64_t)a.ntaps * p.kchunks * b_stage;
     const int nchunks = p.bn / 32;
@@ -813,7 +873,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     const int64_t xslot = p.xslot;
     int nx = 3, nr = p.nres ? 2 : 0;
     auto rings = [&](int nx_, int nr_) { return (int64_t)nx_ * xslot + (int64_t)nr_ * r_stage; };
-    p.resident = (base + w_resident + rings(nx, nr) <= budget) ? 1 : 0;
+    p.resident = (p.nt == 1 && base + w_resident + rings(nx, nr) <= budget) ? 1 : 0;
     int64_t left;
     if (p.resident) {
         p.wstages = a.ntaps * p.kchunks;

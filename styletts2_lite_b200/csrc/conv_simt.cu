@@ -152,7 +152,9 @@ conv_simt_kernel(const ConvArgs a, const bool vecA, const bool vecB, const bool 
         const int m = m0 + ty * TM + i;
         if (m >= a.M) continue;
         const int t = m * a.out_stride + p - a.out_pad;
-        if (t < 0 || t >= a.Tout) continue;
+        // mirror (ReflectionPad1d((1,0)) folded into the store): outputs are shifted by one row, so t == 0 would be output
+        // index -1 of the convolution; row 0 belongs to the mirror write of row 2 alone (two writers raced here)
+        if (t < (a.mirror ? 1 : 0) || t >= a.Tout) continue;
         float v[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bias[j];

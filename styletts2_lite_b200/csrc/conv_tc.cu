@@ -146,7 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int t = m * p.out_stride + ph - p.out_pad;
-        const bool row_ok = (m < p.M) && (t >= 0) && (t < p.Tout);
+        const bool row_ok = (m < p.M) && (t >= (p.mirror ? 1 : 0)) && (t < p.Tout);   // mirror: row 0 is written by the row-2 thread only
         const bool vec = (p.Cout % 4 == 0) && (p.ld_y % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         const bool vres = vec && p.res != nullptr && (p.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
         const bool vbias = p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (n0 % 4 == 0);
