@@ -143,6 +143,21 @@ ST2_API int st2_decoder_get_profile(st2_decoder* d, double* ms, int64_t* launche
 ST2_API int64_t st2_decoder_get_profile_launches(st2_decoder* d, int64_t max_n, int32_t* cat, float* ms,
                                          double* flops, double* bytes);
 
+/* ---- F0 / energy predictor: replaces ProsodyPredictor.F0Ntrain, models.py:448-461 ----
+ * The step right before the Decoder (inference.py:267): shared bidirectional LSTM (models.py:407), two stacks of
+ * three AdainResBlk1d (models.py:408-416) and two 1x1 projections (models.py:418-419).  The handle is an st2_decoder
+ * of a third kind: st2_decoder_set_weight (keys "shared.weight_ih_l0", "F0.1.conv1.weight_v", "N_proj.bias", ...
+ * as in ProsodyPredictor.state_dict()), st2_decoder_finalize, st2_decoder_set_tap, the profile calls and
+ * st2_decoder_destroy apply unchanged; st2_decoder_forward / _workspace_bytes reject it. */
+ST2_API int st2_f0n_create(int32_t d_hid, int32_t style_dim, st2_decoder** out);
+ST2_API int64_t st2_f0n_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision);
+/* en [B, d_hid+style_dim, T] (the length-regulated DurationEncoder output), s [B, style_dim]
+ *   -> f0 [B, 2T], n [B, 2T]   (what Decoder.forward takes as F0_curve and N).
+ * precision: fp32 = SIMT everywhere; bf16 / fp16 = the convolutions and the LSTM input projection on tcgen05 with
+ * fp16 operands (the recurrence itself is always fp32). */
+ST2_API int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, float* f0, float* n, int32_t B, int32_t T,
+                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 
 /* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);

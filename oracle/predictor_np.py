@@ -1,0 +1,73 @@
+"""CPU oracle for SURVEY.md §8(f) N1, `ProsodyPredictor.F0Ntrain`  --  TEST INFRASTRUCTURE ONLY.
+
+numpy restatement of the step right before the Decoder (reference models.py:448-461): the shared
+bidirectional LSTM, two stacks of three AdainResBlk1d and the two 1x1 projections that produce
+`F0_pred` / `N_pred` (inference.py:268).  Same rules as oracle/decoder_np.py: only tests/, smoke() and
+bench.py's CPU legs may import it, never the product package.
+
+Parity pinning: the reference has no tests or fixtures for this function either; the oracle is pinned against
+the reference itself run in the authoring container (tests/golden/make_golden_predictor.py imports
+/root/reference/models.py through a 4-line `munch` shim and commits tests/golden/f0n_*.npz).
+
+The arithmetic of nn.LSTM lives in PyTorch ATen (torch/nn/modules/rnn.py + aten/native/RNN.cpp, torch 2.7.0 in
+uv.lock:2116): gates = x W_ih^T + b_ih + h W_hh^T + b_hh, chunked (i, f, g, o);
+c' = sigmoid(f) c + sigmoid(i) tanh(g); h' = sigmoid(o) tanh(c').  Layout follows the reference: [B, C, T].
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from .decoder_np import F32, Weights, adain_resblk1d, conv1d
+
+
+def _sigmoid(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(F32)
+
+
+def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse: bool):
+    """One direction of nn.LSTM(batch_first=True), zero initial state.  x [B, T, I] -> [B, T, H]."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    gin = (x.reshape(B * T, -1).astype(F32) @ w_ih.T.astype(F32) + b_ih).reshape(B, T, 4 * H).astype(F32)
+    h = np.zeros((B, H), F32)
+    c = np.zeros((B, H), F32)
+    out = np.zeros((B, T, H), F32)
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    for t in order:
+        g = (gin[:, t] + (h @ w_hh.T.astype(F32) + b_hh)).astype(F32)
+        i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+        c = (_sigmoid(f) * c + _sigmoid(i) * np.tanh(gg)).astype(F32)
+        h = (_sigmoid(o) * np.tanh(c)).astype(F32)
+        out[:, t] = h
+    return out
+
+
+def bilstm(W: Weights, name: str, x):
+    """nn.LSTM(d_hid + style_dim, d_hid // 2, 1, batch_first=True, bidirectional=True) (models.py:407).
+    x [B, T, I] -> [B, T, 2H] = cat(forward, reverse)."""
+    outs = []
+    for suffix, rev in (("", False), ("_reverse", True)):
+        outs.append(lstm_direction(x, W.p(name + ".weight_ih_l0" + suffix), W.p(name + ".weight_hh_l0" + suffix),
+                                   W.p(name + ".bias_ih_l0" + suffix), W.p(name + ".bias_hh_l0" + suffix), rev))
+    return np.concatenate(outs, axis=2)
+
+
+def f0n_train(sd: Dict[str, np.ndarray], en, s, taps: Optional[dict] = None, operand: Optional[str] = None):
+    """ProsodyPredictor.F0Ntrain(x, s) (models.py:448-461).  en [B, d_hid+style_dim, T], s [B, style_dim]
+    -> (F0 [B, 2T], N [B, 2T]).  Dropout (p=0.2, models.py:409-416) is the identity in eval mode."""
+    W = Weights(sd)
+    en = np.asarray(en, F32)
+    s = np.asarray(s, F32)
+    x = bilstm(W, "shared", en.transpose(0, 2, 1))            # models.py:449
+    if taps is not None:
+        taps["shared"] = x
+    outs = []
+    for br in ("F0", "N"):
+        h = x.transpose(0, 2, 1)                                # models.py:451 / :456
+        for i, up in enumerate((False, True, False)):           # models.py:409-416 (`upsample=True` on block 1)
+            h = adain_resblk1d(W, "%s.%d" % (br, i), h, s, up, taps=taps, operand=operand)
+        h = conv1d(h, W.w(br + "_proj"), W.b(br + "_proj"))     # models.py:454 / :459
+        outs.append(h[:, 0, :])                                 # .squeeze(1)
+    return outs[0], outs[1]

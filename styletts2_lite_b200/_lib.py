@@ -78,6 +78,9 @@ SIGNATURES = {
                                           C.POINTER(C.c_double)]),
     "st2_decoder_get_profile_launches": (_L, [_P, _L, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                               C.POINTER(C.c_double)]),
+    "st2_f0n_create": (C.c_int, [_I, _I, C.POINTER(_P)]),
+    "st2_f0n_workspace_bytes": (_L, [_P, _I, _I, _I]),
+    "st2_f0n_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "st2_round_durations": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "st2_length_regulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "st2_sinegen_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

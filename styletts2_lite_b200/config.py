@@ -196,3 +196,43 @@ def buffer_specs(cfg: DecoderConfig):
 def is_transposed_conv(name: str) -> bool:
     """True for the ConvTranspose1d modules (generator.ups.*, decode.3.pool)."""
     return ".ups." in name or name.endswith(".pool") or ".pool." in name
+
+
+# ---- §8(f) N1: the F0 / energy predictor that feeds the Decoder (models.py:448-461) -----------------
+@dataclass
+class PredictorConfig:
+    """`ProsodyPredictor(style_dim, d_hid, ...)` as built at models.py:575 from config_example.yaml:38,43.
+    Only the sub-modules `F0Ntrain` uses are covered: `shared`, `F0`, `N`, `F0_proj`, `N_proj`."""
+    d_hid: int = HIDDEN_DIM
+    style_dim: int = STYLE_DIM
+
+
+F0N_PREFIXES = ("shared.", "F0.", "N.", "F0_proj.", "N_proj.")
+
+
+def predictor_param_specs(cfg: PredictorConfig):
+    """[(state_dict key, shape, init-kind)] of the parameters ProsodyPredictor.F0Ntrain reads
+    (models.py:407-419: bidirectional nn.LSTM `shared`, 2 x 3 AdainResBlk1d, two 1x1 Conv1d)."""
+    d, sd = cfg.d_hid, cfg.style_dim
+    h = d // 2
+    specs = []
+    for suffix in ("", "_reverse"):
+        specs.append(("shared.weight_ih_l0" + suffix, (4 * h, d + sd), "lstm:%d" % h))
+        specs.append(("shared.weight_hh_l0" + suffix, (4 * h, h), "lstm:%d" % h))
+        specs.append(("shared.bias_ih_l0" + suffix, (4 * h,), "lstm:%d" % h))
+        specs.append(("shared.bias_hh_l0" + suffix, (4 * h,), "lstm:%d" % h))
+    for br in ("F0", "N"):
+        _adain_resblk1d(specs, br + ".0", d, d, sd, False)
+        _adain_resblk1d(specs, br + ".1", d, h, sd, True)
+        _adain_resblk1d(specs, br + ".2", h, h, sd, False)
+    for br in ("F0_proj", "N_proj"):
+        specs.append((br + ".weight", (1, h, 1), "conv"))
+        specs.append((br + ".bias", None, "bias:" + br + ".weight"))
+    shapes = {n: s for n, s, _ in specs if s is not None}
+    out = []
+    for n, s, kind in specs:
+        if s is None:
+            w = shapes[kind.split(":", 1)[1]]
+            s = (w[0],)                              # Conv1d bias; depthwise pool: groups = Cin = w[0]
+        out.append((n, s, kind))
+    return out

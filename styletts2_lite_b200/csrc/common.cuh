@@ -59,7 +59,8 @@ enum ProfCat {
     PC_MISC = 7,        // layout, style fc, pool, taps
     PC_CONV_FUSED = 8,  // conv_fused_kernel: fused AdaIN/act -> tcgen05 conv -> residual/stats, register-staged (256-ch: tensor)
     PC_CONV_PIPE = 9,   // conv_pipe_kernel: the same fusion fully TMA-fed (C <= 128, ups; bound: hbm / shared memory)
-    PC_COUNT = 10
+    PC_LSTM = 10,       // lstm_bidir_kernel: recurrence of the predictor's shared BiLSTM (bound: latency, T sequential steps)
+    PC_COUNT = 11
 };
 
 // ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------
@@ -110,6 +111,9 @@ int launch_stft_transform(const float* har, const float* wr, const float* wi, fl
                           int S, int n_fft, int hop, cudaStream_t st);
 int launch_istft_head(const float* x, int ld_x, const float* wr, const float* wi, float* out, int B,
                       int frames, int S, int n_fft, int hop, cudaStream_t st);
+
+// BiLSTM recurrence (kernels_lstm.cu): G [B][T][2][4H] input half of the gates, whh [2][H][4H], bhh [2][4H] -> y [B][T][2H]
+int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st);
 
 // length regulator (length_regulator.cu)
 int launch_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur, int32_t* total,

@@ -93,6 +93,13 @@ struct st2_decoder {
     float *stft_fr = nullptr, *stft_fi = nullptr, *stft_br = nullptr, *stft_bi = nullptr;
     std::map<std::string, Tap> taps;
 
+    // variant 2: the F0 / energy predictor ProsodyPredictor.F0Ntrain (models.py:407-419, :448-461); cfg.dim_in = d_hid
+    ConvW lstm_ih[2];                       // x W_ih^T + b_ih per direction, as 1x1 convs
+    float *lstm_whh = nullptr;              // [2][H][4H]  W_hh^T
+    float *lstm_bhh = nullptr;              // [2][4H]
+    ResBlk1dW pred_blk[2][3];               // F0.{0,1,2}, N.{0,1,2}
+    ConvW pred_proj[2];                     // F0_proj, N_proj
+
     // per-launch event profile (one boundary event after every launch of a profiled forward)
     struct ProfRec { int cat; double flops; double bytes; };
     bool profiling = false;
@@ -183,6 +190,28 @@ struct Packer {
             }
         }
     }
+    // nn.Linear / nn.LSTM input matrix [Cout, Cin] as a 1x1 conv (packed [1][Cin][Cout] + 16-bit copies)
+    void linear(ConvW& c, const std::string& wname, const std::string& bname, int Cin, int Cout) {
+        c.Cin = Cin; c.Cout = Cout; c.k = 1; c.transposed = false;
+        const RawTensor* v = get(wname);
+        if (!v) return;
+        if (v->numel() != (int64_t)Cin * Cout || v->shape.empty() || v->shape[0] != Cout) {
+            set_error("weight '%s' has the wrong shape (expected [%d,%d])", wname.c_str(), Cout, Cin);
+            err = ST2_ERR_INVALID;
+            return;
+        }
+        c.w32 = (float*)dalloc((size_t)Cin * Cout * sizeof(float));
+        if (!c.w32) return;
+        if (launch_fold_pack(nullptr, v->ptr, c.w32, Cout, Cin, 1, 0, st) != ST2_OK) err = ST2_ERR_CUDA;
+        if (!bname.empty()) c.bias = copy(bname, Cout);
+        if (d->tc_ok && Cin % 64 == 0 && Cout % 16 == 0) {
+            c.cin_pad = Cin; c.cout_pad = Cout;
+            for (int dt = DT_BF16; dt <= DT_F16; ++dt) {
+                c.w16[dt] = dalloc((size_t)Cin * Cout * 2);
+                if (c.w16[dt] && launch_pack_w16(c.w32, c.w16[dt], 1, Cin, Cout, Cin, Cout, dt, st) != ST2_OK) err = ST2_ERR_CUDA;
+            }
+        }
+    }
     void adain(AdaINRef& a, const std::string& prefix, int C) {
         a.C = C;
         a.h_off = d->fc_rows;
@@ -227,10 +256,41 @@ struct Packer {
     }
 };
 
-static int finalize_impl(st2_decoder* d, cudaStream_t st) {
+// ProsodyPredictor.F0Ntrain weights (models.py:407-419)
+static void pack_predictor(st2_decoder* d, Packer& P) {
+    const int dh = d->cfg.dim_in, H = dh / 2, I = dh + d->cfg.style_dim;
+    d->lstm_whh = (float*)P.dalloc((size_t)2 * H * 4 * H * sizeof(float));
+    d->lstm_bhh = (float*)P.dalloc((size_t)2 * 4 * H * sizeof(float));
+    for (int dir = 0; dir < 2; ++dir) {
+        const std::string sfx = dir ? "_reverse" : "";
+        P.linear(d->lstm_ih[dir], "shared.weight_ih_l0" + sfx, "shared.bias_ih_l0" + sfx, I, 4 * H);
+        const RawTensor* whh = P.get("shared.weight_hh_l0" + sfx);
+        const RawTensor* bhh = P.get("shared.bias_hh_l0" + sfx);
+        if (!whh || !bhh || !d->lstm_whh || !d->lstm_bhh) return;
+        if (whh->numel() != (int64_t)4 * H * H || bhh->numel() != 4 * H) {
+            set_error("shared.weight_hh_l0%s / bias_hh_l0%s have the wrong shape", sfx.c_str(), sfx.c_str());
+            P.err = ST2_ERR_INVALID;
+            return;
+        }
+        // [4H][H] -> [H][4H]: the recurrence kernel reads gate columns contiguously
+        if (launch_fold_pack(nullptr, whh->ptr, d->lstm_whh + (size_t)dir * H * 4 * H, 4 * H, H, 1, 0, P.st) != ST2_OK)
+            P.err = ST2_ERR_CUDA;
+        if (cudaMemcpyAsync(d->lstm_bhh + (size_t)dir * 4 * H, bhh->ptr, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice,
+                            P.st) != cudaSuccess)
+            P.err = ST2_ERR_CUDA;
+    }
+    const char* br[2] = {"F0", "N"};
+    for (int i = 0; i < 2; ++i) {
+        P.resblk1d(d->pred_blk[i][0], std::string(br[i]) + ".0", dh, dh, false);
+        P.resblk1d(d->pred_blk[i][1], std::string(br[i]) + ".1", dh, H, true);
+        P.resblk1d(d->pred_blk[i][2], std::string(br[i]) + ".2", H, H, false);
+        P.conv(d->pred_proj[i], std::string(br[i]) + "_proj", H, 1, 1, false, true, false);
+    }
+}
+
+// Decoder weights (hifigan.py:416-443, istftnet.py:660-690)
+static void pack_decoder(st2_decoder* d, Packer& P) {
     const st2_config& c = d->cfg;
-    Packer P{d, st};
-    d->fc_rows = 0;
     const int dim_in = c.dim_in;
     P.resblk1d(d->encode, "encode", dim_in + 2, 1024, false);
     for (int i = 0; i < 3; ++i) P.resblk1d(d->decode[i], "decode." + std::to_string(i), 1024 + 2 + 64, 1024, false);
@@ -276,6 +336,14 @@ static int finalize_impl(st2_decoder* d, cudaStream_t st) {
         d->stft_br = P.copy("generator.stft.weight_backward_real", (int64_t)bins * n);
         d->stft_bi = P.copy("generator.stft.weight_backward_imag", (int64_t)bins * n);
     }
+}
+
+static int finalize_impl(st2_decoder* d, cudaStream_t st) {
+    const st2_config& c = d->cfg;
+    Packer P{d, st};
+    d->fc_rows = 0;
+    if (c.variant == 2) pack_predictor(d, P);
+    else pack_decoder(d, P);
     if (P.err != ST2_OK) return P.err;
     // all AdaIN fc layers -> one [R,style] matrix (rows: gamma(C) | beta(C) per instance)
     d->fc_w = (float*)P.dalloc((size_t)d->fc_rows * c.style_dim * sizeof(float));
@@ -352,6 +420,7 @@ struct Exec {
     int fmt_for(const std::string& name) const {
         if (prec == ST2_PREC_FP32) return DT_F32;
         if (prec == ST2_PREC_FP16) return DT_F16;
+        if (d->cfg.variant == 2) return DT_F16;   // predictor: 0.4 % of the decoder's FLOPs, its outputs steer the SineGen phase
         // bf16 for the generator resblocks / ups (96 % of the FLOPs).  fp16 operands (same tensor
         // throughput) for generator.noise_res -- bf16 there alone costs ~9 dB of SNR -- and for the
         // front half (encode / decode / asr_res, K up to 3270), whose five chained blocks otherwise
@@ -828,6 +897,64 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     return E.err;
 }
 
+// ProsodyPredictor.F0Ntrain(x, s) (models.py:448-461): en [B, d_hid+style, T], s [B, style] -> F0 [B,2T], N [B,2T]
+static int f0n_forward_impl(st2_decoder* d, const float* en, const float* s, float* f0_out, float* n_out, int B, int T,
+                            int prec, void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
+    const st2_config& c = d->cfg;
+    const int dh = c.dim_in, H = dh / 2, I = dh + c.style_dim;
+    Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    float* Hs = E.allocf((int64_t)B * d->fc_rows);
+    E.H = Hs;
+    E.coef = E.allocf((int64_t)B * 2 * 2048);
+    float* x = E.allocf((int64_t)B * T * I);            // en, channels-last
+    float* G = E.allocf((int64_t)B * T * 8 * H);        // input half of the gates, fwd 4H | rev 4H per row
+    float* y = E.allocf((int64_t)B * T * dh);           // LSTM output, fwd H | rev H
+    if (E.live()) {
+        if (d->profiling) {
+            d->prof_recs.clear();
+            if (d->prof_events.empty()) {
+                cudaEvent_t ev;
+                if (cudaEventCreate(&ev) == cudaSuccess) d->prof_events.push_back(ev);
+            }
+            if (!d->prof_events.empty()) cudaEventRecord(d->prof_events[0], st);
+        }
+        E.chk(launch_style_fc(s, d->fc_w, d->fc_b, Hs, B, d->fc_rows, c.style_dim, st));
+        E.chk(launch_cf_to_cl(en, x, I, B, I, T, st));
+        E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim, 4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * I * T));
+    }
+    // x, _ = self.shared(x.transpose(-1, -2))   (models.py:449)
+    {
+        const int64_t mark = E.off;
+        const int dt = E.fmt_for("shared");
+        const bool tc = E.use_tc(d->lstm_ih[0], dt) && E.use_tc(d->lstm_ih[1], dt);
+        const void* xin = x;
+        if (tc) {
+            void* x16 = E.alloc((int64_t)B * T * I * 2);
+            E.norm_act(x, I, T, I, nullptr, ACT_NONE, 0.f, nullptr, x16, I, dt);
+            xin = x16;
+        }
+        for (int dir = 0; dir < 2; ++dir)
+            E.conv(d->lstm_ih[dir], xin, I, T, tc ? dt : DT_F32, G + (size_t)dir * 4 * H, 8 * H, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
+        if (E.live()) E.chk(launch_lstm_bidir(G, d->lstm_whh, d->lstm_bhh, y, B, T, H, st));
+        E.prof(PC_LSTM, 2.0 * B * T * 2 * 4 * H * H, 4.0 * B * T * (8 * H + 2 * H) + 4.0 * 2 * 4 * H * H);
+        E.off = mark;
+    }
+    E.tap("shared", y, dh, (int64_t)B * T, dh);
+    for (int br = 0; br < 2; ++br) {                     // models.py:451-454 (F0) and :456-459 (N)
+        const int64_t mark = E.off;
+        float* a0 = E.allocf((int64_t)B * T * dh);
+        E.resblk1d(d->pred_blk[br][0], y, dh, T, a0, dh);
+        float* a1 = E.allocf((int64_t)B * 2 * T * H);
+        E.resblk1d(d->pred_blk[br][1], a0, dh, T, a1, H);
+        float* a2 = E.allocf((int64_t)B * 2 * T * H);
+        E.resblk1d(d->pred_blk[br][2], a1, H, 2 * T, a2, H);
+        E.conv(d->pred_proj[br], a2, H, 2 * T, DT_F32, br == 0 ? f0_out : n_out, 1, 2 * T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
+        E.off = mark;
+    }
+    if (peak_out) *peak_out = E.peak;
+    return E.err;
+}
+
 }  // namespace st2
 
 // ------------------------------------------------------------------------------------------
@@ -894,8 +1021,8 @@ int st2_decoder_finalize(st2_decoder* d, void* stream) {
 int64_t st2_decoder_num_params(const st2_decoder* d) { return d ? d->num_params : 0; }
 
 int64_t st2_decoder_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision) {
-    if (!d || !d->finalized || B <= 0 || T <= 0) {
-        st2::set_error("workspace_bytes: handle not finalized or bad shape");
+    if (!d || !d->finalized || d->cfg.variant == 2 || B <= 0 || T <= 0) {
+        st2::set_error("workspace_bytes: handle not finalized (or a predictor handle) or bad shape");
         return ST2_ERR_STATE;
     }
     int64_t peak = 0;
@@ -909,8 +1036,8 @@ int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const
                         const float* noise, uint64_t seed, float* out, int32_t B, int32_t T, int32_t precision,
                         void* workspace, int64_t workspace_bytes, void* stream) {
     ST2_REQUIRE(d != nullptr, "forward: null handle");
-    if (!d->finalized) {
-        st2::set_error("forward: st2_decoder_finalize has not been called");
+    if (!d->finalized || d->cfg.variant == 2) {
+        st2::set_error("forward: st2_decoder_finalize has not been called (or this is a predictor handle)");
         return ST2_ERR_STATE;
     }
     ST2_REQUIRE(asr && f0 && n && s && out && workspace, "forward: null tensor");
@@ -924,6 +1051,59 @@ int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const
     st2::g_launch_count = 0;
     int e = st2::forward_impl(d, asr, f0, n, s, noise, seed, out, B, T, precision, workspace, workspace_bytes,
                               (cudaStream_t)stream, false, nullptr);
+    d->last_launches = st2::g_launch_count;
+    return e;
+}
+
+/* ---- F0 / energy predictor: replaces ProsodyPredictor.F0Ntrain, models.py:448-461 ---- */
+int st2_f0n_create(int32_t d_hid, int32_t style_dim, st2_decoder** out) {
+    ST2_REQUIRE(out != nullptr, "f0n_create: null argument");
+    ST2_REQUIRE(d_hid == 512, "f0n_create: d_hid must be 512 (got %d)", d_hid);
+    ST2_REQUIRE(style_dim >= 4 && style_dim <= 1024 && (d_hid + style_dim) % 64 == 0,
+                "f0n_create: d_hid + style_dim must be a multiple of 64 (style_dim=%d)", style_dim);
+    st2_decoder* d = new (std::nothrow) st2_decoder();
+    ST2_REQUIRE(d != nullptr, "f0n_create: out of memory");
+    memset(&d->cfg, 0, sizeof(d->cfg));
+    d->cfg.variant = 2;
+    d->cfg.dim_in = d_hid;
+    d->cfg.style_dim = style_dim;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+        d->tc_ok = (prop.major == 10);
+    *out = d;
+    return ST2_OK;
+}
+
+int64_t st2_f0n_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision) {
+    if (!d || !d->finalized || d->cfg.variant != 2 || B <= 0 || T <= 0) {
+        st2::set_error("f0n_workspace_bytes: not a finalized predictor handle, or bad shape");
+        return ST2_ERR_STATE;
+    }
+    int64_t peak = 0;
+    int e = st2::f0n_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, nullptr, B, T, precision, nullptr, 0,
+                                  nullptr, true, &peak);
+    if (e != ST2_OK) return e;
+    return peak + 256;
+}
+
+int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, float* f0, float* n, int32_t B, int32_t T,
+                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+    ST2_REQUIRE(d != nullptr, "f0n_forward: null handle");
+    if (!d->finalized || d->cfg.variant != 2) {
+        st2::set_error("f0n_forward: not a finalized predictor handle (st2_f0n_create + st2_decoder_finalize)");
+        return ST2_ERR_STATE;
+    }
+    ST2_REQUIRE(en && s && f0 && n && workspace, "f0n_forward: null tensor");
+    ST2_REQUIRE(B > 0 && T >= 1, "f0n_forward: need B>0 and T>=1 (got B=%d T=%d)", B, T);
+    ST2_REQUIRE(precision >= ST2_PREC_FP32 && precision <= ST2_PREC_FP16, "f0n_forward: bad precision %d", precision);
+    if (precision != ST2_PREC_FP32 && !d->tc_ok) {
+        st2::set_error("f0n_forward: tensor-core precision requires an sm_100 device");
+        return ST2_ERR_UNSUPPORTED;
+    }
+    ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "f0n_forward: workspace must be 256-byte aligned");
+    st2::g_launch_count = 0;
+    int e = st2::f0n_forward_impl(d, en, s, f0, n, B, T, precision, workspace, workspace_bytes, (cudaStream_t)stream, false, nullptr);
     d->last_launches = st2::g_launch_count;
     return e;
 }
@@ -954,7 +1134,7 @@ int st2_profile_num_categories(void) { return st2::PC_COUNT; }
 
 const char* st2_profile_category_name(int32_t cat) {
     static const char* names[st2::PC_COUNT] = {"conv_tc", "conv_simt", "norm_stats", "norm_coef", "affine_act",
-                                               "source", "post", "misc", "conv_fused", "conv_pipe"};
+                                               "source", "post", "misc", "conv_fused", "conv_pipe", "lstm"};
     return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
 }
 

@@ -21,7 +21,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from .config import DecoderConfig, param_specs, buffer_specs, HARMONICS
+from .config import DecoderConfig, PredictorConfig, param_specs, predictor_param_specs, buffer_specs, HARMONICS, HIDDEN_DIM, STYLE_DIM
 
 
 def _fan_in(shape):
@@ -33,8 +33,28 @@ def _fan_in(shape):
 
 def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = _draw(param_specs(cfg), g, perturb)
+    for name, shape in buffer_specs(cfg):
+        sd[name] = stft_buffers(cfg)[name]
+    return {k: v.float().contiguous() for k, v in sd.items()}
+
+
+def make_predictor_state_dict(cfg: PredictorConfig | None = None, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
+    """The F0Ntrain subset of a ProsodyPredictor state_dict (models.py:407-419), drawn like make_state_dict."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = _draw(predictor_param_specs(cfg or PredictorConfig()), g, perturb)
+    return {k: v.float().contiguous() for k, v in sd.items()}
+
+
+def make_predictor_inputs(B: int, T: int, seed: int = 2000, cfg: PredictorConfig | None = None) -> Dict[str, torch.Tensor]:
+    """en [B, d_hid+style_dim, T] (the length-regulated DurationEncoder output, inference.py:267) and s [B, style_dim]."""
+    cfg = cfg or PredictorConfig()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return {"en": torch.randn(B, cfg.d_hid + cfg.style_dim, T, generator=g), "s": torch.randn(B, cfg.style_dim, generator=g)}
+
+
+def _draw(specs, g, perturb: bool) -> Dict[str, torch.Tensor]:
     sd: Dict[str, torch.Tensor] = {}
-    specs = param_specs(cfg)
     # pass 1: everything that does not depend on another tensor
     for name, shape, kind in specs:
         if kind == "conv":
@@ -51,6 +71,9 @@ def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> 
                 sd[name] = 0.6 + 0.8 * torch.rand(shape, generator=g)
             else:
                 sd[name] = torch.ones(shape)
+        elif kind.startswith("lstm:"):                      # nn.LSTM init: U(-1/sqrt(hidden), 1/sqrt(hidden))
+            bound = 1.0 / math.sqrt(int(kind.split(":")[1]))
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
     # pass 2: g and conv biases
     for name, shape, kind in specs:
         if kind.startswith("g:"):
@@ -63,9 +86,7 @@ def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> 
             w = sd[kind[5:]]
             bound = 1.0 / math.sqrt(_fan_in(w.shape))
             sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
-    for name, shape in buffer_specs(cfg):
-        sd[name] = stft_buffers(cfg)[name]
-    return {k: v.float().contiguous() for k, v in sd.items()}
+    return sd
 
 
 def stft_buffers(cfg: DecoderConfig) -> Dict[str, torch.Tensor]:
@@ -128,3 +149,12 @@ def make_durations(B: int, L: int, F: int, seed: int = 7) -> torch.Tensor:
         extra = torch.randint(0, L, (F - L,), generator=g)
         dur[b] += torch.bincount(extra, minlength=L)
     return dur
+
+
+def make_chain_inputs(B: int, L: int, T: int, seed: int = 3003) -> Dict[str, torch.Tensor]:
+    """Inputs of the chained slice inference.py:257-270 (cfg 3 after the text modules): integer durations [B,L]
+    summing to T, DurationEncoder output d [B,L,640], TextEncoder output t_en [B,512,L], style s, SineGen noise."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return {"dur": make_durations(B, L, T, seed=seed + 8), "d": torch.randn(B, L, HIDDEN_DIM + STYLE_DIM, generator=g),
+            "t_en": torch.randn(B, HIDDEN_DIM, L, generator=g), "s": torch.randn(B, STYLE_DIM, generator=g),
+            "noise": torch.randn(B, 600 * T, HARMONICS, generator=g)}

@@ -1,0 +1,140 @@
+"""-m gpu: SURVEY.md §8(f) N1 -- `ProsodyPredictor.F0Ntrain` through the drop-in module / C ABI, and the chained
+cfg-3 slice inference.py:257-270 (length regulator -> F0Ntrain -> Decoder) against fixtures of the unmodified reference.
+
+fp32 path: max-abs <= 1e-4 against the reference's F0 / N (same bar as the decoder's fp32 path); 16-bit path:
+per-layer relative L2 <= 1e-2 and output SNR >= 40 dB."""
+import numpy as np
+import pytest
+import torch
+
+from styletts2_lite_b200.config import DecoderConfig
+from styletts2_lite_b200 import synth
+from oracle import predictor_np as P
+from helpers import golden, rel_l2, snr_db
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_util as G
+    from styletts2_lite_b200 import _lib, length_regulator as LR
+    from styletts2_lite_b200.decoder import B200Decoder
+    from styletts2_lite_b200.predictor import B200F0NPredictor
+
+_CACHE = {}
+
+
+def _predictor():
+    if "p" not in _CACHE:
+        m = B200F0NPredictor(style_dim=128, d_hid=512, nlayers=3, max_dur=50, dropout=0.2)
+        m.load_state_dict(synth.make_predictor_state_dict(seed=0))
+        _CACHE["p"] = m.to("cuda").eval()
+    return _CACHE["p"]
+
+
+def _np_sd():
+    return {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0).items()}
+
+
+def _run(m, inp, precision="fp32"):
+    with torch.no_grad():
+        f0, n = m.F0Ntrain(inp["en"].cuda(), inp["s"].cuda(), precision=precision)
+    torch.cuda.synchronize()
+    return f0.cpu().numpy(), n.cpu().numpy()
+
+
+def test_f0n_small_fp32_golden_and_taps():
+    g = golden("f0n_B2_T6_w0_i2001.npz")
+    m = _predictor()
+    inp = synth.make_predictor_inputs(2, 6, seed=2001)
+    shapes = {"shared": (6, 512), "F0.0": (6, 512), "F0.1": (12, 256), "F0.2": (12, 256), "N.1": (12, 256)}
+    bufs = {k: m.set_tap(k, 2, r, c) for k, (r, c) in shapes.items()}
+    f0, n = _run(m, inp)
+    m.clear_taps()
+    assert np.abs(f0 - g["F0"]).max() <= 1e-4 and np.abs(n - g["N"]).max() <= 1e-4
+    ref_shared = g["tap:shared"]                                   # [B, T, 512] (batch_first LSTM output)
+    assert np.abs(bufs["shared"].cpu().numpy() - ref_shared).max() <= 2e-5
+    for k in ("F0.0", "F0.1", "F0.2", "N.1"):
+        assert rel_l2(g["tap:" + k], G.cf(bufs[k].cpu().numpy())) <= 2e-5, k
+
+
+def test_f0n_3s_fp32_golden():
+    g = golden("f0n_B1_T120_w0_i2002.npz")
+    f0, n = _run(_predictor(), synth.make_predictor_inputs(1, 120, seed=2002))
+    assert np.abs(f0 - g["F0"]).max() <= 1e-4 and np.abs(n - g["N"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(11, 37), (1, 1), (17, 2)])
+def test_f0n_ragged_batches_vs_oracle(B, T):
+    """Batch sizes that do not fill the 8-utterance clusters of the LSTM kernel, odd lengths, a single frame."""
+    inp = synth.make_predictor_inputs(B, T, seed=2100 + B)
+    f0, n = _run(_predictor(), inp)
+    rf0, rn = P.f0n_train(_np_sd(), inp["en"].numpy(), inp["s"].numpy())
+    # InstanceNorm over 2-4 time steps is ill-conditioned (two nearly equal samples -> rstd up to 1/sqrt(eps) = 316
+    # amplifies rounding differences of the producing conv): looser bound for the degenerate lengths only
+    tol = 1e-4 if T >= 8 else 1e-3
+    assert np.abs(f0 - rf0).max() <= tol and np.abs(n - rn).max() <= tol
+
+
+def test_f0n_batch_independence():
+    inp = synth.make_predictor_inputs(9, 50, seed=2200)
+    m = _predictor()
+    f0, n = _run(m, inp)
+    one = {"en": inp["en"][4:5], "s": inp["s"][4:5]}
+    f1, n1 = _run(m, one)
+    assert np.array_equal(f0[4:5], f1) and np.array_equal(n[4:5], n1)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_f0n_tensor_core_path(prec):
+    """cfg-3 batch shape (32 x 8 s): 16-bit operands on the convolutions against this library's fp32 path (itself
+    within 1e-4 of the reference) -- SNR >= 40 dB on both outputs, and per-layer taps within 1e-2."""
+    B, T = 32, 320
+    inp = synth.make_predictor_inputs(B, T, seed=2300)
+    m = _predictor()
+    shapes = {"shared": (T, 512), "F0.0": (T, 512), "F0.1": (2 * T, 256), "F0.2": (2 * T, 256), "N.2": (2 * T, 256)}
+    bufs = {k: m.set_tap(k, B, r, c) for k, (r, c) in shapes.items()}
+    f0, n = _run(m, inp)
+    ref = {k: v.cpu().numpy().copy() for k, v in bufs.items()}
+    f0h, nh = _run(m, inp, precision=prec)
+    m.clear_taps()
+    for k in shapes:
+        assert rel_l2(ref[k], bufs[k].cpu().numpy()) <= 1e-2, k
+    assert snr_db(f0, f0h) >= 40.0 and snr_db(n, nh) >= 40.0
+
+
+def test_f0n_error_behaviour():
+    m = _predictor()
+    with pytest.raises(_lib.St2Error):
+        m.F0Ntrain(torch.zeros(1, 640, 4), torch.zeros(1, 128))            # CPU tensors: no CPU path
+    with pytest.raises(ValueError):
+        m.F0Ntrain(torch.zeros(1, 512, 4).cuda(), torch.zeros(1, 128).cuda())
+    lib = _lib.load()
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.st2_f0n_create(384, 128, C.byref(h)) == -1                  # ST2_ERR_INVALID, message set
+    assert b"d_hid" in lib.st2_last_error()
+    # a predictor handle is rejected by the decoder entry points
+    assert lib.st2_decoder_workspace_bytes(m._handle, 1, 4, 0) < 0
+
+
+def test_chain_regulator_predictor_decoder_matches_reference():
+    """inference.py:257-270 on the GPU: durations -> (bit-exact) length regulation of d and t_en -> F0Ntrain ->
+    Decoder, against the same chain run through the unmodified reference (tests/golden/make_golden_predictor.py)."""
+    g = golden("chain_B2_L9_T16_w0.npz")
+    B, L, T = 2, 9, 16
+    ci = synth.make_chain_inputs(B, L, T, seed=3003)
+    dur = ci["dur"].to(torch.int32).cuda()
+    assert np.array_equal(dur.cpu().numpy(), g["dur"])
+    en = LR.length_regulate(ci["d"].transpose(1, 2).contiguous().cuda(), dur, T)       # d^T @ alignment (inference.py:266)
+    asr = LR.length_regulate(ci["t_en"].cuda(), dur, T)                                # t_en @ alignment (inference.py:269)
+    assert torch.equal(en.cpu(), torch.from_numpy(g["en"])) and torch.equal(asr.cpu(), torch.from_numpy(g["asr"]))
+    s = ci["s"].cuda()
+    with torch.no_grad():
+        f0, n = _predictor().F0Ntrain(en, s)
+        assert np.abs(f0.cpu().numpy() - g["F0"]).max() <= 1e-4 and np.abs(n.cpu().numpy() - g["N"]).max() <= 1e-4
+        cfg = DecoderConfig.hifigan()
+        dec = B200Decoder(cfg, "fp32")
+        dec.load_state_dict(synth.make_state_dict(cfg, 0, True))
+        dec = dec.to("cuda").eval()
+        out = dec(asr, f0, n, s, noise=ci["noise"].cuda())
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= 1e-4

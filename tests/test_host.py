@@ -66,6 +66,26 @@ def test_state_dict_schema_matches_reference(variant):
     assert torch.equal(m.state_dict()["generator.conv_post.weight_v"], sd["generator.conv_post.weight_v"])
 
 
+def test_predictor_state_dict_schema_matches_reference():
+    """F0Ntrain subset of ProsodyPredictor.state_dict() (models.py:407-419), checked against the reference module when
+    the fixture was made; a full predictor state_dict loads with the duration half ignored."""
+    from styletts2_lite_b200.config import PredictorConfig, predictor_param_specs
+    from styletts2_lite_b200.predictor import B200F0NPredictor
+    schema = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")))["predictor_f0n"]
+    assert {n: list(s) for n, s, _ in predictor_param_specs(PredictorConfig())} == schema["state_dict"]
+    m = B200F0NPredictor(style_dim=128, d_hid=512, nlayers=3, max_dur=50, dropout=0.2)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == schema["state_dict"]
+    sd = synth.make_predictor_state_dict(seed=0)
+    full = dict(sd)
+    full["duration_proj.linear_layer.weight"] = torch.zeros(50, 512)      # entries of the duration half are skipped
+    full["lstm.weight_ih_l0"] = torch.zeros(1024, 640)
+    r = m.load_state_dict(full)
+    assert not r.missing_keys and not r.unexpected_keys
+    assert torch.equal(m.state_dict()["shared.weight_hh_l0_reverse"], sd["shared.weight_hh_l0_reverse"])
+    with pytest.raises(Exception):
+        m.F0Ntrain(torch.zeros(1, 640, 4), torch.zeros(1, 128))           # no CPU path
+
+
 def test_no_cpu_fallback():
     from styletts2_lite_b200 import hifigan, length_regulator
     m = hifigan.Decoder(style_dim=128)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from styletts2_lite_b200.config import DecoderConfig
+from styletts2_lite_b200 import synth
 from oracle import decoder_np as O
 from helpers import golden, np_inputs, np_state_dict, sha, rel_l2
 
@@ -136,3 +137,44 @@ def test_torch_cpu_port_matches_golden():
         inp = synth.make_inputs(B, T, seed, cfg)
         out = OT.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"]).numpy()
         assert np.abs(out - g["out"]).max() <= WAVE_TOL, name
+
+
+# ---------------------------------------------------------------- §8(f) N1: F0Ntrain
+def test_predictor_oracle_matches_reference_fixtures():
+    from oracle import predictor_np as P
+    sd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0).items()}
+    g = golden("f0n_B2_T6_w0_i2001.npz")
+    inp = synth.make_predictor_inputs(2, 6, seed=2001)
+    taps = {}
+    f0, n = P.f0n_train(sd, inp["en"].numpy(), inp["s"].numpy(), taps=taps)
+    assert np.abs(f0 - g["F0"]).max() <= 1e-5 and np.abs(n - g["N"]).max() <= 1e-5
+    assert np.abs(taps["shared"] - g["tap:shared"]).max() <= 5e-6
+    for k in ("F0.0", "F0.1", "F0.2", "N.1"):
+        assert np.abs(taps[k] - g["tap:" + k]).max() <= 2e-5, k
+    g = golden("f0n_B1_T120_w0_i2002.npz")
+    inp = synth.make_predictor_inputs(1, 120, seed=2002)
+    f0, n = P.f0n_train(sd, inp["en"].numpy(), inp["s"].numpy())
+    assert np.abs(f0 - g["F0"]).max() <= 1e-5 and np.abs(n - g["N"]).max() <= 1e-5
+
+
+def test_chain_fixture_is_consistent_with_oracle():
+    """The chained cfg-3 fixture: oracle regulator reproduces en / asr bit-exactly, oracle F0Ntrain the F0 / N."""
+    from oracle import predictor_np as P
+    g = golden("chain_B2_L9_T16_w0.npz")
+    ci = synth.make_chain_inputs(2, 9, 16, seed=3003)
+    en = O.length_regulate_batch(ci["d"].numpy().transpose(0, 2, 1), g["dur"].astype(np.int64), 16)
+    assert np.array_equal(en, g["en"])
+    assert np.array_equal(O.length_regulate_batch(ci["t_en"].numpy(), g["dur"].astype(np.int64), 16), g["asr"])
+    sd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0).items()}
+    f0, n = P.f0n_train(sd, en, ci["s"].numpy())
+    assert np.abs(f0 - g["F0"]).max() <= 1e-5 and np.abs(n - g["N"]).max() <= 1e-5
+
+
+def test_predictor_torch_port_matches_reference_fixture():
+    import torch
+    from oracle import predictor_torch as PT
+    g = golden("f0n_B1_T120_w0_i2002.npz")
+    inp = synth.make_predictor_inputs(1, 120, seed=2002)
+    with torch.no_grad():
+        f0, n = PT.f0n_train(synth.make_predictor_state_dict(seed=0), inp["en"], inp["s"])
+    assert np.abs(f0.numpy() - g["F0"]).max() <= 1e-6 and np.abs(n.numpy() - g["N"]).max() <= 1e-6
