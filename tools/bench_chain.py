@@ -1,0 +1,78 @@
+"""BASELINE.json configs[2] after the text modules, on the GPU box: inference.py:257-270 as one pass
+    durations -> length regulation of d and t_en -> F0Ntrain -> Decoder
+for 32 utterances x 8 s (T=320, 64 tokens each, seeded integer durations as SURVEY.md 8(d) cfg 3 prescribes).
+Times the pass with CUDA events (inputs resident), reports the three parts and checks the 16-bit result against the fp32 path.
+    python tools/bench_chain.py [--batch 32] [--frames 320] [--tokens 64] [--iters 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from styletts2_lite_b200 import length_regulator as LR, synth  # noqa: E402
+from styletts2_lite_b200.config import DecoderConfig  # noqa: E402
+from styletts2_lite_b200.decoder import B200Decoder  # noqa: E402
+from styletts2_lite_b200.predictor import B200F0NPredictor  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--frames", type=int, default=320)
+ap.add_argument("--tokens", type=int, default=64)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--precision", default="bf16")
+a = ap.parse_args()
+B, L, T = a.batch, a.tokens, a.frames
+
+cfg = DecoderConfig.hifigan()
+dec = B200Decoder(cfg, a.precision)
+dec.load_state_dict(synth.make_state_dict(cfg, 0, True))
+dec = dec.cuda().eval()
+pred = B200F0NPredictor(precision=a.precision)
+pred.load_state_dict(synth.make_predictor_state_dict(seed=0))
+pred = pred.cuda().eval()
+ci = synth.make_chain_inputs(B, L, T, seed=3100)
+dur = ci["dur"].to(torch.int32).cuda()
+d_t = ci["d"].transpose(1, 2).contiguous().cuda()          # [B,640,L]
+t_en, s, noise = ci["t_en"].cuda(), ci["s"].cuda(), ci["noise"].cuda()
+
+
+def chain(precision, seed=None, tape=None, ev=None):
+    en = LR.length_regulate(d_t, dur, T)
+    asr = LR.length_regulate(t_en, dur, T)
+    if ev: ev[1].record()
+    f0, n = pred.F0Ntrain(en, s, precision=precision)
+    if ev: ev[2].record()
+    out = dec(asr, f0, n, s, noise=tape, seed=seed, precision=precision)
+    if ev: ev[3].record()
+    return out
+
+
+with torch.no_grad():
+    ref = chain("fp32", tape=noise)
+    got = chain(a.precision, tape=noise)
+    e = (got - ref).double()
+    snr = float(10 * torch.log10((ref.double() ** 2).sum() / (e ** 2).sum()))
+    for i in range(3):
+        chain(a.precision, seed=i)
+    torch.cuda.synchronize()
+    parts = np.zeros(3)
+    tot = 0.0
+    for i in range(a.iters):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        chain(a.precision, seed=10 + i, ev=ev)
+        torch.cuda.synchronize()
+        parts += [ev[j].elapsed_time(ev[j + 1]) for j in range(3)]
+        tot += ev[0].elapsed_time(ev[3])
+secs = B * T / 40.0
+print(json.dumps({"path": "length regulator -> F0Ntrain -> Decoder (inference.py:257-270)", "batch": B, "tokens": L, "frames": T,
+                  "audio_s": secs, "precision": a.precision, "ms": round(tot / a.iters, 3),
+                  "audio_s_per_s": round(secs / (tot / a.iters) * 1e3, 1),
+                  "ms_parts": {"length_regulator": round(parts[0] / a.iters, 4), "f0n_predictor": round(parts[1] / a.iters, 4),
+                               "decoder": round(parts[2] / a.iters, 4)},
+                  "snr_db_vs_fp32_path": round(snr, 2)}))
