@@ -144,7 +144,8 @@ struct ConvArgs {
     float scale; int accumulate; int mirror;
     int fmt16;                               // DT_BF16 / DT_F16 for the tensor-core path
     int x16in;                               // fused path: the input tensor x is 16-bit (fmt16) with pitch ld_x elements
-    int y16out;                              // fused path: write y as 16-bit (fmt16); statistics still from the fp32 values
+    int y16out;                              // fused path: write y as fp16; statistics still from the fp32 values
+    int res16;                               // fused path (conv_pipe only): the residual tensor is fp16 with pitch ld_res elements
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);   // tcgen05 + TMA

@@ -71,6 +71,7 @@ struct PipeParams {
     int pair;                   // 1: the MMA warp runs two consecutive tiles against every weight stage (streamed weights,
                                 //    2 K chunks, 4 operand buffers, 4 accumulators): half the weight traffic into shared memory
     int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
+    int r16;                    // the residual tensor is fp16 (the running tensor of AdaINResBlock1): four [32 rows x 32 ch] boxes
     // epilogue
     const float* bias;
     float* y; int ld_y; float scale; int y16out;   // y already shifted by -out_pad*cdiv rows for a transposed conv
@@ -162,6 +163,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
     const uint32_t a_bytes = ((uint32_t)p.rows * arow + 1023u) & ~1023u;
     const uint32_t b_stage_bytes = (uint32_t)p.bn * arow;
     const uint32_t r_stage_bytes = p.nres ? (uint32_t)p.nres * P_RBOX : 0u;
+    const uint32_t r_tx_bytes = p.r16 ? r_stage_bytes - (uint32_t)P_RBOX / 2u : r_stage_bytes;     // an fp16 residual box is half the bytes
     const uint32_t r_bytes = p.nres ? (uint32_t)p.nr * r_stage_bytes : (uint32_t)P_EW * 4096u;   // ring or per-warp staging
     uint8_t* smem_a = smem;                                        // na x [rows][K] 16-bit, swizzled
     uint8_t* smem_b = smem_a + (size_t)p.na * a_bytes;             // resident taps or ring of [bn][K]
@@ -285,14 +287,22 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 }
                 if (!r_done && mbar_test(&r_empty[r_stage], r_par ^ 1)) {
                     r_seq[r_stage] = r_c;
-                    mbar_expect_tx(&r_full[r_stage], r_stage_bytes);
+                    mbar_expect_tx(&r_full[r_stage], r_tx_bytes);
                     uint8_t* dst = smem_r + (size_t)r_stage * r_stage_bytes;
                     // columns [32*r_ch, +32) of accumulator row m are channels co0.. of output row m*ostride + phs - opad
                     //   = phase (phs - opad) mod ostride of row m + floor((phs - opad) / ostride) in the (c, phase, m, b) view
                     const int phs = (r_ch * 32) >> p.cshift, co0 = r_ch * 32 - phs * p.cdiv;
                     int u = phs - p.opad, moff = 0;
                     while (u < 0) { u += p.ostride; --moff; }
-                    tma_load_4d(dst, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
+                    if (p.r16) {
+                        // fp16 residual: one [32 rows x 32 ch] box (64-byte rows, SWIZZLE_64B) per TMEM lane quarter, each at the
+                        // start of the 4 KB region its epilogue warp later reuses as the fp32 transposition buffer
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq)
+                            tma_load_4d(dst + qq * 4096, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff + qq * 32, rt.b);
+                    } else {
+                        tma_load_4d(dst, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
+                    }
                     if (p.nres == 2) tma_load_4d(dst + P_RBOX, &map_o, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
                     ++r_c;
                     if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1; }
@@ -667,12 +677,26 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         if (lane == 0) mbar_arrive(&acc_empty[acc]);
                     }
                     if (NRES) {
+                        if (p.r16) {
+                            // row = lane of this quarter's fp16 box: 64-byte rows, 16-byte slots XOR-swizzled by (row >> 1) & 3
+                            const uint32_t st_h = tile_u32 + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 raw = lds128(st_h + (((uint32_t)i ^ sw) << 4));
+                                const float4 r0 = unpack16x4(make_uint2(__float_as_uint(raw.x), __float_as_uint(raw.y)), 0);
+                                const float4 r1 = unpack16x4(make_uint2(__float_as_uint(raw.z), __float_as_uint(raw.w)), 0);
+                                v[8 * i] += r0.x; v[8 * i + 1] += r0.y; v[8 * i + 2] += r0.z; v[8 * i + 3] += r0.w;
+                                v[8 * i + 4] += r1.x; v[8 * i + 5] += r1.y; v[8 * i + 6] += r1.z; v[8 * i + 7] += r1.w;
+                            }
+                            __syncwarp();                 // the fp32 rows written below overlap other lanes' fp16 rows
+                        } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 r = lds128(st_w + (((uint32_t)i ^ l7) << 4));
                             const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(r.x, r.y));
                             const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
                             v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+                        }
                         }
                         if (NRES == 2) {
 #pragma unroll
@@ -726,7 +750,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 if (p.y16out) run_chunks(std::integral_constant<int, 0>{}, std::true_type{});
                 else run_chunks(std::integral_constant<int, 0>{}, std::false_type{});
             } else if (p.nres == 1) {
-                run_chunks(std::integral_constant<int, 1>{}, std::false_type{});
+                if (p.y16out) run_chunks(std::integral_constant<int, 1>{}, std::true_type{});
+                else run_chunks(std::integral_constant<int, 1>{}, std::false_type{});
             } else {
                 run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
             }
@@ -747,6 +772,8 @@ int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad,
 int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
 int make_map_4d_f32_sw128(CUtensorMap* map, const void* base, uint64_t C, uint64_t phases, uint64_t rows, uint64_t B,
                           uint64_t ld_bytes, uint64_t batch_bytes, uint32_t b0, uint32_t b2);
+int make_map_4d_f16_sw64(CUtensorMap* map, const void* base, uint64_t C, uint64_t rows, uint64_t B, uint64_t ld_bytes,
+                         uint64_t batch_bytes, uint32_t b0, uint32_t b2);
 int make_map_3d_any(CUtensorMap* map, int dtype /*0 f32, 1 bf16, 2 f16*/, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle128);
 
@@ -782,10 +809,10 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if ((a.Cout & (a.Cout - 1)) != 0) return false;        // column -> phase is a shift
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
     // x16in / y16out: the intra-block tensor of AdaINResBlock1 stored as fp16 (plain stride-1 convs only)
-    if ((a.x16in || a.y16out) && tr) return false;
+    if ((a.x16in || a.y16out || a.res16) && tr) return false;
     if (a.y16out && a.accumulate) return false;
-    if (a.x16in && a.y16out) return false;
-    if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % 4 != 0)) return false;
+    if (a.res16 && a.res == nullptr) return false;
+    if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % (a.res16 ? 8 : 4) != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
     const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
     return span <= 64 && (tr || (a.in_off <= 0 && a.in_off + span >= 0));
@@ -844,6 +871,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     while (cols < p.nacc * p.bn) cols <<= 1;
     p.tmem_cols = cols;
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+    p.r16 = a.res16 ? 1 : 0;
     p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
     if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && p.nres > 0 && !tr_)) p.eg = v; }
     // 3 groups need 4 accumulators: a group's previous tile is tcnt-3, so MMA(tcnt-4) -- the previous use of its accumulator
@@ -953,7 +981,11 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     if (e != ST2_OK) return e;
     map_r = map_x;
     map_o = map_x;
-    if (a.res != nullptr) {
+    if (a.res != nullptr && a.res16) {
+        e = make_map_4d_f16_sw64(&map_r, a.res, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_res * 2,
+                                 (uint64_t)a.Tout * a.ld_res * 2, 32, 32);
+        if (e != ST2_OK) return e;
+    } else if (a.res != nullptr) {
         e = make_map_4d_f32_sw128(&map_r, a.res, (uint64_t)a.Cout, (uint64_t)a.phases, (uint64_t)(a.Tout / a.phases), (uint64_t)a.B,
                                   (uint64_t)a.ld_res * 4, (uint64_t)a.Tout * a.ld_res * 4, 32, P_MT);
         if (e != ST2_OK) return e;

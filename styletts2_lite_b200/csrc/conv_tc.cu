@@ -362,6 +362,31 @@ int make_map_4d_f32_sw128(CUtensorMap* map, const void* base, uint64_t C, uint64
     return ST2_OK;
 }
 
+// fp16 [B][T][C] tensor viewed as (c, 1, t, b): 64-byte-swizzled boxes of b0 = 32 channels x b2 rows (the fp16 residual boxes
+// of conv_pipe.cu; same coordinate order as make_map_4d_f32_sw128 so the producer issues both the same way)
+int make_map_4d_f16_sw64(CUtensorMap* map, const void* base, uint64_t C, uint64_t rows, uint64_t B, uint64_t ld_bytes,
+                         uint64_t batch_bytes, uint32_t b0, uint32_t b2) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST2_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {C, 1, rows, B};
+    cuuint64_t strides[3] = {ld_bytes, ld_bytes, batch_bytes};
+    cuuint32_t box[4] = {b0, 1, b2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(4d f16) failed (%d) dims=[%llu,1,%llu,%llu] ld=%llu batch=%llu", (int)r,
+                  (unsigned long long)C, (unsigned long long)rows, (unsigned long long)B, (unsigned long long)ld_bytes,
+                  (unsigned long long)batch_bytes);
+        return ST2_ERR_CUDA;
+    }
+    return ST2_OK;
+}
+
 int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn) {
     return make_map_3d(map, is_bf16, w16, (uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)ktaps, (uint64_t)cin_pad * 2,
                        (uint64_t)cin_pad * cout_pad * 2, TC_KC, (uint32_t)bn);

@@ -574,20 +574,20 @@ struct Exec {
     }
     // would launch_conv_fused run this stride-1 conv on the TMA pipeline kernel (conv_pipe.cu) with these storage types?
     bool pipe_ok(const ConvW& w, int ld_x, int ld_y, int T, int padding, int dilation, bool has_res, int accumulate, int dt,
-                 int x16in, int y16out) {
+                 int x16in, int y16out, int res16 = 0) {
         ConvArgs a;
         if (!fill_args(a, w, T, T, 1, padding, dilation, 0)) return false;
         a.accumulate = accumulate;
         a.ld_x = ld_x; a.ld_y = ld_y; a.ld_res = ld_y; a.res = has_res ? (const float*)this : nullptr;   // only null-ness matters
         a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
-        a.x16in = x16in; a.y16out = y16out; a.scale = 1.f;
+        a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.scale = 1.f;
         return conv_pipe_supported(a);
     }
     // y = epilogue( conv( act(coef.a * x + coef.b) ) ), statistics of y -> stats_out (float2 partials)
     void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
                     float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
                     int res_shift, float scale, int accumulate, void* stats_out, int out_row_shift = 0, int mirror = 0,
-                    int x16in = 0, int y16out = 0) {
+                    int x16in = 0, int y16out = 0, int res16 = 0) {
         if (!live()) return;
         ConvArgs a;
         if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
@@ -595,11 +595,11 @@ struct Exec {
         a.y = y; a.ld_y = ld_y;
         a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
         a.x = x; a.ld_x = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
-        a.x16in = x16in; a.y16out = y16out;
+        a.x16in = x16in; a.y16out = y16out; a.res16 = res16;
         chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const double bytes = (double)B * ((double)w.Cin * Tin * (x16in ? 2 : 4) +
-                                          (double)w.Cout * Tout * ((y16out ? 2 : 4) + 4 * ((res ? 1 : 0) + (accumulate ? 1 : 0)))) +
+                                          (double)w.Cout * Tout * ((y16out ? 2 : 4) + (res ? (res16 ? 2 : 4) : 0) + (accumulate ? 4 : 0))) +
                              (double)w.k * w.Cin * w.Cout * 2;
         prof(conv_pipe_supported(a) ? PC_CONV_PIPE : PC_CONV_FUSED, flops, bytes);
     }
@@ -678,22 +678,38 @@ struct Exec {
                     xt16 = 0;
             }
             float* xt = (float*)alloc((int64_t)B * T * C * 4);      // sized for fp32 (the dry run must not depend on the device)
+            // The running tensor between the three iterations (x + conv2 output of iterations 0 and 1; read as conv1's
+            // input and conv2's residual by the next iteration) is private to the block: stored as fp16 as well when every
+            // conv of the block takes it (25 % fewer HBM bytes per block; AdaIN statistics still come from the fp32 values in
+            // the epilogue, the stage output the last iteration writes stays fp32).  ST2_NO_RUN16=1 keeps it fp32.
+            int run16 = (xt16 && getenv("ST2_NO_RUN16") == nullptr) ? 1 : 0;
+            for (int j = 0; j < 3 && run16; ++j) {
+                const int dil = w.dil[j];
+                if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, j > 0, 1) ||
+                    !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, j == 2 ? accumulate : 0, dt, 1, j < 2, j > 0))
+                    run16 = 0;
+            }
+            void* r16buf = alloc((int64_t)B * T * C * 2);           // allocated either way: same workspace on every device
             StatRef cur_st = in_stats ? *in_stats : stats_standalone(x_in, C, T, C);
             const float* cur = x_in;
+            int cur16 = 0;
             for (int j = 0; j < 3; ++j) {
                 const int dil = w.dil[j];
                 coef_from(cur_st, &w.n1[j], T, C, C);
                 conv_fused(w.c1[j], cur, C, T, dt, ACT_SNAKE, 0.f, w.alpha1[j], xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr,
-                           0, 0, 1.f, 0, st_xt, 0, 0, 0, xt16);
+                           0, 0, 1.f, 0, st_xt, 0, 0, cur16, xt16);
                 if (!xt16) tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
                 else tap16(w.name + ".convs1." + std::to_string(j), xt, (int64_t)B * T * C);
                 coef_from(StatRef{st_xt, nparts, true}, &w.n2[j], T, C, C);
                 const bool last = (j == 2);
-                float* out = last ? dest : run;
+                const int out16 = (run16 && !last) ? 1 : 0;
+                float* out = last ? dest : (out16 ? (float*)r16buf : run);
                 conv_fused(w.c2[j], xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
-                           last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, 0);
-                if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
+                           last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, out16, cur16);
+                if (out16) tap16(w.name + ".iter" + std::to_string(j), out, (int64_t)B * T * C);
+                else if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
                 cur = out;
+                cur16 = out16;
                 cur_st = StatRef{st_run, nparts, true};
             }
             off = mark;
