@@ -809,7 +809,7 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if ((a.Cout & (a.Cout - 1)) != 0) return false;        // column -> phase is a shift
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
     // x16in / y16out: the intra-block tensor of AdaINResBlock1 stored as fp16 (plain stride-1 convs only)
-    if ((a.x16in || a.y16out || a.res16) && tr) return false;
+    if ((a.x16in || a.res16) && tr) return false;
     if (a.y16out && a.accumulate) return false;
     if (a.res16 && a.res == nullptr) return false;
     if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % (a.res16 ? 8 : 4) != 0)) return false;
@@ -878,7 +878,8 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     // -- has completed when it waits; with 2 accumulators the previous use is tile tcnt-2 and the parity wait could pass early
     if (p.nacc < 4) p.eg = 2;
     p.bias = a.bias; p.scale = a.scale; p.y16out = a.y16out;
-    p.y = a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout]); out_pad = 0 when y16out
+    p.y = a.y16out ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.y) - (int64_t)a.out_pad * a.ld_y)
+                   : a.y - (int64_t)a.out_pad * a.ld_y;            // row m, column c  ->  y[b][m*ostride - opad][c]  (dense [M][ph*Cout])
     p.ld_y = ph * a.ld_y;
     p.ybatch = (long long)a.Tout * a.ld_y;
 

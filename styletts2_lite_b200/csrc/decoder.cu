@@ -583,6 +583,15 @@ struct Exec {
         a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.scale = 1.f;
         return conv_pipe_supported(a);
     }
+    // would launch_conv_fused run this upsampling conv on the TMA pipeline kernel and write a 16-bit output?
+    bool pipe_ok_ups16(const ConvW& w, int ld_x, int ld_y, int Tin, int Tout, int stride, int padding, int shift, int dt) {
+        ConvArgs a;
+        if (shift != 0 || !fill_args(a, w, Tin, Tout, stride, padding, 1, 0)) return false;
+        a.ld_x = ld_x; a.ld_y = ld_y; a.ld_res = ld_y; a.res = (const float*)this;                        // only null-ness matters
+        a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
+        a.y16out = 1; a.scale = 1.f;
+        return conv_pipe_supported(a);
+    }
     // y = epilogue( conv( act(coef.a * x + coef.b) ) ), statistics of y -> stats_out (float2 partials)
     void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
                     float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
@@ -656,8 +665,20 @@ struct Exec {
     // AdaINResBlock1.forward (hifigan.py:65-74) on x_in [B,T,C]; the running tensor lives in `run`
     // (may alias x_in for an in-place block); the last iteration writes
     // dest = (dest_old*accumulate + conv2 + run) * scale.
+    // would resblock1 take its input tensor as fp16 (every conv of the block on the TMA pipeline kernel)?
+    bool resblock1_x16_ok(const ResBlock1W& w, int T, int accumulate) {
+        const int C = w.C, dt = fmt_for(w.name);
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16")) return false;
+        for (int j = 0; j < 3; ++j) {
+            const int dil = w.dil[j];
+            if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 1, 1) ||
+                !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, j == 2 ? accumulate : 0, dt, 1, j < 2, 1))
+                return false;
+        }
+        return true;
+    }
     void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate,
-                   const StatRef* in_stats = nullptr) {
+                   const StatRef* in_stats = nullptr, int x16 = 0) {
         const int64_t mark = off;
         const int C = w.C;
         const int dt = fmt_for(w.name);
@@ -685,14 +706,18 @@ struct Exec {
             int run16 = (xt16 && getenv("ST2_NO_RUN16") == nullptr) ? 1 : 0;
             for (int j = 0; j < 3 && run16; ++j) {
                 const int dil = w.dil[j];
-                if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, j > 0, 1) ||
-                    !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, j == 2 ? accumulate : 0, dt, 1, j < 2, j > 0))
+                if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, j > 0 || x16, 1) ||
+                    !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, j == 2 ? accumulate : 0, dt, 1, j < 2, j > 0 || x16))
                     run16 = 0;
             }
             void* r16buf = alloc((int64_t)B * T * C * 2);           // allocated either way: same workspace on every device
+            if (x16 && !(run16 && in_stats) && err == ST2_OK) {      // the caller asks resblock1_x16_ok first
+                set_error("resblock1: fp16 block input needs the fp16 running-tensor path and producer statistics");
+                err = ST2_ERR_STATE;
+            }
             StatRef cur_st = in_stats ? *in_stats : stats_standalone(x_in, C, T, C);
             const float* cur = x_in;
-            int cur16 = 0;
+            int cur16 = x16;
             for (int j = 0; j < 3; ++j) {
                 const int dil = w.dil[j];
                 coef_from(cur_st, &w.n1[j], T, C, C);
@@ -863,6 +888,14 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         float* xu = E.allocf((int64_t)B * Tout * C);
         Exec::StatRef xu_stats{nullptr, 0, true};
         const bool fuse_u = E.can_fuse(d->ups[i], dtu, Cin, C, u, 1);
+        // The stage input xu = ups(x) + x_source is read six times (input and residual of the first iteration of the three
+        // resblocks): stored as fp16 when the ups conv and all six convs run on the TMA pipeline kernel (ST2_NO_XU16=1: fp32)
+        int xu16 = 0;
+        if (fuse_u && getenv("ST2_NO_XU16") == nullptr && E.pipe_ok_ups16(d->ups[i], Cin, C, Tin, Tout, u, pu, shift, dtu)) {
+            xu16 = 1;
+            for (int j = 0; j < c.n_kernels; ++j)
+                if (!E.resblock1_x16_ok(d->resblocks[i * c.n_kernels + j], Tout, j > 0 ? 1 : 0)) xu16 = 0;
+        }
         if (fuse_u) {
             // Snake / LeakyReLU applied on the A-operand path; InstanceNorm statistics of xu from the epilogue
             xu_stats.nparts = E.fused_parts(d->ups[i], Tout, u, pu, shift);
@@ -870,7 +903,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
             xu_stats.ptr = st_xu;
             E.coef_from(Exec::StatRef{nullptr, 0, false}, nullptr, Tin, Cin, Cin);
             E.conv_fused(d->ups[i], x, Cin, Tin, dtu, istft ? ACT_LRELU : ACT_SNAKE, 0.1f, istft ? nullptr : d->gen_alpha[i], xu, C,
-                         Tout, u, pu, 1, nc, C, 0, 1.f, 0, st_xu, shift, shift);
+                         Tout, u, pu, 1, nc, C, 0, 1.f, 0, st_xu, shift, shift, 0, xu16);
         } else {
             void* xs = E.alloc((int64_t)B * Tin * Cin * (tcu ? 2 : 4));
             if (istft) E.norm_act(x, Cin, Tin, Cin, nullptr, ACT_LRELU, 0.1f, nullptr, xs, Cin, tcu ? dtu : DT_F32);
@@ -878,12 +911,13 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
             // istftnet: ReflectionPad1d((1,0)) after the last ups = write at row t+1 and mirror row 2 into row 0
             E.conv(d->ups[i], xs, Cin, Tin, tcu ? dtu : DT_F32, xu, C, Tout, u, pu, 1, nc, C, 0, 1.f, 0, shift, shift);
         }
-        E.tap("generator.stage" + is + ".in", xu, C, (int64_t)B * Tout, C);
+        if (xu16) E.tap16("generator.stage" + is + ".in", xu, (int64_t)B * Tout * C);
+        else E.tap("generator.stage" + is + ".in", xu, C, (int64_t)B * Tout, C);
         float* run = E.allocf((int64_t)B * Tout * C);
         for (int j = 0; j < c.n_kernels; ++j) {
             const bool lastk = (j + 1 == c.n_kernels);
             E.resblock1(d->resblocks[i * c.n_kernels + j], xu, run, Tout, stage_out[i], lastk ? 1.f / (float)c.n_kernels : 1.f,
-                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr);
+                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr, xu16);
         }
         E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
         x = stage_out[i];
