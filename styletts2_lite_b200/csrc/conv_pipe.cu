@@ -848,6 +848,10 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
         if ((a.Cin == 64 && a.ntaps == 7) || (a.Cin == 128 && a.ntaps == 3 && nres_ == 0) || (a.Cin == 128 && a.ntaps == 7 && nres_ == 1))
             xmax = 8192;
         if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
+        if (a.x16in) {
+            if (xmax > 8192) xmax = 8192;     // fp16 input: a 12 KB block would be a whole tile for one warp (8 KB: 1-8 % faster on the k=3 layers)
+            if (const char* e = getenv("ST2_PIPE_XMAX16")) { const int v = atoi(e); if (v >= 1024 && v <= P_XSLOT_MAX) xmax = v; }
+        }
         int nblk = 1;
         for (;; ++nblk) {
             p.xr = (cdiv(p.rows, nblk) + rpp - 1) / rpp * rpp;
