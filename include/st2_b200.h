@@ -158,6 +158,17 @@ ST2_API int64_t st2_f0n_workspace_bytes(const st2_decoder* d, int32_t B, int32_t
 ST2_API int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, float* f0, float* n, int32_t B, int32_t T,
                     int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Duration half of the same predictor: replaces inference.py:242-245 --
+ *   d = predictor.text_encoder(t_en, s, lengths, mask)        DurationEncoder.forward, models.py:485-520
+ *   x, _ = predictor.lstm(d) ; duration = sigmoid(predictor.duration_proj(x)).sum(-1)
+ * for a batch of equal-length utterances (no padding).  Available when the handle was also given the reference keys
+ * "text_encoder.lstms.*", "lstm.*" and "duration_proj.linear_layer.*" before st2_decoder_finalize.
+ *   t_en [B, d_hid, L], s [B, style_dim]  ->  d [B, L, d_hid+style_dim] (the reference's layout), duration [B, L]
+ * (feed `duration` to st2_round_durations and `d`, transposed, to st2_length_regulate). */
+ST2_API int64_t st2_dur_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision);
+ST2_API int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B,
+                    int32_t L, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 
 /* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);

@@ -71,3 +71,50 @@ def f0n_train(sd: Dict[str, np.ndarray], en, s, taps: Optional[dict] = None, ope
         h = conv1d(h, W.w(br + "_proj"), W.b(br + "_proj"))     # models.py:454 / :459
         outs.append(h[:, 0, :])                                 # .squeeze(1)
     return outs[0], outs[1]
+
+
+# ----------------------------------------------------------------------------
+# the duration half (inference.py:242-245)
+# ----------------------------------------------------------------------------
+def ada_layer_norm(x, s, fc_w, fc_b, eps=1e-5):
+    """AdaLayerNorm.forward (models.py:372-392) on x [B, L, C]: LayerNorm over C (biased variance, eps 1e-5, no affine)
+    then (1 + gamma) * x + beta with gamma | beta = fc(s) [B, 2C]."""
+    h = (s.astype(F32) @ fc_w.T.astype(F32) + fc_b).astype(F32)
+    C = x.shape[2]
+    gamma, beta = h[:, None, :C], h[:, None, C:]
+    x64 = x.astype(np.float64)
+    mean = x64.mean(axis=2, keepdims=True)
+    var = x64.var(axis=2, keepdims=True)
+    xn = ((x64 - mean) / np.sqrt(var + eps)).astype(F32)
+    return ((1 + gamma) * xn + beta).astype(F32)
+
+
+def duration_encoder(W: Weights, t_en, s, nlayers=3, taps: Optional[dict] = None):
+    """DurationEncoder.forward (models.py:485-520) for equal-length batches (no padding: every mask is False, the
+    pack / pad round trip is the identity).  t_en [B, d_hid, L], s [B, style] -> d [B, L, d_hid + style]."""
+    B, _, L = t_en.shape
+    sty = np.repeat(s[:, None, :], L, axis=1).astype(F32)                    # style broadcast over tokens (models.py:489)
+    x = np.concatenate([t_en.transpose(0, 2, 1), sty], axis=2).astype(F32)   # [B, L, 640] (models.py:490)
+    for i in range(nlayers):
+        y = bilstm(W, "text_encoder.lstms.%d" % (2 * i), x)                  # models.py:503-509
+        if taps is not None:
+            taps["text_encoder.lstms.%d" % (2 * i)] = y
+        n = "text_encoder.lstms.%d" % (2 * i + 1)
+        y = ada_layer_norm(y, s, W.p(n + ".fc.weight"), W.p(n + ".fc.bias"))  # models.py:498
+        x = np.concatenate([y, sty], axis=2).astype(F32)                     # models.py:499
+    return x
+
+
+def predict_duration(sd: Dict[str, np.ndarray], t_en, s, taps: Optional[dict] = None):
+    """inference.py:242-245: d = predictor.text_encoder(t_en, s, lengths, mask); x, _ = predictor.lstm(d);
+    duration = sigmoid(predictor.duration_proj(x)).sum(-1).  Returns (d [B, L, 640], duration [B, L])."""
+    W = Weights(sd)
+    t_en = np.asarray(t_en, F32)
+    s = np.asarray(s, F32)
+    d = duration_encoder(W, t_en, s, taps=taps)
+    x = bilstm(W, "lstm", d)
+    if taps is not None:
+        taps["lstm"] = x
+    logits = (x @ W.p("duration_proj.linear_layer.weight").T.astype(F32) + W.p("duration_proj.linear_layer.bias")).astype(F32)
+    duration = _sigmoid(logits).sum(axis=2).astype(F32)
+    return d, duration

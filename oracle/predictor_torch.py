@@ -35,3 +35,22 @@ def f0n_train(sd: Dict[str, torch.Tensor], en: torch.Tensor, s: torch.Tensor):
         h = F.conv1d(h, W.w(br + "_proj"), W.b(br + "_proj"))
         outs.append(h.squeeze(1))
     return outs[0], outs[1]
+
+
+def predict_duration(sd: Dict[str, torch.Tensor], t_en: torch.Tensor, s: torch.Tensor, nlayers: int = 3):
+    """inference.py:242-245 for equal-length batches: DurationEncoder.forward (models.py:485-520), predictor.lstm,
+    duration_proj, sigmoid-sum.  Returns (d [B, L, 640], duration [B, L])."""
+    W = sd if isinstance(sd, TorchWeights) else TorchWeights(sd)
+    L = t_en.shape[2]
+    sty = s[:, None, :].expand(-1, L, -1)
+    x = torch.cat([t_en.transpose(1, 2), sty], dim=2)
+    for i in range(nlayers):
+        y = bilstm(W, "text_encoder.lstms.%d" % (2 * i), x)
+        n = "text_encoder.lstms.%d" % (2 * i + 1)
+        h = F.linear(s, W.p(n + ".fc.weight"), W.p(n + ".fc.bias"))
+        gamma, beta = torch.chunk(h[:, None, :], 2, dim=2)
+        y = (1 + gamma) * F.layer_norm(y, (y.shape[2],), eps=1e-5) + beta
+        x = torch.cat([y, sty], dim=2)
+    z = bilstm(W, "lstm", x)
+    dur = torch.sigmoid(F.linear(z, W.p("duration_proj.linear_layer.weight"), W.p("duration_proj.linear_layer.bias"))).sum(-1)
+    return x, dur

@@ -236,3 +236,29 @@ def predictor_param_specs(cfg: PredictorConfig):
             s = (w[0],)                              # Conv1d bias; depthwise pool: groups = Cin = w[0]
         out.append((n, s, kind))
     return out
+
+
+DUR_PREFIXES = ("text_encoder.", "lstm.", "duration_proj.")
+
+
+def _lstm(specs, name, d_in, h):
+    for suffix in ("", "_reverse"):
+        specs.append((name + ".weight_ih_l0" + suffix, (4 * h, d_in), "lstm:%d" % h))
+        specs.append((name + ".weight_hh_l0" + suffix, (4 * h, h), "lstm:%d" % h))
+        specs.append((name + ".bias_ih_l0" + suffix, (4 * h,), "lstm:%d" % h))
+        specs.append((name + ".bias_hh_l0" + suffix, (4 * h,), "lstm:%d" % h))
+
+
+def duration_param_specs(cfg: PredictorConfig, nlayers: int = 3, max_dur: int = 50):
+    """§8(f) N2: the duration half of ProsodyPredictor -- DurationEncoder `text_encoder` (models.py:468-483: nlayers x
+    [bidirectional LSTM, AdaLayerNorm]), `lstm` (models.py:404) and `duration_proj` = LinearNorm(d_hid, max_dur)
+    (models.py:405, :152-162)."""
+    d, sd = cfg.d_hid, cfg.style_dim
+    specs = []
+    for i in range(nlayers):
+        _lstm(specs, "text_encoder.lstms.%d" % (2 * i), d + sd, d // 2)
+        _adain(specs, "text_encoder.lstms.%d" % (2 * i + 1), sd, d)        # AdaLayerNorm.fc: Linear(style, 2*channels)
+    _lstm(specs, "lstm", d + sd, d // 2)
+    specs.append(("duration_proj.linear_layer.weight", (max_dur, d), "linear"))
+    specs.append(("duration_proj.linear_layer.bias", (max_dur,), "linear_bias:%d" % d))
+    return specs

@@ -115,6 +115,13 @@ int launch_istft_head(const float* x, int ld_x, const float* wr, const float* wi
 // BiLSTM recurrence (kernels_lstm.cu): G [B][T][2][4H] input half of the gates, whh [2][H][4H], bhh [2][4H] -> y [B][T][2H]
 int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st);
 
+// duration half of the predictor (kernels_lstm.cu)
+int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, int L, cudaStream_t st);
+int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, float* y, int ld_y, int B, int L, int C,
+                          cudaStream_t st);
+int launch_duration_head(const float* x, const float* W, const float* bias, float* duration, int B, int L, int C, int nbins,
+                         cudaStream_t st);
+
 // length regulator (length_regulator.cu)
 int launch_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur, int32_t* total,
                            int B, int L, cudaStream_t st);

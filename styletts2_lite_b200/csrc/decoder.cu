@@ -65,6 +65,12 @@ struct ResBlk1dW {            // AdainResBlk1d (hifigan.py:359-403)
     std::string name;
 };
 
+struct LstmW {                // bidirectional nn.LSTM(I, H): input half as two 1x1 convs, W_hh^T / b_hh for the recurrence kernel
+    ConvW ih[2];
+    float* whh = nullptr;     // [2][H][4H]
+    float* bhh = nullptr;     // [2][4H]
+};
+
 struct Tap { float* dst; int64_t cap; };
 
 }  // namespace st2
@@ -94,9 +100,16 @@ struct st2_decoder {
     std::map<std::string, Tap> taps;
 
     // variant 2: the F0 / energy predictor ProsodyPredictor.F0Ntrain (models.py:407-419, :448-461); cfg.dim_in = d_hid
-    ConvW lstm_ih[2];                       // x W_ih^T + b_ih per direction, as 1x1 convs
-    float *lstm_whh = nullptr;              // [2][H][4H]  W_hh^T
-    float *lstm_bhh = nullptr;              // [2][4H]
+    LstmW shared;                           // models.py:407
+    // duration half (row N2; packed only when the caller handed its weights over): DurationEncoder (models.py:468-483),
+    // `lstm` (models.py:404), `duration_proj` (models.py:405)
+    bool has_duration = false;
+    int dur_layers = 0;
+    LstmW enc_lstm[4];
+    AdaINRef enc_norm[4];                   // AdaLayerNorm fc rows (gamma(C) | beta(C)) in the shared style matrix
+    LstmW dur_lstm;
+    float *dur_w = nullptr, *dur_b = nullptr;   // duration_proj.linear_layer [max_dur][d_hid], [max_dur]
+    int max_dur = 0;
     ResBlk1dW pred_blk[2][3];               // F0.{0,1,2}, N.{0,1,2}
     ConvW pred_proj[2];                     // F0_proj, N_proj
 
@@ -256,28 +269,53 @@ struct Packer {
     }
 };
 
-// ProsodyPredictor.F0Ntrain weights (models.py:407-419)
-static void pack_predictor(st2_decoder* d, Packer& P) {
-    const int dh = d->cfg.dim_in, H = dh / 2, I = dh + d->cfg.style_dim;
-    d->lstm_whh = (float*)P.dalloc((size_t)2 * H * 4 * H * sizeof(float));
-    d->lstm_bhh = (float*)P.dalloc((size_t)2 * 4 * H * sizeof(float));
+// one bidirectional nn.LSTM: W_ih as 1x1 convs (+ b_ih), W_hh transposed for the recurrence kernel
+static void pack_lstm(st2_decoder* d, Packer& P, LstmW& w, const std::string& name, int I, int H) {
+    w.whh = (float*)P.dalloc((size_t)2 * H * 4 * H * sizeof(float));
+    w.bhh = (float*)P.dalloc((size_t)2 * 4 * H * sizeof(float));
     for (int dir = 0; dir < 2; ++dir) {
         const std::string sfx = dir ? "_reverse" : "";
-        P.linear(d->lstm_ih[dir], "shared.weight_ih_l0" + sfx, "shared.bias_ih_l0" + sfx, I, 4 * H);
-        const RawTensor* whh = P.get("shared.weight_hh_l0" + sfx);
-        const RawTensor* bhh = P.get("shared.bias_hh_l0" + sfx);
-        if (!whh || !bhh || !d->lstm_whh || !d->lstm_bhh) return;
+        P.linear(w.ih[dir], name + ".weight_ih_l0" + sfx, name + ".bias_ih_l0" + sfx, I, 4 * H);
+        const RawTensor* whh = P.get(name + ".weight_hh_l0" + sfx);
+        const RawTensor* bhh = P.get(name + ".bias_hh_l0" + sfx);
+        if (!whh || !bhh || !w.whh || !w.bhh) return;
         if (whh->numel() != (int64_t)4 * H * H || bhh->numel() != 4 * H) {
-            set_error("shared.weight_hh_l0%s / bias_hh_l0%s have the wrong shape", sfx.c_str(), sfx.c_str());
+            set_error("%s.weight_hh_l0%s / bias_hh_l0%s have the wrong shape", name.c_str(), sfx.c_str(), sfx.c_str());
             P.err = ST2_ERR_INVALID;
             return;
         }
         // [4H][H] -> [H][4H]: the recurrence kernel reads gate columns contiguously
-        if (launch_fold_pack(nullptr, whh->ptr, d->lstm_whh + (size_t)dir * H * 4 * H, 4 * H, H, 1, 0, P.st) != ST2_OK)
+        if (launch_fold_pack(nullptr, whh->ptr, w.whh + (size_t)dir * H * 4 * H, 4 * H, H, 1, 0, P.st) != ST2_OK)
             P.err = ST2_ERR_CUDA;
-        if (cudaMemcpyAsync(d->lstm_bhh + (size_t)dir * 4 * H, bhh->ptr, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice,
+        if (cudaMemcpyAsync(w.bhh + (size_t)dir * 4 * H, bhh->ptr, (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice,
                             P.st) != cudaSuccess)
             P.err = ST2_ERR_CUDA;
+    }
+}
+
+// ProsodyPredictor weights: F0Ntrain (models.py:407-419) and, when present, the duration half (models.py:399-405)
+static void pack_predictor(st2_decoder* d, Packer& P) {
+    const int dh = d->cfg.dim_in, H = dh / 2, I = dh + d->cfg.style_dim;
+    pack_lstm(d, P, d->shared, "shared", I, H);
+    d->has_duration = d->raw.count("duration_proj.linear_layer.weight") != 0;
+    if (d->has_duration) {
+        d->dur_layers = 0;
+        while (d->dur_layers < 4 && d->raw.count("text_encoder.lstms." + std::to_string(2 * d->dur_layers) + ".weight_ih_l0"))
+            ++d->dur_layers;
+        for (int i = 0; i < d->dur_layers; ++i) {
+            pack_lstm(d, P, d->enc_lstm[i], "text_encoder.lstms." + std::to_string(2 * i), I, H);
+            P.adain(d->enc_norm[i], "text_encoder.lstms." + std::to_string(2 * i + 1), dh);
+        }
+        pack_lstm(d, P, d->dur_lstm, "lstm", I, H);
+        const RawTensor* w = P.get("duration_proj.linear_layer.weight");
+        if (w && w->shape.size() == 2 && w->shape[1] == dh) {
+            d->max_dur = (int)w->shape[0];
+            d->dur_w = P.copy("duration_proj.linear_layer.weight", (int64_t)d->max_dur * dh);
+            d->dur_b = P.copy("duration_proj.linear_layer.bias", d->max_dur);
+        } else if (P.err == ST2_OK) {
+            set_error("duration_proj.linear_layer.weight must be [max_dur, %d]", dh);
+            P.err = ST2_ERR_INVALID;
+        }
     }
     const char* br[2] = {"F0", "N"};
     for (int i = 0; i < 2; ++i) {
@@ -947,6 +985,25 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     return E.err;
 }
 
+// bidirectional LSTM over channels-last x [B][T][I] -> y [B][T][2H]; G [B][T][8H] scratch for the input half of the gates
+static void bilstm(Exec& E, const LstmW& w, const char* name, const float* x, float* G, float* y, int T, int I, int H) {
+    const int B = E.B;
+    const int64_t mark = E.off;
+    const int dt = E.fmt_for(name);
+    const bool tc = E.use_tc(w.ih[0], dt) && E.use_tc(w.ih[1], dt);
+    const void* xin = x;
+    if (tc) {
+        void* x16 = E.alloc((int64_t)B * T * I * 2);
+        E.norm_act(x, I, T, I, nullptr, ACT_NONE, 0.f, nullptr, x16, I, dt);
+        xin = x16;
+    }
+    for (int dir = 0; dir < 2; ++dir)
+        E.conv(w.ih[dir], xin, I, T, tc ? dt : DT_F32, G + (size_t)dir * 4 * H, 8 * H, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
+    if (E.live()) E.chk(launch_lstm_bidir(G, w.whh, w.bhh, y, B, T, H, E.st));
+    E.prof(PC_LSTM, 2.0 * B * T * 2 * 4 * H * H, 4.0 * B * T * (8 * H + 2 * H) + 4.0 * 2 * 4 * H * H);
+    E.off = mark;
+}
+
 // ProsodyPredictor.F0Ntrain(x, s) (models.py:448-461): en [B, d_hid+style, T], s [B, style] -> F0 [B,2T], N [B,2T]
 static int f0n_forward_impl(st2_decoder* d, const float* en, const float* s, float* f0_out, float* n_out, int B, int T,
                             int prec, void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
@@ -973,22 +1030,7 @@ static int f0n_forward_impl(st2_decoder* d, const float* en, const float* s, flo
         E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim, 4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * I * T));
     }
     // x, _ = self.shared(x.transpose(-1, -2))   (models.py:449)
-    {
-        const int64_t mark = E.off;
-        const int dt = E.fmt_for("shared");
-        const bool tc = E.use_tc(d->lstm_ih[0], dt) && E.use_tc(d->lstm_ih[1], dt);
-        const void* xin = x;
-        if (tc) {
-            void* x16 = E.alloc((int64_t)B * T * I * 2);
-            E.norm_act(x, I, T, I, nullptr, ACT_NONE, 0.f, nullptr, x16, I, dt);
-            xin = x16;
-        }
-        for (int dir = 0; dir < 2; ++dir)
-            E.conv(d->lstm_ih[dir], xin, I, T, tc ? dt : DT_F32, G + (size_t)dir * 4 * H, 8 * H, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
-        if (E.live()) E.chk(launch_lstm_bidir(G, d->lstm_whh, d->lstm_bhh, y, B, T, H, st));
-        E.prof(PC_LSTM, 2.0 * B * T * 2 * 4 * H * H, 4.0 * B * T * (8 * H + 2 * H) + 4.0 * 2 * 4 * H * H);
-        E.off = mark;
-    }
+    bilstm(E, d->shared, "shared", x, G, y, T, I, H);
     E.tap("shared", y, dh, (int64_t)B * T, dh);
     for (int br = 0; br < 2; ++br) {                     // models.py:451-454 (F0) and :456-459 (N)
         const int64_t mark = E.off;
@@ -1001,6 +1043,54 @@ static int f0n_forward_impl(st2_decoder* d, const float* en, const float* s, flo
         E.conv(d->pred_proj[br], a2, H, 2 * T, DT_F32, br == 0 ? f0_out : n_out, 1, 2 * T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
         E.off = mark;
     }
+    if (peak_out) *peak_out = E.peak;
+    return E.err;
+}
+
+// inference.py:242-245 for an equal-length batch: d = predictor.text_encoder(t_en, s, lengths, mask) (DurationEncoder.forward,
+// models.py:485-520), x = predictor.lstm(d), duration = sigmoid(duration_proj(x)).sum(-1).
+// t_en [B, d_hid, L], s [B, style] -> d_out [B, L, d_hid+style] (the reference's layout of `d`), duration [B, L]
+static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int B, int L,
+                            int prec, void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
+    const st2_config& c = d->cfg;
+    const int dh = c.dim_in, H = dh / 2, I = dh + c.style_dim;
+    Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    float* Hs = E.allocf((int64_t)B * d->fc_rows);
+    E.H = Hs;
+    E.coef = E.allocf((int64_t)B * 2 * 2048);
+    float* xa = E.allocf((int64_t)B * L * I);           // layer input [B][L][d_hid | style]
+    float* G = E.allocf((int64_t)B * L * 8 * H);
+    float* y = E.allocf((int64_t)B * L * dh);
+    if (E.live()) {
+        if (d->profiling) {
+            d->prof_recs.clear();
+            if (d->prof_events.empty()) {
+                cudaEvent_t ev;
+                if (cudaEventCreate(&ev) == cudaSuccess) d->prof_events.push_back(ev);
+            }
+            if (!d->prof_events.empty()) cudaEventRecord(d->prof_events[0], st);
+        }
+        E.chk(launch_style_fc(s, d->fc_w, d->fc_b, Hs, B, d->fc_rows, c.style_dim, st));
+        E.chk(launch_cf_to_cl(t_en, xa, I, B, dh, L, st));                       // x.permute / cat([x, s]) (models.py:488-490)
+        E.chk(launch_concat_style(xa, I, dh, s, c.style_dim, B, L, st));
+        E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim, 4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * I * L));
+    }
+    for (int i = 0; i < d->dur_layers; ++i) {
+        const std::string nm = "text_encoder.lstms." + std::to_string(2 * i);
+        bilstm(E, d->enc_lstm[i], nm.c_str(), xa, G, y, L, I, H);                 // models.py:503-509
+        E.tap(nm, y, dh, (int64_t)B * L, dh);
+        float* dst = (i + 1 == d->dur_layers) ? d_out : xa;                        // the last layer's output is `d`
+        if (E.live()) {
+            E.chk(launch_ada_layer_norm(y, Hs, d->fc_rows, d->enc_norm[i].h_off, dst, I, B, L, dh, st));   // models.py:498
+            E.chk(launch_concat_style(dst, I, dh, s, c.style_dim, B, L, st));      // models.py:499
+        }
+        E.prof(PC_AFFINE_ACT, 0, 8.0 * B * L * dh);
+        E.tap("text_encoder.lstms." + std::to_string(2 * i + 1), dst, I, (int64_t)B * L, dh);
+    }
+    bilstm(E, d->dur_lstm, "lstm", d_out, G, y, L, I, H);                          // inference.py:243
+    E.tap("lstm", y, dh, (int64_t)B * L, dh);
+    if (E.live()) E.chk(launch_duration_head(y, d->dur_w, d->dur_b, duration, B, L, dh, d->max_dur, st));   // inference.py:244-245
+    E.prof(PC_MISC, 2.0 * B * L * dh * d->max_dur, 4.0 * B * L * (dh + 1));
     if (peak_out) *peak_out = E.peak;
     return E.err;
 }
@@ -1154,6 +1244,41 @@ int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, float* f0, 
     ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "f0n_forward: workspace must be 256-byte aligned");
     st2::g_launch_count = 0;
     int e = st2::f0n_forward_impl(d, en, s, f0, n, B, T, precision, workspace, workspace_bytes, (cudaStream_t)stream, false, nullptr);
+    d->last_launches = st2::g_launch_count;
+    return e;
+}
+
+/* duration half: inference.py:242-245 */
+int64_t st2_dur_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision) {
+    if (!d || !d->finalized || d->cfg.variant != 2 || !d->has_duration || B <= 0 || L <= 0) {
+        st2::set_error("dur_workspace_bytes: not a finalized predictor handle with the duration weights, or bad shape");
+        return ST2_ERR_STATE;
+    }
+    int64_t peak = 0;
+    int e = st2::dur_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, nullptr, B, L, precision, nullptr, 0,
+                                  nullptr, true, &peak);
+    if (e != ST2_OK) return e;
+    return peak + 256;
+}
+
+int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B, int32_t L,
+                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+    ST2_REQUIRE(d != nullptr, "dur_forward: null handle");
+    if (!d->finalized || d->cfg.variant != 2 || !d->has_duration) {
+        st2::set_error("dur_forward: needs a finalized predictor handle that was given text_encoder.* / lstm.* / duration_proj.*");
+        return ST2_ERR_STATE;
+    }
+    ST2_REQUIRE(t_en && s && d_out && duration && workspace, "dur_forward: null tensor");
+    ST2_REQUIRE(B > 0 && L >= 1, "dur_forward: need B>0 and L>=1 (got B=%d L=%d)", B, L);
+    ST2_REQUIRE(precision >= ST2_PREC_FP32 && precision <= ST2_PREC_FP16, "dur_forward: bad precision %d", precision);
+    if (precision != ST2_PREC_FP32 && !d->tc_ok) {
+        st2::set_error("dur_forward: tensor-core precision requires an sm_100 device");
+        return ST2_ERR_UNSUPPORTED;
+    }
+    ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "dur_forward: workspace must be 256-byte aligned");
+    st2::g_launch_count = 0;
+    int e = st2::dur_forward_impl(d, t_en, s, d_out, duration, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream,
+                                  false, nullptr);
     d->last_launches = st2::g_launch_count;
     return e;
 }

@@ -118,3 +118,119 @@ int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float*
 }
 
 }  // namespace st2
+
+// ------------------------------------------------------------------------------------------------------------------
+// Duration half of the predictor (reference models.py:372-392, :485-520, inference.py:242-245)
+// ------------------------------------------------------------------------------------------------------------------
+namespace st2 {
+
+// x[b][l][C .. C+S) = s[b][0 .. S): the style columns DurationEncoder concatenates to every token (models.py:489-490, :499)
+__global__ void concat_style_kernel(float* __restrict__ x, int ld, int C, const float* __restrict__ s, int S, int64_t rows, int L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * S) return;
+    const int64_t row = i / S;
+    const int c = (int)(i - row * S);
+    x[row * ld + C + c] = s[(row / L) * S + c];
+}
+
+// AdaLayerNorm (models.py:372-392) on channels-last x [B][L][C]: LayerNorm over C (biased variance, eps 1e-5), then
+// (1 + gamma) * xhat + beta with gamma | beta = h[b][h_off .. h_off + 2C); writes y[row][0..C) with pitch ld_y.
+// One warp per token; C = 512 -> 16 values per lane kept in registers, mean and variance by warp shuffles (two pass).
+template <int C>
+__global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ h, int ld_h, int h_off,
+                                      float* __restrict__ y, int ld_y, int64_t rows, int L) {
+    constexpr int PER = C / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * C;
+    float v[PER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        sum += (t.x + t.y) + (t.z + t.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { const float dlt = v[i] - mean; sq = fmaf(dlt, dlt, sq); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.f / C) + 1e-5f);
+    const float* hb = h + (row / L) * ld_h + h_off;
+    float* yr = y + row * ld_y;
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(hb + c), b = *reinterpret_cast<const float4*>(hb + C + c);
+        float4 o;
+        o.x = fmaf(1.f + g.x, (v[4 * i] - mean) * rstd, b.x);
+        o.y = fmaf(1.f + g.y, (v[4 * i + 1] - mean) * rstd, b.y);
+        o.z = fmaf(1.f + g.z, (v[4 * i + 2] - mean) * rstd, b.z);
+        o.w = fmaf(1.f + g.w, (v[4 * i + 3] - mean) * rstd, b.w);
+        *reinterpret_cast<float4*>(yr + c) = o;
+    }
+}
+
+// duration[row] = sum_j sigmoid(x[row] . W[j] + bias[j])   (duration_proj + torch.sigmoid(...).sum(-1), inference.py:244-245)
+// One warp per token: x row in registers, one warp-reduced dot product per output bin.
+template <int C>
+__global__ void duration_head_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                     float* __restrict__ duration, int64_t rows, int nbins) {
+    constexpr int PER = C / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(x + row * C + (i * 32 + lane) * 4);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    float total = 0.f;
+    for (int j = 0; j < nbins; ++j) {
+        const float* wj = W + (size_t)j * C;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER / 4; ++i) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wj + (i * 32 + lane) * 4));
+            acc = fmaf(v[4 * i], w.x, acc); acc = fmaf(v[4 * i + 1], w.y, acc);
+            acc = fmaf(v[4 * i + 2], w.z, acc); acc = fmaf(v[4 * i + 3], w.w, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        total += sigmoid_f(acc + __ldg(bias + j));
+    }
+    if (lane == 0) duration[row] = total;
+}
+
+int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, int L, cudaStream_t st) {
+    const int64_t n = (int64_t)B * L * S;
+    concat_style_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, ld, C, s, S, (int64_t)B * L, L);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, float* y, int ld_y, int B, int L, int C,
+                          cudaStream_t st) {
+    ST2_REQUIRE(C == 512 && ld_y % 4 == 0 && ld_h % 4 == 0 && h_off % 4 == 0, "ada_layer_norm: needs 512 channels (got %d)", C);
+    const int64_t rows = (int64_t)B * L;
+    ada_layer_norm_kernel<512><<<cdiv(rows, 8), 256, 0, st>>>(x, h, ld_h, h_off, y, ld_y, rows, L);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_duration_head(const float* x, const float* W, const float* bias, float* duration, int B, int L, int C, int nbins,
+                         cudaStream_t st) {
+    ST2_REQUIRE(C == 512 && nbins > 0, "duration_head: needs 512 channels (got %d)", C);
+    const int64_t rows = (int64_t)B * L;
+    duration_head_kernel<512><<<cdiv(rows, 8), 256, 0, st>>>(x, W, bias, duration, rows, nbins);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+}  // namespace st2

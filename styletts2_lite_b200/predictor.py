@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .config import F0N_PREFIXES, PredictorConfig, predictor_param_specs
+from .config import DUR_PREFIXES, F0N_PREFIXES, PredictorConfig, duration_param_specs, predictor_param_specs
 from .decoder import _register
 
 
@@ -25,7 +25,7 @@ class B200F0NPredictor(nn.Module):
     fp16 operands, recurrence in fp32."""
 
     def __init__(self, style_dim: int = 128, d_hid: int = 512, nlayers: int = 3, max_dur: int = 50, dropout: float = 0.1,
-                 precision: str = "fp32"):
+                 precision: str = "fp32", duration: bool = False):
         super().__init__()
         if precision not in _lib.PREC:
             raise ValueError("precision must be one of %s" % list(_lib.PREC))
@@ -33,6 +33,12 @@ class B200F0NPredictor(nn.Module):
         self.precision = precision
         for name, shape, _ in predictor_param_specs(self.cfg):
             _register(self, name, torch.zeros(shape))
+        # duration=True adds the duration half (row N2): `text_encoder` (DurationEncoder), `lstm`, `duration_proj`
+        self.has_duration = duration
+        self._prefixes = F0N_PREFIXES + (DUR_PREFIXES if duration else ())
+        if duration:
+            for name, shape, _ in duration_param_specs(self.cfg, nlayers, max_dur):
+                _register(self, name, torch.zeros(shape))
         self._handle: Optional[C.c_void_p] = None
         self._dirty = True
         self._workspace: Optional[torch.Tensor] = None
@@ -46,7 +52,7 @@ class B200F0NPredictor(nn.Module):
 
     def load_state_dict(self, state_dict, strict: bool = True, *a, **k):
         """Accepts a full reference `predictor` state_dict: entries outside F0Ntrain are ignored."""
-        sub = {key: v for key, v in state_dict.items() if key.startswith(F0N_PREFIXES)}
+        sub = {key: v for key, v in state_dict.items() if key.startswith(self._prefixes)}
         r = super().load_state_dict(sub, strict, *a, **k)
         self._dirty = True
         return r
@@ -113,6 +119,40 @@ class B200F0NPredictor(nn.Module):
                                            _lib.ptr(self._workspace), self._workspace.numel(), C.c_void_p(stream)),
                        "st2_f0n_forward")
         return f0, n
+
+    def predict_duration(self, t_en: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None):
+        """inference.py:242-245 for a batch of equal-length utterances:
+        `d = predictor.text_encoder(t_en, s, lengths, mask); x, _ = predictor.lstm(d);
+        duration = sigmoid(predictor.duration_proj(x)).sum(-1)`.
+        t_en [B, d_hid, L], s [B, style_dim] -> (d [B, L, d_hid+style_dim], duration [B, L])."""
+        if not self.has_duration:
+            raise RuntimeError("construct B200F0NPredictor(duration=True) to get the duration half")
+        if self.training:
+            raise RuntimeError("B200F0NPredictor is inference-only; call .eval()")
+        if not t_en.is_cuda:
+            raise _lib.St2Error("B200F0NPredictor has no CPU path: inputs must be CUDA tensors")
+        lib = _lib.load()
+        dev = t_en.device
+        B, Cin, L = t_en.shape
+        if Cin != self.cfg.d_hid or tuple(s.shape) != (B, self.cfg.style_dim):
+            raise ValueError("expected t_en [B,%d,L] and s [B,%d]; got %s %s" % (self.cfg.d_hid, self.cfg.style_dim,
+                                                                              tuple(t_en.shape), tuple(s.shape)))
+        prec = _lib.PREC[precision or self.precision]
+        with torch.cuda.device(dev):
+            if self._dirty or self._handle is None:
+                self._sync(dev)
+            x_, s_ = t_en.detach().float().contiguous(), s.detach().float().contiguous()
+            need = _lib.check(lib.st2_dur_workspace_bytes(self._handle, B, L, prec), "st2_dur_workspace_bytes")
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            d = torch.empty(B, L, self.cfg.d_hid + self.cfg.style_dim, dtype=torch.float32, device=dev)
+            duration = torch.empty(B, L, dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.st2_dur_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(d), _lib.ptr(duration), B, L, prec,
+                                           _lib.ptr(self._workspace), self._workspace.numel(), C.c_void_p(stream)),
+                       "st2_dur_forward")
+        return d, duration
 
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0

@@ -21,7 +21,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from .config import DecoderConfig, PredictorConfig, param_specs, predictor_param_specs, buffer_specs, HARMONICS, HIDDEN_DIM, STYLE_DIM
+from .config import DecoderConfig, PredictorConfig, param_specs, predictor_param_specs, duration_param_specs, buffer_specs, HARMONICS, HIDDEN_DIM, STYLE_DIM
 
 
 def _fan_in(shape):
@@ -39,11 +39,24 @@ def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> 
     return {k: v.float().contiguous() for k, v in sd.items()}
 
 
-def make_predictor_state_dict(cfg: PredictorConfig | None = None, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
-    """The F0Ntrain subset of a ProsodyPredictor state_dict (models.py:407-419), drawn like make_state_dict."""
+def make_predictor_state_dict(cfg: PredictorConfig | None = None, seed: int = 0, perturb: bool = True,
+                              duration: bool = False) -> Dict[str, torch.Tensor]:
+    """The F0Ntrain subset of a ProsodyPredictor state_dict (models.py:407-419), drawn like make_state_dict;
+    `duration=True` adds the duration half (text_encoder / lstm / duration_proj, models.py:399-405), drawn after it from
+    the same generator so the F0Ntrain tensors do not depend on the flag."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    sd = _draw(predictor_param_specs(cfg or PredictorConfig()), g, perturb)
+    cfg = cfg or PredictorConfig()
+    sd = _draw(predictor_param_specs(cfg), g, perturb)
+    if duration:
+        sd.update(_draw(duration_param_specs(cfg), g, perturb))
     return {k: v.float().contiguous() for k, v in sd.items()}
+
+
+def make_duration_inputs(B: int, L: int, seed: int = 4000, cfg: PredictorConfig | None = None) -> Dict[str, torch.Tensor]:
+    """t_en [B, d_hid, L] (TextEncoder output, inference.py:239) and the style s [B, style_dim]."""
+    cfg = cfg or PredictorConfig()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return {"t_en": torch.randn(B, cfg.d_hid, L, generator=g), "s": torch.randn(B, cfg.style_dim, generator=g)}
 
 
 def make_predictor_inputs(B: int, T: int, seed: int = 2000, cfg: PredictorConfig | None = None) -> Dict[str, torch.Tensor]:

@@ -32,7 +32,7 @@ _m = types.ModuleType("munch")
 _m.Munch = type("Munch", (dict,), {"__getattr__": dict.get, "__setattr__": dict.__setitem__})
 sys.modules.setdefault("munch", _m)
 
-from styletts2_lite_b200.config import DecoderConfig, PredictorConfig, F0N_PREFIXES  # noqa: E402
+from styletts2_lite_b200.config import DecoderConfig, PredictorConfig, F0N_PREFIXES, DUR_PREFIXES  # noqa: E402
 from styletts2_lite_b200 import synth  # noqa: E402
 
 
@@ -48,6 +48,47 @@ def build_predictor(sd):
     missing, unexpected = p.load_state_dict(sd, strict=False)
     assert not unexpected and all(not k.startswith(F0N_PREFIXES) for k in missing)
     return p.eval()
+
+
+def build_full_predictor(sd):
+    """ProsodyPredictor with both halves loaded (strict: every parameter of the reference module is in `sd`)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from models import ProsodyPredictor
+    p = ProsodyPredictor(style_dim=128, d_hid=512, nlayers=3, max_dur=50, dropout=0.2)
+    ref = p.state_dict()
+    assert set(ref) == set(sd), set(ref) ^ set(sd)
+    for k in ref:
+        assert tuple(ref[k].shape) == tuple(sd[k].shape), (k, ref[k].shape, sd[k].shape)
+    p.load_state_dict(sd)
+    return p.eval()
+
+
+def run_duration(B, L, wseed, iseed, tap_names=()):
+    """inference.py:236-245 after the TextEncoder: mask -> predictor.text_encoder -> predictor.lstm -> duration_proj ->
+    sigmoid-sum, for an equal-length batch."""
+    sd = synth.make_predictor_state_dict(PredictorConfig(), seed=wseed, perturb=True, duration=True)
+    p = build_full_predictor(sd)
+    inp = synth.make_duration_inputs(B, L, seed=iseed)
+    lengths = torch.full((B,), L, dtype=torch.long)
+    mask = p.length_to_mask(lengths)                                    # inference.py:237 (all False here)
+    taps, hooks = {}, []
+    mods = dict(p.named_modules())
+    def grab(o):
+        o = o[0] if isinstance(o, tuple) else o
+        if isinstance(o, torch.nn.utils.rnn.PackedSequence):            # the inner LSTMs run on packed sequences (models.py:503)
+            o = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True)[0]
+        return o.detach().clone()
+
+    for n in tap_names:
+        hooks.append(mods[n].register_forward_hook(lambda mod, i, o, n=n: taps.__setitem__(n, grab(o))))
+    with torch.no_grad():
+        d = p.text_encoder(inp["t_en"], inp["s"], lengths, mask)        # inference.py:242
+        x, _ = p.lstm(d)                                                # inference.py:243
+        duration = torch.sigmoid(p.duration_proj(x)).sum(axis=-1)       # inference.py:244-245
+    for h in hooks:
+        h.remove()
+    return d, duration, taps, sd
 
 
 def run_f0n(B, T, wseed, iseed, tap_names=()):
@@ -78,6 +119,17 @@ def main():
     f0, n, _, _ = run_f0n(1, 120, 0, 2002)
     np.savez_compressed(os.path.join(HERE, "f0n_B1_T120_w0_i2002.npz"), F0=f0.numpy(), N=n.numpy())
     print("f0n 3 s", f0.shape, float(f0.abs().max()))
+
+    # ---- duration half
+    d, dur, taps, full_sd = run_duration(2, 7, 0, 4001, ["text_encoder.lstms.0", "text_encoder.lstms.1", "lstm"])
+    dd = {"d": d.numpy(), "duration": dur.numpy()}
+    for k, v in taps.items():
+        dd["tap:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "dur_B2_L7_w0_i4001.npz"), **dd)
+    print("duration small", d.shape, dur.numpy().round(3))
+    d, dur, _, _ = run_duration(1, 64, 0, 4002)
+    np.savez_compressed(os.path.join(HERE, "dur_B1_L64_w0_i4002.npz"), d=d.numpy(), duration=dur.numpy())
+    print("duration L=64", float(dur.mean()))
 
     # ---- chained slice of inference.py:257-270 (cfg 3 after the text modules)
     from make_golden import build_reference, NoiseTape
@@ -113,6 +165,8 @@ def main():
     schema = json.load(open(path))
     schema["predictor_f0n"] = {"num_params": sum(v.numel() for v in psd.values()),
                                "state_dict": {k: list(v.shape) for k, v in psd.items()}}
+    schema["predictor"] = {"num_params": sum(v.numel() for v in full_sd.values()),
+                           "state_dict": {k: list(v.shape) for k, v in full_sd.items()}}
     json.dump(schema, open(path, "w"), sort_keys=True)
 
 

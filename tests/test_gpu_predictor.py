@@ -138,3 +138,73 @@ def test_chain_regulator_predictor_decoder_matches_reference():
         dec = dec.to("cuda").eval()
         out = dec(asr, f0, n, s, noise=ci["noise"].cuda())
     assert np.abs(out.cpu().numpy() - g["out"]).max() <= 1e-4
+
+
+# ---------------------------------------------------------------- §8(f) N2: duration half
+def _dur_predictor():
+    if "d" not in _CACHE:
+        m = B200F0NPredictor(style_dim=128, d_hid=512, nlayers=3, max_dur=50, dropout=0.2, duration=True)
+        m.load_state_dict(synth.make_predictor_state_dict(seed=0, duration=True))
+        _CACHE["d"] = m.to("cuda").eval()
+    return _CACHE["d"]
+
+
+def test_duration_small_fp32_golden_and_taps():
+    g = golden("dur_B2_L7_w0_i4001.npz")
+    m = _dur_predictor()
+    inp = synth.make_duration_inputs(2, 7, seed=4001)
+    bufs = {k: m.set_tap(k, 2, 7, 512) for k in ("text_encoder.lstms.0", "text_encoder.lstms.1", "lstm")}
+    with torch.no_grad():
+        d, dur = m.predict_duration(inp["t_en"].cuda(), inp["s"].cuda())
+    m.clear_taps()
+    assert np.abs(bufs["text_encoder.lstms.0"].cpu().numpy() - g["tap:text_encoder.lstms.0"]).max() <= 2e-5
+    assert np.abs(bufs["text_encoder.lstms.1"].cpu().numpy() - g["tap:text_encoder.lstms.1"]).max() <= 5e-5   # AdaLayerNorm, [B,L,C]
+    assert np.abs(bufs["lstm"].cpu().numpy() - g["tap:lstm"]).max() <= 2e-5
+    assert np.abs(d.cpu().numpy() - g["d"]).max() <= 1e-4
+    assert np.abs(dur.cpu().numpy() - g["duration"]).max() <= 1e-4
+    # the same handle still serves F0Ntrain
+    gf = golden("f0n_B2_T6_w0_i2001.npz")
+    f0, n = _run(m, synth.make_predictor_inputs(2, 6, seed=2001))
+    assert np.abs(f0 - gf["F0"]).max() <= 1e-4 and np.abs(n - gf["N"]).max() <= 1e-4
+
+
+def test_duration_64_tokens_fp32_golden_and_rounding():
+    g = golden("dur_B1_L64_w0_i4002.npz")
+    m = _dur_predictor()
+    inp = synth.make_duration_inputs(1, 64, seed=4002)
+    with torch.no_grad():
+        d, dur = m.predict_duration(inp["t_en"].cuda(), inp["s"].cuda())
+    assert np.abs(d.cpu().numpy() - g["d"]).max() <= 1e-4 and np.abs(dur.cpu().numpy() - g["duration"]).max() <= 1e-4
+    # inference.py:257: the integer durations agree wherever the reference value is not within 1e-3 of a rounding tie
+    pred, _ = LR.round_durations(dur)
+    ref = np.maximum(np.round(g["duration"]), 1).astype(np.int32)
+    safe = np.abs(g["duration"] - np.floor(g["duration"]) - 0.5) > 1e-3
+    assert np.array_equal(pred.cpu().numpy()[safe], ref[safe])
+
+
+@pytest.mark.parametrize("prec", ["fp16"])
+def test_duration_tensor_core_path_and_batch(prec):
+    """cfg-3 batch shape (32 utterances x 64 tokens): ragged cluster fill (B=32 -> 4 clusters per direction), batch
+    independence, and the fp16-operand input projections against the fp32 path."""
+    B, L = 32, 64
+    inp = synth.make_duration_inputs(B, L, seed=4100)
+    m = _dur_predictor()
+    with torch.no_grad():
+        d, dur = m.predict_duration(inp["t_en"].cuda(), inp["s"].cuda())
+        d1, dur1 = m.predict_duration(inp["t_en"][5:6].cuda(), inp["s"][5:6].cuda())
+        dh, durh = m.predict_duration(inp["t_en"].cuda(), inp["s"].cuda(), precision=prec)
+    assert torch.equal(d[5:6], d1) and torch.equal(dur[5:6], dur1)
+    from oracle import predictor_np as PN
+    sd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0, duration=True).items()}
+    rd, rdur = PN.predict_duration(sd, inp["t_en"][:3].numpy(), inp["s"][:3].numpy())
+    assert np.abs(d[:3].cpu().numpy() - rd).max() <= 1e-4 and np.abs(dur[:3].cpu().numpy() - rdur).max() <= 1e-4
+    assert rel_l2(d.cpu().numpy(), dh.cpu().numpy()) <= 1e-2
+    assert snr_db(dur.cpu().numpy(), durh.cpu().numpy()) >= 40.0
+
+
+def test_duration_needs_its_weights():
+    m = _predictor()                                   # built without the duration half
+    with pytest.raises(RuntimeError):
+        m.predict_duration(torch.zeros(1, 512, 4).cuda(), torch.zeros(1, 128).cuda())
+    lib = _lib.load()
+    assert lib.st2_dur_workspace_bytes(m._handle, 1, 4, 0) == -2          # ST2_ERR_STATE

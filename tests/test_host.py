@@ -84,6 +84,14 @@ def test_predictor_state_dict_schema_matches_reference():
     assert torch.equal(m.state_dict()["shared.weight_hh_l0_reverse"], sd["shared.weight_hh_l0_reverse"])
     with pytest.raises(Exception):
         m.F0Ntrain(torch.zeros(1, 640, 4), torch.zeros(1, 128))           # no CPU path
+    # with duration=True the module holds every parameter of the reference ProsodyPredictor
+    from styletts2_lite_b200.config import duration_param_specs
+    full = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")))["predictor"]
+    m2 = B200F0NPredictor(style_dim=128, d_hid=512, nlayers=3, max_dur=50, dropout=0.2, duration=True)
+    assert {k: list(v.shape) for k, v in m2.state_dict().items()} == full["state_dict"]
+    assert sum(p.numel() for p in m2.parameters()) == full["num_params"]
+    r = m2.load_state_dict(synth.make_predictor_state_dict(seed=0, duration=True))
+    assert not r.missing_keys and not r.unexpected_keys
 
 
 def test_no_cpu_fallback():

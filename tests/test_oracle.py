@@ -178,3 +178,25 @@ def test_predictor_torch_port_matches_reference_fixture():
     with torch.no_grad():
         f0, n = PT.f0n_train(synth.make_predictor_state_dict(seed=0), inp["en"], inp["s"])
     assert np.abs(f0.numpy() - g["F0"]).max() <= 1e-6 and np.abs(n.numpy() - g["N"]).max() <= 1e-6
+
+
+def test_duration_oracle_matches_reference_fixtures():
+    """§8(f) N2: numpy restatement and torch-CPU port of inference.py:242-245 against the reference fixtures."""
+    import torch
+    from oracle import predictor_np as P, predictor_torch as PT
+    sdt = synth.make_predictor_state_dict(seed=0, duration=True)
+    sd = {k: v.numpy() for k, v in sdt.items()}
+    g = golden("dur_B2_L7_w0_i4001.npz")
+    inp = synth.make_duration_inputs(2, 7, seed=4001)
+    taps = {}
+    d, dur = P.predict_duration(sd, inp["t_en"].numpy(), inp["s"].numpy(), taps=taps)
+    assert np.abs(d - g["d"]).max() <= 2e-5 and np.abs(dur - g["duration"]).max() <= 1e-5
+    assert np.abs(taps["text_encoder.lstms.0"] - g["tap:text_encoder.lstms.0"]).max() <= 5e-6
+    assert np.abs(taps["lstm"] - g["tap:lstm"]).max() <= 1e-5
+    with torch.no_grad():
+        d2, dur2 = PT.predict_duration(sdt, inp["t_en"], inp["s"])
+    assert np.abs(d2.numpy() - g["d"]).max() <= 2e-5 and np.abs(dur2.numpy() - g["duration"]).max() <= 1e-5
+    g = golden("dur_B1_L64_w0_i4002.npz")
+    inp = synth.make_duration_inputs(1, 64, seed=4002)
+    d, dur = P.predict_duration(sd, inp["t_en"].numpy(), inp["s"].numpy())
+    assert np.abs(d - g["d"]).max() <= 2e-5 and np.abs(dur - g["duration"]).max() <= 2e-5

@@ -1,5 +1,5 @@
-"""BASELINE.json configs[2] after the text modules, on the GPU box: inference.py:257-270 as one pass
-    durations -> length regulation of d and t_en -> F0Ntrain -> Decoder
+"""BASELINE.json configs[2] after the TextEncoder, on the GPU box: inference.py:242-270 as one pass
+    duration half (DurationEncoder, lstm, duration_proj) -> durations -> length regulation of d and t_en -> F0Ntrain -> Decoder
 for 32 utterances x 8 s (T=320, 64 tokens each, seeded integer durations as SURVEY.md 8(d) cfg 3 prescribes).
 Times the pass with CUDA events (inputs resident), reports the three parts and checks the 16-bit result against the fp32 path.
     python tools/bench_chain.py [--batch 32] [--frames 320] [--tokens 64] [--iters 10]
@@ -32,23 +32,27 @@ cfg = DecoderConfig.hifigan()
 dec = B200Decoder(cfg, a.precision)
 dec.load_state_dict(synth.make_state_dict(cfg, 0, True))
 dec = dec.cuda().eval()
-pred = B200F0NPredictor(precision=a.precision)
-pred.load_state_dict(synth.make_predictor_state_dict(seed=0))
+pred = B200F0NPredictor(precision=a.precision, duration=True)
+pred.load_state_dict(synth.make_predictor_state_dict(seed=0, duration=True))
 pred = pred.cuda().eval()
 ci = synth.make_chain_inputs(B, L, T, seed=3100)
 dur = ci["dur"].to(torch.int32).cuda()
-d_t = ci["d"].transpose(1, 2).contiguous().cuda()          # [B,640,L]
+# random-init weights predict ~25 frames for every token, so the seeded integer durations stand in for round(duration)
+# (SURVEY.md 8(d) cfg 3); the duration half still runs and its `d` is what gets regulated
 t_en, s, noise = ci["t_en"].cuda(), ci["s"].cuda(), ci["noise"].cuda()
 
 
 def chain(precision, seed=None, tape=None, ev=None):
-    en = LR.length_regulate(d_t, dur, T)
-    asr = LR.length_regulate(t_en, dur, T)
+    d, duration = pred.predict_duration(t_en, s, precision=precision)          # inference.py:242-245
+    LR.round_durations(duration)                                               # inference.py:257 (result replaced by `dur`)
     if ev: ev[1].record()
-    f0, n = pred.F0Ntrain(en, s, precision=precision)
+    en = LR.length_regulate(d.transpose(1, 2).contiguous(), dur, T)            # inference.py:266
+    asr = LR.length_regulate(t_en, dur, T)                                     # inference.py:269
     if ev: ev[2].record()
-    out = dec(asr, f0, n, s, noise=tape, seed=seed, precision=precision)
+    f0, n = pred.F0Ntrain(en, s, precision=precision)                          # inference.py:267
     if ev: ev[3].record()
+    out = dec(asr, f0, n, s, noise=tape, seed=seed, precision=precision)       # inference.py:270
+    if ev: ev[4].record()
     return out
 
 
@@ -60,19 +64,19 @@ with torch.no_grad():
     for i in range(3):
         chain(a.precision, seed=i)
     torch.cuda.synchronize()
-    parts = np.zeros(3)
+    parts = np.zeros(4)
     tot = 0.0
     for i in range(a.iters):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
         chain(a.precision, seed=10 + i, ev=ev)
         torch.cuda.synchronize()
-        parts += [ev[j].elapsed_time(ev[j + 1]) for j in range(3)]
-        tot += ev[0].elapsed_time(ev[3])
+        parts += [ev[j].elapsed_time(ev[j + 1]) for j in range(4)]
+        tot += ev[0].elapsed_time(ev[4])
 secs = B * T / 40.0
-print(json.dumps({"path": "length regulator -> F0Ntrain -> Decoder (inference.py:257-270)", "batch": B, "tokens": L, "frames": T,
+print(json.dumps({"path": "duration half -> length regulator -> F0Ntrain -> Decoder (inference.py:242-270)", "batch": B, "tokens": L, "frames": T,
                   "audio_s": secs, "precision": a.precision, "ms": round(tot / a.iters, 3),
                   "audio_s_per_s": round(secs / (tot / a.iters) * 1e3, 1),
-                  "ms_parts": {"length_regulator": round(parts[0] / a.iters, 4), "f0n_predictor": round(parts[1] / a.iters, 4),
-                               "decoder": round(parts[2] / a.iters, 4)},
+                  "ms_parts": {"duration_half": round(parts[0] / a.iters, 4), "length_regulator": round(parts[1] / a.iters, 4),
+                               "f0n_predictor": round(parts[2] / a.iters, 4), "decoder": round(parts[3] / a.iters, 4)},
                   "snr_db_vs_fp32_path": round(snr, 2)}))
