@@ -169,6 +169,16 @@ ST2_API int64_t st2_dur_workspace_bytes(const st2_decoder* d, int32_t B, int32_t
 ST2_API int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B,
                     int32_t L, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- TextEncoder: replaces models.py:238-285, called at inference.py:239 ----
+ * nn.Embedding -> depth x [weight-normed Conv1d(k) -> LayerNorm over channels -> LeakyReLU(0.2)] -> bidirectional LSTM, for a
+ * batch of equal-length token sequences.  Same handle type and weight / finalize / tap / destroy calls as above; keys as in
+ * TextEncoder.state_dict() ("embedding.weight", "cnn.0.0.weight_v", "cnn.0.1.gamma", "lstm.weight_hh_l0_reverse", ...).
+ *   tokens [B, L] int64 (device)  ->  out [B, channels, L]  (= t_en, the input of st2_dur_forward and st2_length_regulate) */
+ST2_API int st2_text_create(int32_t channels, int32_t kernel_size, int32_t depth, int32_t n_symbols, st2_decoder** out);
+ST2_API int64_t st2_text_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision);
+ST2_API int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t B, int32_t L, int32_t precision,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 
 /* torch.round (half to even) + clamp(min=1) of the predicted durations (inference.py:257);

@@ -118,3 +118,29 @@ def predict_duration(sd: Dict[str, np.ndarray], t_en, s, taps: Optional[dict] = 
     logits = (x @ W.p("duration_proj.linear_layer.weight").T.astype(F32) + W.p("duration_proj.linear_layer.bias")).astype(F32)
     duration = _sigmoid(logits).sum(axis=2).astype(F32)
     return d, duration
+
+
+# ----------------------------------------------------------------------------
+# TextEncoder (models.py:238-285), equal-length batches
+# ----------------------------------------------------------------------------
+def text_encoder(sd: Dict[str, np.ndarray], tokens, depth=3, taps: Optional[dict] = None, operand: Optional[str] = None):
+    """TextEncoder.forward(x, input_lengths, m) (models.py:258-285) with an all-False mask: embedding -> depth x
+    [weight-normed Conv1d(k=5, 'same') -> LayerNorm over channels (models.py:224-236) -> LeakyReLU(0.2) -> Dropout = id]
+    -> bidirectional LSTM -> [B, channels, L]."""
+    from .decoder_np import leaky_relu
+    W = Weights(sd)
+    x = W.p("embedding.weight")[np.asarray(tokens)]                          # [B, L, C]  (models.py:259)
+    x = x.transpose(0, 2, 1).astype(F32)                                     # [B, C, L]
+    for i in range(depth):
+        n = "cnn.%d" % i
+        k = W.w(n + ".0").shape[2]
+        x = conv1d(x, W.w(n + ".0"), W.b(n + ".0"), padding=(k - 1) // 2, operand=operand)
+        x64 = x.astype(np.float64)
+        mean, var = x64.mean(axis=1, keepdims=True), x64.var(axis=1, keepdims=True)
+        xn = ((x64 - mean) / np.sqrt(var + 1e-5)).astype(F32)
+        x = (xn * W.p(n + ".1.gamma")[None, :, None] + W.p(n + ".1.beta")[None, :, None]).astype(F32)
+        x = leaky_relu(x, 0.2)
+        if taps is not None:
+            taps[n] = x
+    y = bilstm(W, "lstm", x.transpose(0, 2, 1))                              # models.py:271-277
+    return y.transpose(0, 2, 1)

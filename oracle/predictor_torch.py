@@ -54,3 +54,16 @@ def predict_duration(sd: Dict[str, torch.Tensor], t_en: torch.Tensor, s: torch.T
     z = bilstm(W, "lstm", x)
     dur = torch.sigmoid(F.linear(z, W.p("duration_proj.linear_layer.weight"), W.p("duration_proj.linear_layer.bias"))).sum(-1)
     return x, dur
+
+
+def text_encoder(sd: Dict[str, torch.Tensor], tokens: torch.Tensor, depth: int = 3):
+    """TextEncoder.forward (models.py:258-285) for equal-length batches on torch's CPU kernels."""
+    W = sd if isinstance(sd, TorchWeights) else TorchWeights(sd)
+    x = F.embedding(tokens, W.p("embedding.weight")).transpose(1, 2)
+    for i in range(depth):
+        n = "cnn.%d" % i
+        w = W.w(n + ".0")
+        x = F.conv1d(x, w, W.b(n + ".0"), padding=(w.shape[2] - 1) // 2)
+        x = F.layer_norm(x.transpose(1, -1), (x.shape[1],), W.p(n + ".1.gamma"), W.p(n + ".1.beta"), 1e-5).transpose(1, -1)
+        x = F.leaky_relu(x, 0.2)
+    return bilstm(W, "lstm", x.transpose(1, 2)).transpose(1, 2)

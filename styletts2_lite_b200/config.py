@@ -262,3 +262,28 @@ def duration_param_specs(cfg: PredictorConfig, nlayers: int = 3, max_dur: int = 
     specs.append(("duration_proj.linear_layer.weight", (max_dur, d), "linear"))
     specs.append(("duration_proj.linear_layer.bias", (max_dur,), "linear_bias:%d" % d))
     return specs
+
+
+# ---- §8(f) N3: TextEncoder (models.py:238-285) ---------------------------------------------------------------------
+@dataclass
+class TextEncoderConfig:
+    """`TextEncoder(channels=hidden_dim, kernel_size=5, depth=n_layer, n_symbols=n_token)` (models.py:563,
+    config_example.yaml:38-41; inference.py:82 sets n_token = 178)."""
+    channels: int = HIDDEN_DIM
+    kernel_size: int = 5
+    depth: int = 3
+    n_symbols: int = 178
+
+
+def text_encoder_param_specs(cfg: TextEncoderConfig):
+    """[(state_dict key, shape, init-kind)] of TextEncoder: nn.Embedding, depth x [weight-normed Conv1d, LayerNorm],
+    bidirectional nn.LSTM(channels, channels // 2) (models.py:241-256)."""
+    c = cfg.channels
+    specs = [("embedding.weight", (cfg.n_symbols, c), "normal")]
+    for i in range(cfg.depth):
+        _wn(specs, "cnn.%d.0" % i, (c, c, cfg.kernel_size))
+        specs.append(("cnn.%d.1.gamma" % i, (c,), "gamma"))
+        specs.append(("cnn.%d.1.beta" % i, (c,), "beta"))
+    _lstm(specs, "lstm", c, c // 2)
+    shapes = {n: s for n, s, _ in specs if s is not None}
+    return [(n, s if s is not None else (shapes[k.split(":", 1)[1]][0],), k) for n, s, k in specs]

@@ -119,6 +119,10 @@ int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float*
 int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, int L, cudaStream_t st);
 int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, float* y, int ld_y, int B, int L, int C,
                           cudaStream_t st);
+int launch_layer_norm_lrelu(const float* x, const float* gamma, const float* beta, float slope, float* y, int B, int L, int C,
+                            cudaStream_t st);
+int launch_embedding(const int64_t* tok, const float* table, float* y, int B, int L, int C, int n_symbols, cudaStream_t st);
+int launch_cl_to_cf(const float* x, float* y, int B, int L, int C, cudaStream_t st);
 int launch_duration_head(const float* x, const float* W, const float* bias, float* duration, int B, int L, int C, int nbins,
                          cudaStream_t st);
 

@@ -110,6 +110,13 @@ struct st2_decoder {
     LstmW dur_lstm;
     float *dur_w = nullptr, *dur_b = nullptr;   // duration_proj.linear_layer [max_dur][d_hid], [max_dur]
     int max_dur = 0;
+
+    // variant 3: TextEncoder (models.py:238-285); cfg.dim_in = channels
+    int te_depth = 0, te_kernel = 0, te_symbols = 0;
+    float* te_embedding = nullptr;          // [n_symbols][channels]
+    ConvW te_conv[8];
+    float* te_gamma[8] = {};                // gamma[c] followed by beta[c]
+    LstmW te_lstm;
     ResBlk1dW pred_blk[2][3];               // F0.{0,1,2}, N.{0,1,2}
     ConvW pred_proj[2];                     // F0_proj, N_proj
 
@@ -326,6 +333,29 @@ static void pack_predictor(st2_decoder* d, Packer& P) {
     }
 }
 
+// TextEncoder weights (models.py:241-256)
+static void pack_text_encoder(st2_decoder* d, Packer& P) {
+    const int C = d->cfg.dim_in;
+    d->te_embedding = P.copy("embedding.weight", (int64_t)d->te_symbols * C);
+    for (int i = 0; i < d->te_depth; ++i) {
+        const std::string n = "cnn." + std::to_string(i);
+        P.conv(d->te_conv[i], n + ".0", C, C, d->te_kernel, false, true, true);
+        d->te_gamma[i] = (float*)P.dalloc((size_t)2 * C * sizeof(float));
+        const RawTensor* g = P.get(n + ".1.gamma");
+        const RawTensor* b = P.get(n + ".1.beta");
+        if (!g || !b || !d->te_gamma[i]) return;
+        if (g->numel() != C || b->numel() != C) {
+            set_error("%s.1.gamma / beta must have %d elements", n.c_str(), C);
+            P.err = ST2_ERR_INVALID;
+            return;
+        }
+        if (cudaMemcpyAsync(d->te_gamma[i], g->ptr, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, P.st) != cudaSuccess ||
+            cudaMemcpyAsync(d->te_gamma[i] + C, b->ptr, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, P.st) != cudaSuccess)
+            P.err = ST2_ERR_CUDA;
+    }
+    pack_lstm(d, P, d->te_lstm, "lstm", C, C / 2);
+}
+
 // Decoder weights (hifigan.py:416-443, istftnet.py:660-690)
 static void pack_decoder(st2_decoder* d, Packer& P) {
     const st2_config& c = d->cfg;
@@ -381,6 +411,7 @@ static int finalize_impl(st2_decoder* d, cudaStream_t st) {
     Packer P{d, st};
     d->fc_rows = 0;
     if (c.variant == 2) pack_predictor(d, P);
+    else if (c.variant == 3) pack_text_encoder(d, P);
     else pack_decoder(d, P);
     if (P.err != ST2_OK) return P.err;
     // all AdaIN fc layers -> one [R,style] matrix (rows: gamma(C) | beta(C) per instance)
@@ -458,7 +489,7 @@ struct Exec {
     int fmt_for(const std::string& name) const {
         if (prec == ST2_PREC_FP32) return DT_F32;
         if (prec == ST2_PREC_FP16) return DT_F16;
-        if (d->cfg.variant == 2) return DT_F16;   // predictor: 0.4 % of the decoder's FLOPs, its outputs steer the SineGen phase
+        if (d->cfg.variant >= 2) return DT_F16;   // predictor / text encoder: 0.4 % of the decoder's FLOPs, its outputs steer the SineGen phase
         // bf16 for the generator resblocks / ups (96 % of the FLOPs).  fp16 operands (same tensor
         // throughput) for generator.noise_res -- bf16 there alone costs ~9 dB of SNR -- and for the
         // front half (encode / decode / asr_res, K up to 3270), whose five chained blocks otherwise
@@ -1095,6 +1126,51 @@ static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, f
     return E.err;
 }
 
+// TextEncoder.forward(x, input_lengths, m) (models.py:258-285) for an equal-length batch (mask all False):
+// tokens [B, L] int64 -> out [B, channels, L]
+static int text_forward_impl(st2_decoder* d, const int64_t* tokens, float* out, int B, int L, int prec, void* ws, int64_t ws_bytes,
+                             cudaStream_t st, bool dry, int64_t* peak_out) {
+    const int C = d->cfg.dim_in, H = C / 2;
+    Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    E.coef = E.allocf((int64_t)B * 2 * 2048);
+    float* xa = E.allocf((int64_t)B * L * C);
+    float* xb = E.allocf((int64_t)B * L * C);
+    float* G = E.allocf((int64_t)B * L * 8 * H);
+    if (E.live()) {
+        if (d->profiling) {
+            d->prof_recs.clear();
+            if (d->prof_events.empty()) {
+                cudaEvent_t ev;
+                if (cudaEventCreate(&ev) == cudaSuccess) d->prof_events.push_back(ev);
+            }
+            if (!d->prof_events.empty()) cudaEventRecord(d->prof_events[0], st);
+        }
+        E.chk(launch_embedding(tokens, d->te_embedding, xa, B, L, C, d->te_symbols, st));       // models.py:259-260
+        E.prof(PC_MISC, 0, 8.0 * B * L * C);
+    }
+    const int dt = E.fmt_for("cnn");
+    for (int i = 0; i < d->te_depth; ++i) {                                                       // models.py:264-266
+        const int64_t mark = E.off;
+        const bool tc = E.use_tc(d->te_conv[i], dt);
+        const void* xin = xa;
+        if (tc) {
+            void* x16 = E.alloc((int64_t)B * L * C * 2);
+            E.norm_act(xa, C, L, C, nullptr, ACT_NONE, 0.f, nullptr, x16, C, dt);
+            xin = x16;
+        }
+        E.conv(d->te_conv[i], xin, C, L, tc ? dt : DT_F32, xb, C, L, 1, (d->te_kernel - 1) / 2, 1, nullptr, 0, 0, 1.f, 0);
+        if (E.live()) E.chk(launch_layer_norm_lrelu(xb, d->te_gamma[i], d->te_gamma[i] + C, 0.2f, xa, B, L, C, st));
+        E.prof(PC_AFFINE_ACT, 0, 8.0 * B * L * C);
+        E.tap("cnn." + std::to_string(i), xa, C, (int64_t)B * L, C);
+        E.off = mark;
+    }
+    bilstm(E, d->te_lstm, "lstm", xa, G, xb, L, C, H);                                           // models.py:268-277
+    if (E.live()) E.chk(launch_cl_to_cf(xb, out, B, L, C, st));                                   // models.py:279
+    E.prof(PC_MISC, 0, 8.0 * B * L * C);
+    if (peak_out) *peak_out = E.peak;
+    return E.err;
+}
+
 }  // namespace st2
 
 // ------------------------------------------------------------------------------------------
@@ -1161,7 +1237,7 @@ int st2_decoder_finalize(st2_decoder* d, void* stream) {
 int64_t st2_decoder_num_params(const st2_decoder* d) { return d ? d->num_params : 0; }
 
 int64_t st2_decoder_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision) {
-    if (!d || !d->finalized || d->cfg.variant == 2 || B <= 0 || T <= 0) {
+    if (!d || !d->finalized || d->cfg.variant >= 2 || B <= 0 || T <= 0) {
         st2::set_error("workspace_bytes: handle not finalized (or a predictor handle) or bad shape");
         return ST2_ERR_STATE;
     }
@@ -1176,8 +1252,8 @@ int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const
                         const float* noise, uint64_t seed, float* out, int32_t B, int32_t T, int32_t precision,
                         void* workspace, int64_t workspace_bytes, void* stream) {
     ST2_REQUIRE(d != nullptr, "forward: null handle");
-    if (!d->finalized || d->cfg.variant == 2) {
-        st2::set_error("forward: st2_decoder_finalize has not been called (or this is a predictor handle)");
+    if (!d->finalized || d->cfg.variant >= 2) {
+        st2::set_error("forward: st2_decoder_finalize has not been called (or this is a predictor / text-encoder handle)");
         return ST2_ERR_STATE;
     }
     ST2_REQUIRE(asr && f0 && n && s && out && workspace, "forward: null tensor");
@@ -1279,6 +1355,59 @@ int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_
     st2::g_launch_count = 0;
     int e = st2::dur_forward_impl(d, t_en, s, d_out, duration, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream,
                                   false, nullptr);
+    d->last_launches = st2::g_launch_count;
+    return e;
+}
+
+/* ---- TextEncoder: replaces models.py:238-285 ---- */
+int st2_text_create(int32_t channels, int32_t kernel_size, int32_t depth, int32_t n_symbols, st2_decoder** out) {
+    ST2_REQUIRE(out != nullptr, "text_create: null argument");
+    ST2_REQUIRE(channels == 512, "text_create: channels must be 512 (got %d)", channels);
+    ST2_REQUIRE(kernel_size >= 1 && kernel_size <= 15 && (kernel_size & 1) && depth >= 1 && depth <= 8 && n_symbols >= 1,
+                "text_create: unsupported kernel_size / depth / n_symbols (%d, %d, %d)", kernel_size, depth, n_symbols);
+    st2_decoder* d = new (std::nothrow) st2_decoder();
+    ST2_REQUIRE(d != nullptr, "text_create: out of memory");
+    memset(&d->cfg, 0, sizeof(d->cfg));
+    d->cfg.variant = 3;
+    d->cfg.dim_in = channels;
+    d->cfg.style_dim = 4;
+    d->te_depth = depth; d->te_kernel = kernel_size; d->te_symbols = n_symbols;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+        d->tc_ok = (prop.major == 10);
+    *out = d;
+    return ST2_OK;
+}
+
+int64_t st2_text_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision) {
+    if (!d || !d->finalized || d->cfg.variant != 3 || B <= 0 || L <= 0) {
+        st2::set_error("text_workspace_bytes: not a finalized text-encoder handle, or bad shape");
+        return ST2_ERR_STATE;
+    }
+    int64_t peak = 0;
+    int e = st2::text_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, B, L, precision, nullptr, 0, nullptr, true, &peak);
+    if (e != ST2_OK) return e;
+    return peak + 256;
+}
+
+int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t B, int32_t L, int32_t precision, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    ST2_REQUIRE(d != nullptr, "text_forward: null handle");
+    if (!d->finalized || d->cfg.variant != 3) {
+        st2::set_error("text_forward: not a finalized text-encoder handle (st2_text_create + st2_decoder_finalize)");
+        return ST2_ERR_STATE;
+    }
+    ST2_REQUIRE(tokens && out && workspace, "text_forward: null tensor");
+    ST2_REQUIRE(B > 0 && L >= 1, "text_forward: need B>0 and L>=1 (got B=%d L=%d)", B, L);
+    ST2_REQUIRE(precision >= ST2_PREC_FP32 && precision <= ST2_PREC_FP16, "text_forward: bad precision %d", precision);
+    if (precision != ST2_PREC_FP32 && !d->tc_ok) {
+        st2::set_error("text_forward: tensor-core precision requires an sm_100 device");
+        return ST2_ERR_UNSUPPORTED;
+    }
+    ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "text_forward: workspace must be 256-byte aligned");
+    st2::g_launch_count = 0;
+    int e = st2::text_forward_impl(d, tokens, out, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream, false, nullptr);
     d->last_launches = st2::g_launch_count;
     return e;
 }

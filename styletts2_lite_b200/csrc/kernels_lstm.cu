@@ -334,9 +334,11 @@ __global__ void concat_style_kernel(float* __restrict__ x, int ld, int C, const 
 // AdaLayerNorm (models.py:372-392) on channels-last x [B][L][C]: LayerNorm over C (biased variance, eps 1e-5), then
 // (1 + gamma) * xhat + beta with gamma | beta = h[b][h_off .. h_off + 2C); writes y[row][0..C) with pitch ld_y.
 // One warp per token; C = 512 -> 16 values per lane kept in registers, mean and variance by warp shuffles (two pass).
-template <int C>
+// PLAIN: the TextEncoder's LayerNorm (models.py:224-236) + LeakyReLU(slope): y = lrelu(gamma[c] * xhat + beta[c]) with
+// h = gamma, h + ld_h = beta (per channel, shared by every row)
+template <int C, bool PLAIN>
 __global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ h, int ld_h, int h_off,
-                                      float* __restrict__ y, int ld_y, int64_t rows, int L) {
+                                      float* __restrict__ y, int ld_y, int64_t rows, int L, float slope) {
     constexpr int PER = C / 32;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -359,18 +361,52 @@ __global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * (1.f / C) + 1e-5f);
-    const float* hb = h + (row / L) * ld_h + h_off;
+    const float* hb = PLAIN ? h : h + (row / L) * ld_h + h_off;
+    const float* bb = PLAIN ? h + ld_h : hb + C;
+    const float one = PLAIN ? 0.f : 1.f;
     float* yr = y + row * ld_y;
 #pragma unroll
     for (int i = 0; i < PER / 4; ++i) {
         const int c = (i * 32 + lane) * 4;
-        const float4 g = *reinterpret_cast<const float4*>(hb + c), b = *reinterpret_cast<const float4*>(hb + C + c);
+        const float4 g = *reinterpret_cast<const float4*>(hb + c), b = *reinterpret_cast<const float4*>(bb + c);
         float4 o;
-        o.x = fmaf(1.f + g.x, (v[4 * i] - mean) * rstd, b.x);
-        o.y = fmaf(1.f + g.y, (v[4 * i + 1] - mean) * rstd, b.y);
-        o.z = fmaf(1.f + g.z, (v[4 * i + 2] - mean) * rstd, b.z);
-        o.w = fmaf(1.f + g.w, (v[4 * i + 3] - mean) * rstd, b.w);
+        o.x = fmaf(one + g.x, (v[4 * i] - mean) * rstd, b.x);
+        o.y = fmaf(one + g.y, (v[4 * i + 1] - mean) * rstd, b.y);
+        o.z = fmaf(one + g.z, (v[4 * i + 2] - mean) * rstd, b.z);
+        o.w = fmaf(one + g.w, (v[4 * i + 3] - mean) * rstd, b.w);
+        if (PLAIN) {
+            o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+            o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+        }
         *reinterpret_cast<float4*>(yr + c) = o;
+    }
+}
+
+// nn.Embedding lookup into channels-last rows: y[row][0..C) = table[tok[row]][0..C)   (models.py:259)
+__global__ void embedding_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table, float* __restrict__ y, int C,
+                                 int64_t rows, int n_symbols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = C / 4;
+    if (i >= rows * c4) return;
+    const int64_t row = i / c4;
+    const int c = (int)(i - row * c4) * 4;
+    int64_t t = tok[row];
+    t = t < 0 ? 0 : (t >= n_symbols ? n_symbols - 1 : t);          // the host wrapper rejects out-of-range ids; never read outside
+    *reinterpret_cast<float4*>(y + row * C + c) = __ldg(reinterpret_cast<const float4*>(table + t * C + c));
+}
+
+// channels-last [B][L][C] -> the reference's [B][C][L] (32 x 32 tiles through shared memory)
+__global__ void cl_to_cf_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int l = l0 + i, c = c0 + threadIdx.x;
+        if (l < L && c < C) tile[i][threadIdx.x] = x[((size_t)b * L + l) * C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, l = l0 + threadIdx.x;
+        if (l < L && c < C) y[((size_t)b * C + c) * L + l] = tile[threadIdx.x][i];
     }
 }
 
@@ -417,7 +453,31 @@ int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, f
                           cudaStream_t st) {
     ST2_REQUIRE(C == 512 && ld_y % 4 == 0 && ld_h % 4 == 0 && h_off % 4 == 0, "ada_layer_norm: needs 512 channels (got %d)", C);
     const int64_t rows = (int64_t)B * L;
-    ada_layer_norm_kernel<512><<<cdiv(rows, 8), 256, 0, st>>>(x, h, ld_h, h_off, y, ld_y, rows, L);
+    ada_layer_norm_kernel<512, false><<<cdiv(rows, 8), 256, 0, st>>>(x, h, ld_h, h_off, y, ld_y, rows, L, 0.f);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_layer_norm_lrelu(const float* x, const float* gamma, const float* beta, float slope, float* y, int B, int L, int C,
+                            cudaStream_t st) {
+    ST2_REQUIRE(C == 512, "layer_norm: needs 512 channels (got %d)", C);
+    const int64_t rows = (int64_t)B * L;
+    ada_layer_norm_kernel<512, true><<<cdiv(rows, 8), 256, 0, st>>>(x, gamma, (int)(beta - gamma), 0, y, C, rows, L, slope);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_embedding(const int64_t* tok, const float* table, float* y, int B, int L, int C, int n_symbols, cudaStream_t st) {
+    ST2_REQUIRE(C % 4 == 0, "embedding: channels must be a multiple of 4");
+    const int64_t n = (int64_t)B * L * (C / 4);
+    embedding_kernel<<<cdiv(n, 256), 256, 0, st>>>(tok, table, y, C, (int64_t)B * L, n_symbols);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_cl_to_cf(const float* x, float* y, int B, int L, int C, cudaStream_t st) {
+    dim3 grid(cdiv(L, 32), cdiv(C, 32), B), block(32, 8);
+    cl_to_cf_kernel<<<grid, block, 0, st>>>(x, y, L, C);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

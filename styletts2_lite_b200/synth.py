@@ -21,7 +21,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from .config import DecoderConfig, PredictorConfig, param_specs, predictor_param_specs, duration_param_specs, buffer_specs, HARMONICS, HIDDEN_DIM, STYLE_DIM
+from .config import DecoderConfig, PredictorConfig, param_specs, predictor_param_specs, duration_param_specs, TextEncoderConfig, text_encoder_param_specs, buffer_specs, HARMONICS, HIDDEN_DIM, STYLE_DIM
 
 
 def _fan_in(shape):
@@ -84,6 +84,12 @@ def _draw(specs, g, perturb: bool) -> Dict[str, torch.Tensor]:
                 sd[name] = 0.6 + 0.8 * torch.rand(shape, generator=g)
             else:
                 sd[name] = torch.ones(shape)
+        elif kind == "normal":                              # nn.Embedding init
+            sd[name] = torch.randn(shape, generator=g)
+        elif kind == "gamma":                               # LayerNorm scale: 1 in the reference init
+            sd[name] = 0.8 + 0.4 * torch.rand(shape, generator=g) if perturb else torch.ones(shape)
+        elif kind == "beta":
+            sd[name] = 0.2 * (torch.rand(shape, generator=g) - 0.5) if perturb else torch.zeros(shape)
         elif kind.startswith("lstm:"):                      # nn.LSTM init: U(-1/sqrt(hidden), 1/sqrt(hidden))
             bound = 1.0 / math.sqrt(int(kind.split(":")[1]))
             sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
@@ -171,3 +177,19 @@ def make_chain_inputs(B: int, L: int, T: int, seed: int = 3003) -> Dict[str, tor
     return {"dur": make_durations(B, L, T, seed=seed + 8), "d": torch.randn(B, L, HIDDEN_DIM + STYLE_DIM, generator=g),
             "t_en": torch.randn(B, HIDDEN_DIM, L, generator=g), "s": torch.randn(B, STYLE_DIM, generator=g),
             "noise": torch.randn(B, 600 * T, HARMONICS, generator=g)}
+
+
+def make_text_state_dict(cfg: TextEncoderConfig | None = None, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
+    """A TextEncoder state_dict (models.py:238-256), drawn like make_state_dict."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = _draw(text_encoder_param_specs(cfg or TextEncoderConfig()), g, perturb)
+    return {k: v.float().contiguous() for k, v in sd.items()}
+
+
+def make_tokens(B: int, L: int, seed: int = 5000, n_symbols: int = 178) -> torch.Tensor:
+    """Token ids [B, L] int64 with the reference's leading / trailing pad token 0 (inference.py:231-232)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = torch.randint(1, n_symbols, (B, L), generator=g)
+    t[:, 0] = 0
+    t[:, -1] = 0
+    return t

@@ -131,6 +131,28 @@ def main():
     np.savez_compressed(os.path.join(HERE, "dur_B1_L64_w0_i4002.npz"), d=d.numpy(), duration=dur.numpy())
     print("duration L=64", float(dur.mean()))
 
+    # ---- TextEncoder
+    from models import TextEncoder
+    from styletts2_lite_b200.config import TextEncoderConfig
+    tsd = synth.make_text_state_dict(TextEncoderConfig(), seed=0, perturb=True)
+    te = TextEncoder(channels=512, kernel_size=5, depth=3, n_symbols=178)                 # models.py:563
+    ref = te.state_dict()
+    assert set(ref) == set(tsd), set(ref) ^ set(tsd)
+    for k in ref:
+        assert tuple(ref[k].shape) == tuple(tsd[k].shape), (k, ref[k].shape, tsd[k].shape)
+    te.load_state_dict(tsd)
+    te = te.eval()
+    for (B, L, seed, name) in ((2, 9, 5001, "text_B2_L9_w0_i5001.npz"), (1, 64, 5002, "text_B1_L64_w0_i5002.npz")):
+        tok = synth.make_tokens(B, L, seed=seed)
+        lengths = torch.full((B,), L, dtype=torch.long)
+        taps_t = {}
+        hk = te.cnn[0].register_forward_hook(lambda mod, i, o: taps_t.__setitem__("cnn.0", o.detach().clone()))
+        with torch.no_grad():
+            out = te(tok, lengths, te.length_to_mask(lengths))                            # inference.py:239
+        hk.remove()
+        np.savez_compressed(os.path.join(HERE, name), out=out.numpy(), **{"tap:cnn.0": taps_t["cnn.0"].numpy()})
+        print("text encoder", out.shape, float(out.abs().max()))
+
     # ---- chained slice of inference.py:257-270 (cfg 3 after the text modules)
     from make_golden import build_reference, NoiseTape
     B, L, T = 2, 9, 16
@@ -165,6 +187,8 @@ def main():
     schema = json.load(open(path))
     schema["predictor_f0n"] = {"num_params": sum(v.numel() for v in psd.values()),
                                "state_dict": {k: list(v.shape) for k, v in psd.items()}}
+    schema["text_encoder"] = {"num_params": sum(v.numel() for v in tsd.values()),
+                              "state_dict": {k: list(v.shape) for k, v in tsd.items()}}
     schema["predictor"] = {"num_params": sum(v.numel() for v in full_sd.values()),
                            "state_dict": {k: list(v.shape) for k, v in full_sd.items()}}
     json.dump(schema, open(path, "w"), sort_keys=True)

@@ -208,3 +208,83 @@ def test_duration_needs_its_weights():
         m.predict_duration(torch.zeros(1, 512, 4).cuda(), torch.zeros(1, 128).cuda())
     lib = _lib.load()
     assert lib.st2_dur_workspace_bytes(m._handle, 1, 4, 0) == -2          # ST2_ERR_STATE
+
+
+# ---------------------------------------------------------------- §8(f) N3: TextEncoder
+def _text_encoder():
+    if "t" not in _CACHE:
+        from styletts2_lite_b200.text_encoder import B200TextEncoder
+        m = B200TextEncoder(channels=512, kernel_size=5, depth=3, n_symbols=178)
+        m.load_state_dict(synth.make_text_state_dict(seed=0))
+        _CACHE["t"] = m.to("cuda").eval()
+    return _CACHE["t"]
+
+
+@pytest.mark.parametrize("B,L,seed,name", [(2, 9, 5001, "text_B2_L9_w0_i5001.npz"), (1, 64, 5002, "text_B1_L64_w0_i5002.npz")])
+def test_text_encoder_fp32_golden(B, L, seed, name):
+    g = golden(name)
+    m = _text_encoder()
+    tok = synth.make_tokens(B, L, seed=seed).cuda()
+    lengths = torch.full((B,), L, dtype=torch.long)
+    buf = m.set_tap("cnn.0", B, L, 512)
+    with torch.no_grad():
+        out = m(tok, lengths, torch.zeros(B, L, dtype=torch.bool))
+    m.clear_taps()
+    assert np.abs(G.cf(buf.cpu().numpy()) - g["tap:cnn.0"]).max() <= 2e-5
+    assert out.shape == (B, 512, L) and np.abs(out.cpu().numpy() - g["out"]).max() <= 1e-4
+
+
+def test_text_encoder_batch_tensor_core_and_errors():
+    from oracle import predictor_np as PN
+    B, L = 32, 64
+    m = _text_encoder()
+    tok = synth.make_tokens(B, L, seed=5100).cuda()
+    with torch.no_grad():
+        out = m(tok)
+        one = m(tok[7:8])
+        o16 = m(tok, precision="fp16")
+    assert torch.equal(out[7:8], one)
+    sd = {k: v.numpy() for k, v in synth.make_text_state_dict(seed=0).items()}
+    ref = PN.text_encoder(sd, tok[:2].cpu().numpy())
+    assert np.abs(out[:2].cpu().numpy() - ref).max() <= 1e-4
+    assert rel_l2(out.cpu().numpy(), o16.cpu().numpy()) <= 1e-2
+    with pytest.raises(ValueError):
+        m(tok, torch.tensor([L] * (B - 1) + [L - 3]))                      # padded batch
+    with pytest.raises(IndexError):
+        m(torch.full((1, 4), 178, dtype=torch.long).cuda())                # id out of range, like nn.Embedding
+    with pytest.raises(_lib.St2Error):
+        m(tok.cpu())
+
+
+def test_tokens_to_waveform_chain_runs_on_the_gpu():
+    """inference.py:239-270 end to end in this library at a small size: TextEncoder -> duration half -> durations ->
+    length regulation -> F0Ntrain -> Decoder.  Each stage is pinned to the reference by its own fixtures; here the stages are
+    chained through device tensors and checked against the chained oracles."""
+    from oracle import predictor_np as PN, decoder_np as O
+    B, L, T = 2, 9, 16
+    tok = synth.make_tokens(B, L, seed=5200)
+    ci = synth.make_chain_inputs(B, L, T, seed=3003)
+    with torch.no_grad():
+        t_en = _text_encoder()(tok.cuda())
+        pred = _dur_predictor()
+        d, duration = pred.predict_duration(t_en, ci["s"].cuda())
+        dur = ci["dur"].to(torch.int32).cuda()                             # seeded durations summing to T (SURVEY 8(d) cfg 3)
+        en = LR.length_regulate(d.transpose(1, 2).contiguous(), dur, T)
+        asr = LR.length_regulate(t_en, dur, T)
+        f0, n = pred.F0Ntrain(en, ci["s"].cuda())
+        cfg = DecoderConfig.hifigan()
+        dec = B200Decoder(cfg, "fp32")
+        dec.load_state_dict(synth.make_state_dict(cfg, 0, True))
+        out = dec.to("cuda").eval()(asr, f0, n, ci["s"].cuda(), noise=ci["noise"].cuda())
+    s_np = ci["s"].numpy()
+    r_t = PN.text_encoder({k: v.numpy() for k, v in synth.make_text_state_dict(seed=0).items()}, tok.numpy())
+    psd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0, duration=True).items()}
+    r_d, r_dur = PN.predict_duration(psd, r_t, s_np)
+    assert np.abs(t_en.cpu().numpy() - r_t).max() <= 1e-4 and np.abs(duration.cpu().numpy() - r_dur).max() <= 2e-4
+    r_en = O.length_regulate_batch(r_d.transpose(0, 2, 1), ci["dur"].numpy(), T)
+    r_asr = O.length_regulate_batch(r_t, ci["dur"].numpy(), T)
+    r_f0, r_n = PN.f0n_train(psd, r_en, s_np)
+    assert np.abs(f0.cpu().numpy() - r_f0).max() <= 2e-4 and np.abs(n.cpu().numpy() - r_n).max() <= 2e-4
+    r_out = O.decoder_forward({k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()}, cfg, r_asr, r_f0, r_n, s_np,
+                              ci["noise"].numpy())
+    assert np.abs(out.cpu().numpy() - r_out).max() <= 5e-4

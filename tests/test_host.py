@@ -94,6 +94,18 @@ def test_predictor_state_dict_schema_matches_reference():
     assert not r.missing_keys and not r.unexpected_keys
 
 
+def test_text_encoder_state_dict_schema_matches_reference():
+    from styletts2_lite_b200.text_encoder import B200TextEncoder
+    schema = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")))["text_encoder"]
+    m = B200TextEncoder(channels=512, kernel_size=5, depth=3, n_symbols=178)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == schema["state_dict"]
+    assert sum(p.numel() for p in m.parameters()) == schema["num_params"]
+    r = m.load_state_dict(synth.make_text_state_dict(seed=0))
+    assert not r.missing_keys and not r.unexpected_keys
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 4, dtype=torch.long))                            # no CPU path
+
+
 def test_no_cpu_fallback():
     from styletts2_lite_b200 import hifigan, length_regulator
     m = hifigan.Decoder(style_dim=128)

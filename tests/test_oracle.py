@@ -200,3 +200,19 @@ def test_duration_oracle_matches_reference_fixtures():
     inp = synth.make_duration_inputs(1, 64, seed=4002)
     d, dur = P.predict_duration(sd, inp["t_en"].numpy(), inp["s"].numpy())
     assert np.abs(d - g["d"]).max() <= 2e-5 and np.abs(dur - g["duration"]).max() <= 2e-5
+
+
+def test_text_encoder_oracle_matches_reference_fixtures():
+    """§8(f) N3: numpy restatement and torch-CPU port of TextEncoder.forward against the reference fixtures."""
+    import torch
+    from oracle import predictor_np as P, predictor_torch as PT
+    sdt = synth.make_text_state_dict(seed=0)
+    sd = {k: v.numpy() for k, v in sdt.items()}
+    for B, L, seed, name in ((2, 9, 5001, "text_B2_L9_w0_i5001.npz"), (1, 64, 5002, "text_B1_L64_w0_i5002.npz")):
+        g = golden(name)
+        tok = synth.make_tokens(B, L, seed=seed)
+        taps = {}
+        out = P.text_encoder(sd, tok.numpy(), taps=taps)
+        assert np.abs(out - g["out"]).max() <= 5e-6 and np.abs(taps["cnn.0"] - g["tap:cnn.0"]).max() <= 1e-5
+        with torch.no_grad():
+            assert np.abs(PT.text_encoder(sdt, tok).numpy() - g["out"]).max() <= 5e-6
