@@ -1,5 +1,6 @@
-"""BASELINE.json configs[2] after the TextEncoder, on the GPU box: inference.py:242-270 as one pass
-    duration half (DurationEncoder, lstm, duration_proj) -> durations -> length regulation of d and t_en -> F0Ntrain -> Decoder
+"""BASELINE.json configs[2] on the GPU box: inference.py:239-270 as one pass
+    TextEncoder -> duration half (DurationEncoder, lstm, duration_proj) -> durations -> length regulation of d and t_en
+    -> F0Ntrain -> Decoder
 for 32 utterances x 8 s (T=320, 64 tokens each, seeded integer durations as SURVEY.md 8(d) cfg 3 prescribes).
 Times the pass with CUDA events (inputs resident), reports the three parts and checks the 16-bit result against the fp32 path.
     python tools/bench_chain.py [--batch 32] [--frames 320] [--tokens 64] [--iters 10]
@@ -18,6 +19,7 @@ from styletts2_lite_b200 import length_regulator as LR, synth  # noqa: E402
 from styletts2_lite_b200.config import DecoderConfig  # noqa: E402
 from styletts2_lite_b200.decoder import B200Decoder  # noqa: E402
 from styletts2_lite_b200.predictor import B200F0NPredictor  # noqa: E402
+from styletts2_lite_b200.text_encoder import B200TextEncoder  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
@@ -35,14 +37,20 @@ dec = dec.cuda().eval()
 pred = B200F0NPredictor(precision=a.precision, duration=True)
 pred.load_state_dict(synth.make_predictor_state_dict(seed=0, duration=True))
 pred = pred.cuda().eval()
+text = B200TextEncoder(precision=a.precision)
+text.load_state_dict(synth.make_text_state_dict(seed=0))
+text = text.cuda().eval()
+tokens = synth.make_tokens(B, L, seed=5300).cuda()
 ci = synth.make_chain_inputs(B, L, T, seed=3100)
 dur = ci["dur"].to(torch.int32).cuda()
 # random-init weights predict ~25 frames for every token, so the seeded integer durations stand in for round(duration)
 # (SURVEY.md 8(d) cfg 3); the duration half still runs and its `d` is what gets regulated
-t_en, s, noise = ci["t_en"].cuda(), ci["s"].cuda(), ci["noise"].cuda()
+s, noise = ci["s"].cuda(), ci["noise"].cuda()
 
 
 def chain(precision, seed=None, tape=None, ev=None):
+    t_en = text(tokens, precision=precision)                                   # inference.py:239
+    if ev: ev[5].record()
     d, duration = pred.predict_duration(t_en, s, precision=precision)          # inference.py:242-245
     LR.round_durations(duration)                                               # inference.py:257 (result replaced by `dur`)
     if ev: ev[1].record()
@@ -64,19 +72,20 @@ with torch.no_grad():
     for i in range(3):
         chain(a.precision, seed=i)
     torch.cuda.synchronize()
-    parts = np.zeros(4)
+    parts = np.zeros(5)
     tot = 0.0
     for i in range(a.iters):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
         chain(a.precision, seed=10 + i, ev=ev)
         torch.cuda.synchronize()
-        parts += [ev[j].elapsed_time(ev[j + 1]) for j in range(4)]
+        parts += [ev[0].elapsed_time(ev[5]), ev[5].elapsed_time(ev[1])] + [ev[j].elapsed_time(ev[j + 1]) for j in range(1, 4)]
         tot += ev[0].elapsed_time(ev[4])
 secs = B * T / 40.0
-print(json.dumps({"path": "duration half -> length regulator -> F0Ntrain -> Decoder (inference.py:242-270)", "batch": B, "tokens": L, "frames": T,
+print(json.dumps({"path": "TextEncoder -> duration half -> length regulator -> F0Ntrain -> Decoder (inference.py:239-270)", "batch": B, "tokens": L, "frames": T,
                   "audio_s": secs, "precision": a.precision, "ms": round(tot / a.iters, 3),
                   "audio_s_per_s": round(secs / (tot / a.iters) * 1e3, 1),
-                  "ms_parts": {"duration_half": round(parts[0] / a.iters, 4), "length_regulator": round(parts[1] / a.iters, 4),
-                               "f0n_predictor": round(parts[2] / a.iters, 4), "decoder": round(parts[3] / a.iters, 4)},
+                  "ms_parts": {"text_encoder": round(parts[0] / a.iters, 4), "duration_half": round(parts[1] / a.iters, 4),
+                               "length_regulator": round(parts[2] / a.iters, 4), "f0n_predictor": round(parts[3] / a.iters, 4),
+                               "decoder": round(parts[4] / a.iters, 4)},
                   "snr_db_vs_fp32_path": round(snr, 2)}))
