@@ -157,6 +157,8 @@ struct ConvArgs {
     int x16in;                               // fused path: the input tensor x is 16-bit (fmt16) with pitch ld_x elements
     int y16out;                              // fused path: write y as fp16; statistics still from the fp32 values
     int res16;                               // fused path (conv_pipe only): the residual tensor is fp16 with pitch ld_res elements
+    const void* acc_src; int acc16;          // fused path (conv_pipe only): with accumulate, read the old values from acc_src (pitch
+                                             // ld_y; fp16 when acc16) instead of y -- partial sums of a stage kept in fp16
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);   // tcgen05 + TMA

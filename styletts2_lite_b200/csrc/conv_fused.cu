@@ -660,7 +660,7 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     p.x = a.x; p.ld_x = a.ld_x; p.Tin = a.Tin;
     p.x16in = a.x16in; p.y16out = a.y16out;
     ST2_REQUIRE(!(a.y16out && (a.accumulate || a.mirror)), "conv_fused: 16-bit output cannot accumulate / mirror");
-    ST2_REQUIRE(!a.res16, "conv_fused: a 16-bit residual is only supported by the TMA pipeline kernel");
+    ST2_REQUIRE(!a.res16 && a.acc_src == nullptr, "conv_fused: a 16-bit residual / separate accumulate source is only supported by the TMA pipeline kernel");
     p.coef = coef; p.coef_ld = coef_ld; p.alpha = alpha; p.slope = slope;
     p.Cin = a.Cin; p.kchunks = a.w16_cin_pad / F_KC;
     p.B = a.B; p.M = a.M; p.Tout = a.Tout; p.Cout = a.Cout;

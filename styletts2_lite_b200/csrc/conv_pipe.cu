@@ -72,6 +72,7 @@ struct PipeParams {
                                 //    2 K chunks, 4 operand buffers, 4 accumulators): half the weight traffic into shared memory
     int nx, nr, nres;           // ring depths; nres = residual sources per stage (0, 1, or 2 = residual + old y)
     int r16;                    // the residual tensor is fp16 (the running tensor of AdaINResBlock1): four [32 rows x 32 ch] boxes
+    int o16;                    // the old values of an accumulate layer are fp16 (partial sums of a stage), same box layout
     // epilogue
     const float* bias;
     float* y; int ld_y; float scale; int y16out;   // y already shifted by -out_pad*cdiv rows for a transposed conv
@@ -163,7 +164,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
     const uint32_t a_bytes = ((uint32_t)p.rows * arow + 1023u) & ~1023u;
     const uint32_t b_stage_bytes = (uint32_t)p.bn * arow;
     const uint32_t r_stage_bytes = p.nres ? (uint32_t)p.nres * P_RBOX : 0u;
-    const uint32_t r_tx_bytes = p.r16 ? r_stage_bytes - (uint32_t)P_RBOX / 2u : r_stage_bytes;     // an fp16 residual box is half the bytes
+    const uint32_t r_tx_bytes = r_stage_bytes - (p.r16 ? (uint32_t)P_RBOX / 2u : 0u) -             // an fp16 box is half the bytes
+                                (p.nres == 2 && p.o16 ? (uint32_t)P_RBOX / 2u : 0u);
     const uint32_t r_bytes = p.nres ? (uint32_t)p.nr * r_stage_bytes : (uint32_t)P_EW * 4096u;   // ring or per-warp staging
     uint8_t* smem_a = smem;                                        // na x [rows][K] 16-bit, swizzled
     uint8_t* smem_b = smem_a + (size_t)p.na * a_bytes;             // resident taps or ring of [bn][K]
@@ -303,7 +305,15 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                     } else {
                         tma_load_4d(dst, &map_r, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
                     }
-                    if (p.nres == 2) tma_load_4d(dst + P_RBOX, &map_o, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
+                    if (p.nres == 2) {
+                        if (p.o16) {
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq)
+                                tma_load_4d(dst + P_RBOX + qq * 4096, &map_o, &r_full[r_stage], co0, u, rt.mt * P_MT + moff + qq * 32, rt.b);
+                        } else {
+                            tma_load_4d(dst + P_RBOX, &map_o, &r_full[r_stage], co0, u, rt.mt * P_MT + moff, rt.b);
+                        }
+                    }
                     ++r_c;
                     if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1; }
                     if (++r_ch == nchunks) { r_ch = 0; rt.next(p); r_done = !rt.valid(p); }
@@ -699,12 +709,24 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                         }
                         }
                         if (NRES == 2) {
+                            if (p.o16) {
+                                const uint32_t st_h = tile_u32 + (uint32_t)P_RBOX + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 raw = lds128(st_h + (((uint32_t)i ^ sw) << 4));
+                                    const float4 r0 = unpack16x4(make_uint2(__float_as_uint(raw.x), __float_as_uint(raw.y)), 0);
+                                    const float4 r1 = unpack16x4(make_uint2(__float_as_uint(raw.z), __float_as_uint(raw.w)), 0);
+                                    v[8 * i] += r0.x; v[8 * i + 1] += r0.y; v[8 * i + 2] += r0.z; v[8 * i + 3] += r0.w;
+                                    v[8 * i + 4] += r1.x; v[8 * i + 5] += r1.y; v[8 * i + 6] += r1.z; v[8 * i + 7] += r1.w;
+                                }
+                            } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 r = lds128(st_w + (uint32_t)P_RBOX + (((uint32_t)i ^ l7) << 4));
                                 const float2 lo = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(r.x, r.y));
                                 const float2 hi = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(r.z, r.w));
                                 v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+                            }
                             }
                         }
                     }
@@ -753,7 +775,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
                 if (p.y16out) run_chunks(std::integral_constant<int, 1>{}, std::true_type{});
                 else run_chunks(std::integral_constant<int, 1>{}, std::false_type{});
             } else {
-                run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
+                if (p.y16out) run_chunks(std::integral_constant<int, 2>{}, std::true_type{});
+                else run_chunks(std::integral_constant<int, 2>{}, std::false_type{});
             }
           }
         }
@@ -810,7 +833,8 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
     if (a.w16_cin_pad != (a.Cin == 32 ? 64 : a.Cin)) return false;
     // x16in / y16out: the intra-block tensor of AdaINResBlock1 stored as fp16 (plain stride-1 convs only)
     if ((a.x16in || a.res16) && tr) return false;
-    if (a.y16out && a.accumulate) return false;
+    if (a.acc_src != nullptr && !a.accumulate) return false;
+    if (a.y16out && a.accumulate && !(a.acc_src != nullptr && a.acc16)) return false;     // fp16 in-place sums need an fp16 source
     if (a.res16 && a.res == nullptr) return false;
     if (a.ld_x % (a.x16in ? 8 : 4) != 0 || a.ld_y % 4 != 0 || (a.res != nullptr && a.ld_res % (a.res16 ? 8 : 4) != 0)) return false;
     if (a.accumulate && a.res == nullptr) return false;
@@ -876,6 +900,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.tmem_cols = cols;
     p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
     p.r16 = a.res16 ? 1 : 0;
+    p.o16 = (a.accumulate && a.acc_src != nullptr && a.acc16) ? 1 : 0;
     p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
     if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && p.nres > 0 && !tr_)) p.eg = v; }
     // 3 groups need 4 accumulators: a group's previous tile is tcnt-3, so MMA(tcnt-4) -- the previous use of its accumulator
@@ -996,8 +1021,13 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         if (e != ST2_OK) return e;
     }
     if (a.accumulate) {
-        e = make_map_4d_f32_sw128(&map_o, a.y, (uint64_t)a.Cout, 1, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 4,
-                                  (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT);
+        const void* old = a.acc_src != nullptr ? a.acc_src : (const void*)a.y;
+        if (p.o16)
+            e = make_map_4d_f16_sw64(&map_o, old, (uint64_t)a.Cout, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 2,
+                                     (uint64_t)a.Tout * a.ld_y * 2, 32, 32);
+        else
+            e = make_map_4d_f32_sw128(&map_o, old, (uint64_t)a.Cout, 1, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 4,
+                                      (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT);
         if (e != ST2_OK) return e;
     }
     static int num_sms = 0;

@@ -643,13 +643,14 @@ struct Exec {
     }
     // would launch_conv_fused run this stride-1 conv on the TMA pipeline kernel (conv_pipe.cu) with these storage types?
     bool pipe_ok(const ConvW& w, int ld_x, int ld_y, int T, int padding, int dilation, bool has_res, int accumulate, int dt,
-                 int x16in, int y16out, int res16 = 0) {
+                 int x16in, int y16out, int res16 = 0, int acc16 = 0) {
         ConvArgs a;
         if (!fill_args(a, w, T, T, 1, padding, dilation, 0)) return false;
         a.accumulate = accumulate;
         a.ld_x = ld_x; a.ld_y = ld_y; a.ld_res = ld_y; a.res = has_res ? (const float*)this : nullptr;   // only null-ness matters
         a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
         a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.scale = 1.f;
+        if (accumulate && acc16) { a.acc_src = this; a.acc16 = 1; }                                      // only null-ness matters
         return conv_pipe_supported(a);
     }
     // would launch_conv_fused run this upsampling conv on the TMA pipeline kernel and write a 16-bit output?
@@ -665,7 +666,7 @@ struct Exec {
     void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
                     float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
                     int res_shift, float scale, int accumulate, void* stats_out, int out_row_shift = 0, int mirror = 0,
-                    int x16in = 0, int y16out = 0, int res16 = 0) {
+                    int x16in = 0, int y16out = 0, int res16 = 0, const void* acc_src = nullptr, int acc16 = 0) {
         if (!live()) return;
         ConvArgs a;
         if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
@@ -673,11 +674,11 @@ struct Exec {
         a.y = y; a.ld_y = ld_y;
         a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
         a.x = x; a.ld_x = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
-        a.x16in = x16in; a.y16out = y16out; a.res16 = res16;
+        a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.acc_src = acc_src; a.acc16 = acc16;
         chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const double bytes = (double)B * ((double)w.Cin * Tin * (x16in ? 2 : 4) +
-                                          (double)w.Cout * Tout * ((y16out ? 2 : 4) + (res ? (res16 ? 2 : 4) : 0) + (accumulate ? 4 : 0))) +
+                                          (double)w.Cout * Tout * ((y16out ? 2 : 4) + (res ? (res16 ? 2 : 4) : 0) + (accumulate ? (acc16 ? 2 : 4) : 0))) +
                              (double)w.k * w.Cin * w.Cout * 2;
         prof(conv_pipe_supported(a) ? PC_CONV_PIPE : PC_CONV_FUSED, flops, bytes);
     }
@@ -735,6 +736,20 @@ struct Exec {
     // (may alias x_in for an in-place block); the last iteration writes
     // dest = (dest_old*accumulate + conv2 + run) * scale.
     // would resblock1 take its input tensor as fp16 (every conv of the block on the TMA pipeline kernel)?
+    // would the last conv of this block write / accumulate the fp16 partial sum of the stage?
+    //   mode 1: first block of a stage, writes the fp16 sum;  2: middle, fp16 sum in place;  3: last, fp16 sum -> fp32 stage output
+    bool resblock1_sum16_ok(const ResBlock1W& w, int T, int mode, int x16) {
+        const int C = w.C, dt = fmt_for(w.name);
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16") || getenv("ST2_NO_SUM16")) return false;
+        for (int j = 0; j < 3; ++j) {        // every conv of the block on the pipeline kernel with the fp16 tensors it will see
+            const int dil = w.dil[j], in16 = (j > 0 || x16) ? 1 : 0;
+            if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, in16, 1) ||
+                !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, (j == 2 && mode > 1) ? 1 : 0, dt, 1, (j < 2 || mode < 3) ? 1 : 0, in16,
+                         (j == 2 && mode > 1) ? 1 : 0))
+                return false;
+        }
+        return true;
+    }
     bool resblock1_x16_ok(const ResBlock1W& w, int T, int accumulate) {
         const int C = w.C, dt = fmt_for(w.name);
         if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16")) return false;
@@ -746,8 +761,9 @@ struct Exec {
         }
         return true;
     }
+    // sum16 (modes above) with sum16buf: the stage's partial sum lives in fp16 until the last block writes `dest`
     void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate,
-                   const StatRef* in_stats = nullptr, int x16 = 0) {
+                   const StatRef* in_stats = nullptr, int x16 = 0, int sum16 = 0, void* sum16buf = nullptr) {
         const int64_t mark = off;
         const int C = w.C;
         const int dt = fmt_for(w.name);
@@ -780,6 +796,10 @@ struct Exec {
                     run16 = 0;
             }
             void* r16buf = alloc((int64_t)B * T * C * 2);           // allocated either way: same workspace on every device
+            if (sum16 && !run16 && err == ST2_OK) {                  // the caller asks resblock1_sum16_ok first
+                set_error("resblock1: the fp16 stage sum needs the fp16 running-tensor path");
+                err = ST2_ERR_STATE;
+            }
             if (x16 && !(run16 && in_stats) && err == ST2_OK) {      // the caller asks resblock1_x16_ok first
                 set_error("resblock1: fp16 block input needs the fp16 running-tensor path and producer statistics");
                 err = ST2_ERR_STATE;
@@ -796,10 +816,12 @@ struct Exec {
                 else tap16(w.name + ".convs1." + std::to_string(j), xt, (int64_t)B * T * C);
                 coef_from(StatRef{st_xt, nparts, true}, &w.n2[j], T, C, C);
                 const bool last = (j == 2);
-                const int out16 = (run16 && !last) ? 1 : 0;
-                float* out = last ? dest : (out16 ? (float*)r16buf : run);
+                const bool s16 = last && sum16 != 0 && run16;                     // the caller asked resblock1_sum16_ok first
+                const int out16 = ((run16 && !last) || (s16 && sum16 < 3)) ? 1 : 0;
+                float* out = last ? ((s16 && sum16 < 3) ? (float*)sum16buf : dest) : (out16 ? (float*)r16buf : run);
                 conv_fused(w.c2[j], xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
-                           last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, out16, cur16);
+                           last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, out16, cur16,
+                           (s16 && sum16 > 1) ? sum16buf : nullptr, (s16 && sum16 > 1) ? 1 : 0);
                 if (out16) tap16(w.name + ".iter" + std::to_string(j), out, (int64_t)B * T * C);
                 else if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
                 cur = out;
@@ -983,10 +1005,16 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         if (xu16) E.tap16("generator.stage" + is + ".in", xu, (int64_t)B * Tout * C);
         else E.tap("generator.stage" + is + ".in", xu, C, (int64_t)B * Tout, C);
         float* run = E.allocf((int64_t)B * Tout * C);
+        // the partial sum over the resblocks of the stage (written by the first, read + written by the middle ones, read by the
+        // last, which writes the fp32 stage output) is kept in fp16 when all their last convs take it (ST2_NO_SUM16=1: fp32)
+        void* sum16buf = E.alloc((int64_t)B * Tout * C * 2);
+        int sum16 = c.n_kernels >= 2 ? 1 : 0;
+        for (int j = 0; j < c.n_kernels && sum16; ++j)
+            if (!E.resblock1_sum16_ok(d->resblocks[i * c.n_kernels + j], Tout, j == 0 ? 1 : (j + 1 == c.n_kernels ? 3 : 2), xu16)) sum16 = 0;
         for (int j = 0; j < c.n_kernels; ++j) {
             const bool lastk = (j + 1 == c.n_kernels);
             E.resblock1(d->resblocks[i * c.n_kernels + j], xu, run, Tout, stage_out[i], lastk ? 1.f / (float)c.n_kernels : 1.f,
-                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr, xu16);
+                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr, xu16, sum16 ? (j == 0 ? 1 : (lastk ? 3 : 2)) : 0, sum16buf);
         }
         E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
         x = stage_out[i];
