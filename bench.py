@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--variant", default="hifigan", choices=["hifigan", "istftnet"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="skip the auxiliary BASELINE configs[2] measurement (full_path_cfg3)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: --frames)")
     return ap.parse_args()
 
@@ -359,6 +360,17 @@ def run_b200(a, rank, local_rank, world):
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_port_run(a.variant, a.cpu_frames or a.frames, 2, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world == 1 and not a.no_cpu_baseline and not a.no_chain and a.precision != "fp32":
+        # auxiliary, outside the timed region: BASELINE configs[2] (32 x 8 s, token ids -> waveform through the TextEncoder,
+        # the prosody predictor, the length regulator and the Decoder of this library); never allowed to break the main line
+        try:
+            del m
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from bench_chain import run_chain
+            line["full_path_cfg3"] = run_chain(32, 64, 320, a.precision, 5)
+        except Exception as ex:  # noqa: BLE001
+            line["full_path_cfg3"] = {"error": str(ex)[:300]}
     if world > 1:
         dist.destroy_process_group()
     return line
