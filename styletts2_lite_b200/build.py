@@ -19,7 +19,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libst2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["decoder.cu", "api_units.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_source.cu",
+SOURCES = ["decoder.cu", "predictor.cu", "api_units.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_source.cu",
            "length_regulator.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "conv_pipe.cu", "kernels_lstm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(11, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(12, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                   "-Xcompiler", "-fPIC"]
@@ -94,7 +94,7 @@ def _build_variant(defines, out):
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(11, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(12, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     r = subprocess.run([nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                               "-Xcompiler", "-fPIC"], capture_output=True, text=True)
