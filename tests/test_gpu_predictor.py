@@ -288,3 +288,32 @@ def test_tokens_to_waveform_chain_runs_on_the_gpu():
     r_out = O.decoder_forward({k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()}, cfg, r_asr, r_f0, r_n, s_np,
                               ci["noise"].numpy())
     assert np.abs(out.cpu().numpy() - r_out).max() <= 5e-4
+
+
+# ---------------------------------------------------------------- sizes at the edges of the new modules
+@pytest.mark.parametrize("B,L", [(1, 1), (3, 400), (65, 5)])
+def test_text_and_duration_sizes_vs_oracle(B, L):
+    """One token, the longest sentence the reference splits to (~400 tokens), and a batch that needs two waves of LSTM
+    clusters (65 utterances -> 9 groups of 8 per direction > 15 co-resident clusters)."""
+    from oracle import predictor_np as PN
+    tok = synth.make_tokens(B, max(L, 2), seed=5400 + B)[:, :L]
+    s = synth.make_duration_inputs(B, L, seed=4400 + B)["s"]
+    with torch.no_grad():
+        t_en = _text_encoder()(tok.cuda())
+        d, dur = _dur_predictor().predict_duration(t_en, s.cuda())
+    nb = min(B, 2)
+    r_t = PN.text_encoder({k: v.numpy() for k, v in synth.make_text_state_dict(seed=0).items()}, tok[-nb:].numpy())
+    psd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0, duration=True).items()}
+    r_d, r_dur = PN.predict_duration(psd, r_t, s[-nb:].numpy())
+    # a single token makes every LayerNorm / InstanceNorm-free path exact but the conv 'same' padding dominant: same bound
+    assert np.abs(t_en[-nb:].cpu().numpy() - r_t).max() <= 1e-4
+    assert np.abs(d[-nb:].cpu().numpy() - r_d).max() <= 2e-4 and np.abs(dur[-nb:].cpu().numpy() - r_dur).max() <= 2e-4
+
+
+def test_f0n_10s_and_two_waves_vs_oracle():
+    inp = synth.make_predictor_inputs(66, 400, seed=2500)
+    f0, n = _run(_predictor(), inp)
+    rf0, rn = P.f0n_train(_np_sd(), inp["en"][-1:].numpy(), inp["s"][-1:].numpy())
+    assert np.abs(f0[-1:] - rf0).max() <= 1e-4 and np.abs(n[-1:] - rn).max() <= 1e-4
+    one_f0, one_n = _run(_predictor(), {"en": inp["en"][:1], "s": inp["s"][:1]})
+    assert np.array_equal(f0[:1], one_f0) and np.array_equal(n[:1], one_n)
