@@ -401,6 +401,16 @@ int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t ca
     return ST2_OK;
 }
 
+int st2_decoder_set_option(st2_decoder* d, const char* name, int32_t value) {
+    ST2_REQUIRE(d && name, "set_option: bad argument");
+    if (strcmp(name, "fp16_storage") == 0) {
+        d->fp16_storage = value ? 1 : 0;
+        return ST2_OK;
+    }
+    st2::set_error("set_option: unknown option '%s'", name);
+    return ST2_ERR_INVALID;
+}
+
 int st2_decoder_set_seed_buffer(st2_decoder* d, const uint64_t* dev_seed) {
     ST2_REQUIRE(d != nullptr, "set_seed_buffer: null handle");
     d->seed_dev = dev_seed;

@@ -78,6 +78,7 @@ struct st2_decoder {
     int64_t last_launches = 0;
     const uint64_t* seed_dev = nullptr;     // optional device-resident Philox seed (st2_decoder_set_seed_buffer)
     bool tc_ok = false;
+    int fp16_storage = 1;                   // st2_decoder_set_option("fp16_storage"): stage-private tensors of the 16-bit paths in fp16
 
     ResBlk1dW encode, decode[4];
     float *f0_w = nullptr, *f0_b = nullptr, *n_w = nullptr, *n_b = nullptr;
@@ -571,7 +572,7 @@ struct Exec {
     //   mode 1: first block of a stage, writes the fp16 sum;  2: middle, fp16 sum in place;  3: last, fp16 sum -> fp32 stage output
     bool resblock1_sum16_ok(const ResBlock1W& w, int T, int mode, int x16) {
         const int C = w.C, dt = fmt_for(w.name);
-        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16") || getenv("ST2_NO_SUM16")) return false;
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16") || getenv("ST2_NO_SUM16")) return false;
         for (int j = 0; j < 3; ++j) {        // every conv of the block on the pipeline kernel with the fp16 tensors it will see
             const int dil = w.dil[j], in16 = (j > 0 || x16) ? 1 : 0;
             if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, in16, 1) ||
@@ -583,7 +584,7 @@ struct Exec {
     }
     bool resblock1_x16_ok(const ResBlock1W& w, int T, int accumulate) {
         const int C = w.C, dt = fmt_for(w.name);
-        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16")) return false;
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16")) return false;
         for (int j = 0; j < 3; ++j) {
             const int dil = w.dil[j];
             if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 1, 1) ||
@@ -607,7 +608,7 @@ struct Exec {
             // the intra-block tensor xt (conv1 output, only consumed by conv2's transform) is stored as fp16 when both convs
             // run on the TMA pipeline kernel: 20 % fewer HBM bytes per iteration for -0.1 dB of SNR (its statistics still come
             // from the fp32 values in the epilogue).  ST2_NO_XT16=1 keeps it fp32.
-            int xt16 = getenv("ST2_NO_XT16") == nullptr ? 1 : 0;
+            int xt16 = (d->fp16_storage && getenv("ST2_NO_XT16") == nullptr) ? 1 : 0;
             for (int j = 0; j < 3 && xt16; ++j) {
                 const int dil = w.dil[j];
                 if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 0, 1) ||

@@ -38,8 +38,9 @@ class B200Decoder(nn.Module):
     reference), 'bf16' (tcgen05, bf16 operands; generator.noise_res on fp16 operands) or
     'fp16' (tcgen05, fp16 operands)."""
 
-    def __init__(self, cfg: DecoderConfig, precision: str = "fp32"):
+    def __init__(self, cfg: DecoderConfig, precision: str = "fp32", fp16_storage: bool = True):
         super().__init__()
+        self.fp16_storage = fp16_storage        # 16-bit precisions: stage-private generator tensors in fp16 (DESIGN.md section 3)
         if precision not in _lib.PREC:
             raise ValueError("precision must be one of %s" % list(_lib.PREC))
         self.cfg = cfg
@@ -82,6 +83,7 @@ class B200Decoder(nn.Module):
             cc = _lib.St2Config.from_config(self.cfg)
             _lib.check(lib.st2_decoder_create(C.byref(cc), C.byref(h)), "st2_decoder_create")
             self._handle = h
+        _lib.check(lib.st2_decoder_set_option(self._handle, b"fp16_storage", 1 if self.fp16_storage else 0), "set_option")
         keep = []
         for name, t in self.state_dict().items():
             if t.device != device:

@@ -258,6 +258,16 @@ def test_fp16_intra_block_tensor_costs_little():
     assert d >= 45.0
     assert snr_db(g["out"], out16) >= 40.0
     assert snr_db(g["out"], out16) >= snr_db(g["out"], out32) - 1.0
+    # the same switch through the API: B200Decoder(..., fp16_storage=False) / st2_decoder_set_option
+    m.fp16_storage = False
+    m.refresh_weights()
+    try:
+        assert np.array_equal(_run(m, inp, precision="bf16"), out32)
+    finally:
+        m.fp16_storage = True
+        m.refresh_weights()
+    assert np.array_equal(_run(m, inp, precision="bf16"), out16)
+    assert _lib.load().st2_decoder_set_option(m._handle, b"no_such_option", 1) == -1
     # each switch alone changes the result (the path it guards really runs) and stays within the same bound
     for knob in ("ST2_NO_RUN16", "ST2_NO_XU16", "ST2_NO_SUM16"):
         os.environ[knob] = "1"
