@@ -576,6 +576,8 @@ __global__ void __launch_bounds__(1024)
 adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float* __restrict__ h, int ld_h, int h_off,
                      float* __restrict__ coef, int T, int C, int Cpad) {
     __shared__ double ssum[32][33], ssq[32][33];
+    pdl_trigger();
+    pdl_wait();                 // the partials come from the kernel before this one
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     const int b = blockIdx.y;
@@ -626,7 +628,16 @@ adain_coef_f2_kernel(const float2* __restrict__ partial, int nparts, const float
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
                          int C, int Cpad, cudaStream_t st) {
     dim3 grid(cdiv(Cpad, 32), B);
-    adain_coef_f2_kernel<<<grid, 1024, 0, st>>>((const float2*)partial, nparts, h, ld_h, h_off, coef, T, C, Cpad);
+    // programmatic dependent launch for small grids (one-sentence latency; ST2_NO_PDL=1: plain): the CTAs may be scheduled while
+    // the producing conv drains.  Large batches gain nothing and lose SMs to the next conv's early CTAs (conv_pipe.cu)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    const bool pdl = getenv("ST2_NO_PDL") == nullptr && ((int64_t)grid.x * grid.y <= 64 || getenv("ST2_PDL_ALWAYS") != nullptr);
+    cfg.attrs = &attr; cfg.numAttrs = pdl ? 1 : 0;
+    ST2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, adain_coef_f2_kernel, (const float2*)partial, nparts, h, ld_h, h_off, coef, T, C, Cpad));
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

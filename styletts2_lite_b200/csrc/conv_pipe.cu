@@ -235,6 +235,10 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above (barriers, TMEM, zeroed operand buffers) is independent of the previous kernel in the stream: under
+    // programmatic dependent launch it overlaps that kernel; nothing below may run before it has completed
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ===== producer: three independent queues served by one thread with non-blocking barrier tests =====
@@ -1053,7 +1057,20 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     ST2_REQUIRE(act != ACT_SNAKE || alpha != nullptr, "conv_pipe: snake needs alpha");
     ST2_REQUIRE(!a.x16in || act == ACT_SNAKE, "conv_pipe: 16-bit input is only built for the Snake transform");
     if (act != ACT_SNAKE) p.eg = 2;                          // the 3-group variant is only built for Snake
-#define PIPE_LAUNCH(A, BF, X, G) conv_pipe_kernel<A, BF, X, G><<<grid, (P_W_EPI0 + 4 * G) * 32, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p)
+    cudaLaunchConfig_t lcfg = {};
+    lcfg.gridDim = dim3(grid); lcfg.dynamicSmemBytes = smem; lcfg.stream = st;
+    cudaLaunchAttribute lattr;
+    lattr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr.val.programmaticStreamSerializationAllowed = 1;
+    // Only for small problems (a few tiles per CTA, i.e. one-sentence latency: 3.65 -> 3.29 ms at 1 x 3 s): in throughput
+    // runs the early CTAs of this kernel sit on SMs the coefficient kernel in front of it needs, +0.8 ms per 64 x 5 s step
+    const bool pdl = getenv("ST2_NO_PDL") == nullptr && (p.num_tiles <= 16 * num_sms || getenv("ST2_PDL_ALWAYS") != nullptr);
+    lcfg.attrs = &lattr; lcfg.numAttrs = pdl ? 1 : 0;
+#define PIPE_LAUNCH(A, BF, X, G)                                                                                         \
+    do {                                                                                                                 \
+        lcfg.blockDim = dim3((P_W_EPI0 + 4 * G) * 32);                                                                   \
+        ST2_CUDA_CHECK(cudaLaunchKernelEx(&lcfg, conv_pipe_kernel<A, BF, X, G>, map_b, map_x, map_xt, map_r, map_o, p)); \
+    } while (0)
     const bool bf = p.is_bf16 != 0;
     switch (act) {
         case ACT_NONE: if (bf) PIPE_LAUNCH(ACT_NONE, true, false, 2); else PIPE_LAUNCH(ACT_NONE, false, false, 2); break;

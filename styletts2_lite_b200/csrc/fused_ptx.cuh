@@ -138,4 +138,10 @@ __device__ __forceinline__ uint2 transform4(const float4 v, const XfCoef& c, int
     return make_uint2(pack16(y01.x, y01.y, is_bf16), pack16(y23.x, y23.y, is_bf16));
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has completed and its writes are
+// visible (a no-op for a plain launch), pdl_trigger() lets the successor's CTAs be scheduled as resources free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace st2
