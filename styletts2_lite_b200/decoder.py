@@ -78,6 +78,7 @@ class B200Decoder(nn.Module):
 
     def _sync(self, device: torch.device) -> None:
         lib = _lib.load()
+        self._graphs.clear()                      # finalize re-allocates the packed weights captured graphs point to
         if self._handle is None:
             h = C.c_void_p()
             cc = _lib.St2Config.from_config(self.cfg)

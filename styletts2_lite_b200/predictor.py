@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import _lib
 from .config import DUR_PREFIXES, F0N_PREFIXES, PredictorConfig, duration_param_specs, predictor_param_specs
 from .decoder import _register
+from .graphs import GraphReplay
 
 
 class B200F0NPredictor(nn.Module):
@@ -43,6 +44,7 @@ class B200F0NPredictor(nn.Module):
         self._dirty = True
         self._workspace: Optional[torch.Tensor] = None
         self._taps: Dict[str, torch.Tensor] = {}
+        self._graphs = GraphReplay()
         self.train(False)
 
     def _apply(self, fn, *a, **k):
@@ -59,6 +61,7 @@ class B200F0NPredictor(nn.Module):
 
     def _sync(self, device: torch.device) -> None:
         lib = _lib.load()
+        self._graphs.clear()                      # finalize re-allocates the packed weights captured graphs point to
         if self._handle is None:
             h = C.c_void_p()
             _lib.check(lib.st2_f0n_create(self.cfg.d_hid, self.cfg.style_dim, C.byref(h)), "st2_f0n_create")
@@ -92,7 +95,28 @@ class B200F0NPredictor(nn.Module):
             _lib.load().st2_decoder_set_tap(self._handle, name.encode(), None, 0)
         self._taps.clear()
 
-    def F0Ntrain(self, x: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None):
+    def _launch_f0n(self, x_, s_, ws, B, T, prec):
+        lib = _lib.load()
+        dev = x_.device
+        f0 = torch.empty(B, 2 * T, dtype=torch.float32, device=dev)
+        n = torch.empty(B, 2 * T, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.st2_f0n_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(f0), _lib.ptr(n), B, T, prec,
+                                       _lib.ptr(ws), ws.numel(), C.c_void_p(stream)), "st2_f0n_forward")
+        return f0, n
+
+    def _launch_dur(self, x_, s_, ws, B, L, prec):
+        lib = _lib.load()
+        dev = x_.device
+        d = torch.empty(B, L, self.cfg.d_hid + self.cfg.style_dim, dtype=torch.float32, device=dev)
+        duration = torch.empty(B, L, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.st2_dur_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(d), _lib.ptr(duration), B, L, prec,
+                                       _lib.ptr(ws), ws.numel(), C.c_void_p(stream)), "st2_dur_forward")
+        return d, duration
+
+    def F0Ntrain(self, x: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None, cuda_graph: bool = False):
+        """`cuda_graph=True` replays a graph captured once per (B, T, precision) -- one-sentence latency (graphs.py)."""
         if self.training:
             raise RuntimeError("B200F0NPredictor is inference-only (dropout p=0.2 of models.py:409-416 is not implemented); call .eval()")
         if not x.is_cuda:
@@ -109,18 +133,16 @@ class B200F0NPredictor(nn.Module):
                 self._sync(dev)
             x_, s_ = x.detach().float().contiguous(), s.detach().float().contiguous()
             need = _lib.check(lib.st2_f0n_workspace_bytes(self._handle, B, T, prec), "st2_f0n_workspace_bytes")
+            if cuda_graph and not self._taps:
+                return self._graphs.run(("f0n", B, T, prec, dev.index), (x_, s_),
+                                        lambda: torch.empty(need, dtype=torch.uint8, device=dev),
+                                        lambda ins, ws: self._launch_f0n(ins[0], ins[1], ws, B, T, prec))
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            f0 = torch.empty(B, 2 * T, dtype=torch.float32, device=dev)
-            n = torch.empty(B, 2 * T, dtype=torch.float32, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.st2_f0n_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(f0), _lib.ptr(n), B, T, prec,
-                                           _lib.ptr(self._workspace), self._workspace.numel(), C.c_void_p(stream)),
-                       "st2_f0n_forward")
-        return f0, n
+            return self._launch_f0n(x_, s_, self._workspace, B, T, prec)
 
-    def predict_duration(self, t_en: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None):
+    def predict_duration(self, t_en: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None, cuda_graph: bool = False):
         """inference.py:242-245 for a batch of equal-length utterances:
         `d = predictor.text_encoder(t_en, s, lengths, mask); x, _ = predictor.lstm(d);
         duration = sigmoid(predictor.duration_proj(x)).sum(-1)`.
@@ -143,16 +165,14 @@ class B200F0NPredictor(nn.Module):
                 self._sync(dev)
             x_, s_ = t_en.detach().float().contiguous(), s.detach().float().contiguous()
             need = _lib.check(lib.st2_dur_workspace_bytes(self._handle, B, L, prec), "st2_dur_workspace_bytes")
+            if cuda_graph and not self._taps:
+                return self._graphs.run(("dur", B, L, prec, dev.index), (x_, s_),
+                                        lambda: torch.empty(need, dtype=torch.uint8, device=dev),
+                                        lambda ins, ws: self._launch_dur(ins[0], ins[1], ws, B, L, prec))
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            d = torch.empty(B, L, self.cfg.d_hid + self.cfg.style_dim, dtype=torch.float32, device=dev)
-            duration = torch.empty(B, L, dtype=torch.float32, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.st2_dur_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(d), _lib.ptr(duration), B, L, prec,
-                                           _lib.ptr(self._workspace), self._workspace.numel(), C.c_void_p(stream)),
-                       "st2_dur_forward")
-        return d, duration
+            return self._launch_dur(x_, s_, self._workspace, B, L, prec)
 
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0

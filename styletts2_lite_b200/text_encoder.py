@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import _lib
 from .config import TextEncoderConfig, text_encoder_param_specs
 from .decoder import _register
+from .graphs import GraphReplay
 
 
 class B200TextEncoder(nn.Module):
@@ -33,6 +34,7 @@ class B200TextEncoder(nn.Module):
         self._dirty = True
         self._workspace: Optional[torch.Tensor] = None
         self._taps: Dict[str, torch.Tensor] = {}
+        self._graphs = GraphReplay()
         self.train(False)
 
     def _apply(self, fn, *a, **k):
@@ -47,6 +49,7 @@ class B200TextEncoder(nn.Module):
 
     def _sync(self, device: torch.device) -> None:
         lib = _lib.load()
+        self._graphs.clear()                      # finalize re-allocates the packed weights captured graphs point to
         if self._handle is None:
             h = C.c_void_p()
             _lib.check(lib.st2_text_create(self.cfg.channels, self.cfg.kernel_size, self.cfg.depth, self.cfg.n_symbols,
@@ -80,8 +83,17 @@ class B200TextEncoder(nn.Module):
             _lib.load().st2_decoder_set_tap(self._handle, name.encode(), None, 0)
         self._taps.clear()
 
+    def _launch(self, tok, ws, B, L, prec):
+        lib = _lib.load()
+        dev = tok.device
+        out = torch.empty(B, self.cfg.channels, L, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.st2_text_forward(self._handle, _lib.ptr(tok), _lib.ptr(out), B, L, prec, _lib.ptr(ws), ws.numel(),
+                                        C.c_void_p(stream)), "st2_text_forward")
+        return out
+
     def forward(self, x: torch.Tensor, input_lengths: Optional[torch.Tensor] = None, m: Optional[torch.Tensor] = None,
-                precision: Optional[str] = None) -> torch.Tensor:
+                precision: Optional[str] = None, cuda_graph: bool = False) -> torch.Tensor:
         """x: token ids [B, L] (int64); input_lengths [B] and the padding mask m [B, L] as in the reference call
         (inference.py:236-239) -- accepted, and required to describe an unpadded batch."""
         if self.training:
@@ -103,14 +115,14 @@ class B200TextEncoder(nn.Module):
                 self._sync(dev)
             tok = x.detach().to(torch.int64).contiguous()
             need = _lib.check(lib.st2_text_workspace_bytes(self._handle, B, L, prec), "st2_text_workspace_bytes")
+            if cuda_graph and not self._taps:           # graph captured once per (B, L, precision): graphs.py
+                return self._graphs.run(("text", B, L, prec, dev.index), (tok,),
+                                        lambda: torch.empty(need, dtype=torch.uint8, device=dev),
+                                        lambda ins, ws: (self._launch(ins[0], ws, B, L, prec),))[0]
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            out = torch.empty(B, self.cfg.channels, L, dtype=torch.float32, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.st2_text_forward(self._handle, _lib.ptr(tok), _lib.ptr(out), B, L, prec, _lib.ptr(self._workspace),
-                                            self._workspace.numel(), C.c_void_p(stream)), "st2_text_forward")
-        return out
+            return self._launch(tok, self._workspace, B, L, prec)
 
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0

@@ -317,3 +317,28 @@ def test_f0n_10s_and_two_waves_vs_oracle():
     assert np.abs(f0[-1:] - rf0).max() <= 1e-4 and np.abs(n[-1:] - rn).max() <= 1e-4
     one_f0, one_n = _run(_predictor(), {"en": inp["en"][:1], "s": inp["s"][:1]})
     assert np.array_equal(f0[:1], one_f0) and np.array_equal(n[:1], one_n)
+
+
+def test_cuda_graph_replay_of_text_encoder_and_predictor_matches_eager():
+    """cuda_graph=True captures each forward once per shape and replays it (graphs.py): bit-identical to the eager call, on
+    new inputs of the same shape as well, and re-captured after the weights are re-packed."""
+    tok = synth.make_tokens(1, 37, seed=5500).cuda()
+    tok2 = synth.make_tokens(1, 37, seed=5501).cuda()
+    te, pr = _text_encoder(), _dur_predictor()
+    s = synth.make_duration_inputs(1, 37, seed=4500)["s"].cuda()
+    with torch.no_grad():
+        for t in (tok, tok2, tok):
+            e = te(t)
+            assert torch.equal(te(t, cuda_graph=True), e)
+            d_e, dur_e = pr.predict_duration(e, s)
+            d_g, dur_g = pr.predict_duration(e, s, cuda_graph=True)
+            assert torch.equal(d_g, d_e) and torch.equal(dur_g, dur_e)
+            en = d_e.transpose(1, 2).contiguous()[:, :, :16].repeat(1, 1, 2).contiguous()      # any [1,640,32] tensor
+            f_e, n_e = pr.F0Ntrain(en, s)
+            f_g, n_g = pr.F0Ntrain(en, s, cuda_graph=True)
+            assert torch.equal(f_g, f_e) and torch.equal(n_g, n_e)
+        assert len(te._graphs) == 1 and len(pr._graphs) == 2
+        te.load_state_dict(synth.make_text_state_dict(seed=1))         # new weights: old graphs must not be replayed
+        e1 = te(tok)
+        assert not torch.equal(e1, e) and torch.equal(te(tok, cuda_graph=True), e1)
+        te.load_state_dict(synth.make_text_state_dict(seed=0))

@@ -22,7 +22,7 @@ from styletts2_lite_b200.predictor import B200F0NPredictor  # noqa: E402
 from styletts2_lite_b200.text_encoder import B200TextEncoder  # noqa: E402
 
 
-def run_chain(B=32, L=64, T=320, precision="bf16", iters=10):
+def run_chain(B=32, L=64, T=320, precision="bf16", iters=10, graph=False):
     """One pass = inference.py:239-270 on the GPU for B utterances of L tokens / T frames; returns the result dict."""
     cfg = DecoderConfig.hifigan()
     dec = B200Decoder(cfg, precision)
@@ -42,17 +42,18 @@ def run_chain(B=32, L=64, T=320, precision="bf16", iters=10):
     s, noise = ci["s"].cuda(), ci["noise"].cuda()
 
     def chain(prec, seed=None, tape=None, ev=None):
-        t_en = text(tokens, precision=prec)                                    # inference.py:239
+        gr = graph and tape is None                                            # graph replay of every module (timed passes only)
+        t_en = text(tokens, precision=prec, cuda_graph=gr)                     # inference.py:239
         if ev: ev[5].record()
-        d, duration = pred.predict_duration(t_en, s, precision=prec)           # inference.py:242-245
+        d, duration = pred.predict_duration(t_en, s, precision=prec, cuda_graph=gr)   # inference.py:242-245
         LR.round_durations(duration)                                           # inference.py:257 (result replaced by `dur`)
         if ev: ev[1].record()
         en = LR.length_regulate(d.transpose(1, 2).contiguous(), dur, T)        # inference.py:266
         asr = LR.length_regulate(t_en, dur, T)                                 # inference.py:269
         if ev: ev[2].record()
-        f0, n = pred.F0Ntrain(en, s, precision=prec)                           # inference.py:267
+        f0, n = pred.F0Ntrain(en, s, precision=prec, cuda_graph=gr)            # inference.py:267
         if ev: ev[3].record()
-        out = dec(asr, f0, n, s, noise=tape, seed=seed, precision=prec)        # inference.py:270
+        out = dec(asr, f0, n, s, noise=tape, seed=seed, precision=prec, cuda_graph=gr)   # inference.py:270
         if ev: ev[4].record()
         return out
 
@@ -75,7 +76,8 @@ def run_chain(B=32, L=64, T=320, precision="bf16", iters=10):
             tot += ev[0].elapsed_time(ev[4])
     secs = B * T / 40.0
     return {"path": "TextEncoder -> duration half -> length regulator -> F0Ntrain -> Decoder (inference.py:239-270)", "batch": B,
-            "tokens": L, "frames": T, "audio_s": secs, "precision": precision, "ms": round(tot / iters, 3),
+            "tokens": L, "frames": T, "audio_s": secs, "precision": precision, "cuda_graphs": bool(graph),
+            "ms": round(tot / iters, 3),
             "audio_s_per_s": round(secs / (tot / iters) * 1e3, 1),
             "ms_parts": {"text_encoder": round(parts[0] / iters, 4), "duration_half": round(parts[1] / iters, 4),
                          "length_regulator": round(parts[2] / iters, 4), "f0n_predictor": round(parts[3] / iters, 4),
@@ -90,5 +92,6 @@ if __name__ == "__main__":
     ap.add_argument("--tokens", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--graph", action="store_true", help="replay per-module CUDA graphs in the timed passes")
     a = ap.parse_args()
-    print(json.dumps(run_chain(a.batch, a.tokens, a.frames, a.precision, a.iters)))
+    print(json.dumps(run_chain(a.batch, a.tokens, a.frames, a.precision, a.iters, a.graph)))
