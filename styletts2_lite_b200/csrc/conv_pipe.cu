@@ -41,7 +41,6 @@
 namespace st2 {
 
 static constexpr int P_LW = 6;                           // transform warps
-static constexpr int P_EW = 8;                           // epilogue warps of the 2-group kernel (staging buffers of non-residual layers)
 static constexpr int P_W_X0 = 2;                         // first transform warp
 static constexpr int P_W_EPI0 = P_W_X0 + P_LW;           // first epilogue warp (8)
 // threads: (8 + 4*EG) warps.  EG = 2 epilogue groups (512 threads, 128 registers) is the default; the 32-channel layers with
@@ -166,7 +165,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constan
     const uint32_t r_stage_bytes = p.nres ? (uint32_t)p.nres * P_RBOX : 0u;
     const uint32_t r_tx_bytes = r_stage_bytes - (p.r16 ? (uint32_t)P_RBOX / 2u : 0u) -             // an fp16 box is half the bytes
                                 (p.nres == 2 && p.o16 ? (uint32_t)P_RBOX / 2u : 0u);
-    const uint32_t r_bytes = p.nres ? (uint32_t)p.nr * r_stage_bytes : (uint32_t)P_EW * 4096u;   // ring or per-warp staging
+    const uint32_t r_bytes = p.nres ? (uint32_t)p.nr * r_stage_bytes : (uint32_t)(4 * p.eg) * 4096u;   // ring or per-warp staging
     uint8_t* smem_a = smem;                                        // na x [rows][K] 16-bit, swizzled
     uint8_t* smem_b = smem_a + (size_t)p.na * a_bytes;             // resident taps or ring of [bn][K]
     uint8_t* smem_r = smem_b + (size_t)p.wstages * b_stage_bytes;  // residual ring / transposition buffers
@@ -906,7 +905,10 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.r16 = a.res16 ? 1 : 0;
     p.o16 = (a.accumulate && a.acc_src != nullptr && a.acc16) ? 1 : 0;
     p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
-    if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && p.nres > 0 && !tr_)) p.eg = v; }
+    // three groups for the non-residual 32-channel layers too (ST2_PIPE_EG3_NORES=1): measured slower, 0.385 -> 0.416 ms at k = 3 --
+    // the 96-register variant costs the transform warps more than the third group gives the epilogue
+    if (p.cch == 32 && p.nres == 0 && !tr_ && getenv("ST2_PIPE_EG3_NORES") != nullptr) p.eg = 3;
+    if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && !tr_)) p.eg = v; }
     // 3 groups need 4 accumulators: a group's previous tile is tcnt-3, so MMA(tcnt-4) -- the previous use of its accumulator
     // -- has completed when it waits; with 2 accumulators the previous use is tile tcnt-2 and the parity wait could pass early
     if (p.nacc < 4) p.eg = 2;
@@ -928,7 +930,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     const bool pair_ok = p.nt == 1 && p.kchunks == 2 && p.bn <= 128 && p.nacc == 4 && p.nres == 1 &&
                          (int64_t)a.ntaps * p.kchunks * b_stage > 96 * 1024 && getenv("ST2_NO_PIPE_PAIR") == nullptr;
     int na = (pair_ok || p.nt > 1) ? 4 : 2;
-    int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)P_EW * 4096);
+    int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)(4 * p.eg) * 4096);
     const int64_t w_resident = (int64_t)a.ntaps * p.kchunks * b_stage;
     const int nchunks = p.bn / 32;
     // rings: nx activation slots and nr residual stages (FIFO); minimum 3 slots / 2 stages
@@ -975,7 +977,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.na = na;
     p.pair = (pair_ok && !p.resident && na == 4) ? 1 : 0;
     p.lw = na * p.nblk < P_LW ? na * p.nblk : P_LW;
-    const size_t smem = (size_t)(na * a_bytes + (int64_t)p.wstages * b_stage + (p.nres ? (int64_t)p.nr * r_stage : (int64_t)P_EW * 4096) +
+    const size_t smem = (size_t)(na * a_bytes + (int64_t)p.wstages * b_stage + (p.nres ? (int64_t)p.nr * r_stage : (int64_t)(4 * p.eg) * 4096) +
                                  (int64_t)p.nx * p.xslot + 2048 + 1024);
     if (smem > 227 * 1024) return false;
     if ((2 * p.wstages + 16 + 2 * p.nx + 2 * p.nr) * 8 + 16 + (p.nx + p.nr) * 4 > 2048) return false;
