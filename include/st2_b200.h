@@ -246,6 +246,16 @@ ST2_API int st2_adain_conv1d_fused(const float* x, const float* h, const float* 
                            int32_t k, int32_t padding, int32_t dilation, float scale, int32_t accumulate,
                            int32_t precision, void* stream);
 
+/* The same half-step (Snake, C = Cin = Cout in {32, 64}) on the row-per-thread kernel with the storage types of the 16-bit
+ * decoder paths: res / old (the running tensor and the partial stage sum of Modules/hifigan.py:65-74, :338-342) are stored as
+ * fp16 and added by the tensor core; x is stored as fp16 when x16, y is written as fp16 when y16.  All pointers are fp32
+ * channels-last tensors; the conversions happen in scratch.  y = (conv1d(snake(AdaIN(x; h))) + bias + res + old) * scale. */
+ST2_API int64_t st2_adain_conv1d_row_scratch_bytes(int32_t B, int32_t T, int32_t C, int32_t k);
+ST2_API int st2_adain_conv1d_row(const float* x, const float* h, const float* alpha, const float* w, const float* bias,
+                         const float* res, const float* old, float* y, const float* h_next, float* coef_next,
+                         void* scratch, int32_t B, int32_t T, int32_t C, int32_t k, int32_t padding, int32_t dilation,
+                         float scale, int32_t precision, int32_t x16, int32_t y16, void* stream);
+
 /* Generator upsampling step (Modules/hifigan.py:329-334) through the fused tensor-core kernels:
  *   y = conv_transpose1d(act(x), w) + bias + res        x [B,Tin,Cin], w [Cin,Cout,k] (k a multiple of stride),
  * res / y [B,Tout,Cout], Tout = (Tin-1)*stride - 2*padding + k + output_padding.  alpha [Cin] for snake.

@@ -69,15 +69,20 @@ def adain_resblk1d(W, name, x, s, upsample):
     return (h + sc) / math.sqrt(2)
 
 
-def adain_resblock1(W, name, x, s, k, dil=(1, 3, 5)):
-    """AdaINResBlock1.forward, hifigan.py:65-74."""
+def adain_resblock1(W, name, x, s, k, dil=(1, 3, 5), taps=None):
+    """AdaINResBlock1.forward, hifigan.py:65-74.  taps: optional dict that receives the conv1 output (`.convs1.j`) and the
+    running tensor after every iteration (`.iterj`), the names the library's debug taps use."""
     for j, d in enumerate(dil):
         xt = snake(adain(W, "%s.adain1.%d" % (name, j), x, s), W.p("%s.alpha1.%d" % (name, j)))
         xt = F.conv1d(xt, W.w("%s.convs1.%d" % (name, j)), W.b("%s.convs1.%d" % (name, j)), dilation=d,
                       padding=int((k * d - d) / 2))
+        if taps is not None:
+            taps["%s.convs1.%d" % (name, j)] = xt
         xt = snake(adain(W, "%s.adain2.%d" % (name, j), xt, s), W.p("%s.alpha2.%d" % (name, j)))
         xt = F.conv1d(xt, W.w("%s.convs2.%d" % (name, j)), W.b("%s.convs2.%d" % (name, j)), padding=int((k - 1) / 2))
         x = xt + x
+        if taps is not None:
+            taps["%s.iter%d" % (name, j)] = x
     return x
 
 
@@ -97,15 +102,20 @@ def source_module(W, f0_curve, scale, noise):
     return har.transpose(1, 2)
 
 
-def decoder_forward(W, cfg, asr, F0_curve, N, s, noise):
-    """Decoder.forward (eval), hifigan.py:446-475 / istftnet.py:692-721 with Generator.forward inlined."""
+def decoder_forward(W, cfg, asr, F0_curve, N, s, noise, taps=None):
+    """Decoder.forward (eval), hifigan.py:446-475 / istftnet.py:692-721 with Generator.forward inlined.
+    taps: optional dict filled with intermediate tensors [B, C, T] under the library's tap names."""
     with torch.no_grad():
         F0 = F.conv1d(F0_curve[:, None], W.w("F0_conv"), W.b("F0_conv"), stride=2, padding=1)
         Nn = F.conv1d(N[:, None], W.w("N_conv"), W.b("N_conv"), stride=2, padding=1)
         x = adain_resblk1d(W, "encode", torch.cat([asr, F0, Nn], 1), s, False)
         asr_res = F.conv1d(asr, W.w("asr_res.0"), W.b("asr_res.0"))
+        if taps is not None:
+            taps["encode"] = x
         for i in range(4):
             x = adain_resblk1d(W, "decode.%d" % i, torch.cat([x, asr_res, F0, Nn], 1), s, i == 3)
+            if taps is not None:
+                taps["decode.%d" % i] = x
         har = source_module(W, F0_curve, cfg.upsample_scale, noise)
         istft = cfg.is_istft
         if istft:
@@ -122,18 +132,22 @@ def decoder_forward(W, cfg, asr, F0_curve, N, s, noise):
             x = F.leaky_relu(x, 0.1) if istft else snake(x, W.p("generator.alphas.%d" % i))
             _, k, st, pd = cfg.noise_conv_geometry(i)
             xs = F.conv1d(har, W.w("generator.noise_convs.%d" % i), W.b("generator.noise_convs.%d" % i), stride=st, padding=pd)
-            xs = adain_resblock1(W, "generator.noise_res.%d" % i, xs, s, cfg.noise_res_kernel(i))
+            xs = adain_resblock1(W, "generator.noise_res.%d" % i, xs, s, cfg.noise_res_kernel(i), taps=taps)
             ku, u, pu, opu = cfg.ups_geometry(i)
             x = F.conv_transpose1d(x, W.w("generator.ups.%d" % i), W.b("generator.ups.%d" % i), stride=u, padding=pu,
                                    output_padding=opu)
             if istft and i == cfg.num_stages - 1:
                 x = F.pad(x, (1, 0), mode="reflect")
             x = x + xs
+            if taps is not None:
+                taps["generator.stage%d.in" % i] = x
             acc = None
             for j, kr in enumerate(cfg.resblock_kernel_sizes):
-                r = adain_resblock1(W, "generator.resblocks.%d" % (i * nk + j), x, s, kr, cfg.resblock_dilation_sizes[j])
+                r = adain_resblock1(W, "generator.resblocks.%d" % (i * nk + j), x, s, kr, cfg.resblock_dilation_sizes[j], taps=taps)
                 acc = r if acc is None else acc + r
             x = acc / nk
+            if taps is not None:
+                taps["generator.stage%d.out" % i] = x
         if not istft:
             x = snake(x, W.p("generator.alphas.%d" % cfg.num_stages))
             return torch.tanh(F.conv1d(x, W.w("generator.conv_post"), W.b("generator.conv_post"), padding=3))

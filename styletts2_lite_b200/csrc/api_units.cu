@@ -190,6 +190,87 @@ int st2_adain_conv1d_fused(const float* x, const float* h, const float* alpha, i
     return e;
 }
 
+// The same half-step on the row-per-thread kernel (conv_row.cu) with the storage types of the 16-bit decoder paths: x, res
+// and old are given as fp32 tensors and are stored as fp16 first when the x16 flag says so / always (res, old); y is written as fp16
+// and widened when y16.  C = Cin = Cout in {32, 64}, Snake only.
+static int64_t row_unit_offsets(int B, int T, int C, int k, int64_t off[10]) {
+    int64_t o = 0;
+    off[0] = o; o += align256((int64_t)k * C * C * sizeof(float));               // packed fp32 weight
+    off[1] = o; o += align256((int64_t)k * 64 * C * 2);                          // 16-bit weight
+    off[2] = o; o += align256(adain_scratch_bytes(B, T, C));                     // input statistics
+    off[3] = o; o += align256((int64_t)B * 2 * C * sizeof(float));               // input coefficients
+    off[4] = o; o += align256(conv_row_stats_bytes(B, T, C));                    // output partials
+    off[5] = o; o += align256((int64_t)B * T * C * 2);                           // x as fp16
+    off[6] = o; o += align256((int64_t)B * T * C * 2);                           // res as fp16
+    off[7] = o; o += align256((int64_t)B * T * C * 2);                           // old as fp16
+    off[8] = o; o += align256((int64_t)B * T * C * 2);                           // y as fp16
+    off[9] = o;
+    return o;
+}
+
+int64_t st2_adain_conv1d_row_scratch_bytes(int32_t B, int32_t T, int32_t C, int32_t k) {
+    if (B <= 0 || T <= 0 || !(C == 32 || C == 64) || k <= 0) return ST2_ERR_INVALID;
+    int64_t off[10];
+    return row_unit_offsets(B, T, C, k, off);
+}
+
+int st2_adain_conv1d_row(const float* x, const float* h, const float* alpha, const float* w, const float* bias,
+                         const float* res, const float* old, float* y, const float* h_next, float* coef_next, void* scratch,
+                         int32_t B, int32_t T, int32_t C, int32_t k, int32_t padding, int32_t dilation, float scale,
+                         int32_t precision, int32_t x16, int32_t y16, void* stream) {
+    ST2_REQUIRE(x && h && alpha && w && y && scratch && B > 0 && T > 0 && (C == 32 || C == 64) && k > 0 && dilation > 0,
+                "adain_conv1d_row: bad argument");
+    ST2_REQUIRE(precision == ST2_PREC_BF16 || precision == ST2_PREC_FP16, "adain_conv1d_row: 16-bit precisions only");
+    ST2_REQUIRE(2 * padding == dilation * (k - 1), "adain_conv1d_row: length-preserving convolutions only");
+    ST2_REQUIRE((h_next == nullptr) == (coef_next == nullptr), "adain_conv1d_row: h_next and coef_next go together");
+    ST2_REQUIRE(old == nullptr || res != nullptr, "adain_conv1d_row: old values need a residual");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t off[10];
+    row_unit_offsets(B, T, C, k, off);
+    char* base = (char*)scratch;
+    float* wp = (float*)(base + off[0]);
+    void* w16 = base + off[1];
+    void* xstats = base + off[2];
+    float* coef = (float*)(base + off[3]);
+    void* parts = base + off[4];
+    void* x16b = base + off[5];
+    void* r16b = base + off[6];
+    void* o16b = base + off[7];
+    void* y16b = base + off[8];
+    const int dt = precision == ST2_PREC_BF16 ? DT_BF16 : DT_F16;
+    const int64_t n = (int64_t)B * T * C;
+    int e = launch_fold_pack(nullptr, w, wp, C, C, k, 0, st);
+    if (e != ST2_OK) return e;
+    e = launch_pack_w16(wp, w16, k, C, C, 64, C, dt, st);
+    if (e != ST2_OK) return e;
+    e = launch_in_stats(x, C, B, T, C, xstats, st);
+    if (e != ST2_OK) return e;
+    e = launch_adain_coef(xstats, h, 2 * C, 0, coef, B, T, C, C, st);
+    if (e != ST2_OK) return e;
+    if (x16) { e = launch_cast16(x, x16b, n, DT_F16, st); if (e != ST2_OK) return e; }
+    if (res) { e = launch_cast16(res, r16b, n, DT_F16, st); if (e != ST2_OK) return e; }
+    if (old) { e = launch_cast16(old, o16b, n, DT_F16, st); if (e != ST2_OK) return e; }
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.Cin = C; a.Cout = C; a.Tin = T; a.Tout = T; a.M = T;
+    a.x = x16 ? (const float*)x16b : x; a.ld_x = C; a.x16in = x16 ? 1 : 0;
+    a.w = wp; a.w16 = w16; a.w16_cin_pad = 64; a.w16_cout_pad = C; a.fmt16 = dt;
+    a.bias = bias;
+    if (res) { a.res = (const float*)r16b; a.ld_res = C; a.res16 = 1; }
+    if (old) { a.accumulate = 1; a.acc_src = o16b; a.acc16 = 1; }
+    a.y = y16 ? (float*)y16b : y; a.ld_y = C; a.y16out = y16 ? 1 : 0;
+    a.ntaps = k; a.tap_step = dilation; a.in_off = -padding; a.in_stride = 1;
+    a.phases = 1; a.w_step = 1; a.out_stride = 1; a.out_pad = 0;
+    a.scale = scale;
+    ST2_REQUIRE(conv_row_can_launch(a), "adain_conv1d_row: geometry not supported by conv_row");
+    RowStatsDesc rd;
+    e = launch_conv_row(a, coef, C, ACT_SNAKE, alpha, h_next ? parts : nullptr, &rd, st);
+    if (e != ST2_OK) return e;
+    if (y16) { e = launch_half_to_float(y16b, y, n, st); if (e != ST2_OK) return e; }
+    if (h_next != nullptr) e = launch_adain_coef_row(parts, rd, h_next, 2 * C, 0, coef_next, B, T, C, C, st);
+    return e;
+}
+
 // Generator upsampling step (hifigan.py:329-334): y = conv_transpose1d(act(x), w) + bias + res, plus the AdaIN
 // coefficients of y for style h_next, through the fused tensor-core kernels.
 static int64_t fused_t_offsets(int B, int Tin, int Cin, int Cout, int k, int stride, int64_t off[5]) {

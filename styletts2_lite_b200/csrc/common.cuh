@@ -60,7 +60,8 @@ enum ProfCat {
     PC_CONV_FUSED = 8,  // conv_fused_kernel: fused AdaIN/act -> tcgen05 conv -> residual/stats, register-staged (256-ch: tensor)
     PC_CONV_PIPE = 9,   // conv_pipe_kernel: the same fusion fully TMA-fed (C <= 128, ups; bound: hbm / shared memory)
     PC_LSTM = 10,       // lstm_bidir_kernel: recurrence of the predictor's shared BiLSTM (bound: latency, T sequential steps)
-    PC_COUNT = 11
+    PC_CONV_ROW = 11,   // conv_row_kernel: the 32/64-channel resblock convs, row-per-thread epilogue (bound: hbm / shared memory)
+    PC_COUNT = 12
 };
 
 // ---- HBM-bound kernels (kernels_norm.cu) ---------------------------------------------
@@ -174,5 +175,16 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
                      void* stats_out, cudaStream_t st);
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
                          int C, int Cpad, cudaStream_t st);
+// 32 / 64-channel stride-1 Snake convs on fp16 stage-private tensors: row-per-thread epilogue, residual through the tensor
+// core, statistics per (CTA, utterance, epilogue warp) (conv_row.cu).  `desc` describes where the partials of an utterance
+// live; launch_adain_coef_row turns them into AdaIN coefficients.
+struct RowStatsDesc { int grid, J, nwarp, mmt, tq, tr, C; };
+bool conv_row_supported(const ConvArgs& a);                 // geometry, shared-memory plan and enough tiles to fill the grid
+bool conv_row_can_launch(const ConvArgs& a);                // geometry and plan only (unit tests force small problems through it)
+int64_t conv_row_stats_bytes(int B, int T, int C);
+int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, const float* alpha, void* stats_out,
+                    RowStatsDesc* desc, cudaStream_t st);
+int launch_adain_coef_row(const void* partial, const RowStatsDesc& d, const float* h, int ld_h, int h_off, float* coef, int B,
+                          int T, int C, int Cpad, cudaStream_t st);
 
 }  // namespace st2

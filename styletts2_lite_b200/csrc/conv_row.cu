@@ -1,0 +1,762 @@
+// Row-per-thread fused kernel for the 32- and 64-channel convolutions of AdaINResBlock1 (Modules/hifigan.py:65-74):
+//   y = (conv1d(snake(a*x + b), w) + bias [+ res] [+ old]) * scale,  InstanceNorm partial statistics of y
+// with every stage-private tensor (x, res, old, usually y) stored as fp16.  These layers are 22 of the
+// 45.7 ms of a 64 x 5 s forward on conv_pipe.cu and sit at 2-3x their byte floor there: ncu shows its epilogue executing ~360
+// instructions per 32x32 chunk (residual ring, transposition through shared memory, per-tile statistics partials) and the
+// transform warps re-transforming the halo of every 128-row tile.  This kernel changes the decomposition:
+//   * tiles: a CTA owns a CONTIGUOUS range of macro tiles (1, 2 or 4 MMA sub-tiles of 128 rows that share one transformed
+//     operand buffer of sub*128 + span rows), so the halo is transformed once per macro tile and every role walks rows in order;
+//   * residual / accumulate sources never touch a compute warp: their fp16 tiles land by TMA in the K-major UMMA layout and are
+//     added into the accumulator by the tensor core itself (D += R * I with a resident fp16 identity tile; exact in fp32);
+//   * epilogue: one thread = one output row (the TMEM drain layout).  No shared memory: 16 accumulator columns at a time go
+//     TMEM -> registers -> scale/bias -> fp16 pack -> 32 contiguous bytes of the row in global memory (the four stores of a
+//     chunk fill every 32-byte sector they touch), and the InstanceNorm (sum, sum of squares) of the 32 channels a warp owns
+//     stay in 64 registers per thread ACROSS tiles; they are reduced over the 32 lanes by a fixed-order butterfly only when the
+//     utterance changes -- one partial per (CTA, utterance, epilogue warp) instead of one per (tile, 32-row quarter), which also
+//     shrinks what the coefficient kernel reads from ~45 MB to a few hundred KB;
+//   * activation blocks go through PRIVATE rings (one per transform warp, depth xd): plain parity tracking is then enough and the
+//     sequence-number spin of conv_pipe.cu disappears; blocks are always processed in whole batches of 8 passes (the operand
+//     buffer has slack rows for the overshoot), so the slow ragged path only runs on the blocks that touch the zero padding.
+// Roles (20 warps, 96 registers): warp 0 producer, warp 1 TMEM allocator + MMA issuer, then 18 - 4*NCH transform warps and
+// 4*NCH epilogue warps (NCH = C / 32; epilogue warp ew drains TMEM lane quarter (warp & 3), column chunk ew >> 2).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "fused_ptx.cuh"
+
+namespace st2 {
+
+static constexpr int RW_THREADS = 640;                    // 20 warps (ptxas grants 96 registers from 545 threads up)
+static constexpr int RW_X0 = 2;                          // first transform warp
+static constexpr int RW_NA = 2;                          // operand buffers
+static constexpr int RW_MAXGRID = 160;                   // statistics buffers are sized for at most this many CTAs
+
+struct RowParams {
+    // transform
+    const float* coef; int coef_ld;
+    const float* alpha;
+    // geometry
+    int B, M, ntaps, tap_step, halo_min, a_row0;
+    int sub;                    // MMA sub-tiles (128 rows) per macro tile
+    int R, nblk, tail_rows;     // activation blocks: R rows each, nblk per macro tile, the last one loads tail_rows rows
+    int xslot;                  // bytes per activation ring slot
+    int a_bytes;                // bytes per operand buffer (nblk * R rows)
+    int lw, xd;                 // active transform warps, depth of each private activation ring
+    int nacc, nacc_log2, tmem_cols;
+    int nres, nr;               // fp16 sources added by the identity MMA (0, 1, 2), residual ring stages
+    int mmt;                    // macro tiles per utterance
+    int tq, tr;                 // macro tiles per CTA: CTAs [0, tr) own tq + 1, the rest tq (contiguous ranges)
+    int J;                      // statistics slots per CTA (utterances a CTA can touch)
+    // epilogue
+    const float* bias; float scale;
+    void* y; int ld_y; int y16out;
+    float2* stats;              // [grid][J][4 * NCH][32] (sum, sum of squares) or nullptr
+};
+
+__device__ __forceinline__ bool rw_mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Snake constants of 4 consecutive channels (see conv_pipe.cu): yb = a*x + (b + c), t = (2*alpha*a)*x + 2*alpha*b,
+// out = yb - c*cos(t) with c = 1/(2*alpha)
+struct RXf { float2 a01, a23, b01, b23, ta01, ta23, tb01, tb23, nc01, nc23; };
+
+template <bool BF16>
+__device__ __forceinline__ uint2 row_snake4(const float4 v, const RXf& c) {
+    const float2 x01 = make_float2(v.x, v.y), x23 = make_float2(v.z, v.w);
+    float2 y01 = ffma2(c.a01, x01, c.b01), y23 = ffma2(c.a23, x23, c.b23);
+    const float2 t01 = ffma2(c.ta01, x01, c.tb01), t23 = ffma2(c.ta23, x23, c.tb23);
+    const float2 s01 = make_float2(__cosf(t01.x), __cosf(t01.y)), s23 = make_float2(__cosf(t23.x), __cosf(t23.y));
+    y01 = ffma2(c.nc01, s01, y01);
+    y23 = ffma2(c.nc23, s23, y23);
+    return make_uint2(pack16(y01.x, y01.y, BF16 ? 1 : 0), pack16(y23.x, y23.y, BF16 ? 1 : 0));
+}
+
+// sum over the 32 lanes of v[c] for every c; lane l returns the total of column l (fixed order -> deterministic)
+__device__ __forceinline__ float row_reduce_scatter32(float (&v)[32], int lane) {
+#define RW_STAGE(OFF, N)                                                            \
+    {                                                                               \
+        const bool up = (lane & OFF) != 0;                                          \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) {                             \
+            const float send = up ? v[i] : v[i + N];                                \
+            const float keep = up ? v[i + N] : v[i];                                \
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                  \
+        }                                                                           \
+    }
+    RW_STAGE(16, 16)
+    RW_STAGE(8, 8)
+    RW_STAGE(4, 4)
+    RW_STAGE(2, 2)
+    RW_STAGE(1, 1)
+#undef RW_STAGE
+    return v[0];
+}
+
+template <bool BF16, bool X16, int NCH>
+__global__ void __launch_bounds__(RW_THREADS, 1)
+conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
+                const __grid_constant__ CUtensorMap map_o, const RowParams p) {
+    constexpr int C = 32 * NCH;
+    constexpr int NEW = 4 * NCH;                           // epilogue warps
+    constexpr int NTW = 18 - NEW;                          // transform warps
+    constexpr int W_EPI0 = RW_X0 + NTW;                    // first epilogue warp
+    constexpr uint32_t arow = NCH == 1 ? 64u : 128u;       // bytes per operand row (K = C, 16-bit)
+    constexpr uint32_t btile = (uint32_t)C * arow;         // one tap [C][C]: 2 KB / 8 KB
+    constexpr uint32_t rtile = 128u * arow;                // one residual sub-tile [128][C] fp16: 8 KB / 16 KB
+    constexpr int KS = C / 16;                             // K = 16 steps per tap
+    constexpr uint32_t xes = X16 ? 2u : 4u;
+    constexpr uint32_t xrow = (uint32_t)C * xes;           // bytes per activation row in a ring slot
+    constexpr uint32_t PASS = X16 ? 256u : 512u;           // slot bytes one warp pass covers (128 elements)
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;                                              // RW_NA x [a_rows][C] 16-bit, swizzled
+    uint8_t* smem_w = smem_a + (size_t)RW_NA * p.a_bytes;                // ntaps x [C][C] resident taps
+    uint8_t* smem_i = smem_w + (size_t)p.ntaps * btile;                  // fp16 identity [C][C]
+    uint8_t* smem_r = smem_i + btile;                                    // nr x nres x [128][C] fp16 residual tiles
+    uint8_t* smem_x = smem_r + (size_t)p.nr * p.nres * rtile;            // lw x xd activation slots
+    const int nxs = p.lw * p.xd;
+    float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + C);
+    uint64_t* w_full = bars;                    // [1]
+    uint64_t* a_full = bars + 1;                // [2]
+    uint64_t* a_empty = a_full + 2;             // [2]
+    uint64_t* acc_full = a_empty + 2;           // [8]
+    uint64_t* acc_empty = acc_full + 8;         // [8]
+    uint64_t* r_full = acc_empty + 8;           // [nr]
+    uint64_t* r_empty = r_full + p.nr;          // [nr]
+    uint64_t* x_full = r_empty + p.nr;          // [nxs]
+    uint64_t* x_empty = x_full + nxs;           // [nxs]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_empty + nxs);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // this CTA's contiguous range of macro tiles
+    const int cta = blockIdx.x;
+    const int m_lo = cta * p.tq + (cta < p.tr ? cta : p.tr);
+    const int m_n = p.tq + (cta < p.tr ? 1 : 0);
+    const int sub_rows = p.sub * 128;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_b);
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_xt);
+        if (p.nres >= 1) prefetch_tmap(&map_r);
+        if (p.nres >= 2) prefetch_tmap(&map_o);
+        mbar_init(w_full, 1);
+        for (int i = 0; i < RW_NA; ++i) {
+            mbar_init(&a_full[i], (uint32_t)p.nblk);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], (uint32_t)NEW);
+        }
+        for (int i = 0; i < p.nr; ++i) {
+            mbar_init(&r_full[i], 1);
+            mbar_init(&r_empty[i], 1);
+        }
+        for (int i = 0; i < nxs; ++i) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // fp16 identity tile in the K-major swizzled B layout: element (n, k = n) of row n
+    for (uint32_t i = threadIdx.x; i < btile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem_i)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const uint32_t n = threadIdx.x;
+        const uint32_t sw = NCH == 1 ? ((n >> 1) & 3u) : (n & 7u);
+        const uint32_t off = n * arow + (((n >> 3) ^ sw) << 4) + (n & 7u) * 2u;
+        *reinterpret_cast<uint16_t*>(smem_i + off) = 0x3C00u;            // fp16 1.0
+        bias_s[n] = (p.bias != nullptr ? p.bias[n] : 0.f) * p.scale;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== producer: resident weights, then the activation-block and residual-tile queues =====
+        if (elect_one_sync()) {
+            mbar_expect_tx(w_full, (uint32_t)p.ntaps * btile);
+            for (int w = 0; w < p.ntaps; ++w) tma_load_3d(smem_w + (size_t)w * btile, &map_b, w_full, 0, 0, w);
+            // activation queue: block g = (macro tile, blk) -> ring of transform warp g % lw, slot (g / lw) % xd
+            int x_m = 0, x_blk = 0;
+            int x_b = m_lo / p.mmt, x_mm = m_lo - x_b * p.mmt;
+            uint32_t x_w = 0, x_i = 0, x_par = 0;
+            bool x_done = m_n == 0;
+            // residual queue: (macro tile, sub-tile) -> stage
+            int r_m = 0, r_s = 0;
+            int r_b = x_b, r_mm = x_mm;
+            uint32_t r_stage = 0, r_par = 0;
+            bool r_done = p.nres == 0 || m_n == 0;
+            const uint32_t r_tx = (uint32_t)p.nres * rtile;
+            uint32_t idle = 0;
+            while (!(x_done && r_done)) {
+                bool progress = false;
+                if (!x_done) {
+                    const uint32_t slot = x_w * (uint32_t)p.xd + x_i;
+                    if (rw_mbar_test(&x_empty[slot], x_par ^ 1u)) {
+                        const bool tail = (x_blk == p.nblk - 1);
+                        const uint32_t nrows = tail ? (uint32_t)p.tail_rows : (uint32_t)p.R;
+                        mbar_expect_tx(&x_full[slot], nrows * xrow);
+                        tma_load_3d(smem_x + (size_t)slot * p.xslot, tail ? &map_xt : &map_x, &x_full[slot], 0,
+                                    x_mm * sub_rows + p.halo_min + x_blk * p.R, x_b);
+                        if (++x_w == (uint32_t)p.lw) {
+                            x_w = 0;
+                            if (++x_i == (uint32_t)p.xd) { x_i = 0; x_par ^= 1u; }
+                        }
+                        if (++x_blk == p.nblk) {
+                            x_blk = 0;
+                            if (++x_mm == p.mmt) { x_mm = 0; ++x_b; }
+                            x_done = (++x_m == m_n);
+                        }
+                        progress = true;
+                    }
+                }
+                if (!r_done) {
+                    if (rw_mbar_test(&r_empty[r_stage], r_par ^ 1u)) {
+                        uint8_t* dst = smem_r + (size_t)r_stage * p.nres * rtile;
+                        mbar_expect_tx(&r_full[r_stage], r_tx);
+                        const int row = r_mm * sub_rows + r_s * 128;
+                        tma_load_3d(dst, &map_r, &r_full[r_stage], 0, row, r_b);
+                        if (p.nres == 2) tma_load_3d(dst + rtile, &map_o, &r_full[r_stage], 0, row, r_b);
+                        if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1u; }
+                        ++r_s;
+                        if (r_s == p.sub || r_mm * sub_rows + r_s * 128 >= p.M) {
+                            r_s = 0;
+                            if (++r_mm == p.mmt) { r_mm = 0; ++r_b; }
+                            r_done = (++r_m == m_n);
+                        }
+                        progress = true;
+                    }
+                }
+                if (progress) idle = 0;
+                else {
+                    __nanosleep(40);
+                    if (++idle > (1u << 26)) __trap();     // a consumer never freed its slot: fail instead of hanging the GPU
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(128, C, BF16 ? 1 : 0);
+            const uint32_t idesc_id = umma_idesc(128, C, 0);              // fp16 residual x fp16 identity
+            const uint32_t dhi = NCH == 1 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : kDescHi;
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+            const uint32_t a_buf_step = (uint32_t)p.a_bytes >> 4;
+            const uint32_t w_lo0 = desc_lo(smem_u32(smem_w));
+            const uint32_t i_lo = desc_lo(smem_u32(smem_i));
+            const uint32_t r_lo0 = desc_lo(smem_u32(smem_r));
+            const uint32_t r_stage_step = ((uint32_t)p.nres * rtile) >> 4;
+            const uint32_t row_step = (uint32_t)(p.tap_step * (int)(arow >> 4));
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            uint32_t sc = 0;                            // sub-tile counter -> accumulator sc % nacc
+            uint32_t r_stage = 0, r_par = 0;
+            int b = m_lo / p.mmt, mm = m_lo - b * p.mmt;
+            for (int mc = 0; mc < m_n; ++mc) {
+                const uint32_t buf = (uint32_t)mc & 1u;
+                mbar_wait(&a_full[buf], ((uint32_t)mc >> 1) & 1u);
+                tc_fence_after();
+                for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
+                    const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
+                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)C;
+                    mbar_wait(&acc_empty[acc], ((sc >> p.nacc_log2) & 1u) ^ 1u);
+                    tc_fence_after();
+                    uint32_t accum = 0;
+                    if (p.nres) {
+                        mbar_wait(&r_full[r_stage], r_par);
+                        tc_fence_after();
+                        uint32_t r_lo = r_lo0 + r_stage * r_stage_step;
+                        for (int src = 0; src < p.nres; ++src, r_lo += rtile >> 4) {
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) {
+                                umma_f16_lohi(d_tmem, r_lo + 2u * ks, i_lo + 2u * ks, dhi, idesc_id, accum);
+                                accum = 1u;
+                            }
+                        }
+                        umma_commit(&r_empty[r_stage]);
+                        if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1u; }
+                    }
+                    uint32_t a_lo = a_lo0 + buf * a_buf_step + (uint32_t)(s * 128 + p.a_row0) * (arow >> 4);
+                    uint32_t b_lo = w_lo0;
+                    for (int j = 0; j < p.ntaps; ++j) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            umma_f16_lohi(d_tmem, a_lo + 2u * ks, b_lo + 2u * ks, dhi, idesc, accum);
+                            accum = 1u;
+                        }
+                        a_lo += row_step;
+                        b_lo += btile >> 4;
+                    }
+                    umma_commit(&acc_full[acc]);
+                }
+                umma_commit(&a_empty[buf]);
+                if (++mm == p.mmt) { mm = 0; ++b; }
+            }
+        }
+    } else if (warp < W_EPI0) {
+        // ===== transform: activation block -> AdaIN affine + Snake -> swizzled 16-bit operand rows =====
+        const int tw = warp - RW_X0;
+        if (tw < p.lw) {
+            constexpr int lpr_shift = NCH == 1 ? 3 : 4;             // lanes per row: 8 or 16
+            constexpr int rpp = 32 >> lpr_shift;                    // rows per pass: 4 or 2
+            constexpr int BROWS = 8 * rpp;                          // rows per batch of 8 passes: 32 or 16
+            const int rl = lane >> lpr_shift;
+            const int c4 = (lane & ((1 << lpr_shift) - 1)) * 4;
+            const uint32_t smem_a_u32 = smem_u32(smem_a);
+            const uint32_t smem_x_u32 = smem_u32(smem_x);
+            const uint32_t cidx = (uint32_t)(c4 >> 3), csub = (uint32_t)(c4 & 4) * 2u;
+            uint32_t aoff[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t Rr = (uint32_t)(rl + u * rpp);
+                const uint32_t sw = NCH == 1 ? ((Rr >> 1) & 3u) : (Rr & 7u);
+                aoff[u] = Rr * arow + ((cidx ^ sw) << 4) + csub;
+            }
+            int mi = 0, blk = tw;                                   // block = (macro tile mi of this CTA, blk)
+            while (blk >= p.nblk) { blk -= p.nblk; ++mi; }
+            uint32_t xi = 0, xpar = 0;                              // private ring cursor
+            int cur_m = -1, b = 0, mm = 0;
+            int cached_b = -1;
+            RXf cf;
+            while (mi < m_n) {
+                if (mi != cur_m) {
+                    const int gm = m_lo + mi;
+                    b = gm / p.mmt;
+                    mm = gm - b * p.mmt;
+                    cur_m = mi;
+                }
+                if (b != cached_b) {
+                    const float* ca = p.coef + (size_t)b * 2 * p.coef_ld;
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ca + c4));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ca + p.coef_ld + c4));
+                    const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + c4));
+                    const float4 c = make_float4(__fdividef(0.5f, al.x), __fdividef(0.5f, al.y), __fdividef(0.5f, al.z), __fdividef(0.5f, al.w));
+                    cf.a01 = make_float2(a4.x, a4.y); cf.a23 = make_float2(a4.z, a4.w);
+                    cf.ta01 = make_float2(2.f * al.x * a4.x, 2.f * al.y * a4.y); cf.ta23 = make_float2(2.f * al.z * a4.z, 2.f * al.w * a4.w);
+                    cf.tb01 = make_float2(2.f * al.x * b4.x, 2.f * al.y * b4.y); cf.tb23 = make_float2(2.f * al.z * b4.z, 2.f * al.w * b4.w);
+                    cf.b01 = make_float2(b4.x + c.x, b4.y + c.y); cf.b23 = make_float2(b4.z + c.z, b4.w + c.w);
+                    cf.nc01 = make_float2(-c.x, -c.y); cf.nc23 = make_float2(-c.z, -c.w);
+                    cached_b = b;
+                }
+                const uint32_t buf = (uint32_t)mi & 1u, fill = (uint32_t)mi >> 1;
+                const uint32_t slot = (uint32_t)tw * (uint32_t)p.xd + xi;
+                const int r0 = blk * p.R;                                        // first operand row of this block
+                const int nvalid = (blk == p.nblk - 1) ? p.tail_rows : p.R;      // rows the TMA box really loaded
+                const int t0 = mm * sub_rows + p.halo_min + r0;                  // time index of operand row r0
+                mbar_wait_warp(&x_full[slot], xpar);
+                mbar_wait_warp(&a_empty[buf], (fill & 1u) ^ 1u);
+                uint32_t xaddr = smem_x_u32 + slot * (uint32_t)p.xslot + (uint32_t)rl * xrow + (uint32_t)c4 * xes;
+                uint32_t abase = smem_a_u32 + buf * (uint32_t)p.a_bytes + (uint32_t)r0 * arow;
+                // whole batches: rows past nvalid read stale slot bytes and land in slack operand rows no MMA reads
+                for (int rb = 0; rb < nvalid; rb += BROWS, xaddr += 8 * PASS, abase += (uint32_t)BROWS * arow) {
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (X16) v[u] = unpack16x4(lds64(xaddr + (uint32_t)u * PASS), 0);
+                        else v[u] = lds128(xaddr + (uint32_t)u * PASS);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint2 o = row_snake4<BF16>(v[u], cf);
+                        sts64(abase + aoff[u], o.x, o.y);
+                    }
+                }
+                if (t0 < 0 || t0 + nvalid > p.M) {
+                    // zero padding of the convolution (after the activation): rows outside [0, M) of the utterance
+                    __syncwarp();
+                    const uint32_t abuf = smem_a_u32 + buf * (uint32_t)p.a_bytes + csub;
+                    for (int r = rl; r < nvalid; r += rpp) {
+                        const int t = t0 + r;
+                        if (t < 0 || t >= p.M) {
+                            const uint32_t Rr = (uint32_t)(r0 + r);
+                            const uint32_t sw = NCH == 1 ? ((Rr >> 1) & 3u) : (Rr & 7u);
+                            sts64(abuf + Rr * arow + ((cidx ^ sw) << 4), 0u, 0u);
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&x_empty[slot]);
+                    mbar_arrive(&a_full[buf]);
+                }
+                if (++xi == (uint32_t)p.xd) { xi = 0; xpar ^= 1u; }
+                blk += p.lw;
+                while (blk >= p.nblk) { blk -= p.nblk; ++mi; }
+            }
+        }
+    } else {
+        // ===== epilogue: one thread = one output row; 16 columns at a time; statistics in registers across tiles =====
+        const int ew = warp - W_EPI0;                     // 0 .. NEW-1
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int ch = ew >> 2;                           // 32-column chunk this warp owns
+        const uint32_t t_lane = ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        const uint32_t bias_u32 = smem_u32(bias_s) + (uint32_t)(ch * 32) * 4u;
+        const float2 sc2 = make_float2(p.scale, p.scale);
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        const int b_first = m_lo / p.mmt;
+        int b = b_first, mm = m_lo - b_first * p.mmt;
+        uint32_t sc = 0;
+        auto flush = [&](int bb) {
+            if (p.stats != nullptr) {
+                const float t1 = row_reduce_scatter32(s1, lane);
+                const float t2 = row_reduce_scatter32(s2, lane);
+                p.stats[(((size_t)cta * p.J + (bb - b_first)) * NEW + ew) * 32 + lane] = make_float2(t1, t2);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        };
+        for (int mc = 0; mc < m_n; ++mc) {
+            for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
+                const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
+                const int m = mm * sub_rows + s * 128 + q * 32 + lane;        // output row of this thread
+                const bool valid = m < p.M;
+                const size_t yoff = ((size_t)b * p.M + (size_t)(valid ? m : 0)) * p.ld_y + ch * 32;
+                mbar_wait_warp(&acc_full[acc], (sc >> p.nacc_log2) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[16];
+                    __syncwarp();                          // tcgen05.ld is .aligned: re-converge after the `valid` branch
+                    tmem_ld16(tmem_base + t_lane + acc * (uint32_t)C + (uint32_t)(hh * 16), v);
+                    if (hh == 1) {
+                        // the accumulator is in registers: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+                    float2 o[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 bs = lds128(bias_u32 + (uint32_t)(hh * 64 + i * 16));
+                        o[2 * i] = ffma2(make_float2(v[4 * i], v[4 * i + 1]), sc2, make_float2(bs.x, bs.y));
+                        o[2 * i + 1] = ffma2(make_float2(v[4 * i + 2], v[4 * i + 3]), sc2, make_float2(bs.z, bs.w));
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            s1[hh * 16 + 2 * i] += o[i].x;
+                            s1[hh * 16 + 2 * i + 1] += o[i].y;
+                            s2[hh * 16 + 2 * i] = fmaf(o[i].x, o[i].x, s2[hh * 16 + 2 * i]);
+                            s2[hh * 16 + 2 * i + 1] = fmaf(o[i].y, o[i].y, s2[hh * 16 + 2 * i + 1]);
+                        }
+                        if (p.y16out) {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + yoff + hh * 16);
+                            dst[0] = make_uint4(pack16(o[0].x, o[0].y, 0), pack16(o[1].x, o[1].y, 0), pack16(o[2].x, o[2].y, 0),
+                                                pack16(o[3].x, o[3].y, 0));
+                            dst[1] = make_uint4(pack16(o[4].x, o[4].y, 0), pack16(o[5].x, o[5].y, 0), pack16(o[6].x, o[6].y, 0),
+                                                pack16(o[7].x, o[7].y, 0));
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + hh * 16);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
+                        }
+                    }
+                }
+            }
+            if (++mm == p.mmt) {
+                flush(b);
+                mm = 0;
+                ++b;
+            }
+        }
+        if (mm != 0) flush(b);                            // the range ended inside utterance b
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- coefficients from the per-(CTA, utterance, warp) partials
+// grid (B), block 256: thread (c, slice) sums every `nsl`-th partial of channel c in double, then a fixed-order tree over the
+// slices.  The CTAs that hold partials of utterance b are those whose macro-tile range meets [b*mmt, (b+1)*mmt).
+struct RowStatsInfo { int grid, J, nwarp, mmt, tq, tr, C; };
+
+__device__ __forceinline__ int row_cta_start(const RowStatsInfo& s, int c) { return c * s.tq + (c < s.tr ? c : s.tr); }
+__device__ __forceinline__ int row_cta_of(const RowStatsInfo& s, int t) {
+    const int big = s.tr * (s.tq + 1);
+    return t < big ? t / (s.tq + 1) : s.tr + (t - big) / s.tq;
+}
+
+__global__ void __launch_bounds__(256)
+adain_coef_row_kernel(const float2* __restrict__ partial, const RowStatsInfo si, const float* __restrict__ h, int ld_h, int h_off,
+                      float* __restrict__ coef, int T, int Cpad) {
+    __shared__ double ssum[256], ssq[256];
+    pdl_trigger();
+    pdl_wait();
+    const int C = si.C;
+    const int nsl = 256 / C;                     // slices per channel: 8 (C = 32) or 4 (C = 64)
+    const int c = threadIdx.x % C, sl = threadIdx.x / C;
+    const int b = blockIdx.x;
+    const int c_lo = row_cta_of(si, b * si.mmt), c_hi = row_cta_of(si, (b + 1) * si.mmt - 1);
+    const int chunk = c >> 5, col = c & 31;
+    const int per_cta = 4;                       // epilogue warps (TMEM lane quarters) that own a column chunk
+    const int nparts = (c_hi - c_lo + 1) * per_cta;
+    double s = 0, ss = 0;
+    for (int i = sl; i < nparts; i += nsl) {
+        const int cta = c_lo + i / per_cta, wq = i - (i / per_cta) * per_cta;
+        const int j = b - row_cta_start(si, cta) / si.mmt;
+        const float2 v = __ldg(partial + (((size_t)cta * si.J + j) * si.nwarp + chunk * 4 + wq) * 32 + col);
+        s += (double)v.x;
+        ss += (double)v.y;
+    }
+    ssum[threadIdx.x] = s;
+    ssq[threadIdx.x] = ss;
+    __syncthreads();
+    if (sl != 0) return;
+    for (int i = 1; i < nsl; ++i) {
+        s += ssum[i * C + c];
+        ss += ssq[i * C + c];
+    }
+    const double mean = s / (double)T;
+    double var = ss / (double)T - mean * mean;
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + 1e-5);
+    const double gamma = (double)h[(size_t)b * ld_h + h_off + c];
+    const double beta = (double)h[(size_t)b * ld_h + h_off + C + c];
+    const double ad = (1.0 + gamma) * rstd;
+    coef[((size_t)b * 2 + 0) * Cpad + c] = (float)ad;
+    coef[((size_t)b * 2 + 1) * Cpad + c] = (float)(beta - mean * ad);
+}
+
+// ---------------------------------------------------------------- host side
+int make_weight_map(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_pad, int cout_pad, int ktaps, int bn);
+int make_map_3d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes);
+
+static int row_num_sms() {
+    // per device: the SM count of whichever device is current (a process may drive several GPUs)
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
+    }
+    return sms[dev];
+}
+
+static bool row_disabled() {
+    static const bool off = getenv("ST2_NO_ROW") != nullptr;     // read once: A/B switch against conv_pipe.cu
+    return off;
+}
+
+static bool row_geometry_ok(const ConvArgs& a) {
+    if (a.in_stride != 1 || a.mirror || a.res_shift != 0 || a.phases != 1) return false;
+    if (a.out_stride != 1 || a.out_pad != 0 || a.tap_step <= 0 || a.M != a.Tout || a.Tin != a.Tout) return false;
+    if (!(a.Cin == 32 || a.Cin == 64) || a.Cout != a.Cin) return false;
+    if (a.w16 == nullptr || a.w16_cin_pad != 64 || a.w16_cout_pad != a.Cout) return false;
+    if (a.ld_x != a.Cin) return false;
+    if (a.res != nullptr && (!a.res16 || a.ld_res != a.Cout)) return false;            // residual only as an fp16 tile
+    if (a.accumulate && !(a.res != nullptr && a.acc_src != nullptr && a.acc16)) return false;   // old values only as an fp16 tile
+    if (!a.accumulate && a.acc_src != nullptr) return false;
+    if (a.ld_y % 8 != 0) return false;
+    const int span = (a.ntaps - 1) * a.tap_step;
+    return span <= 64 && a.in_off <= 0 && a.in_off + span >= 0;
+}
+
+// geometry + shared-memory plan; false if it does not fit
+static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* grid_out) {
+    memset(&p, 0, sizeof(p));
+    const int C = a.Cin, nch = C / 32;
+    const int arow = nch == 1 ? 64 : 128;
+    const int btile = C * arow, rtile = 128 * arow;
+    const int span = (a.ntaps - 1) * a.tap_step;
+    p.B = a.B; p.M = a.M; p.ntaps = a.ntaps; p.tap_step = a.tap_step;
+    p.halo_min = a.in_off; p.a_row0 = 0;
+    p.nres = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
+    p.nacc = nch == 1 ? 8 : 4;
+    p.nacc_log2 = nch == 1 ? 3 : 2;
+    p.tmem_cols = 256;
+    const int ntw = 18 - 4 * nch;
+    const int xes = a.x16in ? 2 : 4;
+    const int brows = nch == 1 ? 32 : 16;                  // rows per transform batch
+    const int64_t budget = 224 * 1024;
+    bool ok = false;
+    // largest macro tile first (the halo is transformed once per macro tile), then the largest activation blocks, then the
+    // deepest rings
+    for (int sub = 4; sub >= 1 && !ok; sub >>= 1) {
+        const int mr = sub * 128 + span;
+        for (int slot_bytes = 4096; slot_bytes >= 2048 && !ok; slot_bytes >>= 1) {
+            int R = slot_bytes / (C * xes);
+            R = R / brows * brows;
+            if (R < brows) R = brows;
+            const int nblk = cdiv(mr, R);
+            const int tail = mr - (nblk - 1) * R;
+            const int64_t a_bytes = ((int64_t)nblk * R * arow + 1023) & ~(int64_t)1023;
+            const int xslot = R * C * xes;
+            const int lw = RW_NA * nblk < ntw ? RW_NA * nblk : ntw;
+            const int64_t fixed = RW_NA * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
+            const int nr_max = p.nres ? 4 : 0, nr_min = p.nres ? 2 : 0;
+            for (int nr = nr_max; nr >= nr_min && !ok; --nr) {
+                for (int xd = 3; xd >= 2 && !ok; --xd) {
+                    const int64_t tot = fixed + (int64_t)nr * p.nres * rtile + (int64_t)lw * xd * xslot;
+                    if (tot <= budget) {
+                        p.sub = sub; p.R = R; p.nblk = nblk; p.tail_rows = tail; p.xslot = xslot; p.a_bytes = (int)a_bytes;
+                        p.lw = lw; p.xd = xd; p.nr = nr;
+                        *smem_out = (size_t)tot + 1024;
+                        ok = true;
+                    }
+                }
+            }
+        }
+    }
+    if (!ok) return false;
+    p.mmt = cdiv(a.M, p.sub * 128);
+    const int64_t nt = (int64_t)a.B * p.mmt;
+    int grid = row_num_sms();
+    if (grid > RW_MAXGRID) grid = RW_MAXGRID;
+    if (grid > nt) grid = (int)nt;
+    p.tq = (int)(nt / grid); p.tr = (int)(nt % grid);
+    p.J = (p.tq + 1 + p.mmt - 1) / p.mmt + 1;
+    p.bias = a.bias; p.scale = a.scale;
+    p.y = a.y; p.ld_y = a.ld_y; p.y16out = a.y16out;
+    *grid_out = grid;
+    return true;
+}
+
+bool conv_row_can_launch(const ConvArgs& a) {
+    if (!row_geometry_ok(a)) return false;
+    RowParams p;
+    size_t smem;
+    int grid;
+    return row_plan(a, p, &smem, &grid);
+}
+
+// dispatch policy: small problems (one-sentence latency: fewer than 4 macro tiles per SM) stay on conv_pipe.cu, whose 128-row
+// tiles spread them over more SMs
+bool conv_row_supported(const ConvArgs& a) {
+    if (row_disabled() || !row_geometry_ok(a)) return false;
+    RowParams p;
+    size_t smem;
+    int grid;
+    if (!row_plan(a, p, &smem, &grid)) return false;
+    return (int64_t)a.B * p.mmt >= 4 * (int64_t)row_num_sms();
+}
+
+// bytes of the statistics buffer a conv_row launch of this geometry writes (upper bound over devices with <= RW_MAXGRID SMs)
+int64_t conv_row_stats_bytes(int B, int T, int C) {
+    // J <= B + 1 slots per CTA; 4 * NCH warps x 32 columns x float2
+    const int64_t per_cta = (int64_t)(B + 1) * (4 * (C / 32)) * 32 * 8;
+    (void)T;
+    return (int64_t)RW_MAXGRID * per_cta;
+}
+
+int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, const float* alpha, void* stats_out,
+                    RowStatsDesc* desc, cudaStream_t st) {
+    RowParams p;
+    size_t smem = 0;
+    int grid = 0;
+    ST2_REQUIRE(row_geometry_ok(a) && row_plan(a, p, &smem, &grid), "conv_row: unsupported geometry");
+    ST2_REQUIRE(act == ACT_SNAKE && alpha != nullptr, "conv_row: only the Snake transform is built");
+    p.coef = coef; p.coef_ld = coef_ld; p.alpha = alpha;
+    p.stats = (float2*)stats_out;
+    const int C = a.Cin, nch = C / 32;
+    const int is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
+    CUtensorMap map_b, map_x, map_xt, map_r, map_o;
+    int e = nch == 1 ? make_weight_map_k32(&map_b, is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, C)
+                     : make_weight_map(&map_b, is_bf16, a.w16, a.w16_cin_pad, a.w16_cout_pad, a.ntaps, C);
+    if (e != ST2_OK) return e;
+    const int xdt = a.x16in ? 2 : 0;
+    const uint64_t xes = a.x16in ? 2 : 4;
+    e = make_map_3d_sw(&map_x, xdt, a.x, (uint64_t)C, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
+                       (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)C, (uint32_t)p.R, 0);
+    if (e != ST2_OK) return e;
+    e = make_map_3d_sw(&map_xt, xdt, a.x, (uint64_t)C, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.ld_x * xes,
+                       (uint64_t)a.Tin * a.ld_x * xes, (uint32_t)C, (uint32_t)p.tail_rows, 0);
+    if (e != ST2_OK) return e;
+    map_r = map_x;
+    map_o = map_x;
+    const int sw = nch == 1 ? 64 : 128;
+    if (a.res != nullptr) {
+        e = make_map_3d_sw(&map_r, 2, a.res, (uint64_t)C, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_res * 2,
+                           (uint64_t)a.Tout * a.ld_res * 2, (uint32_t)C, 128, sw);
+        if (e != ST2_OK) return e;
+    }
+    if (a.accumulate) {
+        e = make_map_3d_sw(&map_o, 2, a.acc_src, (uint64_t)C, (uint64_t)a.Tout, (uint64_t)a.B, (uint64_t)a.ld_y * 2,
+                           (uint64_t)a.Tout * a.ld_y * 2, (uint32_t)C, 128, sw);
+        if (e != ST2_OK) return e;
+    }
+    if (desc != nullptr) {
+        desc->grid = grid; desc->J = p.J; desc->nwarp = 4 * nch; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
+    }
+    ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * (4 * nch) * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
+                "conv_row: statistics buffer too small");
+    // the opt-in to > 48 KB of dynamic shared memory is per device: once per (device, variant)
+    static bool attr_done[64][8] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+#define ROW_KERNEL(BF, X, N) conv_row_kernel<BF, X, N>
+#define ROW_LAUNCH(BF, X, N)                                                                                                     \
+    do {                                                                                                                         \
+        bool& done = attr_done[dev][(BF ? 4 : 0) + (X ? 2 : 0) + (N - 1)];                                                       \
+        if (!done) {                                                                                                             \
+            ST2_CUDA_CHECK(cudaFuncSetAttribute(ROW_KERNEL(BF, X, N), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            done = true;                                                                                                         \
+        }                                                                                                                        \
+        ROW_KERNEL(BF, X, N)<<<grid, RW_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);                            \
+    } while (0)
+    const bool bf = is_bf16 != 0, x16 = a.x16in != 0;
+    if (nch == 1) {
+        if (bf) { if (x16) ROW_LAUNCH(true, true, 1); else ROW_LAUNCH(true, false, 1); }
+        else { if (x16) ROW_LAUNCH(false, true, 1); else ROW_LAUNCH(false, false, 1); }
+    } else {
+        if (bf) { if (x16) ROW_LAUNCH(true, true, 2); else ROW_LAUNCH(true, false, 2); }
+        else { if (x16) ROW_LAUNCH(false, true, 2); else ROW_LAUNCH(false, false, 2); }
+    }
+#undef ROW_LAUNCH
+#undef ROW_KERNEL
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+int launch_adain_coef_row(const void* partial, const RowStatsDesc& d, const float* h, int ld_h, int h_off, float* coef, int B,
+                          int T, int C, int Cpad, cudaStream_t st) {
+    ST2_REQUIRE(C == d.C && (C == 32 || C == 64) && Cpad == C, "adain_coef_row: bad channel count");
+    RowStatsInfo si;
+    si.grid = d.grid; si.J = d.J; si.nwarp = d.nwarp; si.mmt = d.mmt; si.tq = d.tq; si.tr = d.tr; si.C = d.C;
+    adain_coef_row_kernel<<<B, 256, 0, st>>>((const float2*)partial, si, h, ld_h, h_off, coef, T, Cpad);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+}  // namespace st2

@@ -337,6 +337,34 @@ int make_map_3d_any(CUtensorMap* map, int dtype, const void* base, uint64_t d0, 
     return ST2_OK;
 }
 
+// generic 3-D map with an explicit swizzle mode (0 none, 64 = SWIZZLE_64B, 128 = SWIZZLE_128B): the fp16 residual tiles of
+// conv_row.cu, which land in shared memory in the K-major UMMA operand layout
+int make_map_3d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ST2_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                              : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(sw) failed (%d) dtype=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u] sw=%d", (int)r,
+                  dtype, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, swizzle_bytes);
+        return ST2_ERR_CUDA;
+    }
+    return ST2_OK;
+}
+
 // fp32 [B][T][C] tensor viewed as (c, phase, m, b) with t = m*phases + phase: 128-byte-swizzled boxes of b0 channels x b2
 // rows m of one phase (the residual boxes of conv_pipe.cu; phases = 1 for a plain convolution)
 int make_map_4d_f32_sw128(CUtensorMap* map, const void* base, uint64_t C, uint64_t phases, uint64_t rows, uint64_t B,

@@ -430,7 +430,7 @@ int st2_profile_num_categories(void) { return st2::PC_COUNT; }
 
 const char* st2_profile_category_name(int32_t cat) {
     static const char* names[st2::PC_COUNT] = {"conv_tc", "conv_simt", "norm_stats", "norm_coef", "affine_act",
-                                               "source", "post", "misc", "conv_fused", "conv_pipe", "lstm"};
+                                               "source", "post", "misc", "conv_fused", "conv_pipe", "lstm", "conv_row"};
     return (cat >= 0 && cat < st2::PC_COUNT) ? names[cat] : "";
 }
 

@@ -434,7 +434,17 @@ struct Exec {
     }
 
     // ---- fused path: statistics references, coefficient kernels, fused conv ---------------------
-    struct StatRef { const void* ptr; int nparts; bool f2; };   // f2: float2 tile partials; else double2 slab partials
+    // f2: float2 tile partials (conv_pipe / conv_fused epilogues); row: per-(CTA, utterance, warp) partials of conv_row.cu,
+    // located by `rd`; neither: double2 slab partials of the standalone statistics pass
+    struct StatRef { const void* ptr; int nparts; bool f2; bool row = false; RowStatsDesc rd = {}; };
+    bool last_row = false;        // did the last conv_fused() run on conv_row.cu (statistics in its layout)?
+    RowStatsDesc last_rd = {};
+    StatRef produced(const void* buf, int nparts) const {
+        StatRef r{buf, nparts, true};
+        r.row = last_row;
+        r.rd = last_rd;
+        return r;
+    }
 
     // statistics of a tensor no fused epilogue produced (noise_convs output): standalone pass
     StatRef stats_standalone(const float* x, int ld_x, int T, int C) {
@@ -450,6 +460,8 @@ struct Exec {
         if (!live()) return;
         if (n == nullptr || !sr.f2)
             chk(launch_adain_coef(n ? sr.ptr : nullptr, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
+        else if (sr.row)
+            chk(launch_adain_coef_row(sr.ptr, sr.rd, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
         else
             chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
         prof(PC_NORM_COEF, 0, 0);
@@ -507,12 +519,16 @@ struct Exec {
         a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
         a.x = x; a.ld_x = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad; a.fmt16 = dt;
         a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.acc_src = acc_src; a.acc16 = acc16;
-        chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
+        // the 32 / 64-channel Snake convs on fp16 tensors run on the row-per-thread kernel (conv_row.cu); its statistics
+        // partials have their own layout, recorded in last_rd for the coefficient kernel
+        last_row = act == ACT_SNAKE && !w.transposed && conv_row_supported(a);
+        if (last_row) chk(launch_conv_row(a, coef, coef_ld, act, alpha, stats_out, &last_rd, st));
+        else chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const double bytes = (double)B * ((double)w.Cin * Tin * (x16in ? 2 : 4) +
                                           (double)w.Cout * Tout * ((y16out ? 2 : 4) + (res ? (res16 ? 2 : 4) : 0) + (accumulate ? (acc16 ? 2 : 4) : 0))) +
                              (double)w.k * w.Cin * w.Cout * 2;
-        prof(conv_pipe_supported(a) ? PC_CONV_PIPE : PC_CONV_FUSED, flops, bytes);
+        prof(last_row ? PC_CONV_ROW : (conv_pipe_supported(a) ? PC_CONV_PIPE : PC_CONV_FUSED), flops, bytes);
     }
 
     // AdainResBlk1d.forward (hifigan.py:400-403).  x [B,T,ld_x] (Cin real channels) -> y [B,T or 2T,ld_y]
@@ -603,8 +619,10 @@ struct Exec {
             // fused: 2 tiny coefficient kernels + 2 fused convs per iteration; AdaIN statistics come from the
             // producing conv's epilogue (or from in_stats for the block input)
             const int nparts = fused_parts(w.c1[0], T, 1, 0, 0);
-            void* st_xt = alloc((int64_t)B * nparts * C * 8);
-            void* st_run = alloc((int64_t)B * nparts * C * 8);
+            int64_t st_bytes = (int64_t)B * nparts * C * 8;
+            if ((C == 32 || C == 64) && conv_row_stats_bytes(B, T, C) > st_bytes) st_bytes = conv_row_stats_bytes(B, T, C);
+            void* st_xt = alloc(st_bytes);
+            void* st_run = alloc(st_bytes);
             // the intra-block tensor xt (conv1 output, only consumed by conv2's transform) is stored as fp16 when both convs
             // run on the TMA pipeline kernel: 20 % fewer HBM bytes per iteration for -0.1 dB of SNR (its statistics still come
             // from the fp32 values in the epilogue).  ST2_NO_XT16=1 keeps it fp32.
@@ -646,7 +664,7 @@ struct Exec {
                            0, 0, 1.f, 0, st_xt, 0, 0, cur16, xt16);
                 if (!xt16) tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
                 else tap16(w.name + ".convs1." + std::to_string(j), xt, (int64_t)B * T * C);
-                coef_from(StatRef{st_xt, nparts, true}, &w.n2[j], T, C, C);
+                coef_from(produced(st_xt, nparts), &w.n2[j], T, C, C);
                 const bool last = (j == 2);
                 const bool s16 = last && sum16 != 0 && run16;                     // the caller asked resblock1_sum16_ok first
                 const int out16 = ((run16 && !last) || (s16 && sum16 < 3)) ? 1 : 0;
@@ -658,7 +676,7 @@ struct Exec {
                 else if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
                 cur = out;
                 cur16 = out16;
-                cur_st = StatRef{st_run, nparts, true};
+                cur_st = produced(st_run, nparts);
             }
             off = mark;
             return;

@@ -139,6 +139,29 @@ def adain_conv1d_fused(x_btc, h, alpha, act, w, bias, res_btc, y_old_btc, h_next
     return y.cpu().numpy(), (None if cn is None else cn.cpu().numpy())
 
 
+def adain_conv1d_row(x_btc, h, alpha, w, bias, res_btc, old_btc, h_next, padding, dilation, scale=1.0, precision="bf16",
+                     x16=True, y16=True):
+    """The same half-step on conv_row.cu (fp16 residual / old values added by the tensor core); returns (y, coef_next)."""
+    lib = _lib.load()
+    B, T, Cc = x_btc.shape
+    k = w.shape[2]
+    xd, wd, hd, ad = to_dev(x_btc), to_dev(w), to_dev(h), to_dev(alpha.reshape(-1))
+    bd = None if bias is None else to_dev(bias)
+    rd = None if res_btc is None else to_dev(res_btc)
+    od = None if old_btc is None else to_dev(old_btc)
+    hn = None if h_next is None else to_dev(h_next)
+    cn = None if h_next is None else torch.full((B, 2, Cc), float("nan"), device=dev())
+    y = torch.full((B, T, Cc), float("nan"), device=dev())
+    nbytes = _lib.check(lib.st2_adain_conv1d_row_scratch_bytes(B, T, Cc, k), "row_scratch_bytes")
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    _lib.check(lib.st2_adain_conv1d_row(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(ad), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(rd),
+                                        _lib.ptr(od), _lib.ptr(y), _lib.ptr(hn), _lib.ptr(cn), _lib.ptr(scratch), B, T, Cc, k,
+                                        padding, dilation, C.c_float(scale), _lib.PREC[precision], 1 if x16 else 0,
+                                        1 if y16 else 0, stream()), "adain_conv1d_row")
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), (None if cn is None else cn.cpu().numpy())
+
+
 def act_conv_transpose1d_fused(x_btc, alpha, act, w, bias, res_btc, h_next, stride, padding, output_padding, slope=0.0,
                                precision="bf16"):
     """Fused upsampling step on channels-last tensors; returns (y [B,Tout,Cout], coef_next [B,2,Cout] or None)."""

@@ -338,3 +338,102 @@ def test_pipelined_serving_loop_matches_direct_forward():
     for i, (a, b) in enumerate(zip(direct, got)):
         assert a.shape == b.shape and torch.equal(a, b), i
     assert list(pipe.decode([])) == []
+
+
+# ---------------------------------------------------------------- round-2 fixtures: longer / ragged / true-init cases
+@pytest.mark.parametrize("name,variant,T,ws,iseed,perturb", [
+    ("hifigan_B1_T120_w3_i1007_plain", "hifigan", 120, 3, 1007, False),
+    ("hifigan_B1_T203_w0_i1009", "hifigan", 203, 0, 1009, True),
+    ("istftnet_B1_T120_w0_i1006", "istftnet", 120, 0, 1006, True),
+    ("istftnet_B1_T203_w0_i1008", "istftnet", 203, 0, 1008, True),
+    ("hifigan_B1_T400_w0_i1003", "hifigan", 400, 0, 1003, True)])
+def test_fp32_path_vs_reference_goldens_long_and_ragged(name, variant, T, ws, iseed, perturb):
+    """fp32 path max-abs <= 1e-4 against waveforms of the unmodified reference (tests/golden/make_golden_r2.py): 3 s with the
+    reference's true initialisation, ragged lengths no tile size divides, 3 s iSTFTNet and the 10 s case where SineGen phases
+    reach 1e5 rad (the hardest case for fp32 parity)."""
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    g = golden(name + ".npz")
+    m = _decoder(cfg, ws, perturb)
+    out = _run(m, np_inputs(1, T, iseed, cfg))
+    err = float(np.abs(out - g["out"]).max())
+    G.log("fp32_vs_reference_golden", fixture=name, maxabs=err, snr_db=snr_db(g["out"], out))
+    assert out.shape == g["out"].shape
+    assert err <= 1e-4
+
+
+@pytest.mark.parametrize("name,variant,T,ws,iseed,perturb", [
+    ("hifigan_B1_T120_w3_i1007_plain", "hifigan", 120, 3, 1007, False),
+    ("hifigan_B1_T203_w0_i1009", "hifigan", 203, 0, 1009, True),
+    ("istftnet_B1_T120_w0_i1006", "istftnet", 120, 0, 1006, True),
+    ("istftnet_B1_T203_w0_i1008", "istftnet", 203, 0, 1008, True),
+    ("hifigan_B1_T400_w0_i1003", "hifigan", 400, 0, 1003, True)])
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_tensor_core_paths_vs_reference_goldens_long_and_ragged(name, variant, T, ws, iseed, perturb, prec):
+    """16-bit paths (fp16 stage-private tensors on, the default) against the same reference waveforms: SNR >= 40 dB -- on the
+    reference's true initialisation too, and at 10 s."""
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    g = golden(name + ".npz")
+    m = _decoder(cfg, ws, perturb)
+    out = _run(m, np_inputs(1, T, iseed, cfg), precision=prec)
+    snr = snr_db(g["out"], out)
+    G.log("tc_vs_reference_golden", fixture=name, prec=prec, snr_db=snr, maxabs=float(np.abs(out - g["out"]).max()))
+    assert snr >= 40.0
+
+
+def test_bf16_every_resblock_tap_at_3s():
+    """BASELINE.json: per-layer relative L2 <= 1e-2 on the bf16 path.  Every conv1 output (`.convs1.j`), every running tensor
+    (`.iterj`) and every stage input / output of the generator at T = 120 (3 s: tensors of up to 72,000 rows, hundreds of
+    tiles, the fp16-stored ones included) against the taps of the torch CPU port of the reference (oracle/decoder_torch.py,
+    pinned bit-tight to the reference goldens by tests/test_oracle.py)."""
+    from oracle import decoder_torch as OT
+    cfg = DecoderConfig.hifigan()
+    T = 120
+    m = _decoder(cfg)
+    inp = np_inputs(1, T, 1001, cfg)
+    names = {"encode": (T, 1024), "decode.0": (T, 1024), "decode.3": (2 * T, 512)}
+    lens = [20 * T, 100 * T, 300 * T, 600 * T]
+    for i in range(4):
+        C_ = 256 >> i
+        names["generator.stage%d.in" % i] = (lens[i], C_)
+        names["generator.stage%d.out" % i] = (lens[i], C_)
+        for blk in ["generator.noise_res.%d" % i] + ["generator.resblocks.%d" % (3 * i + j) for j in range(3)]:
+            for j in range(3):
+                names["%s.convs1.%d" % (blk, j)] = (lens[i], C_)
+                if j < 2 or "noise_res" in blk:
+                    names["%s.iter%d" % (blk, j)] = (lens[i], C_)
+    bufs = {n: m.set_tap(n, 1, rows, C_) for n, (rows, C_) in names.items()}
+    out = _run(m, inp, precision="bf16")
+    taps = {}
+    W = OT.TorchWeights(synth.make_state_dict(cfg, 0, True))
+    ti = {k: torch.from_numpy(v) for k, v in inp.items()}
+    ref = OT.decoder_forward(W, cfg, ti["asr"], ti["F0_curve"], ti["N"], ti["s"], ti["noise"], taps=taps).numpy()
+    worst = ("", 0.0)
+    for n, buf in bufs.items():
+        v = rel_l2(taps[n].numpy(), G.cf(buf.cpu().numpy()))
+        if v > worst[1]:
+            worst = (n, v)
+        if v > 5e-3:
+            G.log("bf16_tap_T120", tap=n, rel_l2=v)
+        assert v <= 1e-2, (n, v)
+    m.clear_taps()
+    snr = snr_db(ref, out)
+    G.log("bf16_every_tap_T120", taps=len(bufs), worst_tap=worst[0], worst_rel_l2=worst[1], snr_db=snr)
+    assert snr >= 40.0
+
+
+def test_bench_shape_bf16_tracks_fp32():
+    """The shape bench.py times (BASELINE.json configs[1]: 64 x 5 s): bf16 path against the fp32 path of this library,
+    SNR >= 40 dB, every utterance finite and individually >= 38 dB."""
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    B, T = 64, 200
+    inp = synth.make_inputs(B, T, seed=1002, cfg=cfg, with_noise=False)
+    t = {k: v.cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        ref = m(t["asr"], t["F0_curve"], t["N"], t["s"], seed=5, precision="fp32").float().cpu().numpy()
+        out = m(t["asr"], t["F0_curve"], t["N"], t["s"], seed=5, precision="bf16").float().cpu().numpy()
+    assert out.shape == (B, 1, 600 * T) and np.isfinite(out).all()
+    snr = snr_db(ref, out)
+    per = [snr_db(ref[b], out[b]) for b in range(B)]
+    G.log("bench_shape_bf16_vs_fp32", snr_db=snr, worst_utterance_db=min(per))
+    assert snr >= 40.0 and min(per) >= 38.0

@@ -165,3 +165,53 @@ def test_act_conv_transpose1d_fused_vs_oracle(Cin, Cout, k, stride, pad, opad, T
     assert nan == 0
     assert err <= TOL[prec]
     assert cerr <= 2 * TOL[prec]
+
+
+# ---- conv_row.cu: the 32 / 64-channel half-steps with fp16 stage-private tensors (residual and partial stage sum added by the
+# tensor core through an identity tile, row-per-thread epilogue, statistics per (CTA, utterance, warp)).  The inputs are made
+# fp16-representable first, so the oracle sees exactly what the kernel reads; an fp16 output adds half an fp16 ulp (2^-12).
+def _h(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+ROW_CASES = [
+    # C, k, dil, T, res, old, scale, x16, y16, B
+    (32, 3, 1, 1000, True, False, 1.0, True, True, 3), (32, 11, 5, 777, False, False, 1.0, True, True, 3),
+    (32, 7, 3, 100, False, False, 1.0, False, True, 2), (32, 11, 1, 640, True, True, 1.0 / 3.0, True, False, 3),
+    (32, 3, 5, 5000, True, False, 1.0, True, True, 7), (32, 7, 1, 513, True, True, 1.0, True, True, 1),
+    (64, 3, 5, 515, False, False, 1.0, True, True, 3), (64, 11, 1, 900, True, False, 1.0, True, True, 3),
+    (64, 7, 1, 385, True, True, 1.0, True, False, 2), (64, 11, 5, 400, False, False, 1.0, False, True, 3),
+    (64, 3, 1, 2100, True, False, 1.0, True, True, 5), (64, 7, 3, 129, True, True, 1.0 / 3.0, True, True, 4),
+    (32, 3, 1, 40000, True, False, 1.0, True, True, 2),
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("C_,k,dil,T,use_res,use_old,scale,x16,y16,B", ROW_CASES)
+def test_adain_conv1d_row_vs_oracle(C_, k, dil, T, use_res, use_old, scale, x16, y16, B, prec):
+    rng = np.random.default_rng(C_ * 977 + k * 31 + dil * 7 + T)
+    x = (rng.standard_normal((B, C_, T)) * 1.5 + 0.3).astype(np.float32)
+    if x16:
+        x = _h(x)
+    h = (rng.standard_normal((B, 2 * C_)) * 0.3).astype(np.float32)
+    h_next = (rng.standard_normal((B, 2 * C_)) * 0.3).astype(np.float32)
+    alpha = (0.6 + 0.8 * rng.random((1, C_, 1))).astype(np.float32)
+    w = (rng.standard_normal((C_, C_, k)) / np.sqrt(C_ * k)).astype(np.float32)
+    b = rng.standard_normal(C_).astype(np.float32)
+    res = _h(rng.standard_normal((B, C_, T)).astype(np.float32)) if use_res else None
+    old = _h(rng.standard_normal((B, C_, T)).astype(np.float32)) if use_old else None
+    pad = dil * (k - 1) // 2
+    ref = _ref(x, h, alpha, "snake", 0.0, w, b, res, old, pad, dil, scale, prec)
+    got, coef = G.adain_conv1d_row(G.cl(x), h, alpha, w, b, None if res is None else G.cl(res),
+                                   None if old is None else G.cl(old), h_next, pad, dil, scale=scale, precision=prec,
+                                   x16=x16, y16=y16)
+    got = G.cf(got)
+    nan = int(np.isnan(got).sum())
+    err = float(np.abs(np.nan_to_num(got) - ref).max() / np.abs(ref).max())
+    cref = _coef(ref, h_next)
+    cerr = float(np.abs(np.nan_to_num(coef) - cref).max() / np.abs(cref).max())
+    G.log("adain_conv1d_row", prec=prec, C=C_, k=k, dil=dil, T=T, B=B, res=use_res, old=use_old, x16=x16, y16=y16, relmax=err,
+          coef_relmax=cerr, nan=nan)
+    assert nan == 0
+    assert err <= TOL[prec] + (2.5e-4 if y16 else 0.0)
+    assert cerr <= 2 * TOL[prec]

@@ -216,3 +216,53 @@ def test_text_encoder_oracle_matches_reference_fixtures():
         assert np.abs(out - g["out"]).max() <= 5e-6 and np.abs(taps["cnn.0"] - g["tap:cnn.0"]).max() <= 1e-5
         with torch.no_grad():
             assert np.abs(PT.text_encoder(sdt, tok).numpy() - g["out"]).max() <= 5e-6
+
+
+# ---------------------------------------------------------------- round-2 fixtures (tests/golden/make_golden_r2.py)
+def test_synth_plain_init_is_the_reference_init():
+    """`init_weights` N(0, 0.01) (hifigan.py:37,47,318-319) never reaches the reference's forward: under the legacy weight_norm
+    it rewrites the derived `.weight` only, which the pre-forward hook recomputes from weight_g / weight_v -- and those keep
+    PyTorch's default U(+-1/sqrt(fan_in)) with g = ||v|| (reference_init_stats.json, measured on a freshly constructed
+    reference Decoder).  synth.make_state_dict(perturb=False) draws exactly that distribution."""
+    import json
+    import math
+    import os
+    from helpers import GOLDEN
+    st = json.load(open(os.path.join(GOLDEN, "reference_init_stats.json")))
+    cfg = DecoderConfig.hifigan()
+    sd = np_state_dict(cfg, 3, False)
+    for k in ("generator.resblocks.0.convs1.0", "generator.resblocks.11.convs2.2", "generator.ups.0", "generator.conv_post",
+              "generator.noise_res.0.convs1.0", "encode.conv1"):
+        v, g, r = sd[k + ".weight_v"], sd[k + ".weight_g"], st[k + ".weight_v"]
+        fan_in = v.shape[1] * v.shape[2]
+        bound = 1.0 / math.sqrt(fan_in)
+        # the reference's tensor is uniform on +-bound, not N(0, 0.01): abs-max just under the bound, std = bound / sqrt(3)
+        assert r["absmax"] <= bound * (1 + 1e-6) and r["absmax"] >= 0.97 * bound, k
+        assert abs(r["std"] - bound / math.sqrt(3)) <= (0.15 if v.size < 1000 else 0.02) * bound, k
+        assert abs(v.std() - r["std"]) <= (0.15 if v.size < 1000 else 0.02) * bound and np.abs(v).max() <= bound * (1 + 1e-6), k
+        # g = ||v|| over all dims but 0 in both
+        assert np.abs(g.reshape(-1) - np.sqrt((v.reshape(v.shape[0], -1) ** 2).sum(1))).max() <= 1e-5, k
+    eff = st["__effective__generator.resblocks.0.convs1.0.weight"]
+    assert abs(eff["std"] - st["generator.resblocks.0.convs1.0.weight_v"]["std"]) <= 1e-6     # forward uses (g, v), not N(0, 0.01)
+
+
+@pytest.mark.parametrize("name,variant,T,ws,iseed,perturb", [
+    ("hifigan_B1_T120_w3_i1007_plain", "hifigan", 120, 3, 1007, False),
+    ("hifigan_B1_T203_w0_i1009", "hifigan", 203, 0, 1009, True),
+    ("istftnet_B1_T120_w0_i1006", "istftnet", 120, 0, 1006, True),
+    ("istftnet_B1_T203_w0_i1008", "istftnet", 203, 0, 1008, True),
+    ("hifigan_B1_T400_w0_i1003", "hifigan", 400, 0, 1003, True)])
+def test_torch_cpu_port_matches_round2_goldens(name, variant, T, ws, iseed, perturb):
+    """3 s / ragged / 10 s fixtures of both decoder variants, incl. the reference's true initialisation: the torch CPU port
+    (what `bench.py --impl reference` times) against the unmodified reference; SineGen phase checksum of the numpy oracle."""
+    from oracle import decoder_torch as OT
+    from styletts2_lite_b200 import synth
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    g = golden(name + ".npz")
+    W = OT.TorchWeights(synth.make_state_dict(cfg, ws, perturb))
+    inp = synth.make_inputs(1, T, iseed, cfg)
+    out = OT.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"]).numpy()
+    assert out.shape == g["out"].shape
+    assert np.abs(out - g["out"]).max() <= WAVE_TOL, name
+    ph = O.sinegen_phase(inp["F0_curve"].numpy(), cfg.upsample_scale)
+    assert sha(ph) == str(g["phase_sha256"]), name
