@@ -233,6 +233,20 @@ ST2_API int st2_conv1d(const float* x, const float* w, const float* bias, float*
                int32_t padding, int32_t dilation, int32_t output_padding, int32_t transposed,
                int32_t precision, void* stream);
 
+/* SURVEY.md 8(f) N4 -- waveform post-processing and wire format, the step after the path:
+ *   StyleTTS2.generate, inference.py:314-319:  wav_i = wav_i[trim:-trim] (trim = 4000) for every sentence, concatenate,
+ *                                              pad `pad` (= 4000) zeros on both sides (float64 from here on);
+ *   Demo/infer.py:51-54:                       r = r / max|r|;  soundfile.write(..., 24000) -> PCM_16 = lrint(r * 32767)
+ *                                              (libsndfile pcm.c d2s_array; soundfile 0.13.1, uv.lock:1925).
+ * wav [B,S] fp32 device tensor (the decoder output of one batch of sentences), lengths [B] int32 device (samples of each
+ * sentence, NULL: all S).  out_f64 / out_pcm (either may be NULL) need st2_postprocess_max_samples() elements; *out_total
+ * (device int64) receives the number of samples written.  Bit-exact against the numpy restatement (oracle/postprocess_np.py).
+ * An all-zero input gives zeros (the reference would divide by zero). */
+ST2_API int64_t st2_postprocess_scratch_bytes(int32_t B);
+ST2_API int64_t st2_postprocess_max_samples(int32_t B, int32_t S, int32_t trim, int32_t pad);
+ST2_API int st2_postprocess(const float* wav, const int32_t* lengths, int32_t B, int32_t S, int32_t trim, int32_t pad,
+                    double* out_f64, int16_t* out_pcm, int64_t* out_total, void* scratch, void* stream);
+
 /* One fused half-step of AdaINResBlock1 (Modules/hifigan.py:67-73) on channels-last fp32 tensors, through the
  * tensor-core fused kernels (16-bit operands, fp32 accumulate):
  *   y = (conv1d(act(AdaIN(x; h)), w) + bias + res (+ y_old if accumulate)) * scale

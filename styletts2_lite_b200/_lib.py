@@ -97,6 +97,9 @@ SIGNATURES = {
     "st2_adain_conv1d_fused_scratch_bytes": (_L, [_I, _I, _I, _I, _I]),
     "st2_adain_conv1d_fused": (C.c_int, [_P, _P, _P, _I, C.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I,
                                          C.c_float, _I, _I, _P]),
+    "st2_postprocess_scratch_bytes": (_L, [_I]),
+    "st2_postprocess_max_samples": (_L, [_I, _I, _I, _I]),
+    "st2_postprocess": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "st2_adain_conv1d_row_scratch_bytes": (_L, [_I, _I, _I, _I]),
     "st2_adain_conv1d_row": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_float, _I, _I, _I,
                                        _P]),

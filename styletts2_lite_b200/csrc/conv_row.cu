@@ -622,17 +622,20 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
             const int tail = mr - (nblk - 1) * R;
             const int64_t a_bytes = ((int64_t)nblk * R * arow + 1023) & ~(int64_t)1023;
             const int xslot = R * C * xes;
-            const int lw = RW_NA * nblk < ntw ? RW_NA * nblk : ntw;
+            const int lw_max = RW_NA * nblk < ntw ? RW_NA * nblk : ntw;
             const int64_t fixed = RW_NA * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
             const int nr_max = p.nres ? 4 : 0, nr_min = p.nres ? 2 : 0;
-            for (int nr = nr_max; nr >= nr_min && !ok; --nr) {
-                for (int xd = 3; xd >= 2 && !ok; --xd) {
-                    const int64_t tot = fixed + (int64_t)nr * p.nres * rtile + (int64_t)lw * xd * xslot;
-                    if (tot <= budget) {
-                        p.sub = sub; p.R = R; p.nblk = nblk; p.tail_rows = tail; p.xslot = xslot; p.a_bytes = (int)a_bytes;
-                        p.lw = lw; p.xd = xd; p.nr = nr;
-                        *smem_out = (size_t)tot + 1024;
-                        ok = true;
+            // all transform warps with the deepest rings that fit; the smallest macro tile may idle up to a third of them
+            for (int lw = lw_max; lw >= (sub == 1 ? (2 * lw_max + 2) / 3 : lw_max) && !ok; --lw) {
+                for (int nr = nr_max; nr >= nr_min && !ok; --nr) {
+                    for (int xd = 3; xd >= 2 && !ok; --xd) {
+                        const int64_t tot = fixed + (int64_t)nr * p.nres * rtile + (int64_t)lw * xd * xslot;
+                        if (tot <= budget) {
+                            p.sub = sub; p.R = R; p.nblk = nblk; p.tail_rows = tail; p.xslot = xslot; p.a_bytes = (int)a_bytes;
+                            p.lw = lw; p.xd = xd; p.nr = nr;
+                            *smem_out = (size_t)tot + 1024;
+                            ok = true;
+                        }
                     }
                 }
             }

@@ -10,7 +10,6 @@ if [ $rc -ne 0 ]; then
   echo "== row tests failed: run them all (no -x) for the failure pattern"
   timeout 900 python -m pytest tests/test_gpu_fused.py -q -k "row" > gpurun_out/r2a_row_tests_all.log 2>&1
   tail -40 gpurun_out/r2a_row_tests_all.log
-  export ST2_NO_ROW=1
 fi
 echo "== full gpu suite (ST2_NO_ROW=${ST2_NO_ROW:-unset})"
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_gpu_tests.log 2>&1; echo "suite rc=$?"
