@@ -122,8 +122,15 @@ ST2_API int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, in
 
 /* Options of the 16-bit precisions.  "fp16_storage" (default 1): keep the stage-private tensors of the generator (conv1
  * output and running tensor of AdaINResBlock1, stage input, partial sum over the resblocks) in fp16 between kernels --
- * a third fewer HBM bytes for ~0.4 dB of SNR; 0 stores every tensor as fp32.  Unknown names fail. */
+ * a third fewer HBM bytes for ~0.4 dB of SNR; 0 stores every tensor as fp32.  "fp16_xt", "fp16_run",
+ * "fp16_xu", "fp16_sum" (default 1 each) switch the four kinds of tensors individually.  Unknown names fail. */
 ST2_API int st2_decoder_set_option(st2_decoder* d, const char* name, int32_t value);
+
+/* Process-wide kernel-selection / planner switches for A/B measurements and for testing a fallback kernel ("no_pipe", "no_row",
+ * "no_fused", "no_pdl", "pipe_xmax", ...; the full list is kTuneFields in csrc/decoder.cu).  Each is initialised ONCE from the
+ * environment variable ST2_<NAME> when the library first needs it; this call is the only other way to change one -- nothing
+ * on the forward path reads the environment.  Not synchronised: call it while no forward is running.  Unknown names fail. */
+ST2_API int st2_set_tuning(const char* name, int32_t value);
 
 /* Optional device-resident Philox seed: when set (non-NULL), the harmonic source reads its noise seed from *dev_seed
  * at run time instead of the `seed` argument of st2_decoder_forward, so a forward captured in a CUDA graph

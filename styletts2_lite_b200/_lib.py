@@ -70,6 +70,7 @@ SIGNATURES = {
     "st2_decoder_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint64, _P, _I, _I, _I, _P, _L, _P]),
     "st2_decoder_set_tap": (C.c_int, [_P, C.c_char_p, _P, _L]),
     "st2_decoder_set_option": (C.c_int, [_P, C.c_char_p, _I]),
+    "st2_set_tuning": (C.c_int, [C.c_char_p, _I]),
     "st2_decoder_set_seed_buffer": (C.c_int, [_P, _P]),
     "st2_decoder_last_launch_count": (_L, [_P]),
     "st2_decoder_set_profiling": (C.c_int, [_P, _I]),

@@ -45,6 +45,30 @@ extern thread_local int64_t g_launch_count;
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Process-wide kernel-selection / planner switches (A/B experiments, tests of a fallback path).  They are read ONCE from the ST2_*
+// environment variables when first used -- so a sweep script can still set them per process -- and changed afterwards only
+// through st2_set_tuning(); nothing on the forward path calls getenv.  Not synchronised: set them while no forward is running.
+struct Tune {
+    int no_pdl = 0, pdl_always = 0, no_k32 = 0, no_xstage = 0, no_fused = 0;
+    int no_pipe = 0, no_pipe_ups = 0, no_pipe_nt = 0, no_pipe_pair = 0, no_row = 0;
+    int pipe_xmax = 0, pipe_xmax16 = 0, pipe_nacc = 0, pipe_eg3_nores = 0, pipe_eg = 0;
+    int pipe_nxg = 0, pipe_nrg = 0, pipe_na = 0, pipe_nx = 0, pipe_nr = 0;
+    int verbose = 0, tc_halo = 0, lstm_bt = 0;
+    int no_xt16 = 0, no_run16 = 0, no_xu16 = 0, no_sum16 = 0;   // defaults of the per-handle storage options (st2_decoder_set_option)
+};
+const Tune& tune();
+int tune_set(const char* name, int value);    // ST2_OK, or ST2_ERR_INVALID for an unknown name
+
+// per-device cache of one-time function attributes / properties: a process may drive several GPUs, and
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies to the device that was current when it was set
+static constexpr int kMaxDevices = 64;
+static inline int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+int device_num_sms();                          // SM count of the current device (cached per device)
+
 enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2 };
 enum OutDtype { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 // kernel categories of the per-launch event profile (st2_decoder_get_profile)

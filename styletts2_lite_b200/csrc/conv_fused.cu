@@ -635,7 +635,7 @@ int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
-    const bool pdl = getenv("ST2_NO_PDL") == nullptr && ((int64_t)grid.x * grid.y <= 64 || getenv("ST2_PDL_ALWAYS") != nullptr);
+    const bool pdl = !tune().no_pdl && ((int64_t)grid.x * grid.y <= 64 || tune().pdl_always);
     cfg.attrs = &attr; cfg.numAttrs = pdl ? 1 : 0;
     ST2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, adain_coef_f2_kernel, (const float2*)partial, nparts, h, ld_h, h_off, coef, T, C, Cpad));
     ST2_LAUNCH_CHECK();
@@ -698,14 +698,14 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     p.stats = (float2*)stats_out;
     // shared-memory plan (one persistent CTA per SM, <= ~224 KB)
     const int64_t budget = 224 * 1024;
-    p.k32 = (a.Cin == 32 && a.w16_cin_pad == 64 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
+    p.k32 = (a.Cin == 32 && a.w16_cin_pad == 64 && !tune().no_k32) ? 1 : 0;
     const int64_t arow = p.k32 ? 64 : 128;
     const int64_t a_bytes = ((int64_t)p.rows * arow + 1023) & ~(int64_t)1023;
     const int64_t b_stage = (int64_t)bn * arow;
     const int64_t base_fixed = 2 * a_bytes + EW * 32 * 32 * 4 + (int64_t)EG * 4 * bn * 8 + 160 * 8 + 1024;
     // activations by TMA into an fp32 staging ring for single-chunk layers (C <= 64), when the ring fits
     const int64_t x_bytes = (((int64_t)p.rows * a.Cin * (a.x16in ? 2 : 4)) + 1023) & ~(int64_t)1023;
-    p.xstage = (p.kchunks == 1 && a.ld_x * (a.x16in ? 2 : 4) % 16 == 0 && getenv("ST2_NO_XSTAGE") == nullptr) ? 1 : 0;
+    p.xstage = (p.kchunks == 1 && a.ld_x * (a.x16in ? 2 : 4) % 16 == 0 && !tune().no_xstage) ? 1 : 0;
     int64_t fixed = base_fixed + (p.xstage ? NSTG * x_bytes : 0);
     const int ktaps_total = a.phases > 1 ? a.ntaps * a.phases : a.ntaps;
     p.ktaps_total = ktaps_total;
@@ -747,28 +747,16 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
     } else {
         map_x = map_b;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool attr_done[kMaxDevices] = {};
+    const int num_sms = device_num_sms();
+    if (!attr_done[current_device_slot()]) {
         ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<ACT_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_fused_kernel<ACT_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[current_device_slot()] = true;
     }
     int grid = num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    // debug: ST2_FUSED_TRACE="<launch index>:<file>" dumps the role timeline of CTA 0 of that launch
-    static int launch_idx = 0;
-    const char* tr = getenv("ST2_FUSED_TRACE");
-    long long* trace_dev = nullptr;
-    const size_t trace_n = 5 * 64 * 8;
-    if (tr != nullptr && atoi(tr) == launch_idx) {
-        cudaMalloc(&trace_dev, trace_n * sizeof(long long));
-        cudaMemset(trace_dev, 0, trace_n * sizeof(long long));
-        p.trace = trace_dev;
-    }
-    ++launch_idx;
     switch (act) {
         case ACT_NONE: conv_fused_kernel<ACT_NONE><<<grid, F_THREADS, smem, st>>>(map_b, map_x, p); break;
         case ACT_LRELU: conv_fused_kernel<ACT_LRELU><<<grid, F_THREADS, smem, st>>>(map_b, map_x, p); break;
@@ -779,31 +767,6 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
         default: set_error("conv_fused: bad act %d", act); return ST2_ERR_INVALID;
     }
     ST2_LAUNCH_CHECK();
-    if (trace_dev != nullptr) {
-        std::vector<long long> h(trace_n);
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h.data(), trace_dev, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
-        cudaFree(trace_dev);
-        const char* colon = strchr(tr, ':');
-        FILE* f = fopen(colon ? colon + 1 : "fused_trace.txt", "w");
-        if (f) {
-            long long t0 = 0;
-            for (size_t i = 0; i < trace_n; ++i)
-                if (h[i] != 0 && (t0 == 0 || h[i] < t0)) t0 = h[i];
-            fprintf(f, "# Cin=%d Cout=%d taps=%d rows=%d bn=%d stages=%d resident=%d xstage=%d tiles=%d grid=%d smem=%zu\n", p.Cin,
-                    p.Cout, p.ntaps, p.rows, p.bn, p.stages, p.resident, p.xstage, p.num_tiles, grid, smem);
-            for (int role = 0; role < 5; ++role)
-                for (int sq = 0; sq < 64; ++sq) {
-                    bool any = false;
-                    for (int ev = 0; ev < 8; ++ev) any |= h[(role * 64 + sq) * 8 + ev] != 0;
-                    if (!any) continue;
-                    fprintf(f, "role %d tile %2d:", role, sq);
-                    for (int ev = 0; ev < 8; ++ev) fprintf(f, " %8lld", h[(role * 64 + sq) * 8 + ev] ? h[(role * 64 + sq) * 8 + ev] - t0 : -1LL);
-                    fprintf(f, "\n");
-                }
-            fclose(f);
-        }
-    }
     return ST2_OK;
 }
 

@@ -804,14 +804,14 @@ int make_map_3d_any(CUtensorMap* map, int dtype /*0 f32, 1 bf16, 2 f16*/, const 
                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle128);
 
 static bool pipe_geometry_ok(const ConvArgs& a) {
-    if (getenv("ST2_NO_PIPE") != nullptr) return false;
+    if (tune().no_pipe) return false;
     if (a.in_stride != 1 || a.mirror || a.res_shift != 0) return false;
     const bool tr = a.phases > 1;          // polyphase ConvTranspose1d -> dense conv with N = phases * Cout
     if (tr) {
         if (a.out_stride != a.phases || a.w_step != a.phases || a.tap_step != -1 || a.in_off != 0 || a.accumulate) return false;
         if (a.ld_y != a.Cout || (a.res != nullptr && a.ld_res != a.Cout)) return false;
         if (a.Tout % a.phases != 0 || a.out_pad < 0 || a.out_pad > a.phases) return false;
-        if (getenv("ST2_NO_PIPE_UPS") != nullptr) return false;
+        if (tune().no_pipe_ups) return false;
     } else if (a.out_stride != 1 || a.out_pad != 0 || a.tap_step <= 0 || a.M != a.Tout) {
         return false;
     }
@@ -821,7 +821,7 @@ static bool pipe_geometry_ok(const ConvArgs& a) {
         // tile that stays resident in the 4 operand buffers (<= 4 K chunks)
         const int ntot = a.phases * a.w16_cout_pad, kch = a.w16_cin_pad / 64;
         const bool one_pass = ntot <= 192;
-        const bool n_pass = ntot % 128 == 0 && ntot <= 1024 && (kch == 1 || kch == 2 || kch == 4) && getenv("ST2_NO_PIPE_NT") == nullptr;
+        const bool n_pass = ntot % 128 == 0 && ntot <= 1024 && (kch == 1 || kch == 2 || kch == 4) && !tune().no_pipe_nt;
         if (!one_pass && !n_pass) return false;
         // measured on the 256-channel layers (N passes here vs conv_fused.cu): k=3 0.278 -> 0.165 ms, k=7 0.293 -> 0.276
         // (no residual) and 0.337 -> 0.313 (accumulate), ups 256->128 1.14 -> 0.37; k=7 with one residual and k=11 are
@@ -850,7 +850,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     memset(&p, 0, sizeof(p));
     p.Cin = a.Cin; p.kchunks = a.w16_cin_pad / 64; p.cch = a.Cin == 32 ? 32 : 64;
     p.x16in = a.x16in; p.is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;
-    p.k32 = (a.Cin == 32 && getenv("ST2_NO_K32") == nullptr) ? 1 : 0;
+    p.k32 = (a.Cin == 32 && !tune().no_k32) ? 1 : 0;
     const int ph = a.phases;               // 1, or the stride of a transposed conv (columns = ph * Cout)
     const bool tr_ = a.phases > 1;
     p.B = a.B; p.M = a.M; p.Tin = a.Tin; p.Cout = ph * a.Cout;
@@ -874,10 +874,10 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
         const int nres_ = (a.res != nullptr ? 1 : 0) + (a.accumulate ? 1 : 0);
         if ((a.Cin == 64 && a.ntaps == 7) || (a.Cin == 128 && a.ntaps == 3 && nres_ == 0) || (a.Cin == 128 && a.ntaps == 7 && nres_ == 1))
             xmax = 8192;
-        if (const char* e = getenv("ST2_PIPE_XMAX")) { const int v = atoi(e); if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
+        { const int v = tune().pipe_xmax; if (v >= 2048 && v <= P_XSLOT_MAX) xmax = v; }
         if (a.x16in) {
             if (xmax > 8192) xmax = 8192;     // fp16 input: a 12 KB block would be a whole tile for one warp (8 KB: 1-8 % faster on the k=3 layers)
-            if (const char* e = getenv("ST2_PIPE_XMAX16")) { const int v = atoi(e); if (v >= 1024 && v <= P_XSLOT_MAX) xmax = v; }
+            { const int v = tune().pipe_xmax16; if (v >= 1024 && v <= P_XSLOT_MAX) xmax = v; }
         }
         int nblk = 1;
         for (;; ++nblk) {
@@ -896,7 +896,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.mtiles = cdiv(a.M, P_MT);
     p.num_tiles = a.B * p.mtiles;
     p.nacc = p.bn <= 128 ? 4 : 2;
-    if (const char* e = getenv("ST2_PIPE_NACC")) { const int v = atoi(e); if (v == 2 || (v == 4 && p.bn <= 128)) p.nacc = v; }
+    { const int v = tune().pipe_nacc; if (v == 2 || (v == 4 && p.bn <= 128)) p.nacc = v; }
     p.nacc_log2 = p.nacc == 4 ? 2 : 1;
     int cols = 32;
     while (cols < p.nacc * p.bn) cols <<= 1;
@@ -907,8 +907,8 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     p.eg = (p.cch == 32 && p.nres > 0 && !tr_) ? 3 : 2;
     // three groups for the non-residual 32-channel layers too (ST2_PIPE_EG3_NORES=1): measured slower, 0.385 -> 0.416 ms at k = 3 --
     // the 96-register variant costs the transform warps more than the third group gives the epilogue
-    if (p.cch == 32 && p.nres == 0 && !tr_ && getenv("ST2_PIPE_EG3_NORES") != nullptr) p.eg = 3;
-    if (const char* e = getenv("ST2_PIPE_EG")) { const int v = atoi(e); if (v == 2 || (v == 3 && !tr_)) p.eg = v; }
+    if (p.cch == 32 && p.nres == 0 && !tr_ && tune().pipe_eg3_nores) p.eg = 3;
+    { const int v = tune().pipe_eg; if (v == 2 || (v == 3 && !tr_)) p.eg = v; }
     // 3 groups need 4 accumulators: a group's previous tile is tcnt-3, so MMA(tcnt-4) -- the previous use of its accumulator
     // -- has completed when it waits; with 2 accumulators the previous use is tile tcnt-2 and the parity wait could pass early
     if (p.nacc < 4) p.eg = 2;
@@ -928,7 +928,7 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     // (measured on the 128-channel layers: conv2 with one residual 0.405 -> 0.36 ms (k=7), 0.535 -> 0.507 (k=11); layers without
     // a residual, whose epilogue staging leaves less room for the rings, and the accumulate layers lose, so only nres == 1)
     const bool pair_ok = p.nt == 1 && p.kchunks == 2 && p.bn <= 128 && p.nacc == 4 && p.nres == 1 &&
-                         (int64_t)a.ntaps * p.kchunks * b_stage > 96 * 1024 && getenv("ST2_NO_PIPE_PAIR") == nullptr;
+                         (int64_t)a.ntaps * p.kchunks * b_stage > 96 * 1024 && !tune().no_pipe_pair;
     int na = (pair_ok || p.nt > 1) ? 4 : 2;
     int64_t base = na * a_bytes + 2048 + (p.nres ? 0 : (int64_t)(4 * p.eg) * 4096);
     const int64_t w_resident = (int64_t)a.ntaps * p.kchunks * b_stage;
@@ -951,12 +951,12 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     left -= rings(nx, nr);
     int nr_goal = p.nres ? (2 * nchunks + 2 > 8 ? 8 : 2 * nchunks + 2) : 0;
     int nx_goal = 10;
-    if (const char* e = getenv("ST2_PIPE_NXG")) { const int v = atoi(e); if (v >= 3 && v <= 16) nx_goal = v; }
-    if (const char* e = getenv("ST2_PIPE_NRG")) { const int v = atoi(e); if (p.nres && v >= 2 && v <= 12) nr_goal = v; }
+    { const int v = tune().pipe_nxg; if (v >= 3 && v <= 16) nx_goal = v; }
+    { const int v = tune().pipe_nrg; if (p.nres && v >= 2 && v <= 12) nr_goal = v; }
     // resident weights of a 2-chunk layer (128 channels, k = 3: 96 KB) leave little for the rings: two operand buffers and
     // deeper rings measured 0.319 -> 0.264 ms (no residual), 0.356 -> 0.310 (residual), 0.546 -> 0.478 (accumulate)
     int na_goal = (p.resident && p.kchunks >= 2) ? 2 : 4;
-    if (const char* e = getenv("ST2_PIPE_NA")) { const int v = atoi(e); if (v >= 2 && v <= 4) na_goal = v; }
+    { const int v = tune().pipe_na; if (v >= 2 && v <= 4) na_goal = v; }
     for (bool grew = true; grew;) {
         grew = false;
         // a third / fourth operand buffer as soon as the rings hold ~32 KB / ~48 KB each (or all they are allowed to)
@@ -971,8 +971,8 @@ static bool pipe_plan(const ConvArgs& a, PipeParams& p, size_t* smem_out) {
     }
     if (!p.resident)
         while (p.wstages < 8 && left >= b_stage) { ++p.wstages; left -= b_stage; }
-    if (const char* e = getenv("ST2_PIPE_NX")) { const int v = atoi(e); if (v >= 2 && v <= nx) nx = v; }
-    if (const char* e = getenv("ST2_PIPE_NR")) { const int v = atoi(e); if (p.nres && v >= 1 && v <= nr) nr = v; }
+    { const int v = tune().pipe_nx; if (v >= 2 && v <= nx) nx = v; }
+    { const int v = tune().pipe_nr; if (p.nres && v >= 1 && v <= nr) nr = v; }
     p.nx = nx; p.nr = nr;
     p.na = na;
     p.pair = (pair_ok && !p.resident && na == 4) ? 1 : 0;
@@ -1036,11 +1036,10 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
                                       (uint64_t)a.Tout * a.ld_y * 4, 32, P_MT);
         if (e != ST2_OK) return e;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    // the opt-in to > 48 KB of dynamic shared memory applies to the device that is current: once per device
+    static bool attr_done[kMaxDevices] = {};
+    const int num_sms = device_num_sms();
+    if (!attr_done[current_device_slot()]) {
 #define PIPE_ATTR(A, BF, X, G) ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<A, BF, X, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
         PIPE_ATTR(ACT_NONE, true, false, 2); PIPE_ATTR(ACT_NONE, false, false, 2);
         PIPE_ATTR(ACT_LRELU, true, false, 2); PIPE_ATTR(ACT_LRELU, false, false, 2);
@@ -1049,10 +1048,11 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
         PIPE_ATTR(ACT_SNAKE, true, false, 3); PIPE_ATTR(ACT_SNAKE, false, false, 3);
         PIPE_ATTR(ACT_SNAKE, true, true, 3); PIPE_ATTR(ACT_SNAKE, false, true, 3);
 #undef PIPE_ATTR
+        attr_done[current_device_slot()] = true;
     }
     int grid = num_sms;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    if (getenv("ST2_PIPE_VERBOSE") != nullptr)
+    if (tune().verbose)
         fprintf(stderr, "conv_pipe: Cin=%d Cout=%d taps=%d step=%d rows=%d nblk=%d tail=%d xr=%d resident=%d wstages=%d na=%d nacc=%d lw=%d nx=%d nr=%d nres=%d smem=%zu tiles=%d\n",
                 p.Cin, p.Cout, p.ntaps, p.tap_step, p.rows, p.nblk, p.tail_rows, p.xr, p.resident, p.wstages, p.na, p.nacc, p.lw, p.nx, p.nr, p.nres, smem,
                 p.num_tiles);
@@ -1066,7 +1066,7 @@ int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act,
     lattr.val.programmaticStreamSerializationAllowed = 1;
     // Only for small problems (a few tiles per CTA, i.e. one-sentence latency: 3.65 -> 3.29 ms at 1 x 3 s): in throughput
     // runs the early CTAs of this kernel sit on SMs the coefficient kernel in front of it needs, +0.8 ms per 64 x 5 s step
-    const bool pdl = getenv("ST2_NO_PDL") == nullptr && (p.num_tiles <= 16 * num_sms || getenv("ST2_PDL_ALWAYS") != nullptr);
+    const bool pdl = !tune().no_pdl && (p.num_tiles <= 16 * num_sms || tune().pdl_always);
     lcfg.attrs = &lattr; lcfg.numAttrs = pdl ? 1 : 0;
 #define PIPE_LAUNCH(A, BF, X, G)                                                                                         \
     do {                                                                                                                 \

@@ -14,11 +14,14 @@
 //     stay in 64 registers per thread ACROSS tiles; they are reduced over the 32 lanes by a fixed-order butterfly only when the
 //     utterance changes -- one partial per (CTA, utterance, epilogue warp) instead of one per (tile, 32-row quarter), which also
 //     shrinks what the coefficient kernel reads from ~45 MB to a few hundred KB;
-//   * activation blocks go through PRIVATE rings (one per transform warp, depth xd): plain parity tracking is then enough and the
-//     sequence-number spin of conv_pipe.cu disappears; blocks are always processed in whole batches of 8 passes (the operand
-//     buffer has slack rows for the overshoot), so the slow ragged path only runs on the blocks that touch the zero padding.
-// Roles (20 warps, 96 registers): warp 0 producer, warp 1 TMEM allocator + MMA issuer, then 18 - 4*NCH transform warps and
-// 4*NCH epilogue warps (NCH = C / 32; epilogue warp ew drains TMEM lane quarter (warp & 3), column chunk ew >> 2).
+//   * activation blocks go through PRIVATE, SELF-FED rings (one per transform warp, depth xd): the warp that consumes a slot
+//     issues the TMA load that refills it, so there is no producer thread in the activation path (the first build had one
+//     thread test-waiting and issuing 9 blocks + 4 residual tiles per macro tile: ncu showed the transform warps at an mbarrier
+//     in 44 % of all samples), no empty barrier and no sequence-number spin; blocks are always processed in whole batches of 8
+//     passes (the operand buffer has slack rows for the overshoot), so the ragged path only runs next to the zero padding.
+// Roles (20 warps, 96 registers): warp 0 residual-tile producer, warp 1 TMEM allocator + MMA issuer, 10 transform warps,
+// 8 epilogue warps (TMEM lane quarter warp & 3; NCH = 2: group ew >> 2 owns column chunk ew >> 2 of every sub-tile,
+// NCH = 1: the two groups take alternate sub-tiles).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -53,7 +56,7 @@ struct RowParams {
     // epilogue
     const float* bias; float scale;
     void* y; int ld_y; int y16out;
-    float2* stats;              // [grid][J][4 * NCH][32] (sum, sum of squares) or nullptr
+    float2* stats;              // [grid][J][8 epilogue warps][32] (sum, sum of squares) or nullptr
 };
 
 __device__ __forceinline__ bool rw_mbar_test(uint64_t* bar, uint32_t parity) {
@@ -109,8 +112,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
                 const __grid_constant__ CUtensorMap map_o, const RowParams p) {
     constexpr int C = 32 * NCH;
-    constexpr int NEW = 4 * NCH;                           // epilogue warps
-    constexpr int NTW = 18 - NEW;                          // transform warps
+    constexpr int NEW = 8;                                 // epilogue warps: two groups of four TMEM lane quarters
+    constexpr int NTW = 10;                                // transform warps
     constexpr int W_EPI0 = RW_X0 + NTW;                    // first epilogue warp
     constexpr uint32_t arow = NCH == 1 ? 64u : 128u;       // bytes per operand row (K = C, 16-bit)
     constexpr uint32_t btile = (uint32_t)C * arow;         // one tap [C][C]: 2 KB / 8 KB
@@ -138,8 +141,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     uint64_t* r_full = acc_empty + 8;           // [nr]
     uint64_t* r_empty = r_full + p.nr;          // [nr]
     uint64_t* x_full = r_empty + p.nr;          // [nxs]
-    uint64_t* x_empty = x_full + nxs;           // [nxs]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_empty + nxs);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_full + nxs);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -163,16 +165,13 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         }
         for (int i = 0; i < 8; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], (uint32_t)NEW);
+            mbar_init(&acc_empty[i], (uint32_t)(4 * NCH));   // the warps that drain one accumulator
         }
         for (int i = 0; i < p.nr; ++i) {
             mbar_init(&r_full[i], 1);
             mbar_init(&r_empty[i], 1);
         }
-        for (int i = 0; i < nxs; ++i) {
-            mbar_init(&x_full[i], 1);
-            mbar_init(&x_empty[i], 1);
-        }
+        for (int i = 0; i < nxs; ++i) mbar_init(&x_full[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -200,65 +199,26 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     pdl_wait();
 
     if (warp == 0) {
-        // ===== producer: resident weights, then the activation-block and residual-tile queues =====
+        // ===== producer: resident weights, then the residual-tile queue (activations are loaded by their consumers) =====
         if (elect_one_sync()) {
             mbar_expect_tx(w_full, (uint32_t)p.ntaps * btile);
             for (int w = 0; w < p.ntaps; ++w) tma_load_3d(smem_w + (size_t)w * btile, &map_b, w_full, 0, 0, w);
-            // activation queue: block g = (macro tile, blk) -> ring of transform warp g % lw, slot (g / lw) % xd
-            int x_m = 0, x_blk = 0;
-            int x_b = m_lo / p.mmt, x_mm = m_lo - x_b * p.mmt;
-            uint32_t x_w = 0, x_i = 0, x_par = 0;
-            bool x_done = m_n == 0;
-            // residual queue: (macro tile, sub-tile) -> stage
-            int r_m = 0, r_s = 0;
-            int r_b = x_b, r_mm = x_mm;
-            uint32_t r_stage = 0, r_par = 0;
-            bool r_done = p.nres == 0 || m_n == 0;
-            const uint32_t r_tx = (uint32_t)p.nres * rtile;
-            uint32_t idle = 0;
-            while (!(x_done && r_done)) {
-                bool progress = false;
-                if (!x_done) {
-                    const uint32_t slot = x_w * (uint32_t)p.xd + x_i;
-                    if (rw_mbar_test(&x_empty[slot], x_par ^ 1u)) {
-                        const bool tail = (x_blk == p.nblk - 1);
-                        const uint32_t nrows = tail ? (uint32_t)p.tail_rows : (uint32_t)p.R;
-                        mbar_expect_tx(&x_full[slot], nrows * xrow);
-                        tma_load_3d(smem_x + (size_t)slot * p.xslot, tail ? &map_xt : &map_x, &x_full[slot], 0,
-                                    x_mm * sub_rows + p.halo_min + x_blk * p.R, x_b);
-                        if (++x_w == (uint32_t)p.lw) {
-                            x_w = 0;
-                            if (++x_i == (uint32_t)p.xd) { x_i = 0; x_par ^= 1u; }
-                        }
-                        if (++x_blk == p.nblk) {
-                            x_blk = 0;
-                            if (++x_mm == p.mmt) { x_mm = 0; ++x_b; }
-                            x_done = (++x_m == m_n);
-                        }
-                        progress = true;
-                    }
-                }
-                if (!r_done) {
-                    if (rw_mbar_test(&r_empty[r_stage], r_par ^ 1u)) {
+            if (p.nres != 0) {
+                // (macro tile, sub-tile) -> stage
+                int r_b = m_lo / p.mmt, r_mm = m_lo - r_b * p.mmt;
+                uint32_t r_stage = 0, r_par = 0;
+                const uint32_t r_tx = (uint32_t)p.nres * rtile;
+                for (int r_m = 0; r_m < m_n; ++r_m) {
+                    for (int r_s = 0; r_s < p.sub && r_mm * sub_rows + r_s * 128 < p.M; ++r_s) {
+                        mbar_wait(&r_empty[r_stage], r_par ^ 1u);
                         uint8_t* dst = smem_r + (size_t)r_stage * p.nres * rtile;
                         mbar_expect_tx(&r_full[r_stage], r_tx);
                         const int row = r_mm * sub_rows + r_s * 128;
                         tma_load_3d(dst, &map_r, &r_full[r_stage], 0, row, r_b);
                         if (p.nres == 2) tma_load_3d(dst + rtile, &map_o, &r_full[r_stage], 0, row, r_b);
                         if (++r_stage == (uint32_t)p.nr) { r_stage = 0; r_par ^= 1u; }
-                        ++r_s;
-                        if (r_s == p.sub || r_mm * sub_rows + r_s * 128 >= p.M) {
-                            r_s = 0;
-                            if (++r_mm == p.mmt) { r_mm = 0; ++r_b; }
-                            r_done = (++r_m == m_n);
-                        }
-                        progress = true;
                     }
-                }
-                if (progress) idle = 0;
-                else {
-                    __nanosleep(40);
-                    if (++idle > (1u << 26)) __trap();     // a consumer never freed its slot: fail instead of hanging the GPU
+                    if (++r_mm == p.mmt) { r_mm = 0; ++r_b; }
                 }
             }
         }
@@ -340,19 +300,34 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const uint32_t sw = NCH == 1 ? ((Rr >> 1) & 3u) : (Rr & 7u);
                 aoff[u] = Rr * arow + ((cidx ^ sw) << 4) + csub;
             }
-            int mi = 0, blk = tw;                                   // block = (macro tile mi of this CTA, blk)
-            while (blk >= p.nblk) { blk -= p.nblk; ++mi; }
-            uint32_t xi = 0, xpar = 0;                              // private ring cursor
-            int cur_m = -1, b = 0, mm = 0;
+            // this warp's blocks: g = tw, tw + lw, ... -> (macro tile mi of this CTA, blk); two cursors walk them, the load
+            // cursor xd blocks ahead of the compute cursor
+            const int b0 = m_lo / p.mmt, mm0 = m_lo - b0 * p.mmt;
+            int mi = 0, blk = tw, b = b0, mm = mm0;                 // compute cursor
+            while (blk >= p.nblk) { blk -= p.nblk; ++mi; if (++mm == p.mmt) { mm = 0; ++b; } }
+            int l_mi = mi, l_blk = blk, l_b = b, l_mm = mm;         // load cursor
+            uint32_t l_i = 0;                                       // ring slot the next load goes to
+            auto issue_load = [&]() {                               // lane 0 only; the slot is free (this warp consumed it)
+                const uint32_t slot = (uint32_t)tw * (uint32_t)p.xd + l_i;
+                const bool tail = (l_blk == p.nblk - 1);
+                const uint32_t nrows = tail ? (uint32_t)p.tail_rows : (uint32_t)p.R;
+                mbar_expect_tx(&x_full[slot], nrows * xrow);
+                tma_load_3d(smem_x + (size_t)slot * p.xslot, tail ? &map_xt : &map_x, &x_full[slot], 0,
+                            l_mm * sub_rows + p.halo_min + l_blk * p.R, l_b);
+            };
+            auto advance_load = [&]() {
+                if (++l_i == (uint32_t)p.xd) l_i = 0;
+                l_blk += p.lw;
+                while (l_blk >= p.nblk) { l_blk -= p.nblk; ++l_mi; if (++l_mm == p.mmt) { l_mm = 0; ++l_b; } }
+            };
+            for (int i = 0; i < p.xd; ++i) {                        // prologue: fill the ring
+                if (l_mi < m_n && lane == 0) issue_load();
+                if (l_mi < m_n) advance_load();
+            }
+            uint32_t xi = 0, xpar = 0;                              // ring cursor of the compute side
             int cached_b = -1;
             RXf cf;
             while (mi < m_n) {
-                if (mi != cur_m) {
-                    const int gm = m_lo + mi;
-                    b = gm / p.mmt;
-                    mm = gm - b * p.mmt;
-                    cur_m = mi;
-                }
                 if (b != cached_b) {
                     const float* ca = p.coef + (size_t)b * 2 * p.coef_ld;
                     const float4 a4 = __ldg(reinterpret_cast<const float4*>(ca + c4));
@@ -403,43 +378,50 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     }
                 }
                 fence_proxy_async();
-                __syncwarp();
+                __syncwarp();                                        // every lane has read the slot and written its rows
                 if (lane == 0) {
-                    mbar_arrive(&x_empty[slot]);
                     mbar_arrive(&a_full[buf]);
+                    if (l_mi < m_n) issue_load();                    // refill the slot just consumed (l_i == xi)
                 }
+                if (l_mi < m_n) advance_load();
                 if (++xi == (uint32_t)p.xd) { xi = 0; xpar ^= 1u; }
                 blk += p.lw;
-                while (blk >= p.nblk) { blk -= p.nblk; ++mi; }
+                while (blk >= p.nblk) { blk -= p.nblk; ++mi; if (++mm == p.mmt) { mm = 0; ++b; } }
             }
         }
     } else {
         // ===== epilogue: one thread = one output row; 16 columns at a time; statistics in registers across tiles =====
-        const int ew = warp - W_EPI0;                     // 0 .. NEW-1
+        const int ew = warp - W_EPI0;                     // 0 .. 7
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int ch = ew >> 2;                           // 32-column chunk this warp owns
+        const int grp = ew >> 2;                          // NCH = 2: column chunk of every sub-tile; NCH = 1: parity of the sub-tiles
+        const int ch = NCH == 2 ? grp : 0;
         const uint32_t t_lane = ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         const uint32_t bias_u32 = smem_u32(bias_s) + (uint32_t)(ch * 32) * 4u;
         const float2 sc2 = make_float2(p.scale, p.scale);
-        float s1[32], s2[32];
+        float2 s1[16], s2[16];                            // (sum, sum of squares) of channel pairs (2i, 2i + 1) of this row
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        for (int i = 0; i < 16; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
         const int b_first = m_lo / p.mmt;
         int b = b_first, mm = m_lo - b_first * p.mmt;
         uint32_t sc = 0;
         auto flush = [&](int bb) {
             if (p.stats != nullptr) {
-                const float t1 = row_reduce_scatter32(s1, lane);
-                const float t2 = row_reduce_scatter32(s2, lane);
+                float a1[32], a2[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a1[2 * i] = s1[i].x; a1[2 * i + 1] = s1[i].y; a2[2 * i] = s2[i].x; a2[2 * i + 1] = s2[i].y; }
+                const float t1 = row_reduce_scatter32(a1, lane);
+                const float t2 = row_reduce_scatter32(a2, lane);
                 p.stats[(((size_t)cta * p.J + (bb - b_first)) * NEW + ew) * 32 + lane] = make_float2(t1, t2);
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+            for (int i = 0; i < 16; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
         };
         for (int mc = 0; mc < m_n; ++mc) {
+            const int row0 = mm * sub_rows + q * 32 + lane;
             for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
+                if (NCH == 1 && (int)(sc & 1u) != grp) continue;               // the other group's sub-tile
                 const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
-                const int m = mm * sub_rows + s * 128 + q * 32 + lane;        // output row of this thread
+                const int m = row0 + s * 128;                                    // output row of this thread
                 const bool valid = m < p.M;
                 const size_t yoff = ((size_t)b * p.M + (size_t)(valid ? m : 0)) * p.ld_y + ch * 32;
                 mbar_wait_warp(&acc_full[acc], (sc >> p.nacc_log2) & 1u);
@@ -465,10 +447,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     if (valid) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            s1[hh * 16 + 2 * i] += o[i].x;
-                            s1[hh * 16 + 2 * i + 1] += o[i].y;
-                            s2[hh * 16 + 2 * i] = fmaf(o[i].x, o[i].x, s2[hh * 16 + 2 * i]);
-                            s2[hh * 16 + 2 * i + 1] = fmaf(o[i].y, o[i].y, s2[hh * 16 + 2 * i + 1]);
+                            s1[hh * 8 + i] = fadd2(s1[hh * 8 + i], o[i]);
+                            s2[hh * 8 + i] = ffma2(o[i], o[i], s2[hh * 8 + i]);
                         }
                         if (p.y16out) {
                             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + yoff + hh * 16);
@@ -524,13 +504,13 @@ adain_coef_row_kernel(const float2* __restrict__ partial, const RowStatsInfo si,
     const int b = blockIdx.x;
     const int c_lo = row_cta_of(si, b * si.mmt), c_hi = row_cta_of(si, (b + 1) * si.mmt - 1);
     const int chunk = c >> 5, col = c & 31;
-    const int per_cta = 4;                       // epilogue warps (TMEM lane quarters) that own a column chunk
+    const int per_cta = si.nwarp / (C >> 5);     // epilogue warps that hold partials of this column chunk: 8 (C = 32) or 4 (C = 64)
     const int nparts = (c_hi - c_lo + 1) * per_cta;
     double s = 0, ss = 0;
     for (int i = sl; i < nparts; i += nsl) {
         const int cta = c_lo + i / per_cta, wq = i - (i / per_cta) * per_cta;
         const int j = b - row_cta_start(si, cta) / si.mmt;
-        const float2 v = __ldg(partial + (((size_t)cta * si.J + j) * si.nwarp + chunk * 4 + wq) * 32 + col);
+        const float2 v = __ldg(partial + (((size_t)cta * si.J + j) * si.nwarp + chunk * per_cta + wq) * 32 + col);
         s += (double)v.x;
         ss += (double)v.y;
     }
@@ -559,24 +539,8 @@ int make_weight_map_k32(CUtensorMap* map, int is_bf16, const void* w16, int cin_
 int make_map_3d_sw(CUtensorMap* map, int dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                    uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes);
 
-static int row_num_sms() {
-    // per device: the SM count of whichever device is current (a process may drive several GPUs)
-    static int sms[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return 148;
-    if (sms[dev] == 0) {
-        int v = 0;
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        sms[dev] = v > 0 ? v : 148;
-    }
-    return sms[dev];
-}
-
-static bool row_disabled() {
-    static const bool off = getenv("ST2_NO_ROW") != nullptr;     // read once: A/B switch against conv_pipe.cu
-    return off;
-}
+static int row_num_sms() { return device_num_sms(); }
+static bool row_disabled() { return tune().no_row != 0; }
 
 static bool row_geometry_ok(const ConvArgs& a) {
     if (a.in_stride != 1 || a.mirror || a.res_shift != 0 || a.phases != 1) return false;
@@ -605,7 +569,7 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
     p.nacc = nch == 1 ? 8 : 4;
     p.nacc_log2 = nch == 1 ? 3 : 2;
     p.tmem_cols = 256;
-    const int ntw = 18 - 4 * nch;
+    const int ntw = 10;
     const int xes = a.x16in ? 2 : 4;
     const int brows = nch == 1 ? 32 : 16;                  // rows per transform batch
     const int64_t budget = 224 * 1024;
@@ -676,9 +640,9 @@ bool conv_row_supported(const ConvArgs& a) {
 
 // bytes of the statistics buffer a conv_row launch of this geometry writes (upper bound over devices with <= RW_MAXGRID SMs)
 int64_t conv_row_stats_bytes(int B, int T, int C) {
-    // J <= B + 1 slots per CTA; 4 * NCH warps x 32 columns x float2
-    const int64_t per_cta = (int64_t)(B + 1) * (4 * (C / 32)) * 32 * 8;
-    (void)T;
+    // J <= B + 1 slots per CTA; 8 epilogue warps x 32 columns x float2
+    const int64_t per_cta = (int64_t)(B + 1) * 8 * 32 * 8;
+    (void)T; (void)C;
     return (int64_t)RW_MAXGRID * per_cta;
 }
 
@@ -719,15 +683,13 @@ int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, 
         if (e != ST2_OK) return e;
     }
     if (desc != nullptr) {
-        desc->grid = grid; desc->J = p.J; desc->nwarp = 4 * nch; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
+        desc->grid = grid; desc->J = p.J; desc->nwarp = 8; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
     }
-    ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * (4 * nch) * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
+    ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * 8 * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
                 "conv_row: statistics buffer too small");
     // the opt-in to > 48 KB of dynamic shared memory is per device: once per (device, variant)
-    static bool attr_done[64][8] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
+    static bool attr_done[kMaxDevices][8] = {};
+    const int dev = current_device_slot();
 #define ROW_KERNEL(BF, X, N) conv_row_kernel<BF, X, N>
 #define ROW_LAUNCH(BF, X, N)                                                                                                     \
     do {                                                                                                                         \

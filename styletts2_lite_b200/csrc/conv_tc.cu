@@ -452,7 +452,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < bn) cols <<= 1;
     p.tmem_cols = cols;
-    static const bool want_halo = getenv("ST2_TC_HALO") != nullptr && atoi(getenv("ST2_TC_HALO")) != 0;
+    const bool want_halo = tune().tc_halo != 0;
     const int span = (a.ntaps - 1) * (a.tap_step < 0 ? -a.tap_step : a.tap_step);
     if (want_halo && p.kchunks == 1 && TC_BM + span <= 256) {
         p.halo_rows = TC_BM + span;
@@ -476,10 +476,10 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
                     (uint64_t)a.w16_cin_pad * 2, (uint64_t)a.w16_cin_pad * a.w16_cout_pad * 2, TC_KC, (uint32_t)bn);
     if (e != ST2_OK) return e;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};      // per device (the attribute applies to the current device)
+    if (!attr_set[current_device_slot()]) {
         ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[current_device_slot()] = true;
     }
     dim3 grid(cdiv(a.M, TC_BM), a.w16_cout_pad / bn, a.B * a.phases);
     conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);

@@ -232,7 +232,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         // The stage input xu = ups(x) + x_source is read six times (input and residual of the first iteration of the three
         // resblocks): stored as fp16 when the ups conv and all six convs run on the TMA pipeline kernel (ST2_NO_XU16=1: fp32)
         int xu16 = 0;
-        if (fuse_u && getenv("ST2_NO_XU16") == nullptr && E.pipe_ok_ups16(d->ups[i], Cin, C, Tin, Tout, u, pu, shift, dtu)) {
+        if (fuse_u && d->opt_xu16 && E.pipe_ok_ups16(d->ups[i], Cin, C, Tin, Tout, u, pu, shift, dtu)) {
             xu16 = 1;
             for (int j = 0; j < c.n_kernels; ++j)
                 if (!E.resblock1_x16_ok(d->resblocks[i * c.n_kernels + j], Tout, j > 0 ? 1 : 0)) xu16 = 0;
@@ -294,6 +294,55 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     return E.err;
 }
 
+// ---- process-wide tuning switches (common.cuh)
+namespace {
+struct TuneField { const char* name; const char* env; int Tune::*field; bool flag; };
+const TuneField kTuneFields[] = {
+    {"no_pdl", "ST2_NO_PDL", &Tune::no_pdl, true}, {"pdl_always", "ST2_PDL_ALWAYS", &Tune::pdl_always, true},
+    {"no_k32", "ST2_NO_K32", &Tune::no_k32, true}, {"no_xstage", "ST2_NO_XSTAGE", &Tune::no_xstage, true},
+    {"no_fused", "ST2_NO_FUSED", &Tune::no_fused, true}, {"no_pipe", "ST2_NO_PIPE", &Tune::no_pipe, true},
+    {"no_pipe_ups", "ST2_NO_PIPE_UPS", &Tune::no_pipe_ups, true}, {"no_pipe_nt", "ST2_NO_PIPE_NT", &Tune::no_pipe_nt, true},
+    {"no_pipe_pair", "ST2_NO_PIPE_PAIR", &Tune::no_pipe_pair, true}, {"no_row", "ST2_NO_ROW", &Tune::no_row, true},
+    {"pipe_xmax", "ST2_PIPE_XMAX", &Tune::pipe_xmax, false}, {"pipe_xmax16", "ST2_PIPE_XMAX16", &Tune::pipe_xmax16, false},
+    {"pipe_nacc", "ST2_PIPE_NACC", &Tune::pipe_nacc, false}, {"pipe_eg3_nores", "ST2_PIPE_EG3_NORES", &Tune::pipe_eg3_nores, true},
+    {"pipe_eg", "ST2_PIPE_EG", &Tune::pipe_eg, false}, {"pipe_nxg", "ST2_PIPE_NXG", &Tune::pipe_nxg, false},
+    {"pipe_nrg", "ST2_PIPE_NRG", &Tune::pipe_nrg, false}, {"pipe_na", "ST2_PIPE_NA", &Tune::pipe_na, false},
+    {"pipe_nx", "ST2_PIPE_NX", &Tune::pipe_nx, false}, {"pipe_nr", "ST2_PIPE_NR", &Tune::pipe_nr, false},
+    {"verbose", "ST2_PIPE_VERBOSE", &Tune::verbose, true}, {"tc_halo", "ST2_TC_HALO", &Tune::tc_halo, false},
+    {"lstm_bt", "ST2_LSTM_BT", &Tune::lstm_bt, false}, {"no_xt16", "ST2_NO_XT16", &Tune::no_xt16, true},
+    {"no_run16", "ST2_NO_RUN16", &Tune::no_run16, true}, {"no_xu16", "ST2_NO_XU16", &Tune::no_xu16, true},
+    {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}};
+Tune& tune_storage() {
+    static Tune t = [] {
+        Tune v;
+        for (const TuneField& f : kTuneFields)
+            if (const char* e = getenv(f.env)) v.*(f.field) = f.flag ? 1 : atoi(e);    // the only getenv calls of the library
+        return v;
+    }();
+    return t;
+}
+}  // namespace
+const Tune& tune() { return tune_storage(); }
+int tune_set(const char* name, int value) {
+    for (const TuneField& f : kTuneFields)
+        if (strcmp(name, f.name) == 0) {
+            tune_storage().*(f.field) = value;
+            return ST2_OK;
+        }
+    set_error("set_tuning: unknown switch '%s'", name);
+    return ST2_ERR_INVALID;
+}
+int device_num_sms() {
+    static int sms[kMaxDevices] = {};
+    const int dev = current_device_slot();
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
+    }
+    return sms[dev];
+}
+
 }  // namespace st2
 
 // ------------------------------------------------------------------------------------------
@@ -320,6 +369,7 @@ int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
     st2_decoder* d = new (std::nothrow) st2_decoder();
     ST2_REQUIRE(d != nullptr, "create: out of memory");
     d->cfg = *cfg;
+    d->init_options();
     int dev = 0;
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
@@ -403,12 +453,20 @@ int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t ca
 
 int st2_decoder_set_option(st2_decoder* d, const char* name, int32_t value) {
     ST2_REQUIRE(d && name, "set_option: bad argument");
-    if (strcmp(name, "fp16_storage") == 0) {
-        d->fp16_storage = value ? 1 : 0;
-        return ST2_OK;
-    }
+    struct { const char* n; int* v; } opts[] = {{"fp16_storage", &d->fp16_storage}, {"fp16_xt", &d->opt_xt16}, {"fp16_run", &d->opt_run16},
+                                                {"fp16_xu", &d->opt_xu16}, {"fp16_sum", &d->opt_sum16}};
+    for (auto& o : opts)
+        if (strcmp(name, o.n) == 0) {
+            *o.v = value ? 1 : 0;
+            return ST2_OK;
+        }
     st2::set_error("set_option: unknown option '%s'", name);
     return ST2_ERR_INVALID;
+}
+
+int st2_set_tuning(const char* name, int32_t value) {
+    ST2_REQUIRE(name != nullptr, "set_tuning: null name");
+    return st2::tune_set(name, value);
 }
 
 int st2_decoder_set_seed_buffer(st2_decoder* d, const uint64_t* dev_seed) {

@@ -280,39 +280,30 @@ static int launch_lstm_v2(const float* G, const float* whh, const float* bhh, fl
 int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st) {
     ST2_REQUIRE(H == 256, "lstm: hidden size %d is not supported (d_hid must be 512)", H);
     ST2_REQUIRE(B > 0 && T > 0, "lstm: bad shape B=%d T=%d", B, T);
-    if (getenv("ST2_LSTM_V1") == nullptr) {
-        // 4 utterances per cluster while all clusters are still co-resident (an 8-CTA cluster must sit inside one GPC, so
-        // fewer fit than 148 / 8: the occupancy API says 15 on the B200; measured over 4 x 64 steps: B <= 24, 12 clusters of
-        // BT = 4: 0.47 ms against 0.67 ms with BT = 8; B = 32, 16 clusters of BT = 4: two waves, 0.90 ms)
-        static int max_clusters4 = -1;
-        if (max_clusters4 < 0) {
-            constexpr int HH4 = 256;
-            const size_t smem4 = ((size_t)HH4 * 4 * (HH4 / kLstmCluster) + 2 * 4 * HH4 + (kLstmThreads / 32) * 4 * 4 * (HH4 / kLstmCluster)) * sizeof(float) + 16;
-            cudaFuncSetAttribute(lstm_bidir_v2_kernel<HH4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kLstmCluster, 2, 64);
-            cfg.blockDim = dim3(kLstmThreads);
-            cfg.dynamicSmemBytes = smem4;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = kLstmCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr; cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, lstm_bidir_v2_kernel<HH4, 4>, &cfg) != cudaSuccess) { n = 8; cudaGetLastError(); }
-            max_clusters4 = n;
-            if (getenv("ST2_PIPE_VERBOSE")) fprintf(stderr, "lstm: %d co-resident clusters of 8 CTAs (BT=4 configuration)\n", n);
-        }
-        const bool bt4 = getenv("ST2_LSTM_BT4") != nullptr ||
-                         (getenv("ST2_LSTM_BT8") == nullptr && cdiv(B, 4) * 2 <= max_clusters4);
-        return bt4 ? launch_lstm_v2<4>(G, whh, bhh, y, B, T, st) : launch_lstm_v2<8>(G, whh, bhh, y, B, T, st);
+    // 4 utterances per cluster while all clusters are still co-resident (an 8-CTA cluster must sit inside one GPC, so
+    // fewer fit than 148 / 8: the occupancy API says 15 on the B200; measured over 4 x 64 steps: B <= 24, 12 clusters of
+    // BT = 4: 0.47 ms against 0.67 ms with BT = 8; B = 32, 16 clusters of BT = 4: two waves, 0.90 ms)
+    static int max_clusters4[kMaxDevices] = {};          // per device: 0 = not asked yet
+    int& mc4 = max_clusters4[current_device_slot()];
+    if (mc4 == 0) {
+        constexpr int HH4 = 256;
+        const size_t smem4 = ((size_t)HH4 * 4 * (HH4 / kLstmCluster) + 2 * 4 * HH4 + (kLstmThreads / 32) * 4 * 4 * (HH4 / kLstmCluster)) * sizeof(float) + 16;
+        cudaFuncSetAttribute(lstm_bidir_v2_kernel<HH4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kLstmCluster, 2, 64);
+        cfg.blockDim = dim3(kLstmThreads);
+        cfg.dynamicSmemBytes = smem4;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kLstmCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, lstm_bidir_v2_kernel<HH4, 4>, &cfg) != cudaSuccess || n <= 0) { n = 8; cudaGetLastError(); }
+        mc4 = n;
+        if (tune().verbose) fprintf(stderr, "lstm: %d co-resident clusters of 8 CTAs (BT=4 configuration)\n", n);
     }
-    constexpr int HH = 256;
-    const size_t smem = ((size_t)HH * 4 * (HH / kLstmCluster) + 2 * kLstmBt * HH + 4 * kLstmBt * (HH / kLstmCluster)) * sizeof(float);
-    ST2_CUDA_CHECK(cudaFuncSetAttribute(lstm_bidir_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(kLstmCluster, 2, cdiv(B, kLstmBt));
-    lstm_bidir_kernel<HH><<<grid, kLstmThreads, smem, st>>>(G, whh, bhh, y, B, T);
-    ST2_LAUNCH_CHECK();
-    return ST2_OK;
+    const bool bt4 = tune().lstm_bt == 4 || (tune().lstm_bt != 8 && cdiv(B, 4) * 2 <= mc4);
+    return bt4 ? launch_lstm_v2<4>(G, whh, bhh, y, B, T, st) : launch_lstm_v2<8>(G, whh, bhh, y, B, T, st);
 }
 
 }  // namespace st2

@@ -110,10 +110,11 @@ int launch_style_fc(const float* s, const float* W, const float* bias, float* h,
     ST2_REQUIRE(K % 4 == 0 && K <= 1024, "style_fc: style_dim %d must be a multiple of 4 and <= 1024", K);
     dim3 grid(cdiv(R, 4 * kFcRq), cdiv(B, kFcB));
     const size_t smem = (size_t)K * kFcB * sizeof(float);
-    static size_t max_set = 0;
-    if (smem > 48 * 1024 && smem > max_set) {
+    static size_t max_set[kMaxDevices] = {};     // per device (the attribute applies to the current device)
+    size_t& ms = max_set[current_device_slot()];
+    if (smem > 48 * 1024 && smem > ms) {
         ST2_CUDA_CHECK(cudaFuncSetAttribute(style_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set = smem;
+        ms = smem;
     }
     style_fc_kernel<<<grid, kFcB * kFcRq, smem, st>>>(s, W, bias, h, B, R, K);
     ST2_LAUNCH_CHECK();
@@ -416,10 +417,11 @@ int launch_noise_conv(const float* har, const float* w, const float* bias, float
     const int ntile = cdiv(Tout, kNcTile);
     const int rpp = 256 / (C / 4);
     size_t smem = ((size_t)k * C + (kNcTile - 1) * stride + k + (size_t)rpp * C * 2) * sizeof(float);
-    static size_t max_set = 0;
-    if (smem > 48 * 1024 && smem > max_set) {
+    static size_t max_set[kMaxDevices] = {};     // per device (the attribute applies to the current device)
+    size_t& ms = max_set[current_device_slot()];
+    if (smem > 48 * 1024 && smem > ms) {
         ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set = smem;
+        ms = smem;
     }
     dim3 grid(ntile, B);
     noise_conv_kernel<<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);

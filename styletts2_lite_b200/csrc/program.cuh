@@ -79,6 +79,13 @@ struct st2_decoder {
     const uint64_t* seed_dev = nullptr;     // optional device-resident Philox seed (st2_decoder_set_seed_buffer)
     bool tc_ok = false;
     int fp16_storage = 1;                   // st2_decoder_set_option("fp16_storage"): stage-private tensors of the 16-bit paths in fp16
+    // ... and each of the four kinds alone ("fp16_xt", "fp16_run", "fp16_xu", "fp16_sum").  Defaults come
+    // from the process-wide switches once, at create time.
+    int opt_xt16 = 1, opt_run16 = 1, opt_xu16 = 1, opt_sum16 = 1;
+    void init_options() {
+        const st2::Tune& t = st2::tune();
+        opt_xt16 = !t.no_xt16; opt_run16 = !t.no_run16; opt_xu16 = !t.no_xu16; opt_sum16 = !t.no_sum16;
+    }
 
     ResBlk1dW encode, decode[4];
     float *f0_w = nullptr, *f0_b = nullptr, *n_w = nullptr, *n_b = nullptr;
@@ -468,7 +475,7 @@ struct Exec {
         coef_ld = Cpad;
     }
     bool can_fuse(const ConvW& w, int dt, int ld_x, int ld_y, int stride, int dilation) {
-        if (!use_tc(w, dt) || getenv("ST2_NO_FUSED") != nullptr) return false;
+        if (!use_tc(w, dt) || tune().no_fused) return false;
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.in_stride = 1; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad;
@@ -588,7 +595,7 @@ struct Exec {
     //   mode 1: first block of a stage, writes the fp16 sum;  2: middle, fp16 sum in place;  3: last, fp16 sum -> fp32 stage output
     bool resblock1_sum16_ok(const ResBlock1W& w, int T, int mode, int x16) {
         const int C = w.C, dt = fmt_for(w.name);
-        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16") || getenv("ST2_NO_SUM16")) return false;
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || !d->opt_xt16 || !d->opt_run16 || !d->opt_sum16) return false;
         for (int j = 0; j < 3; ++j) {        // every conv of the block on the pipeline kernel with the fp16 tensors it will see
             const int dil = w.dil[j], in16 = (j > 0 || x16) ? 1 : 0;
             if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, in16, 1) ||
@@ -600,7 +607,7 @@ struct Exec {
     }
     bool resblock1_x16_ok(const ResBlock1W& w, int T, int accumulate) {
         const int C = w.C, dt = fmt_for(w.name);
-        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || getenv("ST2_NO_XT16") || getenv("ST2_NO_RUN16")) return false;
+        if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || !d->opt_xt16 || !d->opt_run16) return false;
         for (int j = 0; j < 3; ++j) {
             const int dil = w.dil[j];
             if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 1, 1) ||
@@ -625,8 +632,8 @@ struct Exec {
             void* st_run = alloc(st_bytes);
             // the intra-block tensor xt (conv1 output, only consumed by conv2's transform) is stored as fp16 when both convs
             // run on the TMA pipeline kernel: 20 % fewer HBM bytes per iteration for -0.1 dB of SNR (its statistics still come
-            // from the fp32 values in the epilogue).  ST2_NO_XT16=1 keeps it fp32.
-            int xt16 = (d->fp16_storage && getenv("ST2_NO_XT16") == nullptr) ? 1 : 0;
+            // from the fp32 values in the epilogue).  option fp16_xt = 0 keeps it fp32.
+            int xt16 = (d->fp16_storage && d->opt_xt16) ? 1 : 0;
             for (int j = 0; j < 3 && xt16; ++j) {
                 const int dil = w.dil[j];
                 if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, 0, 1) ||
@@ -637,8 +644,8 @@ struct Exec {
             // The running tensor between the three iterations (x + conv2 output of iterations 0 and 1; read as conv1's
             // input and conv2's residual by the next iteration) is private to the block: stored as fp16 as well when every
             // conv of the block takes it (25 % fewer HBM bytes per block; AdaIN statistics still come from the fp32 values in
-            // the epilogue, the stage output the last iteration writes stays fp32).  ST2_NO_RUN16=1 keeps it fp32.
-            int run16 = (xt16 && getenv("ST2_NO_RUN16") == nullptr) ? 1 : 0;
+            // the epilogue, the stage output the last iteration writes stays fp32).  option fp16_run = 0 keeps it fp32.
+            int run16 = (xt16 && d->opt_run16) ? 1 : 0;
             for (int j = 0; j < 3 && run16; ++j) {
                 const int dil = w.dil[j];
                 if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, j > 0 || x16, 1) ||

@@ -238,45 +238,49 @@ def test_istftnet_small_tensor_core_snr(prec):
 
 def test_fp16_intra_block_tensor_costs_little():
     """The fused resblocks keep four kinds of stage-private tensors in fp16 (conv1 output, the running
-    tensor between iterations, the stage input, the partial sum over the resblocks); ST2_NO_XT16=1 turns all of them off.
+    tensor between iterations, the stage input, the partial sum over the resblocks); option "fp16_storage" / "fp16_xt" = 0 turns
+    all of them off, "fp16_run" / "fp16_xu" / "fp16_sum" one kind each.
     Against the fp32-stored variant the waveform differs by about as much as two bf16 runs with different rounding do
     (bound 45 dB) and the SNR against the reference stays within a few tenths of a dB (bar 40 dB)."""
-    import os
     cfg = DecoderConfig.hifigan()
     g = golden("hifigan_B1_T120_w0_i1001.npz")
     m = _decoder(cfg)
+    lib = _lib.load()
     inp = np_inputs(1, 120, 1001, cfg)
     out16 = _run(m, inp, precision="bf16")
-    os.environ["ST2_NO_XT16"] = "1"
+    # everything fp32: the module attribute (B200Decoder(..., fp16_storage=False) / st2_decoder_set_option)
+    m.fp16_storage = False
+    m.refresh_weights()
     try:
         out32 = _run(m, inp, precision="bf16")
     finally:
-        os.environ.pop("ST2_NO_XT16", None)
+        m.fp16_storage = True
+        m.refresh_weights()
     d = snr_db(out32, out16)
     G.log("xt16_vs_xt32", snr_between_db=d, snr16=snr_db(g["out"], out16), snr32=snr_db(g["out"], out32))
     assert not np.array_equal(out16, out32)      # the fp16 path really ran
     assert d >= 45.0
     assert snr_db(g["out"], out16) >= 40.0
     assert snr_db(g["out"], out16) >= snr_db(g["out"], out32) - 1.0
-    # the same switch through the API: B200Decoder(..., fp16_storage=False) / st2_decoder_set_option
-    m.fp16_storage = False
-    m.refresh_weights()
+    assert np.array_equal(_run(m, inp, precision="bf16"), out16)
+    assert lib.st2_decoder_set_option(m._handle, b"no_such_option", 1) == -1
+    assert lib.st2_set_tuning(b"no_such_switch", 1) == -1
+    # "fp16_xt" = 0 turns all four kinds off (the others build on the fp16 conv1 output) ...
+    _lib.check(lib.st2_decoder_set_option(m._handle, b"fp16_xt", 0))
     try:
         assert np.array_equal(_run(m, inp, precision="bf16"), out32)
     finally:
-        m.fp16_storage = True
-        m.refresh_weights()
-    assert np.array_equal(_run(m, inp, precision="bf16"), out16)
-    assert _lib.load().st2_decoder_set_option(m._handle, b"no_such_option", 1) == -1
-    # each switch alone changes the result (the path it guards really runs) and stays within the same bound
-    for knob in ("ST2_NO_RUN16", "ST2_NO_XU16", "ST2_NO_SUM16"):
-        os.environ[knob] = "1"
+        _lib.check(lib.st2_decoder_set_option(m._handle, b"fp16_xt", 1))
+    # ... and each of the other three alone changes the result (the path it guards really runs) within the same bound
+    for knob in (b"fp16_run", b"fp16_xu", b"fp16_sum"):
+        _lib.check(lib.st2_decoder_set_option(m._handle, knob, 0))
         try:
             o = _run(m, inp, precision="bf16")
         finally:
-            os.environ.pop(knob, None)
+            _lib.check(lib.st2_decoder_set_option(m._handle, knob, 1))
         assert not np.array_equal(o, out16), knob
         assert snr_db(out32, o) >= 45.0 and snr_db(g["out"], o) >= 40.0, knob
+    assert np.array_equal(_run(m, inp, precision="bf16"), out16)
 
 
 @pytest.mark.parametrize("variant,B,T", [("hifigan", 8, 400), ("istftnet", 1, 2400), ("hifigan", 3, 203)])

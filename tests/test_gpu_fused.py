@@ -78,13 +78,13 @@ def test_adain_conv1d_fused_vs_oracle(C_, k, dil, T, use_res, acc, scale, act, p
     pad = dil * (k - 1) // 2
     ref = _ref(x, h, alpha, act, 0.1, w, b, res, y_old, pad, dil, scale, prec)
     if path == "tile":
-        os.environ["ST2_NO_PIPE"] = "1"
+        G._lib.check(G._lib.load().st2_set_tuning(b"no_pipe", 1))
     try:
         got, coef = G.adain_conv1d_fused(G.cl(x), h, alpha if act == "snake" else None, act, w, b,
                                          None if res is None else G.cl(res), None if y_old is None else G.cl(y_old),
                                          h_next, pad, dil, scale=scale, slope=0.1, precision=prec)
     finally:
-        os.environ.pop("ST2_NO_PIPE", None)
+        G._lib.check(G._lib.load().st2_set_tuning(b"no_pipe", 0))
     got = G.cf(got)
     nan = int(np.isnan(got).sum())
     err = float(np.abs(np.nan_to_num(got) - ref).max() / np.abs(ref).max())
@@ -148,12 +148,12 @@ def test_act_conv_transpose1d_fused_vs_oracle(Cin, Cout, k, stride, pad, opad, T
     res = rng.standard_normal(ref.shape).astype(np.float32)
     ref = (ref + res).astype(np.float32)
     if path == "tile":
-        os.environ["ST2_NO_PIPE"] = "1"
+        G._lib.check(G._lib.load().st2_set_tuning(b"no_pipe", 1))
     try:
         got, coef = G.act_conv_transpose1d_fused(G.cl(x), alpha if act == "snake" else None, act, w, b, G.cl(res), h_next,
                                                  stride, pad, opad, slope=0.1, precision=prec)
     finally:
-        os.environ.pop("ST2_NO_PIPE", None)
+        G._lib.check(G._lib.load().st2_set_tuning(b"no_pipe", 0))
     got = G.cf(got)
     assert got.shape == ref.shape
     nan = int(np.isnan(got).sum())
