@@ -19,9 +19,9 @@
 //     thread test-waiting and issuing 9 blocks + 4 residual tiles per macro tile: ncu showed the transform warps at an mbarrier
 //     in 44 % of all samples), no empty barrier and no sequence-number spin; blocks are always processed in whole batches of 8
 //     passes (the operand buffer has slack rows for the overshoot), so the ragged path only runs next to the zero padding.
-// Roles (20 warps, 96 registers): warp 0 residual-tile producer, warp 1 TMEM allocator + MMA issuer, 10 transform warps,
-// 8 epilogue warps (TMEM lane quarter warp & 3; NCH = 2: group ew >> 2 owns column chunk ew >> 2 of every sub-tile,
-// NCH = 1: the two groups take alternate sub-tiles).
+// Roles (20 warps; 96 registers at launch, re-split by setmaxnreg to 80-88 / 120 for the epilogue): warp 0 residual-tile
+// producer, warp 1 TMEM allocator + MMA issuer, 18 - 4*NCH transform warps, 4*NCH epilogue warps (NCH = C / 32; epilogue warp
+// ew drains TMEM lane quarter warp & 3 of column chunk ew >> 2 of every sub-tile).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,8 +55,8 @@ struct RowParams {
     int J;                      // statistics slots per CTA (utterances a CTA can touch)
     // epilogue
     const float* bias; float scale;
-    void* y; int ld_y; int y16out;
-    float2* stats;              // [grid][J][8 epilogue warps][32] (sum, sum of squares) or nullptr
+    void* y; int ld_y;
+    float2* stats;              // [grid][J][4 * NCH epilogue warps][32] (sum, sum of squares) or nullptr
 };
 
 __device__ __forceinline__ bool rw_mbar_test(uint64_t* bar, uint32_t parity) {
@@ -106,14 +106,14 @@ __device__ __forceinline__ float row_reduce_scatter32(float (&v)[32], int lane) 
     return v[0];
 }
 
-template <bool BF16, bool X16, int NCH>
+template <bool BF16, bool X16, bool Y16, int NCH>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
                 const __grid_constant__ CUtensorMap map_o, const RowParams p) {
     constexpr int C = 32 * NCH;
-    constexpr int NEW = 8;                                 // epilogue warps: two groups of four TMEM lane quarters
-    constexpr int NTW = 10;                                // transform warps
+    constexpr int NEW = 4 * NCH;                           // epilogue warps: one group of four TMEM lane quarters per column chunk
+    constexpr int NTW = 18 - NEW;                          // transform warps: 14 (C = 32) or 10 (C = 64)
     constexpr int W_EPI0 = RW_X0 + NTW;                    // first epilogue warp
     constexpr uint32_t arow = NCH == 1 ? 64u : 128u;       // bytes per operand row (K = C, 16-bit)
     constexpr uint32_t btile = (uint32_t)C * arow;         // one tap [C][C]: 2 KB / 8 KB
@@ -197,7 +197,13 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
     pdl_trigger();
     pdl_wait();
-
+    // register split (the kernel launches with 96 per thread): the two epilogue warpgroups (warps 12-19) keep a whole 32-column
+    // accumulator chunk plus 64 statistics registers, everybody else gives 16 back:  3 x 128 x 80 + 2 x 128 x 120 = 640 x 96
+    // (each setmaxnreg dominates the code of its roles, so ptxas allocates the two regions with their own budgets)
+    if (warp < W_EPI0) {
+    // 640 x 96 = (16 x 32) x 88 + 128 x 120 (C = 32)  =  (12 x 32) x 80 + 256 x 120 (C = 64)
+    if (NCH == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
     if (warp == 0) {
         // ===== producer: resident weights, then the residual-tile queue (activations are loaded by their consumers) =====
         if (elect_one_sync()) {
@@ -281,7 +287,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 if (++mm == p.mmt) { mm = 0; ++b; }
             }
         }
-    } else if (warp < W_EPI0) {
+    } else {
         // ===== transform: activation block -> AdaIN affine + Snake -> swizzled 16-bit operand rows =====
         const int tw = warp - RW_X0;
         if (tw < p.lw) {
@@ -389,15 +395,18 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 while (blk >= p.nblk) { blk -= p.nblk; ++mi; if (++mm == p.mmt) { mm = 0; ++b; } }
             }
         }
+    }
     } else {
-        // ===== epilogue: one thread = one output row; 16 columns at a time; statistics in registers across tiles =====
-        const int ew = warp - W_EPI0;                     // 0 .. 7
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;" ::: "memory");
+        // ===== epilogue: one thread = one output row; statistics in registers across tiles =====
+        const int ew = warp - W_EPI0;                     // 0 .. NEW-1
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int grp = ew >> 2;                          // NCH = 2: column chunk of every sub-tile; NCH = 1: parity of the sub-tiles
-        const int ch = NCH == 2 ? grp : 0;
-        const uint32_t t_lane = ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        const int ch = ew >> 2;                           // 32-column chunk this warp owns
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         const uint32_t bias_u32 = smem_u32(bias_s) + (uint32_t)(ch * 32) * 4u;
         const float2 sc2 = make_float2(p.scale, p.scale);
+        constexpr size_t yes = Y16 ? 2 : 4;               // bytes per output element
+        const size_t sub_bytes = (size_t)128 * p.ld_y * yes;
         float2 s1[16], s2[16];                            // (sum, sum of squares) of channel pairs (2i, 2i + 1) of this row
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
@@ -406,63 +415,57 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         uint32_t sc = 0;
         auto flush = [&](int bb) {
             if (p.stats != nullptr) {
-                float a1[32], a2[32];
+                float a1[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { a1[2 * i] = s1[i].x; a1[2 * i + 1] = s1[i].y; a2[2 * i] = s2[i].x; a2[2 * i + 1] = s2[i].y; }
+                for (int i = 0; i < 16; ++i) { a1[2 * i] = s1[i].x; a1[2 * i + 1] = s1[i].y; }
                 const float t1 = row_reduce_scatter32(a1, lane);
-                const float t2 = row_reduce_scatter32(a2, lane);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a1[2 * i] = s2[i].x; a1[2 * i + 1] = s2[i].y; }
+                const float t2 = row_reduce_scatter32(a1, lane);
                 p.stats[(((size_t)cta * p.J + (bb - b_first)) * NEW + ew) * 32 + lane] = make_float2(t1, t2);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
         };
         for (int mc = 0; mc < m_n; ++mc) {
-            const int row0 = mm * sub_rows + q * 32 + lane;
-            for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
-                if (NCH == 1 && (int)(sc & 1u) != grp) continue;               // the other group's sub-tile
+            int m = mm * sub_rows + q * 32 + lane;                              // output row of this thread in sub-tile 0
+            uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y) + (((size_t)b * p.M + (size_t)m) * p.ld_y + ch * 32) * yes;
+            for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc, m += 128, yrow += sub_bytes) {
                 const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
-                const int m = row0 + s * 128;                                    // output row of this thread
-                const bool valid = m < p.M;
-                const size_t yoff = ((size_t)b * p.M + (size_t)(valid ? m : 0)) * p.ld_y + ch * 32;
                 mbar_wait_warp(&acc_full[acc], (sc >> p.nacc_log2) & 1u);
                 tc_fence_after();
+                float v[32];
+                tmem_ld32(t_lane + acc * (uint32_t)C, v);
+                // the accumulator chunk is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (m < p.M) {
+                    float2 o[16];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float v[16];
-                    __syncwarp();                          // tcgen05.ld is .aligned: re-converge after the `valid` branch
-                    tmem_ld16(tmem_base + t_lane + acc * (uint32_t)C + (uint32_t)(hh * 16), v);
-                    if (hh == 1) {
-                        // the accumulator is in registers: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                    }
-                    float2 o[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 bs = lds128(bias_u32 + (uint32_t)(hh * 64 + i * 16));
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bs = lds128(bias_u32 + (uint32_t)(i * 16));
                         o[2 * i] = ffma2(make_float2(v[4 * i], v[4 * i + 1]), sc2, make_float2(bs.x, bs.y));
                         o[2 * i + 1] = ffma2(make_float2(v[4 * i + 2], v[4 * i + 3]), sc2, make_float2(bs.z, bs.w));
                     }
-                    if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            s1[hh * 8 + i] = fadd2(s1[hh * 8 + i], o[i]);
-                            s2[hh * 8 + i] = ffma2(o[i], o[i], s2[hh * 8 + i]);
-                        }
-                        if (p.y16out) {
-                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + yoff + hh * 16);
-                            dst[0] = make_uint4(pack16(o[0].x, o[0].y, 0), pack16(o[1].x, o[1].y, 0), pack16(o[2].x, o[2].y, 0),
-                                                pack16(o[3].x, o[3].y, 0));
-                            dst[1] = make_uint4(pack16(o[4].x, o[4].y, 0), pack16(o[5].x, o[5].y, 0), pack16(o[6].x, o[6].y, 0),
-                                                pack16(o[7].x, o[7].y, 0));
-                        } else {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + hh * 16);
+                    for (int i = 0; i < 16; ++i) {
+                        s1[i] = fadd2(s1[i], o[i]);
+                        s2[i] = ffma2(o[i], o[i], s2[i]);
+                    }
+                    if (Y16) {
+                        uint4* dst = reinterpret_cast<uint4*>(yrow);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
-                        }
+                        for (int i = 0; i < 4; ++i)
+                            dst[i] = make_uint4(pack16(o[4 * i].x, o[4 * i].y, 0), pack16(o[4 * i + 1].x, o[4 * i + 1].y, 0),
+                                                pack16(o[4 * i + 2].x, o[4 * i + 2].y, 0), pack16(o[4 * i + 3].x, o[4 * i + 3].y, 0));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(yrow);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
                     }
                 }
+                __syncwarp();                              // re-converge before the next .aligned TMEM load
             }
             if (++mm == p.mmt) {
                 flush(b);
@@ -569,16 +572,17 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
     p.nacc = nch == 1 ? 8 : 4;
     p.nacc_log2 = nch == 1 ? 3 : 2;
     p.tmem_cols = 256;
-    const int ntw = 10;
+    const int ntw = 18 - 4 * nch;
     const int xes = a.x16in ? 2 : 4;
     const int brows = nch == 1 ? 32 : 16;                  // rows per transform batch
     const int64_t budget = 224 * 1024;
     bool ok = false;
-    // largest macro tile first (the halo is transformed once per macro tile), then the largest activation blocks, then the
-    // deepest rings
-    for (int sub = 4; sub >= 1 && !ok; sub >>= 1) {
-        const int mr = sub * 128 + span;
-        for (int slot_bytes = 4096; slot_bytes >= 2048 && !ok; slot_bytes >>= 1) {
+    // 4 KB activation blocks (two transform batches per barrier round trip: 2 KB blocks measured 0.36 vs 0.30 ms on the
+    // 64-channel k = 3 layer) with the largest macro tile that fits (the halo is transformed once per macro tile), then the
+    // deepest rings; 2 KB blocks only where nothing else fits
+    for (int slot_bytes = 4096; slot_bytes >= 2048 && !ok; slot_bytes >>= 1) {
+        for (int sub = 4; sub >= 1 && !ok; sub >>= 1) {
+            const int mr = sub * 128 + span;
             int R = slot_bytes / (C * xes);
             R = R / brows * brows;
             if (R < brows) R = brows;
@@ -589,8 +593,8 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
             const int lw_max = RW_NA * nblk < ntw ? RW_NA * nblk : ntw;
             const int64_t fixed = RW_NA * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
             const int nr_max = p.nres ? 4 : 0, nr_min = p.nres ? 2 : 0;
-            // all transform warps with the deepest rings that fit; the smallest macro tile may idle up to a third of them
-            for (int lw = lw_max; lw >= (sub == 1 ? (2 * lw_max + 2) / 3 : lw_max) && !ok; --lw) {
+            // as many transform warps as have a ring (at least 10; 7 for the smallest macro tile) with the deepest rings that fit
+            for (int lw = lw_max; lw >= (lw_max < 10 ? lw_max : (sub == 1 ? 7 : 10)) && !ok; --lw) {
                 for (int nr = nr_max; nr >= nr_min && !ok; --nr) {
                     for (int xd = 3; xd >= 2 && !ok; --xd) {
                         const int64_t tot = fixed + (int64_t)nr * p.nres * rtile + (int64_t)lw * xd * xslot;
@@ -614,7 +618,7 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
     p.tq = (int)(nt / grid); p.tr = (int)(nt % grid);
     p.J = (p.tq + 1 + p.mmt - 1) / p.mmt + 1;
     p.bias = a.bias; p.scale = a.scale;
-    p.y = a.y; p.ld_y = a.ld_y; p.y16out = a.y16out;
+    p.y = a.y; p.ld_y = a.ld_y;
     *grid_out = grid;
     return true;
 }
@@ -683,33 +687,36 @@ int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, 
         if (e != ST2_OK) return e;
     }
     if (desc != nullptr) {
-        desc->grid = grid; desc->J = p.J; desc->nwarp = 8; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
+        desc->grid = grid; desc->J = p.J; desc->nwarp = 4 * nch; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
     }
-    ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * 8 * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
+    if (tune().verbose)
+        fprintf(stderr, "conv_row: C=%d taps=%d step=%d x16=%d y16=%d nres=%d sub=%d R=%d nblk=%d tail=%d lw=%d xd=%d nr=%d smem=%zu grid=%d tq=%d J=%d\n",
+                C, p.ntaps, p.tap_step, a.x16in, a.y16out, p.nres, p.sub, p.R, p.nblk, p.tail_rows, p.lw, p.xd, p.nr, smem, grid, p.tq, p.J);
+    ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * (4 * nch) * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
                 "conv_row: statistics buffer too small");
     // the opt-in to > 48 KB of dynamic shared memory is per device: once per (device, variant)
-    static bool attr_done[kMaxDevices][8] = {};
+    static bool attr_done[kMaxDevices][16] = {};
     const int dev = current_device_slot();
-#define ROW_KERNEL(BF, X, N) conv_row_kernel<BF, X, N>
-#define ROW_LAUNCH(BF, X, N)                                                                                                     \
+#define ROW_LAUNCH(BF, X, Y, N)                                                                                                  \
     do {                                                                                                                         \
-        bool& done = attr_done[dev][(BF ? 4 : 0) + (X ? 2 : 0) + (N - 1)];                                                       \
+        bool& done = attr_done[dev][(BF ? 8 : 0) + (X ? 4 : 0) + (Y ? 2 : 0) + (N - 1)];                                         \
         if (!done) {                                                                                                             \
-            ST2_CUDA_CHECK(cudaFuncSetAttribute(ROW_KERNEL(BF, X, N), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_row_kernel<BF, X, Y, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             done = true;                                                                                                         \
         }                                                                                                                        \
-        ROW_KERNEL(BF, X, N)<<<grid, RW_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);                            \
+        conv_row_kernel<BF, X, Y, N><<<grid, RW_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);                     \
     } while (0)
+#define ROW_LAUNCH_Y(BF, X, N) do { if (a.y16out) ROW_LAUNCH(BF, X, true, N); else ROW_LAUNCH(BF, X, false, N); } while (0)
     const bool bf = is_bf16 != 0, x16 = a.x16in != 0;
     if (nch == 1) {
-        if (bf) { if (x16) ROW_LAUNCH(true, true, 1); else ROW_LAUNCH(true, false, 1); }
-        else { if (x16) ROW_LAUNCH(false, true, 1); else ROW_LAUNCH(false, false, 1); }
+        if (bf) { if (x16) ROW_LAUNCH_Y(true, true, 1); else ROW_LAUNCH_Y(true, false, 1); }
+        else { if (x16) ROW_LAUNCH_Y(false, true, 1); else ROW_LAUNCH_Y(false, false, 1); }
     } else {
-        if (bf) { if (x16) ROW_LAUNCH(true, true, 2); else ROW_LAUNCH(true, false, 2); }
-        else { if (x16) ROW_LAUNCH(false, true, 2); else ROW_LAUNCH(false, false, 2); }
+        if (bf) { if (x16) ROW_LAUNCH_Y(true, true, 2); else ROW_LAUNCH_Y(true, false, 2); }
+        else { if (x16) ROW_LAUNCH_Y(false, true, 2); else ROW_LAUNCH_Y(false, false, 2); }
     }
+#undef ROW_LAUNCH_Y
 #undef ROW_LAUNCH
-#undef ROW_KERNEL
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

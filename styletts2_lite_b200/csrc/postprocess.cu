@@ -33,6 +33,7 @@ post_peak_kernel(const float* __restrict__ wav, const int32_t* __restrict__ leng
         *total = o + pad;
     }
     const int i = blockIdx.y;
+    if (i >= B) return;                            // B == 0: the grid still has one row of blocks for the offsets
     const int kept = pp_kept(lengths, S, trim, i);
     const float* src = wav + (size_t)i * S + trim;
     float m = 0.f;

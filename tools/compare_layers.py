@@ -10,7 +10,7 @@ for f in files:
     d=collections.OrderedDict()
     for line in open(f):
         m=re.match(r'(\S+)\s+(\d+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)\s+GF=([\d.]+) MB=([\d.]+)',line)
-        if m and m.group(1) in ('conv_fused','conv_pipe'):
+        if m and m.group(1) in ('conv_fused','conv_pipe','conv_row'):
             k=(float(m.group(8)),float(m.group(9)))
             d[k]=(int(m.group(2)),float(m.group(4)))
             if k not in keys: keys.append(k)
@@ -21,7 +21,7 @@ def cls(gf,mb):
         per=2*64*T*C*C/1e9
         k=gf/per
         if abs(k-round(k))<0.02 and round(k) in (3,7,11):
-            tb=64*T*C*4/1e6
+            tb=64*T*C*2/1e6          # passes in units of one fp16 tensor (x, y, residual, old values)
             n=mb/tb
             return C,int(round(k)),round(n)
     return None
@@ -30,7 +30,7 @@ for k in keys:
     c=cls(*k)
     rows.append((c if c else (999,0,0),k))
 rows.sort()
-print('%-22s'%'layer (C,k,passes) n', ' '.join('%8s'%('cfg%d'%i) for i in range(len(files))), '  floor')
+print('%-22s'%'layer (C,k,fp16 passes) n', ' '.join('%8s'%('cfg%d'%i) for i in range(len(files))), '  floor')
 tot=[0]*len(files)
 for c,k in rows:
     n=[t.get(k,(0,0))[0] for t in tabs][0]
