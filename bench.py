@@ -7,19 +7,24 @@ One "step" = Decoder.forward over one synthetic batch of BASELINE.json configs[1
 (hifigan, B=64 utterances x 5 s = T 200 frames, random-init weights, bf16 tensor-core path).
 Rank 0 prints ONE JSON line.  For N>1 (torchrun) every rank runs its own batch (utterances
 shard with no cross-rank math, weak scaling) and the waveforms are gathered to rank 0 over NCCL
-inside the timed step.
+inside the timed region: each step's batch goes point-to-point into its slice of one preallocated
+buffer on rank 0, on a side stream, so the gather of step k overlaps the forward of step k+1
+(parallel.ShardedGather).  Auxiliary keys (outside the timed region): `cfg4_sharded_1024x10s`
+(N>1: BASELINE configs[3], 1024 x 10 s sharded in micro-batches, gathered to rank 0),
+`cfg5_istftnet_60s` (configs[4]), `full_path_cfg3` (configs[2]) and `eager_gpu` (the reference
+decoder through PyTorch eager on the same GPU, fp32 and bf16 autocast: the pre-existing GPU path).
 
   value     whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the package's host-fed serving loop (streaming.PipelinedDecoder around the drop-in
             module): HOST (pinned) inputs copied in and the waveform copied back to pinned host memory every step,
             inside the timed region, overlapped with the neighbouring forwards on copy streams
-  roofline  the dominant kernel (conv_pipe_kernel: fused AdaIN/Snake -> tcgen05 conv -> residual/stats): algorithmic
-            bytes / event-timed duration vs the measured HBM copy peak of MEASURED_PEAKS.json; `kernels` lists
+  roofline  the dominant kernel (conv_row_kernel / conv_pipe_kernel: fused AdaIN/Snake -> tcgen05 conv -> residual/stats):
+            algorithmic bytes / event-timed duration vs the measured HBM copy peak of MEASURED_PEAKS.json; `kernels` lists
             every kernel category with its time share, TFLOP/s and GB/s
-  cpu_baseline  the torch-CPU port of the reference decoder (oracle/decoder_torch.py) on the host cores (rank 0, N=1)
+  cpu_baseline  the reference decoder on the host cores (rank 0, N=1): the UNMODIFIED reference modules when they are staged
+            under baseline/_ref (oracle/stage_reference.py; kind "reference"), else the torch-CPU port (kind "port")
 
---impl reference times that same CPU port (the reference itself is pure Python/PyTorch and
-cannot travel to the GPU box) on a bounded sample of the workload.
+--impl reference times that same CPU arm on a bounded sample of the workload (8 utterances per step).
 """
 from __future__ import annotations
 
@@ -52,6 +57,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chain", action="store_true", help="skip the auxiliary BASELINE configs[2] measurement (full_path_cfg3)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: --frames)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm")
+    ap.add_argument("--no-aux", action="store_true", help="skip every auxiliary measurement (cfg3/cfg4/cfg5/eager_gpu)")
     return ap.parse_args()
 
 
@@ -66,39 +73,60 @@ def workload_config(a, n_gpus):
                       "bf16": "tcgen05 bf16 operands (generator.noise_res + front half on fp16 operands), fp32 accumulate"}[a.precision],
         "noise": "SineGen noise drawn on the device (Philox) inside the step",
         "l2": "L2 flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2",
-        "parallelism": "replicas: utterances sharded per rank, no cross-rank math; NCCL gather of waveforms to rank 0 inside the step" if n_gpus > 1 else "single GPU",
+        "parallelism": ("replicas: utterances sharded per rank, no cross-rank math; every step's waveforms go point-to-point (NCCL) "
+                        "into one preallocated buffer on rank 0, on a side stream that overlaps the next forward; all transfers "
+                        "complete inside the timed region") if n_gpus > 1 else "single GPU",
     }
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference decoder restated on torch CPU kernels (oracle/decoder_torch.py), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(variant, frames, steps, warmup):
+def cpu_reference_run(variant, frames, steps, warmup, batch=8):
+    """The reference decoder on the host cores, `batch` utterances per step.  kind "reference": the unmodified Modules/
+    staged under baseline/_ref by oracle/stage_reference.py; kind "port": oracle/decoder_torch.py (same ATen kernels)."""
     import torch
     from styletts2_lite_b200 import synth
     from styletts2_lite_b200.config import DecoderConfig
-    # the CPU baseline leg is one of the places allowed to run the oracle: decoder_torch is the reference decoder
-    # restated on the very ATen CPU kernels the reference dispatches to (oneDNN conv, native_batch_norm, ...)
+    # the CPU baseline leg is one of the places allowed to run the oracle / the staged reference
     from oracle import decoder_torch as O
+    from oracle import stage_reference as SREF
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
-    W = O.TorchWeights(synth.make_state_dict(cfg, 0, True))
-    inp = synth.make_inputs(1, frames, 1000, cfg)
+    sd = synth.make_state_dict(cfg, 0, True)
+    inp = synth.make_inputs(batch, frames, 1000, cfg, with_noise=False)
+    ref = None
+    try:
+        ref = SREF.build_reference(cfg, sd)
+    except Exception:  # noqa: BLE001
+        ref = None
+    if ref is not None:
+        kind, what = "reference", "UNMODIFIED reference Modules/%s.py Decoder (staged under baseline/_ref), its own RNG draws" % cfg.type
+
+        def fwd():
+            with torch.no_grad():
+                return ref(inp["asr"], inp["F0_curve"], inp["N"], inp["s"])
+    else:
+        kind, what = "port", ("torch-CPU port of the reference decoder (oracle/decoder_torch.py: the same ATen/oneDNN kernels the "
+                              "reference dispatches to); baseline/_ref is not staged on this box")
+        W = O.TorchWeights(sd)
+        noise = torch.randn(batch, 600 * frames, 9)
+
+        def fwd():
+            return O.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], noise)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], inp["noise"])
+        out = fwd()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    assert tuple(out.shape) == (1, 1, 600 * frames) and bool(torch.isfinite(out).all())
-    secs = frames * 600 / SR
+    assert tuple(out.shape) == (batch, 1, 600 * frames) and bool(torch.isfinite(out).all())
+    secs = batch * frames * 600 / SR
     mean = sum(times) / len(times)
-    return {"value": secs / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": "1 utterance x %.1f s (T=%d) of the workload; torch-CPU port of the reference decoder (same ATen/oneDNN "
-                      "kernels the reference dispatches to; the reference itself is pure PyTorch and cannot travel), "
-                      "%d threads, %d runs after %d warm-up, mean %.2f s/utterance" % (secs, frames, torch.get_num_threads(),
-                                                                                     steps, warmup, mean),
+    return {"value": secs / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+            "sample": "%d utterances x %.1f s (T=%d) of the workload per step; %s; %d threads, %d steps after %d warm-up, "
+                      "mean %.2f s/step" % (batch, frames * 600 / SR, frames, what, torch.get_num_threads(), steps, warmup, mean),
             "ms_per_step": mean * 1e3}
 
 
@@ -107,7 +135,7 @@ def run_reference(a, rank, world):
         return None
     frames = a.cpu_frames or a.frames
     steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
-    r = cpu_port_run(a.variant, frames, steps, warmup)
+    r = cpu_reference_run(a.variant, frames, steps, warmup, batch=a.cpu_batch)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
@@ -166,7 +194,7 @@ class ClockSampler:
 
 # DRAM bytes per launch of a kernel category, from the committed ncu launch list (profiles/<tag>_traffic.json,
 # written by tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`)
-CATEGORY_KERNELS = {"conv_pipe": ("conv_pipe_kernel",), "conv_fused": ("conv_fused_kernel",), "conv_tc": ("conv_tc_kernel",),
+CATEGORY_KERNELS = {"conv_row": ("conv_row_kernel",), "conv_pipe": ("conv_pipe_kernel",), "conv_fused": ("conv_fused_kernel",), "conv_tc": ("conv_tc_kernel",),
                     "conv_simt": ("conv_simt_kernel",)}
 
 
@@ -188,6 +216,143 @@ def ncu_traffic(category):
 
 
 # ------------------------------------------------------------------------------------------------
+# auxiliary measurements (outside the timed region of the headline; none of them may break the main line)
+# ------------------------------------------------------------------------------------------------
+def _event_ms(torch, fn, warmup, iters):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def aux_cfg5(torch, dev, precision):
+    """BASELINE configs[4]: iSTFTNet decoder, long-form 60 s utterances (8 per batch), one GPU, inputs resident."""
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.config import DecoderConfig
+    from styletts2_lite_b200.decoder import B200Decoder
+    cfg = DecoderConfig.istftnet()
+    B, T = 8, 2400
+    m = B200Decoder(cfg, precision)
+    m.load_state_dict(synth.make_state_dict(cfg, 0, True))
+    m = m.to(dev).eval()
+    inp = {k: v.to(dev) for k, v in synth.make_inputs(B, T, seed=1005, cfg=cfg, with_noise=False).items()}
+    out = [None]
+
+    def fwd(i):
+        with torch.no_grad():
+            out[0] = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], seed=77 + i)
+    ms = _event_ms(torch, fwd, 2, 5)
+    ok = tuple(out[0].shape) == (B, 1, 600 * T) and bool(torch.isfinite(out[0]).all())
+    res = {"workload": "istftnet Decoder.forward, %d utterances x 60 s (T=%d), inputs resident" % (B, T), "precision": precision,
+           "ms": round(ms, 3), "audio_s_per_s": round(B * 60.0 / (ms / 1e3), 1), "launches": int(m.last_launch_count()), "finite": ok}
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
+def aux_eager_gpu(torch, dev, variant, B, T):
+    """The pre-existing GPU path: the reference decoder through PyTorch eager (cuDNN / ATen kernels) on the same GPU and shape,
+    fp32 and bf16 autocast.  The unmodified reference modules when staged (baseline/_ref), else the torch port of them."""
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.config import DecoderConfig
+    from oracle import decoder_torch as O
+    from oracle import stage_reference as SREF
+    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    sd = synth.make_state_dict(cfg, 0, True)
+    inp = {k: v.to(dev) for k, v in synth.make_inputs(B, T, seed=1002, cfg=cfg, with_noise=False).items()}
+    ref = None
+    try:
+        ref = SREF.build_reference(cfg, sd)
+    except Exception:  # noqa: BLE001
+        ref = None
+    if ref is not None:
+        ref = ref.to(dev)
+        kind = "reference"
+
+        def fwd(i):
+            with torch.no_grad():
+                return ref(inp["asr"], inp["F0_curve"], inp["N"], inp["s"])
+    else:
+        kind = "port"
+        W = O.TorchWeights({k: v.to(dev) for k, v in sd.items()})
+        noise = torch.randn(B, 600 * T, 9, device=dev)
+
+        def fwd(i):
+            return O.decoder_forward(W, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], noise)
+    res = {"kind": kind, "workload": "%s Decoder.forward through PyTorch eager on the GPU, %d x %.1f s" % (variant, B, T * 600 / SR)}
+    secs = B * T * 600 / SR
+    ms32 = _event_ms(torch, fwd, 1, 3)
+    res["fp32"] = {"ms": round(ms32, 2), "audio_s_per_s": round(secs / (ms32 / 1e3), 1)}
+
+    def fwd_bf16(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return fwd(i)
+    try:
+        ms16 = _event_ms(torch, fwd_bf16, 1, 3)
+        res["bf16_autocast"] = {"ms": round(ms16, 2), "audio_s_per_s": round(secs / (ms16 / 1e3), 1)}
+    except Exception as ex:  # noqa: BLE001
+        res["bf16_autocast"] = {"error": str(ex)[:200]}
+    del ref
+    torch.cuda.empty_cache()
+    return res
+
+
+def aux_cfg4(torch, dist, m, dev, rank, world, precision):
+    """BASELINE configs[3]: 1024 utterances x 10 s sharded over the ranks (parallel.shard_range), decoded in micro-batches of 32
+    per rank, every micro-batch sent into its slice of ONE preallocated [1024,1,240000] buffer on rank 0 while the next one
+    is being decoded (parallel.ShardedGather).  Timed on the device, max over ranks, second of two passes."""
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.parallel import ShardedGather
+    N_UTT, T, MB = 1024, 400, 32
+    S = 600 * T
+    g = ShardedGather(N_UTT, S, MB, dev)
+    inp = {k: v.to(dev) for k, v in synth.make_inputs(MB, T, seed=1004 + rank, cfg=m.cfg, with_noise=False).items()}
+    mine = g.my_micro_batches()
+
+    def one_pass(seed0):
+        for j, (lo, hi) in enumerate(mine):
+            n = hi - lo
+            with torch.no_grad():
+                out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=seed0 + j, precision=precision)
+            g.submit(j, out)
+        return g.finish()
+    one_pass(100)                                    # warm-up pass (allocators, NCCL connections)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for j, (lo, hi) in enumerate(mine):
+        n = hi - lo
+        with torch.no_grad():
+            out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=5000 + j, precision=precision)
+        g.submit(j, out)
+    e1.record()                                      # the last forward is issued; what follows is the exposed tail of the gather
+    full = g.finish()
+    e2.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, tail_ms = float(t[0].item()), float(t[1].item())
+    ok = True
+    if rank == 0:
+        ok = tuple(full.shape) == (N_UTT, 1, S) and bool(torch.isfinite(full[::97]).all())
+    return {"workload": "hifigan Decoder, 1024 utterances x 10 s sharded over %d GPUs, micro-batches of %d, gathered to rank 0" % (world, MB),
+            "utterances_per_rank": [hi - lo for lo, hi in g.spans], "micro_batches_per_rank": len(mine), "precision": precision,
+            "ms": round(ms, 2), "audio_s_per_s": round(N_UTT * 10.0 / (ms / 1e3), 1),
+            "gather_bytes_to_rank0": int((N_UTT - (g.spans[0][1] - g.spans[0][0])) * S * 4),
+            "exposed_gather_tail_ms": round(tail_ms, 3), "finite": ok,
+            "limiter": "rank 0 ingests (world-1)/world of 983 MB over its NVLink ports while it decodes its own shard; only the "
+                       "tail after the last forward (exposed_gather_tail_ms) is not hidden"}
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(a, rank, local_rank, world):
@@ -196,7 +361,7 @@ def run_b200(a, rank, local_rank, world):
     from styletts2_lite_b200 import synth
     from styletts2_lite_b200.config import DecoderConfig
     from styletts2_lite_b200.decoder import B200Decoder
-    from styletts2_lite_b200.parallel import gather_waveforms
+    from styletts2_lite_b200.parallel import ShardedGather
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
@@ -220,29 +385,43 @@ def run_b200(a, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: one job = world x B utterances, one micro-batch per rank per step, straight into rank 0's preallocated buffer
+    gatherer = ShardedGather(B * world, S, B, dev) if world > 1 else None
+    gather_calls = [0]
+
+    def submit_gather(out):
+        gatherer.submit(0, out)
+        gather_calls[0] += 1
+        if gather_calls[0] % 8 == 0:                 # bound the number of in-flight sends (their sources are kept alive)
+            gatherer.finish()
+
     def step_resident(i):
         with torch.no_grad():
             out = m(res["asr"], res["F0_curve"], res["N"], res["s"], seed=1234 + i)
         if world > 1:
-            gather_waveforms(out)
+            submit_gather(out)
         return out
 
     # end to end through the package's host-fed serving loop (styletts2_lite_b200/streaming.py): every step copies its
     # inputs from pinned host memory and its waveform back to pinned host memory; the copies of neighbouring steps
     # overlap the decoder on separate streams
     from styletts2_lite_b200.streaming import PipelinedDecoder
-    pipe = PipelinedDecoder(m, dev, after_forward=(gather_waveforms if world > 1 else None))
+    pipe = PipelinedDecoder(m, dev, after_forward=(submit_gather if world > 1 else None))
 
     def run_e2e(steps, first_seed):
         seeds = iter(range(first_seed, first_seed + steps))
         last = None
         for wav in pipe.decode((host for _ in range(steps)), seeds):
             last = wav
+        if gatherer is not None:
+            gatherer.finish()
         return last
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
+        if gatherer is not None:
+            gatherer.finish()
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_wall = time.perf_counter()
@@ -250,6 +429,8 @@ def run_b200(a, rank, local_rank, world):
             flush.fill_(i & 0xFF)                    # L2 flush, outside the event pair
             evs[i][0].record()
             fn(warmup + i)
+            if gatherer is not None and i == steps - 1:
+                gatherer.finish()                    # every gather of the timed steps completes inside the last event pair
             evs[i][1].record()
         barrier()
         wall = time.perf_counter() - t_wall
@@ -293,6 +474,8 @@ def run_b200(a, rank, local_rank, world):
                 for k in p[c]:
                     prof_acc[c][k] += p[c][k]
     m.set_profiling(False)
+    if gatherer is not None:
+        gatherer.finish()
     torch.cuda.synchronize()
 
     audio_s = B * world * S / SR
@@ -341,6 +524,13 @@ def run_b200(a, rank, local_rank, world):
         g = prof_acc["affine_act"]["bytes"] / prof_acc["affine_act"]["ms"] / 1e6
         roof["affine_act_hbm"] = {"achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak}
 
+    cfg4 = None
+    if world > 1 and not a.no_aux and a.precision != "fp32" and a.variant == "hifigan":
+        # BASELINE configs[3] on every rank (a collective job); after the headline's timed regions
+        try:
+            cfg4 = aux_cfg4(torch, dist, m, dev, rank, world, a.precision)
+        except Exception as ex:  # noqa: BLE001
+            cfg4 = {"error": str(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,19 +548,30 @@ def run_b200(a, rank, local_rank, world):
             "clocks": clocks, "roofline": roof, "wall_s_timed_region": round(wall, 3),
             "per_step_ms": [round(x, 3) for x in per_step]}
     if world == 1 and not a.no_cpu_baseline:
-        r = cpu_port_run(a.variant, a.cpu_frames or a.frames, 2, 1)
+        r = cpu_reference_run(a.variant, a.cpu_frames or a.frames, 2, 1, batch=a.cpu_batch)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    if world == 1 and not a.no_cpu_baseline and not a.no_chain and a.precision != "fp32":
+    if cfg4 is not None:
+        line["cfg4_sharded_1024x10s"] = cfg4
+    aux_on = not a.no_aux and a.precision != "fp32"
+    if world == 1 and aux_on and not a.no_cpu_baseline and not a.no_chain:
         # auxiliary, outside the timed region: BASELINE configs[2] (32 x 8 s, token ids -> waveform through the TextEncoder,
         # the prosody predictor, the length regulator and the Decoder of this library); never allowed to break the main line
         try:
-            del m
-            torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from bench_chain import run_chain
             line["full_path_cfg3"] = run_chain(32, 64, 320, a.precision, 5)
         except Exception as ex:  # noqa: BLE001
             line["full_path_cfg3"] = {"error": str(ex)[:300]}
+    if world == 1 and aux_on:
+        del m
+        torch.cuda.empty_cache()
+        for key, fn in (("cfg5_istftnet_60s", lambda: aux_cfg5(torch, dev, a.precision)),
+                        ("eager_gpu", lambda: aux_eager_gpu(torch, dev, a.variant, B, T))):
+            try:
+                line[key] = fn()
+            except Exception as ex:  # noqa: BLE001
+                line[key] = {"error": str(ex)[:300]}
+                torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
     return line

@@ -34,7 +34,7 @@ namespace st2 {
 
 static constexpr int RW_THREADS = 640;                    // 20 warps (ptxas grants 96 registers from 545 threads up)
 static constexpr int RW_X0 = 2;                          // first transform warp
-static constexpr int RW_NA = 2;                          // operand buffers
+static constexpr int RW_NA_MAX = 3;                      // operand buffers: p.na = 2 or 3
 static constexpr int RW_MAXGRID = 160;                   // statistics buffers are sized for at most this many CTAs
 
 struct RowParams {
@@ -47,6 +47,7 @@ struct RowParams {
     int R, nblk, tail_rows;     // activation blocks: R rows each, nblk per macro tile, the last one loads tail_rows rows
     int xslot;                  // bytes per activation ring slot
     int a_bytes;                // bytes per operand buffer (nblk * R rows)
+    int na;                     // operand buffers (macro tiles in flight between transform and MMA): 2 or 3
     int lw, xd;                 // active transform warps, depth of each private activation ring
     int nacc, nacc_log2, tmem_cols;
     int nres, nr;               // fp16 sources added by the identity MMA (0, 1, 2), residual ring stages
@@ -125,8 +126,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_a = smem;                                              // RW_NA x [a_rows][C] 16-bit, swizzled
-    uint8_t* smem_w = smem_a + (size_t)RW_NA * p.a_bytes;                // ntaps x [C][C] resident taps
+    uint8_t* smem_a = smem;                                              // na x [a_rows][C] 16-bit, swizzled
+    uint8_t* smem_w = smem_a + (size_t)p.na * p.a_bytes;                // ntaps x [C][C] resident taps
     uint8_t* smem_i = smem_w + (size_t)p.ntaps * btile;                  // fp16 identity [C][C]
     uint8_t* smem_r = smem_i + btile;                                    // nr x nres x [128][C] fp16 residual tiles
     uint8_t* smem_x = smem_r + (size_t)p.nr * p.nres * rtile;            // lw x xd activation slots
@@ -134,9 +135,9 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + C);
     uint64_t* w_full = bars;                    // [1]
-    uint64_t* a_full = bars + 1;                // [2]
-    uint64_t* a_empty = a_full + 2;             // [2]
-    uint64_t* acc_full = a_empty + 2;           // [8]
+    uint64_t* a_full = bars + 1;                // [3]
+    uint64_t* a_empty = a_full + 3;             // [3]
+    uint64_t* acc_full = a_empty + 3;           // [8]
     uint64_t* acc_empty = acc_full + 8;         // [8]
     uint64_t* r_full = acc_empty + 8;           // [nr]
     uint64_t* r_empty = r_full + p.nr;          // [nr]
@@ -159,7 +160,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         if (p.nres >= 1) prefetch_tmap(&map_r);
         if (p.nres >= 2) prefetch_tmap(&map_o);
         mbar_init(w_full, 1);
-        for (int i = 0; i < RW_NA; ++i) {
+        for (int i = 0; i < p.na; ++i) {
             mbar_init(&a_full[i], (uint32_t)p.nblk);
             mbar_init(&a_empty[i], 1);
         }
@@ -246,9 +247,9 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             uint32_t sc = 0;                            // sub-tile counter -> accumulator sc % nacc
             uint32_t r_stage = 0, r_par = 0;
             int b = m_lo / p.mmt, mm = m_lo - b * p.mmt;
+            uint32_t buf = 0, buf_par = 0;              // operand buffer of macro tile mc: mc % na, fill parity (mc / na) & 1
             for (int mc = 0; mc < m_n; ++mc) {
-                const uint32_t buf = (uint32_t)mc & 1u;
-                mbar_wait(&a_full[buf], ((uint32_t)mc >> 1) & 1u);
+                mbar_wait(&a_full[buf], buf_par);
                 tc_fence_after();
                 for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
                     const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
@@ -284,6 +285,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     umma_commit(&acc_full[acc]);
                 }
                 umma_commit(&a_empty[buf]);
+                if (++buf == (uint32_t)p.na) { buf = 0; buf_par ^= 1u; }
                 if (++mm == p.mmt) { mm = 0; ++b; }
             }
         }
@@ -347,7 +349,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     cf.nc01 = make_float2(-c.x, -c.y); cf.nc23 = make_float2(-c.z, -c.w);
                     cached_b = b;
                 }
-                const uint32_t buf = (uint32_t)mi & 1u, fill = (uint32_t)mi >> 1;
+                const uint32_t fill = (uint32_t)mi / (uint32_t)p.na, buf = (uint32_t)mi - fill * (uint32_t)p.na;
                 const uint32_t slot = (uint32_t)tw * (uint32_t)p.xd + xi;
                 const int r0 = blk * p.R;                                        // first operand row of this block
                 const int nvalid = (blk == p.nblk - 1) ? p.tail_rows : p.R;      // rows the TMA box really loaded
@@ -581,7 +583,9 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
     // 64-channel k = 3 layer) with the largest macro tile that fits (the halo is transformed once per macro tile), then the
     // deepest rings; 2 KB blocks only where nothing else fits
     for (int slot_bytes = 4096; slot_bytes >= 2048 && !ok; slot_bytes >>= 1) {
+        if (tune().row_slot && slot_bytes != tune().row_slot) continue;
         for (int sub = 4; sub >= 1 && !ok; sub >>= 1) {
+            if (tune().row_sub && sub != tune().row_sub) continue;
             const int mr = sub * 128 + span;
             int R = slot_bytes / (C * xes);
             R = R / brows * brows;
@@ -590,8 +594,12 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
             const int tail = mr - (nblk - 1) * R;
             const int64_t a_bytes = ((int64_t)nblk * R * arow + 1023) & ~(int64_t)1023;
             const int xslot = R * C * xes;
-            const int lw_max = RW_NA * nblk < ntw ? RW_NA * nblk : ntw;
-            const int64_t fixed = RW_NA * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
+            // three operand buffers for single-sub-tile macro tiles when they fit (the MMA of tile m otherwise gates the
+            // transform of tile m + 2 after every 128 rows)
+            for (int na = (sub == 1 ? 3 : 2); na >= 2 && !ok; --na) {
+            if (tune().row_na && na != tune().row_na) continue;
+            const int lw_max = na * nblk < ntw ? na * nblk : ntw;
+            const int64_t fixed = na * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
             const int nr_max = p.nres ? 4 : 0, nr_min = p.nres ? 2 : 0;
             // as many transform warps as have a ring (at least 10; 7 for the smallest macro tile) with the deepest rings that fit
             for (int lw = lw_max; lw >= (lw_max < 10 ? lw_max : (sub == 1 ? 7 : 10)) && !ok; --lw) {
@@ -600,12 +608,13 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
                         const int64_t tot = fixed + (int64_t)nr * p.nres * rtile + (int64_t)lw * xd * xslot;
                         if (tot <= budget) {
                             p.sub = sub; p.R = R; p.nblk = nblk; p.tail_rows = tail; p.xslot = xslot; p.a_bytes = (int)a_bytes;
-                            p.lw = lw; p.xd = xd; p.nr = nr;
+                            p.lw = lw; p.xd = xd; p.nr = nr; p.na = na;
                             *smem_out = (size_t)tot + 1024;
                             ok = true;
                         }
                     }
                 }
+            }
             }
         }
     }
@@ -690,8 +699,8 @@ int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, 
         desc->grid = grid; desc->J = p.J; desc->nwarp = 4 * nch; desc->mmt = p.mmt; desc->tq = p.tq; desc->tr = p.tr; desc->C = C;
     }
     if (tune().verbose)
-        fprintf(stderr, "conv_row: C=%d taps=%d step=%d x16=%d y16=%d nres=%d sub=%d R=%d nblk=%d tail=%d lw=%d xd=%d nr=%d smem=%zu grid=%d tq=%d J=%d\n",
-                C, p.ntaps, p.tap_step, a.x16in, a.y16out, p.nres, p.sub, p.R, p.nblk, p.tail_rows, p.lw, p.xd, p.nr, smem, grid, p.tq, p.J);
+        fprintf(stderr, "conv_row: C=%d taps=%d step=%d x16=%d y16=%d nres=%d sub=%d R=%d nblk=%d tail=%d na=%d lw=%d xd=%d nr=%d smem=%zu grid=%d tq=%d J=%d\n",
+                C, p.ntaps, p.tap_step, a.x16in, a.y16out, p.nres, p.sub, p.R, p.nblk, p.tail_rows, p.na, p.lw, p.xd, p.nr, smem, grid, p.tq, p.J);
     ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * (4 * nch) * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
                 "conv_row: statistics buffer too small");
     // the opt-in to > 48 KB of dynamic shared memory is per device: once per (device, variant)

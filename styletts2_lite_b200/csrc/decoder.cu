@@ -311,7 +311,8 @@ const TuneField kTuneFields[] = {
     {"verbose", "ST2_PIPE_VERBOSE", &Tune::verbose, true}, {"tc_halo", "ST2_TC_HALO", &Tune::tc_halo, false},
     {"lstm_bt", "ST2_LSTM_BT", &Tune::lstm_bt, false}, {"no_xt16", "ST2_NO_XT16", &Tune::no_xt16, true},
     {"no_run16", "ST2_NO_RUN16", &Tune::no_run16, true}, {"no_xu16", "ST2_NO_XU16", &Tune::no_xu16, true},
-    {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}};
+    {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}, {"row_sub", "ST2_ROW_SUB", &Tune::row_sub, false},
+    {"row_slot", "ST2_ROW_SLOT", &Tune::row_slot, false}, {"row_na", "ST2_ROW_NA", &Tune::row_na, false}};
 Tune& tune_storage() {
     static Tune t = [] {
         Tune v;

@@ -1,12 +1,17 @@
 """Utterance sharding across the GPUs of one box.
 
-Every op of the decoder is per utterance, so ranks never exchange activations: rank r of W
-decodes utterances [r*B/W, (r+1)*B/W) with replicated weights, and the only collective is the
-gather of the waveforms to rank 0 (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Every op of the decoder is per utterance, so ranks never exchange activations: rank r of W decodes utterances
+[r*B/W, (r+1)*B/W) with replicated weights, and the only collective is the gather of the waveforms to rank 0 (NCCL over
+NVLink on the GPU box, gloo in the CPU tests).
+
+`ShardedGather` is the production path: rank 0 owns ONE preallocated [n_total, 1, S] buffer, every micro-batch a rank decodes is
+sent straight into its slice of that buffer (point-to-point, no staging copies, no concatenation, no per-step allocation), and
+the transfers are issued on a side stream behind an event of the compute stream, so the gather of micro-batch k overlaps the
+forward of micro-batch k + 1.  `gather_waveforms` is the one-shot convenience form on top of the same buffer logic.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -21,20 +26,136 @@ def shard_range(n_utterances: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class ShardedGather:
+    """Gather of a job of `n_total` utterances, decoded in micro-batches of at most `micro_batch` per rank, to rank `dst`.
+
+        g = ShardedGather(n_total, S, micro_batch, device)
+        for j, (lo, hi) in enumerate(g.my_micro_batches()):      # utterance indices of this rank, global numbering
+            wave = decoder(...inputs of utterances lo..hi...)    # [hi - lo, 1, S]
+            g.submit(j, wave)                                    # asynchronous: returns at once
+        full = g.finish()                                        # [n_total, 1, S] on dst (None elsewhere), all transfers done
+
+    The buffer on `dst` is allocated once and reused by every job of the same shape (`reset()` starts the next one)."""
+
+    def __init__(self, n_total: int, samples: int, micro_batch: int, device: torch.device, dst: int = 0,
+                 dtype: torch.dtype = torch.float32):
+        self.n_total, self.S, self.mb, self.dst = int(n_total), int(samples), max(1, int(micro_batch)), dst
+        self.device = torch.device(device)
+        self.on = _dist_on()
+        self.world = dist.get_world_size() if self.on else 1
+        self.rank = dist.get_rank() if self.on else 0
+        self.spans = [shard_range(self.n_total, r, self.world) for r in range(self.world)]
+        self.full = torch.empty((self.n_total, 1, self.S), dtype=dtype, device=self.device) if self.rank == dst else None
+        self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._works: List = []
+        self._keep: List[torch.Tensor] = []
+
+    def micro_batches_of(self, rank: int) -> List[Tuple[int, int]]:
+        a, b = self.spans[rank]
+        return [(lo, min(lo + self.mb, b)) for lo in range(a, b, self.mb)]
+
+    def my_micro_batches(self) -> List[Tuple[int, int]]:
+        return self.micro_batches_of(self.rank)
+
+    def reset(self) -> None:
+        self.finish()
+
+    def submit(self, j: int, wave: torch.Tensor) -> None:
+        """Micro-batch j of this rank is ready on the current stream: move it (and, on dst, everybody's j-th micro-batch)."""
+        mine = self.my_micro_batches()
+        lo, hi = mine[j]
+        if tuple(wave.shape) != (hi - lo, 1, self.S):
+            raise ValueError("micro-batch %d: expected %s, got %s" % (j, (hi - lo, 1, self.S), tuple(wave.shape)))
+        wave = wave.contiguous()
+
+        def issue():
+            if self.rank == self.dst:
+                self.full[lo:hi].copy_(wave, non_blocking=True)
+                if not self.on:
+                    return
+                ops = []
+                for r in range(self.world):
+                    if r == self.dst:
+                        continue
+                    theirs = self.micro_batches_of(r)
+                    if j < len(theirs):
+                        ops.append(dist.P2POp(dist.irecv, self.full[theirs[j][0]:theirs[j][1]], r))
+                if ops:
+                    self._works.extend(dist.batch_isend_irecv(ops))
+            elif self.on:
+                self._works.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, wave, self.dst)]))
+                self._keep.append(wave)                     # alive until finish(): the send reads it asynchronously
+
+        # ranks with fewer micro-batches than dst's j simply have nothing to send; dst posts only the receives that exist
+        if self.side is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                issue()
+                wave.record_stream(self.side)
+        else:
+            issue()
+
+    def drain_remote(self) -> None:
+        """dst only: post the receives of micro-batches that other ranks have beyond dst's own count (ragged shards)."""
+        if not (self.on and self.rank == self.dst):
+            return
+        mine = len(self.my_micro_batches())
+        ops = []
+        for r in range(self.world):
+            if r == self.dst:
+                continue
+            for lo, hi in self.micro_batches_of(r)[mine:]:
+                ops.append(dist.P2POp(dist.irecv, self.full[lo:hi], r))
+        if ops:
+            ctx = torch.cuda.stream(self.side) if self.side is not None else _Null()
+            with ctx:
+                self._works.extend(dist.batch_isend_irecv(ops))
+
+    def finish(self) -> Optional[torch.Tensor]:
+        """Wait for every transfer issued so far (the current stream waits on the side stream); returns the buffer on dst."""
+        self.drain_remote()
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self._keep.clear()
+        return self.full
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_ONE_SHOT: Dict[tuple, ShardedGather] = {}
+
+
 def gather_waveforms(wave: torch.Tensor, counts: Optional[List[int]] = None, dst: int = 0) -> Optional[torch.Tensor]:
-    """Gather per-rank waveforms [b_r,1,S] to `dst`; returns the concatenated [sum b_r,1,S] there, None elsewhere.
-    `counts` = utterances per rank (needed when shards are ragged; equal shards by default)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    """Gather per-rank waveforms [b_r,1,S] to `dst`; returns the [sum b_r,1,S] buffer there (a cached buffer that the next
+    call with the same shapes overwrites), None elsewhere.  `counts` = utterances per rank (equal shards by default; with
+    ragged shards they must follow shard_range)."""
+    if not _dist_on():
         return wave
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world = dist.get_world_size()
     counts = counts or [wave.shape[0]] * world
-    bmax = max(counts)
-    send = wave
-    if wave.shape[0] < bmax:                      # pad ragged shards to a common shape for the collective
-        send = torch.zeros((bmax,) + tuple(wave.shape[1:]), dtype=wave.dtype, device=wave.device)
-        send[: wave.shape[0]] = wave
-    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send.contiguous(), bufs, dst=dst)
-    if rank != dst:
-        return None
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    n_total, S = int(sum(counts)), int(wave.shape[-1])
+    key = (n_total, S, tuple(counts), wave.device, wave.dtype, dst)
+    g = _ONE_SHOT.get(key)
+    if g is None:
+        g = ShardedGather(n_total, S, max(counts), wave.device, dst=dst, dtype=wave.dtype)
+        if [b - a for a, b in g.spans] != list(counts):
+            raise ValueError("counts %s do not follow shard_range (%s)" % (counts, [b - a for a, b in g.spans]))
+        _ONE_SHOT[key] = g
+    if wave.shape[0] > 0:
+        g.submit(0, wave)
+    return g.finish()

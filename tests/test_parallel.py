@@ -1,4 +1,5 @@
-"""CPU tests of the N>1 host logic (gloo, world_size 2): sharding and the gather to rank 0."""
+"""CPU tests of the N>1 host logic (gloo, world_size 2): sharding, the one-shot gather and the micro-batched ShardedGather
+(every micro-batch lands in its slice of ONE preallocated buffer on rank 0)."""
 import os
 
 import pytest
@@ -6,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from styletts2_lite_b200.parallel import gather_waveforms, shard_range
+from styletts2_lite_b200.parallel import ShardedGather, gather_waveforms, shard_range
 
 
 def test_shard_range_is_a_partition():
@@ -21,29 +22,60 @@ def test_shard_range_is_a_partition():
         shard_range(8, 2, 2)
 
 
-def _worker(rank, world, port, ragged, q):
+def test_sharded_gather_single_process_is_a_copy():
+    g = ShardedGather(5, 12, 2, torch.device("cpu"))
+    full = torch.arange(5 * 12, dtype=torch.float32).reshape(5, 1, 12)
+    assert g.my_micro_batches() == [(0, 2), (2, 4), (4, 5)]
+    for j, (lo, hi) in enumerate(g.my_micro_batches()):
+        g.submit(j, full[lo:hi].clone())
+    assert torch.equal(g.finish(), full)
+    with pytest.raises(ValueError):
+        g.submit(0, full[0:1])
+
+
+def _worker(rank, world, port, mode, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n, S = (5 if ragged else 6), 48
-        a, b = shard_range(n, rank, world)
-        counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
-        full = torch.arange(n * S, dtype=torch.float32).reshape(n, 1, S)
-        out = gather_waveforms(full[a:b].clone(), counts)
-        if rank == 0:
-            q.put(bool(torch.equal(out, full)))
+        S = 48
+        if mode in ("equal", "ragged"):
+            n = 5 if mode == "ragged" else 6
+            a, b = shard_range(n, rank, world)
+            counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+            full = torch.arange(n * S, dtype=torch.float32).reshape(n, 1, S)
+            out = gather_waveforms(full[a:b].clone(), counts)
+            again = gather_waveforms(full[a:b].clone() + 1.0, counts)        # the cached buffer is reused, not re-allocated
+            if rank == 0:
+                q.put(bool(torch.equal(again, full + 1.0)) and out.data_ptr() == again.data_ptr())
+            else:
+                assert out is None and again is None
         else:
-            assert out is None
+            # micro-batched job: 11 utterances, micro-batches of 2 -> rank 0 has 3 micro-batches (6 utterances), rank 1 has 3 (5)
+            n, mb = (11, 2) if mode == "micro" else (9, 4)                   # "micro_uneven": 5 + 4 utterances, 2 vs 1 micro-batches
+            full = torch.arange(n * S, dtype=torch.float32).reshape(n, 1, S)
+            g = ShardedGather(n, S, mb, torch.device("cpu"))
+            for rep in range(2):                                             # the same object serves consecutive jobs
+                for j, (lo, hi) in enumerate(g.my_micro_batches()):
+                    g.submit(j, full[lo:hi].clone() + rep)
+                out = g.finish()
+                if rank == 0:
+                    ok = bool(torch.equal(out, full + rep))
+                    if rep == 1:
+                        q.put(ok)
+                    else:
+                        assert ok
+                else:
+                    assert out is None
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ragged", [False, True])
-def test_gather_to_rank0_gloo(ragged):
+@pytest.mark.parametrize("mode", ["equal", "ragged", "micro", "micro_uneven"])
+def test_gather_to_rank0_gloo(mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29711 + (1 if ragged else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ragged, q)) for r in range(2)]
+    port = 29711 + ["equal", "ragged", "micro", "micro_uneven"].index(mode)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
