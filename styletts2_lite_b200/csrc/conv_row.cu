@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "fused_ptx.cuh"
@@ -34,7 +36,14 @@ namespace st2 {
 
 static constexpr int RW_THREADS = 640;                    // 20 warps (ptxas grants 96 registers from 545 threads up)
 static constexpr int RW_X0 = 2;                          // first transform warp
-static constexpr int RW_NA_MAX = 3;                      // operand buffers: p.na = 2 or 3
+#ifndef RW_SECTIONS
+// 1: operand buffers are handed over per 128-row section (the MMA of sub-tile s starts when its rows are transformed, the
+// transform of tile m + na starts when the first sub-tiles of tile m are done); 0: per macro tile.  Measured on one box (build
+// variants, tools/gpu_r2h.sh): sections lose on the k >= 7 layers (C = 32 k = 7: 0.284 -> 0.330 ms) -- the extra barrier waits
+// and commits serialise in the single MMA-issuing thread -- and change nothing elsewhere, so the default is per macro tile.
+#define RW_SECTIONS 0
+#endif
+static constexpr int RW_NSEC = 5;                        // 128-row sections of an operand buffer: sub (<= 4) + the halo section
 static constexpr int RW_MAXGRID = 160;                   // statistics buffers are sized for at most this many CTAs
 
 struct RowParams {
@@ -113,7 +122,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
                 const __grid_constant__ CUtensorMap map_o, const RowParams p) {
     constexpr int C = 32 * NCH;
-    constexpr int NEW = 4 * NCH;                           // epilogue warps: one group of four TMEM lane quarters per column chunk
+    constexpr int NEW = 4 * NCH;                           // epilogue warps: four TMEM lane quarters per 32-column chunk
     constexpr int NTW = 18 - NEW;                          // transform warps: 14 (C = 32) or 10 (C = 64)
     constexpr int W_EPI0 = RW_X0 + NTW;                    // first epilogue warp
     constexpr uint32_t arow = NCH == 1 ? 64u : 128u;       // bytes per operand row (K = C, 16-bit)
@@ -135,9 +144,9 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + C);
     uint64_t* w_full = bars;                    // [1]
-    uint64_t* a_full = bars + 1;                // [3]
-    uint64_t* a_empty = a_full + 3;             // [3]
-    uint64_t* acc_full = a_empty + 3;           // [8]
+    uint64_t* a_full = bars + 1;                // [3 buffers][RW_NSEC sections of 128 operand rows]
+    uint64_t* a_empty = a_full + 3 * RW_NSEC;   // [3][RW_NSEC]
+    uint64_t* acc_full = a_empty + 3 * RW_NSEC; // [8]
     uint64_t* acc_empty = acc_full + 8;         // [8]
     uint64_t* r_full = acc_empty + 8;           // [nr]
     uint64_t* r_empty = r_full + p.nr;          // [nr]
@@ -160,10 +169,19 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         if (p.nres >= 1) prefetch_tmap(&map_r);
         if (p.nres >= 2) prefetch_tmap(&map_o);
         mbar_init(w_full, 1);
-        for (int i = 0; i < p.na; ++i) {
-            mbar_init(&a_full[i], (uint32_t)p.nblk);
-            mbar_init(&a_empty[i], 1);
-        }
+        // operand buffers are handed over in sections of 128 rows: section s < sub is written by 128 / R blocks and read by
+        // sub-tiles s - 1 and s, the halo section (s == sub) by the remaining blocks and the last sub-tile
+        const int bps = 128 / p.R;
+        for (int i = 0; i < p.na; ++i)
+            for (int sec = 0; sec <= p.sub; ++sec) {
+                if (RW_SECTIONS) {
+                    mbar_init(&a_full[i * RW_NSEC + sec], (uint32_t)(sec < p.sub ? bps : p.nblk - p.sub * bps));
+                    mbar_init(&a_empty[i * RW_NSEC + sec], (sec == 0 || sec == p.sub) ? 1u : 2u);
+                } else {
+                    mbar_init(&a_full[i * RW_NSEC + sec], (uint32_t)p.nblk);
+                    mbar_init(&a_empty[i * RW_NSEC + sec], 1u);
+                }
+            }
         for (int i = 0; i < 8; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], (uint32_t)(4 * NCH));   // the warps that drain one accumulator
@@ -249,9 +267,23 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             int b = m_lo / p.mmt, mm = m_lo - b * p.mmt;
             uint32_t buf = 0, buf_par = 0;              // operand buffer of macro tile mc: mc % na, fill parity (mc / na) & 1
             for (int mc = 0; mc < m_n; ++mc) {
-                mbar_wait(&a_full[buf], buf_par);
-                tc_fence_after();
-                for (int s = 0; s < p.sub && mm * sub_rows + s * 128 < p.M; ++s, ++sc) {
+                uint64_t* af = a_full + buf * RW_NSEC;
+                uint64_t* ae = a_empty + buf * RW_NSEC;
+                for (int s = 0; s < p.sub; ++s) {
+                    // every section is waited for exactly once per fill (a parity wait only tells adjacent phases apart), also
+                    // by the sub-tiles past the end of the utterance, which contract nothing but still hand their sections back
+                    if (s == 0) mbar_wait(&af[0], buf_par);
+                    if (RW_SECTIONS) mbar_wait(&af[s + 1], buf_par);          // rows [128 s, 128 s + 128 + span) are transformed
+                    tc_fence_after();
+                    if (mm * sub_rows + s * 128 >= p.M) {
+                        if (RW_SECTIONS) {
+                            umma_commit(&ae[s]);
+                            umma_commit(&ae[s + 1]);
+                        } else if (s == p.sub - 1) {
+                            umma_commit(&ae[0]);
+                        }
+                        continue;
+                    }
                     const uint32_t acc = sc & (uint32_t)(p.nacc - 1);
                     const uint32_t d_tmem = tmem_base + acc * (uint32_t)C;
                     mbar_wait(&acc_empty[acc], ((sc >> p.nacc_log2) & 1u) ^ 1u);
@@ -283,8 +315,14 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                         b_lo += btile >> 4;
                     }
                     umma_commit(&acc_full[acc]);
+                    if (RW_SECTIONS) {
+                        umma_commit(&ae[s]);                 // one of the (at most) two readers of each section is done
+                        umma_commit(&ae[s + 1]);
+                    } else if (s == p.sub - 1) {
+                        umma_commit(&ae[0]);
+                    }
+                    ++sc;
                 }
-                umma_commit(&a_empty[buf]);
                 if (++buf == (uint32_t)p.na) { buf = 0; buf_par ^= 1u; }
                 if (++mm == p.mmt) { mm = 0; ++b; }
             }
@@ -355,7 +393,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const int nvalid = (blk == p.nblk - 1) ? p.tail_rows : p.R;      // rows the TMA box really loaded
                 const int t0 = mm * sub_rows + p.halo_min + r0;                  // time index of operand row r0
                 mbar_wait_warp(&x_full[slot], xpar);
-                mbar_wait_warp(&a_empty[buf], (fill & 1u) ^ 1u);
+                const uint32_t sec = RW_SECTIONS ? (uint32_t)r0 >> 7 : 0u;      // 128-row section of the operand buffer
+                mbar_wait_warp(&a_empty[buf * RW_NSEC + sec], (fill & 1u) ^ 1u);
                 uint32_t xaddr = smem_x_u32 + slot * (uint32_t)p.xslot + (uint32_t)rl * xrow + (uint32_t)c4 * xes;
                 uint32_t abase = smem_a_u32 + buf * (uint32_t)p.a_bytes + (uint32_t)r0 * arow;
                 // whole batches: rows past nvalid read stale slot bytes and land in slack operand rows no MMA reads
@@ -388,7 +427,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 fence_proxy_async();
                 __syncwarp();                                        // every lane has read the slot and written its rows
                 if (lane == 0) {
-                    mbar_arrive(&a_full[buf]);
+                    mbar_arrive(&a_full[buf * RW_NSEC + sec]);
                     if (l_mi < m_n) issue_load();                    // refill the slot just consumed (l_i == xi)
                 }
                 if (l_mi < m_n) advance_load();

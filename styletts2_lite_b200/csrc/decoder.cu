@@ -362,6 +362,8 @@ int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
     ST2_REQUIRE(cfg->upsample_initial_channel % 64 == 0 && (cfg->upsample_initial_channel >> cfg->n_stages) >= 4 &&
                     ((cfg->upsample_initial_channel >> cfg->n_stages) % 4) == 0,
                 "create: unsupported upsample_initial_channel");
+    // the AdaIN coefficient buffer of a forward holds 2 x 2048 floats per utterance (Exec::coef)
+    ST2_REQUIRE(cfg->upsample_initial_channel <= 2048, "create: upsample_initial_channel must be <= 2048");
     for (int i = 0; i < cfg->n_stages; ++i)
         ST2_REQUIRE(cfg->upsample_rates[i] >= 1 && cfg->upsample_kernel_sizes[i] % cfg->upsample_rates[i] == 0,
                     "create: upsample kernel must be a multiple of its rate");

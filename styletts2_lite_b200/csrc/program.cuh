@@ -371,6 +371,10 @@ struct Exec {
     void norm_act(const float* x, int ld_x, int T, int C, const AdaINRef* n, int act, float slope, const float* alpha,
                   void* y, int ld_y, int dt) {
         const int Cpad = ld_y < ld_x ? ld_y : ld_x;
+        if (Cpad > 2048 && err == ST2_OK) {
+            set_error("coefficient buffer holds 2048 channels, layer needs %d", Cpad);
+            err = ST2_ERR_UNSUPPORTED;
+        }
         void* scratch = nullptr;
         const int64_t mark = off;
         if (n) scratch = alloc(adain_scratch_bytes(B, T, C));
@@ -463,8 +467,14 @@ struct Exec {
         return StatRef{scratch, 0, false};
     }
     // coef <- (1+gamma)*rstd, beta - mean*(1+gamma)*rstd  (n == nullptr: identity)
+    static constexpr int kCoefMax = 2048;     // channels per utterance the coefficient buffer holds (allocated as B*2*2048)
     void coef_from(const StatRef& sr, const AdaINRef* n, int T, int C, int Cpad) {
         if (!live()) return;
+        if (Cpad > kCoefMax) {
+            set_error("coefficient buffer holds %d channels, layer needs %d", kCoefMax, Cpad);
+            err = ST2_ERR_UNSUPPORTED;
+            return;
+        }
         if (n == nullptr || !sr.f2)
             chk(launch_adain_coef(n ? sr.ptr : nullptr, n ? H : nullptr, d->fc_rows, n ? n->h_off : 0, coef, B, T, C, Cpad, st));
         else if (sr.row)

@@ -9,6 +9,8 @@ owns the tensors, the stream and the workspace.  There is no CPU path.
 """
 from __future__ import annotations
 
+import collections
+
 import ctypes as C
 from typing import Dict, Optional
 
@@ -56,7 +58,10 @@ class B200Decoder(nn.Module):
         self._dirty = True
         self._workspace: Optional[torch.Tensor] = None
         self._taps: Dict[str, torch.Tensor] = {}
-        self._graphs: Dict[tuple, dict] = {}
+        self._graphs: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()   # LRU: newest last
+        self.max_graphs = 8                     # each captured shape owns a private workspace + static I/O: bound the cache
+        self._ws_bytes: Dict[tuple, int] = {}   # (B, T, precision) -> workspace bytes (the host dry run costs ~0.1 ms)
+        self._profiling = False
         self.train(False)
 
     # ---- weights -------------------------------------------------------------------------
@@ -79,6 +84,7 @@ class B200Decoder(nn.Module):
     def _sync(self, device: torch.device) -> None:
         lib = _lib.load()
         self._graphs.clear()                      # finalize re-allocates the packed weights captured graphs point to
+        self._ws_bytes.clear()
         if self._handle is None:
             h = C.c_void_p()
             cc = _lib.St2Config.from_config(self.cfg)
@@ -134,9 +140,13 @@ class B200Decoder(nn.Module):
         prec = _lib.PREC[prec_name]
         key = (B, T, prec, dev.index)
         g = self._graphs.get(key)
+        if g is not None:
+            self._graphs.move_to_end(key)
         if g is None:
+            while len(self._graphs) >= max(1, self.max_graphs):       # least recently used shape goes (frees its workspace)
+                self._graphs.popitem(last=False)
             S = self.cfg.samples_per_frame * T
-            need = _lib.check(lib.st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
+            need = self._workspace_need(B, T, prec)
             g = {"asr": torch.empty(B, self.cfg.dim_in, T, device=dev), "f0": torch.empty(B, 2 * T, device=dev),
                  "n": torch.empty(B, 2 * T, device=dev), "s": torch.empty(B, self.cfg.style_dim, device=dev),
                  "seed": torch.zeros(1, dtype=torch.int64, device=dev), "out": torch.empty(B, 1, S, device=dev),
@@ -198,9 +208,11 @@ class B200Decoder(nn.Module):
                 noise_ = noise.detach().float().contiguous()
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # global torch RNG, like the reference
-            if cuda_graph and noise_ is None and not self._taps:
+            # graph replay needs a launch sequence without host-side state: not with taps, a noise tape or the per-launch
+            # event profile (its cudaEventRecord calls would be captured and later read back as garbage) -> eager
+            if cuda_graph and noise_ is None and not self._taps and not self._profiling:
                 return self._forward_graph(asr_, f0_, n_, s_, seed, precision or self.precision)
-            need = _lib.check(lib.st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
+            need = self._workspace_need(B, T, prec)
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -212,11 +224,22 @@ class B200Decoder(nn.Module):
                                                C.c_void_p(stream)), "st2_decoder_forward")
         return out
 
+    def _workspace_need(self, B: int, T: int, prec: int) -> int:
+        key = (B, T, prec)
+        n = self._ws_bytes.get(key)
+        if n is None:
+            n = _lib.check(_lib.load().st2_decoder_workspace_bytes(self._handle, B, T, prec), "st2_decoder_workspace_bytes")
+            if len(self._ws_bytes) > 256:
+                self._ws_bytes.clear()
+            self._ws_bytes[key] = n
+        return n
+
     def set_profiling(self, enable: bool) -> None:
         """Per-launch CUDA-event profile of the following forwards (bench.py's roofline leg)."""
         if self._handle is None:
             self._sync(next(self.parameters()).device)
         _lib.check(_lib.load().st2_decoder_set_profiling(self._handle, 1 if enable else 0), "set_profiling")
+        self._profiling = bool(enable)
 
     def get_profile(self) -> Dict[str, Dict[str, float]]:
         """{category: {ms, launches, flops, bytes}} of the last profiled forward (waits for it)."""

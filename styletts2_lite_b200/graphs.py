@@ -7,14 +7,19 @@ the graph's static buffers, outputs are clones of its static outputs; each graph
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Tuple
+import collections
+from typing import Callable, Tuple
 
 import torch
 
 
 class GraphReplay:
-    def __init__(self) -> None:
-        self._cache: Dict[tuple, dict] = {}
+    """LRU cache of captured graphs: every entry owns a private workspace and static input / output buffers, so a server that
+    sees many shapes must not keep them all -- the least recently used graph is dropped beyond `max_graphs`."""
+
+    def __init__(self, max_graphs: int = 8) -> None:
+        self._cache: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()
+        self.max_graphs = max_graphs
 
     def clear(self) -> None:
         """Drop every captured graph (the packed weights they point to are about to be re-allocated)."""
@@ -28,7 +33,11 @@ class GraphReplay:
         """`launch(static_inputs, workspace)` must only enqueue work on the current stream and return its output tensors."""
         dev = inputs[0].device
         g = self._cache.get(key)
+        if g is not None:
+            self._cache.move_to_end(key)
         if g is None:
+            while len(self._cache) >= max(1, self.max_graphs):
+                self._cache.popitem(last=False)
             static_in = tuple(torch.empty_like(t) for t in inputs)
             for a, b in zip(static_in, inputs):
                 a.copy_(b)

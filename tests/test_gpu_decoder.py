@@ -441,3 +441,55 @@ def test_bench_shape_bf16_tracks_fp32():
     per = [snr_db(ref[b], out[b]) for b in range(B)]
     G.log("bench_shape_bf16_vs_fp32", snr_db=snr, worst_utterance_db=min(per))
     assert snr >= 40.0 and min(per) >= 38.0
+
+
+def test_graph_cache_is_bounded_and_profiling_falls_back_to_eager():
+    """(1) the CUDA-graph cache is an LRU with a bound (each entry owns a workspace); (2) with the per-launch event
+    profile on, cuda_graph=True runs eagerly (events recorded during capture would be garbage) and the profile stays sane."""
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    old = m.max_graphs
+    m.max_graphs = 2
+    try:
+        m._graphs.clear()
+        ins = {T: {k: v.cuda() for k, v in synth.make_inputs(1, T, seed=70 + T, cfg=cfg, with_noise=False).items()} for T in (6, 7, 8)}
+        with torch.no_grad():
+            for T in (6, 7, 8, 6):
+                a = ins[T]
+                e = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=9, precision="bf16")
+                g = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=9, precision="bf16", cuda_graph=True)
+                assert torch.equal(e, g), T
+                assert len(m._graphs) <= 2
+        assert [k[1] for k in m._graphs] == [8, 6]              # 7 was the least recently used shape when 6 came back
+        m.set_profiling(True)
+        with torch.no_grad():
+            a = ins[6]
+            g = m(a["asr"], a["F0_curve"], a["N"], a["s"], seed=9, precision="bf16", cuda_graph=True)
+        prof = m.get_profile()
+        m.set_profiling(False)
+        assert torch.equal(g, e)
+        total = sum(v["ms"] for v in prof.values())
+        n_prof = sum(v["launches"] for v in prof.values())          # a few setup launches share one profile record
+        assert 0.05 < total < 200.0 and m.last_launch_count() - 8 <= n_prof <= m.last_launch_count()
+    finally:
+        m.set_profiling(False)
+        m.max_graphs = old
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """one-time function attributes (> 48 KB dynamic shared memory) and the SM count are cached per device,
+    so a second GPU driven from the same process launches the large-shared-memory kernels too and agrees bit for bit."""
+    cfg = DecoderConfig.hifigan()
+    sd = synth.make_state_dict(cfg, 0, True)
+    inp = synth.make_inputs(2, 40, seed=31, cfg=cfg, with_noise=False)
+    outs = []
+    for d in (0, 1):
+        m = B200Decoder(cfg, "bf16")
+        m.load_state_dict(sd)
+        m = m.to("cuda:%d" % d).eval()
+        t = {k: v.to("cuda:%d" % d) for k, v in inp.items()}
+        with torch.no_grad():
+            outs.append(m(t["asr"], t["F0_curve"], t["N"], t["s"], seed=3).cpu())
+        torch.cuda.synchronize(d)
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
