@@ -56,7 +56,7 @@ struct RowParams {
     int R, nblk, tail_rows;     // activation blocks: R rows each, nblk per macro tile, the last one loads tail_rows rows
     int xslot;                  // bytes per activation ring slot
     int a_bytes;                // bytes per operand buffer (nblk * R rows)
-    int na;                     // operand buffers (macro tiles in flight between transform and MMA): 2 or 3
+    int na;                     // operand buffers (macro tiles in flight between transform and MMA): 2 .. 4
     int lw, xd;                 // active transform warps, depth of each private activation ring
     int nacc, nacc_log2, tmem_cols;
     int nres, nr;               // fp16 sources added by the identity MMA (0, 1, 2), residual ring stages
@@ -144,9 +144,9 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + C);
     uint64_t* w_full = bars;                    // [1]
-    uint64_t* a_full = bars + 1;                // [3 buffers][RW_NSEC sections of 128 operand rows]
-    uint64_t* a_empty = a_full + 3 * RW_NSEC;   // [3][RW_NSEC]
-    uint64_t* acc_full = a_empty + 3 * RW_NSEC; // [8]
+    uint64_t* a_full = bars + 1;                // [4 buffers][RW_NSEC sections of 128 operand rows]
+    uint64_t* a_empty = a_full + 4 * RW_NSEC;   // [4][RW_NSEC]
+    uint64_t* acc_full = a_empty + 4 * RW_NSEC; // [8]
     uint64_t* acc_empty = acc_full + 8;         // [8]
     uint64_t* r_full = acc_empty + 8;           // [nr]
     uint64_t* r_empty = r_full + p.nr;          // [nr]
@@ -635,7 +635,7 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
             const int xslot = R * C * xes;
             // three operand buffers for single-sub-tile macro tiles when they fit (the MMA of tile m otherwise gates the
             // transform of tile m + 2 after every 128 rows)
-            for (int na = (sub == 1 ? 3 : 2); na >= 2 && !ok; --na) {
+            for (int na = (tune().row_na >= 2 && tune().row_na <= 4 ? tune().row_na : (sub == 1 ? 3 : 2)); na >= 2 && !ok; --na) {
             if (tune().row_na && na != tune().row_na) continue;
             const int lw_max = na * nblk < ntw ? na * nblk : ntw;
             const int64_t fixed = na * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;

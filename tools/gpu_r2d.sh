@@ -1,8 +1,7 @@
 #!/bin/bash
-# planner sweep of conv_row (per-layer profile per setting on one box)
 mkdir -p gpurun_out
 i=0
-for cfg in "ST2_X=0" "ST2_ROW_SUB=1" "ST2_ROW_SUB=2" "ST2_ROW_SLOT=2048" "ST2_ROW_SUB=2 ST2_ROW_SLOT=2048" "ST2_ROW_NA=2" "ST2_ROW_SUB=1 ST2_ROW_NA=2"; do
+for cfg in "ST2_X=0" "ST2_ROW_SUB=2 ST2_ROW_NA=4" "ST2_ROW_SUB=2 ST2_ROW_NA=3" "ST2_ROW_SUB=1 ST2_ROW_NA=4" "ST2_X=0"; do
   echo "== cfg $i: $cfg"
   env $cfg timeout 300 python tools/profile_layers.py > gpurun_out/sweep_r2d_$i.txt 2>&1 || { echo FAILED; tail -3 gpurun_out/sweep_r2d_$i.txt; }
   head -1 gpurun_out/sweep_r2d_$i.txt
