@@ -180,6 +180,14 @@ ST2_API int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, flo
 ST2_API int64_t st2_dur_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision);
 ST2_API int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B,
                     int32_t L, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same call for a PADDED batch, as ProsodyPredictor.forward runs it (models.py:422-442): lengths [B] int32 on the device,
+ * 0 <= lengths[b] <= L (nullptr = st2_dur_forward).  Rows of `d` behind an utterance are zero (the masked_fill_ calls of
+ * models.py:491, :500), every LSTM is the pack_padded_sequence one (models.py:503-509, :426-435: the reverse direction of
+ * utterance b starts at token lengths[b]-1), and `duration` at a padded token is what duration_proj makes of a zero row, as in
+ * the reference.  Utterance b of the result equals the B = 1 call on its first lengths[b] tokens. */
+ST2_API int st2_dur_forward_ragged(st2_decoder* d, const float* t_en, const float* s, const int32_t* lengths, float* d_out,
+                    float* duration, int32_t B, int32_t L, int32_t precision, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 /* ---- TextEncoder: replaces models.py:238-285, called at inference.py:239 ----
  * nn.Embedding -> depth x [weight-normed Conv1d(k) -> LayerNorm over channels -> LeakyReLU(0.2)] -> bidirectional LSTM, for a
@@ -190,6 +198,12 @@ ST2_API int st2_text_create(int32_t channels, int32_t kernel_size, int32_t depth
 ST2_API int64_t st2_text_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int32_t precision);
 ST2_API int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t B, int32_t L, int32_t precision,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* The same call for a PADDED batch (TextEncoder.forward with a non-trivial mask m, models.py:258-285): lengths [B] int32 on the
+ * device, 0 <= lengths[b] <= L (nullptr = st2_text_forward).  Tokens behind an utterance are zeroed after the embedding and after
+ * every cnn block (models.py:262, :266), the LSTM is the packed one (models.py:270-277), columns l >= lengths[b] of `out` are
+ * zero (models.py:279-283). */
+ST2_API int st2_text_forward_ragged(st2_decoder* d, const int64_t* tokens, const int32_t* lengths, float* out, int32_t B, int32_t L,
+                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 

@@ -26,9 +26,17 @@ def _sigmoid(x):
     return (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(F32)
 
 
-def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse: bool):
-    """One direction of nn.LSTM(batch_first=True), zero initial state.  x [B, T, I] -> [B, T, H]."""
+def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse: bool, lengths=None):
+    """One direction of nn.LSTM(batch_first=True), zero initial state.  x [B, T, I] -> [B, T, H].
+    lengths [B]: pack_padded_sequence -> LSTM -> pad_packed_sequence (models.py:271-277, :503-509, :426-435): utterance b is
+    the LSTM over its first lengths[b] rows (the reverse direction starts at row lengths[b] - 1), later rows are zero."""
     B, T, _ = x.shape
+    if lengths is not None:
+        out = np.zeros((B, T, w_hh.shape[1]), F32)
+        for b in range(B):
+            n = int(lengths[b])
+            out[b, :n] = lstm_direction(x[b:b + 1, :n], w_ih, w_hh, b_ih, b_hh, reverse)[0]
+        return out
     H = w_hh.shape[1]
     gin = (x.reshape(B * T, -1).astype(F32) @ w_ih.T.astype(F32) + b_ih).reshape(B, T, 4 * H).astype(F32)
     h = np.zeros((B, H), F32)
@@ -44,13 +52,13 @@ def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse: bool):
     return out
 
 
-def bilstm(W: Weights, name: str, x):
+def bilstm(W: Weights, name: str, x, lengths=None):
     """nn.LSTM(d_hid + style_dim, d_hid // 2, 1, batch_first=True, bidirectional=True) (models.py:407).
-    x [B, T, I] -> [B, T, 2H] = cat(forward, reverse)."""
+    x [B, T, I] -> [B, T, 2H] = cat(forward, reverse); lengths as in lstm_direction."""
     outs = []
     for suffix, rev in (("", False), ("_reverse", True)):
         outs.append(lstm_direction(x, W.p(name + ".weight_ih_l0" + suffix), W.p(name + ".weight_hh_l0" + suffix),
-                                   W.p(name + ".bias_ih_l0" + suffix), W.p(name + ".bias_hh_l0" + suffix), rev))
+                                   W.p(name + ".bias_ih_l0" + suffix), W.p(name + ".bias_hh_l0" + suffix), rev, lengths))
     return np.concatenate(outs, axis=2)
 
 
@@ -89,30 +97,42 @@ def ada_layer_norm(x, s, fc_w, fc_b, eps=1e-5):
     return ((1 + gamma) * xn + beta).astype(F32)
 
 
-def duration_encoder(W: Weights, t_en, s, nlayers=3, taps: Optional[dict] = None):
-    """DurationEncoder.forward (models.py:485-520) for equal-length batches (no padding: every mask is False, the
-    pack / pad round trip is the identity).  t_en [B, d_hid, L], s [B, style] -> d [B, L, d_hid + style]."""
+def _pad_mask(lengths, B, L):
+    """length_to_mask (models.py:463-466): True behind each utterance; all False without lengths."""
+    if lengths is None:
+        return np.zeros((B, L), bool)
+    return np.arange(L)[None, :] >= np.asarray(lengths).reshape(B, 1)
+
+
+def duration_encoder(W: Weights, t_en, s, nlayers=3, taps: Optional[dict] = None, lengths=None):
+    """DurationEncoder.forward (models.py:485-520).  t_en [B, d_hid, L], s [B, style] -> d [B, L, d_hid + style].
+    lengths [B] (None = no padding: every mask is False, the pack / pad round trip is the identity)."""
     B, _, L = t_en.shape
+    m = _pad_mask(lengths, B, L)
     sty = np.repeat(s[:, None, :], L, axis=1).astype(F32)                    # style broadcast over tokens (models.py:489)
     x = np.concatenate([t_en.transpose(0, 2, 1), sty], axis=2).astype(F32)   # [B, L, 640] (models.py:490)
+    x[m] = 0                                                                 # models.py:491
     for i in range(nlayers):
-        y = bilstm(W, "text_encoder.lstms.%d" % (2 * i), x)                  # models.py:503-509
+        y = bilstm(W, "text_encoder.lstms.%d" % (2 * i), x, lengths)         # models.py:503-509
         if taps is not None:
             taps["text_encoder.lstms.%d" % (2 * i)] = y
         n = "text_encoder.lstms.%d" % (2 * i + 1)
         y = ada_layer_norm(y, s, W.p(n + ".fc.weight"), W.p(n + ".fc.bias"))  # models.py:498
         x = np.concatenate([y, sty], axis=2).astype(F32)                     # models.py:499
+        x[m] = 0                                                             # models.py:500
     return x
 
 
-def predict_duration(sd: Dict[str, np.ndarray], t_en, s, taps: Optional[dict] = None):
+def predict_duration(sd: Dict[str, np.ndarray], t_en, s, taps: Optional[dict] = None, lengths=None):
     """inference.py:242-245: d = predictor.text_encoder(t_en, s, lengths, mask); x, _ = predictor.lstm(d);
-    duration = sigmoid(predictor.duration_proj(x)).sum(-1).  Returns (d [B, L, 640], duration [B, L])."""
+    duration = sigmoid(predictor.duration_proj(x)).sum(-1).  Returns (d [B, L, 640], duration [B, L]).
+    With lengths (a padded batch) predictor.lstm is the packed one of ProsodyPredictor.forward (models.py:426-439), so a
+    padded token's duration is sigmoid(duration_proj.bias).sum()."""
     W = Weights(sd)
     t_en = np.asarray(t_en, F32)
     s = np.asarray(s, F32)
-    d = duration_encoder(W, t_en, s, taps=taps)
-    x = bilstm(W, "lstm", d)
+    d = duration_encoder(W, t_en, s, taps=taps, lengths=lengths)
+    x = bilstm(W, "lstm", d, lengths)
     if taps is not None:
         taps["lstm"] = x
     logits = (x @ W.p("duration_proj.linear_layer.weight").T.astype(F32) + W.p("duration_proj.linear_layer.bias")).astype(F32)
@@ -123,14 +143,17 @@ def predict_duration(sd: Dict[str, np.ndarray], t_en, s, taps: Optional[dict] = 
 # ----------------------------------------------------------------------------
 # TextEncoder (models.py:238-285), equal-length batches
 # ----------------------------------------------------------------------------
-def text_encoder(sd: Dict[str, np.ndarray], tokens, depth=3, taps: Optional[dict] = None, operand: Optional[str] = None):
-    """TextEncoder.forward(x, input_lengths, m) (models.py:258-285) with an all-False mask: embedding -> depth x
+def text_encoder(sd: Dict[str, np.ndarray], tokens, depth=3, taps: Optional[dict] = None, operand: Optional[str] = None,
+                 lengths=None):
+    """TextEncoder.forward(x, input_lengths, m) (models.py:258-285); lengths None = all-False mask: embedding -> depth x
     [weight-normed Conv1d(k=5, 'same') -> LayerNorm over channels (models.py:224-236) -> LeakyReLU(0.2) -> Dropout = id]
     -> bidirectional LSTM -> [B, channels, L]."""
     from .decoder_np import leaky_relu
     W = Weights(sd)
     x = W.p("embedding.weight")[np.asarray(tokens)]                          # [B, L, C]  (models.py:259)
     x = x.transpose(0, 2, 1).astype(F32)                                     # [B, C, L]
+    m = _pad_mask(lengths, x.shape[0], x.shape[2])[:, None, :]               # models.py:261
+    x = np.where(m, F32(0), x)                                               # models.py:262
     for i in range(depth):
         n = "cnn.%d" % i
         k = W.w(n + ".0").shape[2]
@@ -140,7 +163,8 @@ def text_encoder(sd: Dict[str, np.ndarray], tokens, depth=3, taps: Optional[dict
         xn = ((x64 - mean) / np.sqrt(var + 1e-5)).astype(F32)
         x = (xn * W.p(n + ".1.gamma")[None, :, None] + W.p(n + ".1.beta")[None, :, None]).astype(F32)
         x = leaky_relu(x, 0.2)
+        x = np.where(m, F32(0), x)                                           # models.py:266
         if taps is not None:
             taps[n] = x
-    y = bilstm(W, "lstm", x.transpose(0, 2, 1))                              # models.py:271-277
-    return y.transpose(0, 2, 1)
+    y = bilstm(W, "lstm", x.transpose(0, 2, 1), lengths)                     # models.py:271-277
+    return np.where(m, F32(0), y.transpose(0, 2, 1))                         # models.py:279-283

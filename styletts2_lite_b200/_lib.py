@@ -85,9 +85,11 @@ SIGNATURES = {
     "st2_f0n_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "st2_dur_workspace_bytes": (_L, [_P, _I, _I, _I]),
     "st2_dur_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
+    "st2_dur_forward_ragged": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "st2_text_create": (C.c_int, [_I, _I, _I, _I, C.POINTER(_P)]),
     "st2_text_workspace_bytes": (_L, [_P, _I, _I, _I]),
     "st2_text_forward": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _L, _P]),
+    "st2_text_forward_ragged": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "st2_round_durations": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "st2_length_regulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "st2_sinegen_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),

@@ -139,7 +139,10 @@ int launch_istft_head(const float* x, int ld_x, const float* wr, const float* wi
                       int frames, int S, int n_fft, int hop, cudaStream_t st);
 
 // BiLSTM recurrence (kernels_lstm.cu): G [B][T][2][4H] input half of the gates, whh [2][H][4H], bhh [2][4H] -> y [B][T][2H]
-int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st);
+// lengths: per-utterance token counts on the device (pack_padded_sequence semantics), nullptr = every utterance has T steps
+int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st,
+                      const int32_t* lengths = nullptr);
+int launch_mask_rows(float* x, int ld, int ncols, const int32_t* lengths, int B, int L, cudaStream_t st);
 
 // duration half of the predictor (kernels_lstm.cu)
 int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, int L, cudaStream_t st);

@@ -1,14 +1,16 @@
-// Recurrence of the bidirectional LSTM `shared` of ProsodyPredictor.F0Ntrain (reference models.py:407, :449;
-// arithmetic: torch nn.LSTM, gates (i, f, g, o), zero initial state, batch_first).
+// Recurrence of the bidirectional LSTMs of the modules in front of the Decoder: `shared` of ProsodyPredictor.F0Ntrain
+// (reference models.py:407, :449), the DurationEncoder's LSTMs and predictor.lstm (models.py:470-480, :402; inference.py:243-244)
+// and the TextEncoder's (models.py:255, :268-277).  Arithmetic: torch nn.LSTM, gates (i, f, g, o), zero initial state, batch_first;
+// with per-utterance lengths it is nn.utils.rnn.pack_padded_sequence -> LSTM -> pad_packed_sequence.
 //
 // The input half of the gates (x W_ih^T + b_ih, one [B*T, 640] x [640, 2048] contraction for both directions) is
 // a 1x1 convolution and runs on the conv kernels.  What is left is T strictly sequential steps of
 //     gates = G[t] + h W_hh^T + b_hh ;  c = sig(f) c + sig(i) tanh(g) ;  h = sig(o) tanh(c)
 // with a [4H, H] = 1 MB fp32 matrix per direction: too large for one SM's shared memory, latency bound if re-read
-// from L2 every step.  One thread-block CLUSTER of 8 CTAs owns one (direction, group of 8 utterances): CTA r keeps
+// from L2 every step.  One thread-block CLUSTER of 8 CTAs owns one (direction, group of 4 or 8 utterances): CTA r keeps
 // the 4 x 32 gate columns of hidden units [32r, 32r+32) resident in shared memory (128 KB) for the whole sequence,
-// computes its slice of the gates, updates its 32 cells and broadcasts the 32 new h values of each utterance to
-// the h buffers of all 8 CTAs through distributed shared memory; one cluster barrier per time step.
+// computes its slice of the gates, updates its 32 cells and sends the 32 new h values of each utterance to
+// the h buffers of all 8 CTAs through distributed shared memory.
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -19,8 +21,7 @@ namespace cg = cooperative_groups;
 namespace st2 {
 
 constexpr int kLstmCluster = 8;      // CTAs per cluster
-constexpr int kLstmBt = 8;           // utterances per cluster
-constexpr int kLstmThreads = 256;    // 8 warps: warp = (gate, half of the utterances) in the gate phase, = utterance in the cell phase
+constexpr int kLstmThreads = 256;    // 8 warps: warp = K slice in the gate phase, = utterance in the cell phase
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -28,91 +29,19 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // whh [2][H][4H]      W_hh^T per direction
 // bhh [2][4H]
 // y   [B][T][2H]      forward h | reverse h   (channels-last, what the AdainResBlk1d stacks read)
-template <int H>
-__global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(kLstmThreads, 1)
-lstm_bidir_kernel(const float* __restrict__ G, const float* __restrict__ whh, const float* __restrict__ bhh,
-                  float* __restrict__ y, int B, int T) {
-    constexpr int UL = H / kLstmCluster;        // hidden units per CTA (32)
-    constexpr int COLS = 4 * UL;                // gate columns per CTA (128)
-    static_assert(UL == 32, "one warp lane per hidden unit of the CTA");
-    extern __shared__ __align__(16) float smem[];
-    float* Ws = smem;                                   // [H][COLS]
-    float* hbuf = Ws + H * COLS;                        // [2][Bt][H]
-    float* gs = hbuf + 2 * kLstmBt * H;                 // [4][Bt][UL]
-
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int dir = blockIdx.y;
-    const int b0 = blockIdx.z * kLstmBt;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // resident weights: Ws[k][g*32 + ul] = W_hh[g*H + 32*rank + ul][k]
-    const float* wsrc = whh + (size_t)dir * H * 4 * H;
-    for (int idx = tid; idx < H * COLS; idx += kLstmThreads) {
-        const int k = idx / COLS, col = idx % COLS;
-        Ws[idx] = wsrc[(size_t)k * 4 * H + (col / UL) * H + rank * UL + (col % UL)];
-    }
-    for (int idx = tid; idx < kLstmBt * H; idx += kLstmThreads) hbuf[idx] = 0.f;      // h_0 = 0
-    // gate phase: this thread's column and utterances
-    const int g = warp & 3, bh = (warp >> 2) * 4;
-    const int gcol = g * H + rank * UL + lane;          // column inside one direction's 4H
-    const float bias = bhh[dir * 4 * H + gcol];
-    // cell phase: this thread's (utterance, unit)
-    const int cb = warp;
-    float c_state = 0.f;
-    float* remote[kLstmCluster];
-#pragma unroll
-    for (int r = 0; r < kLstmCluster; ++r) remote[r] = cluster.map_shared_rank(hbuf, r);
-    cluster.sync();                                     // every CTA of the cluster runs and has zeroed its h_0
-
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? T - 1 - step : step;
-        const int cur = step & 1;
-        // input half of the gates: issued first, consumed after the dot products
-        float gin[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int b = b0 + bh + j;
-            gin[j] = (b < B) ? __ldg(G + (((size_t)b * T + t) * 2 + dir) * 4 * H + gcol) : 0.f;
-        }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* hc = hbuf + (size_t)cur * kLstmBt * H + bh * H;
-        const float* wc = Ws + g * UL + lane;
-#pragma unroll 4
-        for (int k = 0; k < H; k += 4) {
-            const float w0 = wc[(k + 0) * COLS], w1 = wc[(k + 1) * COLS], w2 = wc[(k + 2) * COLS], w3 = wc[(k + 3) * COLS];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 hv = *reinterpret_cast<const float4*>(hc + j * H + k);      // warp-uniform: broadcast
-                acc[j] = fmaf(w0, hv.x, acc[j]);
-                acc[j] = fmaf(w1, hv.y, acc[j]);
-                acc[j] = fmaf(w2, hv.z, acc[j]);
-                acc[j] = fmaf(w3, hv.w, acc[j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gs[(g * kLstmBt + bh + j) * UL + lane] = gin[j] + (acc[j] + bias);
-        __syncthreads();
-        // cell update of (utterance cb, unit rank*32 + lane)
-        const float gi = gs[(0 * kLstmBt + cb) * UL + lane], gf = gs[(1 * kLstmBt + cb) * UL + lane];
-        const float gg = gs[(2 * kLstmBt + cb) * UL + lane], go = gs[(3 * kLstmBt + cb) * UL + lane];
-        c_state = sigmoid_f(gf) * c_state + sigmoid_f(gi) * tanhf(gg);
-        const float h = sigmoid_f(go) * tanhf(c_state);
-        const int hoff = ((cur ^ 1) * kLstmBt + cb) * H + rank * UL + lane;
-#pragma unroll
-        for (int r = 0; r < kLstmCluster; ++r) remote[r][hoff] = h;        // 128 B per warp and destination CTA
-        if (b0 + cb < B) y[((size_t)(b0 + cb) * T + t) * 2 * H + dir * H + rank * UL + lane] = h;
-        cluster.sync();      // h_{t} visible everywhere; everyone is done reading h_{t-1} and the gate exchange buffer
-    }
-}
-
-// ---- version 2 of the recurrence: same cluster decomposition, three changes that cut the step from 4.5 us -------------
+//
+// Three things keep a step near 2 us:
 //  * the h exchange is `st.async` into the peers' shared memory with transaction-count mbarriers (the arrival of the data IS
 //    the signal; no cluster barrier on the critical path, double-buffered h makes the reuse safe: a CTA can only send step
 //    t+1 values after it received every CTA's step-t values, i.e. after every CTA finished reading the buffer being overwritten)
 //  * K is split over the 8 warps (32 k each) so W_hh is read from shared memory once per step instead of four times, with
 //    weights stored as (k even, k odd) pairs and packed fma.rn.f32x2 over the pair; the 8 partial sums meet in shared memory
 //  * BT = 4 or 8 utterances per cluster, so small batches spread over more SMs
+//
+// Ragged batches (`lengths` != nullptr; pack_padded_sequence semantics of models.py:271-277, :503-509, :426-435): utterance b
+// runs len_b steps, the reverse direction starts at its own last token (t = len_b - 1 - step), rows t >= len_b of y are zero
+// (pad_packed_sequence).  The cluster runs max(len) steps of its utterances; a finished utterance keeps its state and re-sends
+// its last h so the transaction count of every step stays the same.
 __device__ __forceinline__ uint32_t lstm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lstm_mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -149,7 +78,7 @@ __device__ __forceinline__ float2 lstm_ffma2(float2 a, float2 b, float2 c) {
 template <int H, int BT>
 __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(kLstmThreads, 1)
 lstm_bidir_v2_kernel(const float* __restrict__ G, const float* __restrict__ whh, const float* __restrict__ bhh,
-                     float* __restrict__ y, int B, int T) {
+                     float* __restrict__ y, int B, int T, const int32_t* __restrict__ lengths) {
     constexpr int UL = H / kLstmCluster;        // 32 hidden units per CTA, one per lane
     constexpr int KS = kLstmThreads / 32;       // 8 K slices, one per warp
     constexpr int KW = H / KS;                  // 32 k per slice
@@ -184,7 +113,19 @@ lstm_bidir_v2_kernel(const float* __restrict__ G, const float* __restrict__ whh,
     // cell phase: thread (utterance cb = warp, unit = lane) for warps < BT
     const int cb = warp;
     const bool cell = warp < BT;
-    float c_state = 0.f;
+    float c_state = 0.f, h_last = 0.f;
+    int steps = T, len = T;                     // steps of this cluster, length of this cell thread's utterance
+    if (lengths != nullptr) {
+        steps = 0;
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b0 + b >= B) break;
+            const int lb = min(max(__ldg(lengths + b0 + b), 0), T);
+            steps = max(steps, lb);
+            if (b == cb) len = lb;
+        }
+        if (!cell || b0 + cb >= B) len = steps;
+    }
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t r_h[kLstmCluster], r_bar[kLstmCluster];
 #pragma unroll
@@ -199,14 +140,15 @@ lstm_bidir_v2_kernel(const float* __restrict__ G, const float* __restrict__ whh,
     cluster.sync();                 // barriers initialised and h_0 zeroed everywhere before the first remote store
 
     constexpr uint32_t kStepBytes = (uint32_t)BT * H * 4u;          // what one step delivers into one CTA's h buffer
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? T - 1 - step : step;
+    for (int step = 0; step < steps; ++step) {
+        const bool act = step < len;
+        const int t = dir ? len - 1 - step : step;
         const int cur = step & 1, nxt = cur ^ 1;
         if (tid == 0)               // arm the buffer this step fills (its previous phase completed before step-1 started)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lstm_smem_u32(&hfull[nxt])), "r"(kStepBytes)
                          : "memory");
         float gin[4] = {0.f, 0.f, 0.f, 0.f};
-        if (cell && b0 + cb < B) {
+        if (cell && act && b0 + cb < B) {
             const float* gp = G + (((size_t)(b0 + cb) * T + t) * 2 + dir) * 4 * H + rank * UL + lane;
 #pragma unroll
             for (int g = 0; g < 4; ++g) gin[g] = __ldg(gp + g * H);
@@ -253,31 +195,38 @@ lstm_bidir_v2_kernel(const float* __restrict__ G, const float* __restrict__ whh,
                 for (int ks = 0; ks < KS; ++ks) sacc += red[((ks * 4 + g) * BT + cb) * UL + lane];
                 gate[g] = gin[g] + (sacc + bias[g]);
             }
-            c_state = sigmoid_f(gate[1]) * c_state + sigmoid_f(gate[0]) * tanhf(gate[2]);
-            const float h = sigmoid_f(gate[3]) * tanhf(c_state);
+            if (act) {
+                c_state = sigmoid_f(gate[1]) * c_state + sigmoid_f(gate[0]) * tanhf(gate[2]);
+                h_last = sigmoid_f(gate[3]) * tanhf(c_state);
+            }
+            const float h = h_last;
             const uint32_t hoff = (uint32_t)((nxt * BT + cb) * H + rank * UL + lane) * 4u;
             const uint32_t boff = (uint32_t)nxt * 8u;
 #pragma unroll
             for (int r = 0; r < kLstmCluster; ++r) lstm_st_async(r_h[r] + hoff, h, r_bar[r] + boff);
-            if (b0 + cb < B) y[((size_t)(b0 + cb) * T + t) * 2 * H + dir * H + rank * UL + lane] = h;
+            if (act && b0 + cb < B) y[((size_t)(b0 + cb) * T + t) * 2 * H + dir * H + rank * UL + lane] = h;
         }
         __syncthreads();            // the partial-sum buffer is rewritten by the next step's gate phase
     }
+    if (lengths != nullptr && cell && b0 + cb < B)          // pad_packed_sequence: zeros behind the utterance
+        for (int t = len; t < T; ++t) y[((size_t)(b0 + cb) * T + t) * 2 * H + dir * H + rank * UL + lane] = 0.f;
     cluster.sync();                 // no CTA leaves while a peer may still be storing into its shared memory
 }
 
 template <int BT>
-static int launch_lstm_v2(const float* G, const float* whh, const float* bhh, float* y, int B, int T, cudaStream_t st) {
+static int launch_lstm_v2(const float* G, const float* whh, const float* bhh, float* y, int B, int T, const int32_t* lengths,
+                          cudaStream_t st) {
     constexpr int HH = 256;
     const size_t smem = ((size_t)HH * 4 * (HH / kLstmCluster) + 2 * BT * HH + (kLstmThreads / 32) * 4 * BT * (HH / kLstmCluster)) * sizeof(float) + 16;
     ST2_CUDA_CHECK(cudaFuncSetAttribute(lstm_bidir_v2_kernel<HH, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(kLstmCluster, 2, cdiv(B, BT));
-    lstm_bidir_v2_kernel<HH, BT><<<grid, kLstmThreads, smem, st>>>(G, whh, bhh, y, B, T);
+    lstm_bidir_v2_kernel<HH, BT><<<grid, kLstmThreads, smem, st>>>(G, whh, bhh, y, B, T, lengths);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
 
-int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st) {
+int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float* y, int B, int T, int H, cudaStream_t st,
+                      const int32_t* lengths) {
     ST2_REQUIRE(H == 256, "lstm: hidden size %d is not supported (d_hid must be 512)", H);
     ST2_REQUIRE(B > 0 && T > 0, "lstm: bad shape B=%d T=%d", B, T);
     // 4 utterances per cluster while all clusters are still co-resident (an 8-CTA cluster must sit inside one GPC, so
@@ -303,7 +252,7 @@ int launch_lstm_bidir(const float* G, const float* whh, const float* bhh, float*
         if (tune().verbose) fprintf(stderr, "lstm: %d co-resident clusters of 8 CTAs (BT=4 configuration)\n", n);
     }
     const bool bt4 = tune().lstm_bt == 4 || (tune().lstm_bt != 8 && cdiv(B, 4) * 2 <= mc4);
-    return bt4 ? launch_lstm_v2<4>(G, whh, bhh, y, B, T, st) : launch_lstm_v2<8>(G, whh, bhh, y, B, T, st);
+    return bt4 ? launch_lstm_v2<4>(G, whh, bhh, y, B, T, lengths, st) : launch_lstm_v2<8>(G, whh, bhh, y, B, T, lengths, st);
 }
 
 }  // namespace st2
@@ -373,6 +322,19 @@ __global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* 
     }
 }
 
+// x[b][l][0 .. ncols) = 0 for l >= lengths[b]: the masked_fill_(m, 0.0) calls of TextEncoder.forward (models.py:262, :266) and
+// DurationEncoder.forward (models.py:491, :500) on channels-last rows of pitch ld.  One warp per row; rows inside the utterance
+// are left alone.
+__global__ void mask_rows_kernel(float* __restrict__ x, int ld, int ncols, const int32_t* __restrict__ lengths, int64_t rows, int L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = (int)(row / L), l = (int)(row - (int64_t)b * L);
+    if (l < __ldg(lengths + b)) return;
+    float* xr = x + row * ld;
+    for (int c = lane; c < ncols; c += 32) xr[c] = 0.f;
+}
+
 // nn.Embedding lookup into channels-last rows: y[row][0..C) = table[tok[row]][0..C)   (models.py:259)
 __global__ void embedding_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table, float* __restrict__ y, int C,
                                  int64_t rows, int n_symbols) {
@@ -431,6 +393,13 @@ __global__ void duration_head_kernel(const float* __restrict__ x, const float* _
         total += sigmoid_f(acc + __ldg(bias + j));
     }
     if (lane == 0) duration[row] = total;
+}
+
+int launch_mask_rows(float* x, int ld, int ncols, const int32_t* lengths, int B, int L, cudaStream_t st) {
+    const int64_t rows = (int64_t)B * L;
+    mask_rows_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(x, ld, ncols, lengths, rows, L);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
 }
 
 int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, int L, cudaStream_t st) {

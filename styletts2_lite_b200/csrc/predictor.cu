@@ -99,7 +99,7 @@ static void bilstm(Exec& E, const LstmW& w, const char* name, const float* x, fl
     }
     for (int dir = 0; dir < 2; ++dir)
         E.conv(w.ih[dir], xin, I, T, tc ? dt : DT_F32, G + (size_t)dir * 4 * H, 8 * H, T, 1, 0, 1, nullptr, 0, 0, 1.f, 0);
-    if (E.live()) E.chk(launch_lstm_bidir(G, w.whh, w.bhh, y, B, T, H, E.st));
+    if (E.live()) E.chk(launch_lstm_bidir(G, w.whh, w.bhh, y, B, T, H, E.st, E.lengths));
     E.prof(PC_LSTM, 2.0 * B * T * 2 * 4 * H * H, 4.0 * B * T * (8 * H + 2 * H) + 4.0 * 2 * 4 * H * H);
     E.off = mark;
 }
@@ -147,14 +147,18 @@ static int f0n_forward_impl(st2_decoder* d, const float* en, const float* s, flo
     return E.err;
 }
 
-// inference.py:242-245 for an equal-length batch: d = predictor.text_encoder(t_en, s, lengths, mask) (DurationEncoder.forward,
-// models.py:485-520), x = predictor.lstm(d), duration = sigmoid(duration_proj(x)).sum(-1).
-// t_en [B, d_hid, L], s [B, style] -> d_out [B, L, d_hid+style] (the reference's layout of `d`), duration [B, L]
-static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int B, int L,
-                            int prec, void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
+// inference.py:242-245: d = predictor.text_encoder(t_en, s, lengths, mask) (DurationEncoder.forward, models.py:485-520),
+// x = predictor.lstm(d), duration = sigmoid(duration_proj(x)).sum(-1).
+// t_en [B, d_hid, L], s [B, style] -> d_out [B, L, d_hid+style] (the reference's layout of `d`), duration [B, L].
+// lengths (device, [B], may be null): the padded batch of ProsodyPredictor.forward (models.py:422-442) -- rows behind an
+// utterance are zeroed where DurationEncoder.forward masks (models.py:491, :500), every LSTM is the packed one (models.py:503-509,
+// :426-435), and duration at a padded token is what duration_proj makes of the zero row there, as in the reference.
+static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, const int32_t* lengths, float* d_out, float* duration,
+                            int B, int L, int prec, void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
     const st2_config& c = d->cfg;
     const int dh = c.dim_in, H = dh / 2, I = dh + c.style_dim;
     Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    E.lengths = lengths;
     float* Hs = E.allocf((int64_t)B * d->fc_rows);
     E.H = Hs;
     E.coef = E.allocf((int64_t)B * 2 * 2048);
@@ -173,6 +177,7 @@ static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, f
         E.chk(launch_style_fc(s, d->fc_w, d->fc_b, Hs, B, d->fc_rows, c.style_dim, st));
         E.chk(launch_cf_to_cl(t_en, xa, I, B, dh, L, st));                       // x.permute / cat([x, s]) (models.py:488-490)
         E.chk(launch_concat_style(xa, I, dh, s, c.style_dim, B, L, st));
+        if (lengths) E.chk(launch_mask_rows(xa, I, I, lengths, B, L, st));         // models.py:491
         E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim, 4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * I * L));
     }
     for (int i = 0; i < d->dur_layers; ++i) {
@@ -183,6 +188,7 @@ static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, f
         if (E.live()) {
             E.chk(launch_ada_layer_norm(y, Hs, d->fc_rows, d->enc_norm[i].h_off, dst, I, B, L, dh, st));   // models.py:498
             E.chk(launch_concat_style(dst, I, dh, s, c.style_dim, B, L, st));      // models.py:499
+            if (lengths) E.chk(launch_mask_rows(dst, I, I, lengths, B, L, st));    // models.py:500
         }
         E.prof(PC_AFFINE_ACT, 0, 8.0 * B * L * dh);
         E.tap("text_encoder.lstms." + std::to_string(2 * i + 1), dst, I, (int64_t)B * L, dh);
@@ -195,12 +201,14 @@ static int dur_forward_impl(st2_decoder* d, const float* t_en, const float* s, f
     return E.err;
 }
 
-// TextEncoder.forward(x, input_lengths, m) (models.py:258-285) for an equal-length batch (mask all False):
-// tokens [B, L] int64 -> out [B, channels, L]
-static int text_forward_impl(st2_decoder* d, const int64_t* tokens, float* out, int B, int L, int prec, void* ws, int64_t ws_bytes,
-                             cudaStream_t st, bool dry, int64_t* peak_out) {
+// TextEncoder.forward(x, input_lengths, m) (models.py:258-285): tokens [B, L] int64 -> out [B, channels, L].
+// lengths (device, [B], may be null = mask all False): tokens behind an utterance are zeroed after the embedding and after every
+// cnn block (models.py:262, :266), the LSTM is the packed one (models.py:270-277), padded columns of `out` are zero (:279-283).
+static int text_forward_impl(st2_decoder* d, const int64_t* tokens, const int32_t* lengths, float* out, int B, int L, int prec,
+                             void* ws, int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
     const int C = d->cfg.dim_in, H = C / 2;
     Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
+    E.lengths = lengths;
     E.coef = E.allocf((int64_t)B * 2 * 2048);
     float* xa = E.allocf((int64_t)B * L * C);
     float* xb = E.allocf((int64_t)B * L * C);
@@ -215,6 +223,7 @@ static int text_forward_impl(st2_decoder* d, const int64_t* tokens, float* out, 
             if (!d->prof_events.empty()) cudaEventRecord(d->prof_events[0], st);
         }
         E.chk(launch_embedding(tokens, d->te_embedding, xa, B, L, C, d->te_symbols, st));       // models.py:259-260
+        if (lengths) E.chk(launch_mask_rows(xa, C, C, lengths, B, L, st));                       // models.py:262
         E.prof(PC_MISC, 0, 8.0 * B * L * C);
     }
     const int dt = E.fmt_for("cnn");
@@ -228,7 +237,10 @@ static int text_forward_impl(st2_decoder* d, const int64_t* tokens, float* out, 
             xin = x16;
         }
         E.conv(d->te_conv[i], xin, C, L, tc ? dt : DT_F32, xb, C, L, 1, (d->te_kernel - 1) / 2, 1, nullptr, 0, 0, 1.f, 0);
-        if (E.live()) E.chk(launch_layer_norm_lrelu(xb, d->te_gamma[i], d->te_gamma[i] + C, 0.2f, xa, B, L, C, st));
+        if (E.live()) {
+            E.chk(launch_layer_norm_lrelu(xb, d->te_gamma[i], d->te_gamma[i] + C, 0.2f, xa, B, L, C, st));
+            if (lengths) E.chk(launch_mask_rows(xa, C, C, lengths, B, L, st));                   // models.py:266
+        }
         E.prof(PC_AFFINE_ACT, 0, 8.0 * B * L * C);
         E.tap("cnn." + std::to_string(i), xa, C, (int64_t)B * L, C);
         E.off = mark;
@@ -304,14 +316,14 @@ int64_t st2_dur_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int3
         return ST2_ERR_STATE;
     }
     int64_t peak = 0;
-    int e = st2::dur_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, nullptr, B, L, precision, nullptr, 0,
-                                  nullptr, true, &peak);
+    int e = st2::dur_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, nullptr, nullptr, B, L, precision,
+                                  nullptr, 0, nullptr, true, &peak);
     if (e != ST2_OK) return e;
     return peak + 256;
 }
 
-int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B, int32_t L,
-                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+int st2_dur_forward_ragged(st2_decoder* d, const float* t_en, const float* s, const int32_t* lengths, float* d_out, float* duration,
+                           int32_t B, int32_t L, int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
     ST2_REQUIRE(d != nullptr, "dur_forward: null handle");
     if (!d->finalized || d->cfg.variant != 2 || !d->has_duration) {
         st2::set_error("dur_forward: needs a finalized predictor handle that was given text_encoder.* / lstm.* / duration_proj.*");
@@ -326,10 +338,15 @@ int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_
     }
     ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "dur_forward: workspace must be 256-byte aligned");
     st2::g_launch_count = 0;
-    int e = st2::dur_forward_impl(d, t_en, s, d_out, duration, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream,
-                                  false, nullptr);
+    int e = st2::dur_forward_impl(d, t_en, s, lengths, d_out, duration, B, L, precision, workspace, workspace_bytes,
+                                  (cudaStream_t)stream, false, nullptr);
     d->last_launches = st2::g_launch_count;
     return e;
+}
+
+int st2_dur_forward(st2_decoder* d, const float* t_en, const float* s, float* d_out, float* duration, int32_t B, int32_t L,
+                    int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
+    return st2_dur_forward_ragged(d, t_en, s, nullptr, d_out, duration, B, L, precision, workspace, workspace_bytes, stream);
 }
 
 /* ---- TextEncoder: replaces models.py:238-285 ---- */
@@ -359,13 +376,14 @@ int64_t st2_text_workspace_bytes(const st2_decoder* d, int32_t B, int32_t L, int
         return ST2_ERR_STATE;
     }
     int64_t peak = 0;
-    int e = st2::text_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, B, L, precision, nullptr, 0, nullptr, true, &peak);
+    int e = st2::text_forward_impl(const_cast<st2_decoder*>(d), nullptr, nullptr, nullptr, B, L, precision, nullptr, 0, nullptr, true,
+                                   &peak);
     if (e != ST2_OK) return e;
     return peak + 256;
 }
 
-int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t B, int32_t L, int32_t precision, void* workspace,
-                     int64_t workspace_bytes, void* stream) {
+int st2_text_forward_ragged(st2_decoder* d, const int64_t* tokens, const int32_t* lengths, float* out, int32_t B, int32_t L,
+                            int32_t precision, void* workspace, int64_t workspace_bytes, void* stream) {
     ST2_REQUIRE(d != nullptr, "text_forward: null handle");
     if (!d->finalized || d->cfg.variant != 3) {
         st2::set_error("text_forward: not a finalized text-encoder handle (st2_text_create + st2_decoder_finalize)");
@@ -380,9 +398,15 @@ int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t 
     }
     ST2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "text_forward: workspace must be 256-byte aligned");
     st2::g_launch_count = 0;
-    int e = st2::text_forward_impl(d, tokens, out, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream, false, nullptr);
+    int e = st2::text_forward_impl(d, tokens, lengths, out, B, L, precision, workspace, workspace_bytes, (cudaStream_t)stream, false,
+                                   nullptr);
     d->last_launches = st2::g_launch_count;
     return e;
+}
+
+int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, int32_t B, int32_t L, int32_t precision, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    return st2_text_forward_ragged(d, tokens, nullptr, out, B, L, precision, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -296,6 +296,7 @@ struct Exec {
     const float* H = nullptr; // style rows [B][fc_rows]
     float* coef = nullptr;    // [B][2][2048]
     int coef_ld = 0;          // stride the last coefficient kernel wrote with
+    const int32_t* lengths = nullptr;   // ragged token batches of the text modules (device, [B]); nullptr = equal lengths
 
     void* alloc(int64_t bytes) {
         off = (off + 255) / 256 * 256;

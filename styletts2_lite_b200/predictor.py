@@ -105,14 +105,15 @@ class B200F0NPredictor(nn.Module):
                                        _lib.ptr(ws), ws.numel(), C.c_void_p(stream)), "st2_f0n_forward")
         return f0, n
 
-    def _launch_dur(self, x_, s_, ws, B, L, prec):
+    def _launch_dur(self, x_, s_, lens, ws, B, L, prec):
         lib = _lib.load()
         dev = x_.device
         d = torch.empty(B, L, self.cfg.d_hid + self.cfg.style_dim, dtype=torch.float32, device=dev)
         duration = torch.empty(B, L, dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.st2_dur_forward(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(d), _lib.ptr(duration), B, L, prec,
-                                       _lib.ptr(ws), ws.numel(), C.c_void_p(stream)), "st2_dur_forward")
+        _lib.check(lib.st2_dur_forward_ragged(self._handle, _lib.ptr(x_), _lib.ptr(s_), _lib.ptr(lens) if lens is not None else None,
+                                              _lib.ptr(d), _lib.ptr(duration), B, L, prec, _lib.ptr(ws), ws.numel(),
+                                              C.c_void_p(stream)), "st2_dur_forward")
         return d, duration
 
     def F0Ntrain(self, x: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None, cuda_graph: bool = False):
@@ -142,11 +143,14 @@ class B200F0NPredictor(nn.Module):
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
             return self._launch_f0n(x_, s_, self._workspace, B, T, prec)
 
-    def predict_duration(self, t_en: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None, cuda_graph: bool = False):
-        """inference.py:242-245 for a batch of equal-length utterances:
+    def predict_duration(self, t_en: torch.Tensor, s: torch.Tensor, precision: Optional[str] = None, cuda_graph: bool = False,
+                         input_lengths: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+        """inference.py:242-245:
         `d = predictor.text_encoder(t_en, s, lengths, mask); x, _ = predictor.lstm(d);
         duration = sigmoid(predictor.duration_proj(x)).sum(-1)`.
-        t_en [B, d_hid, L], s [B, style_dim] -> (d [B, L, d_hid+style_dim], duration [B, L])."""
+        t_en [B, d_hid, L], s [B, style_dim] -> (d [B, L, d_hid+style_dim], duration [B, L]).
+        With input_lengths (and / or its mask) the batch is padded and handled as ProsodyPredictor.forward does
+        (models.py:422-442): masked rows of d are zero, every LSTM is packed, utterance b equals its own B = 1 call."""
         if not self.has_duration:
             raise RuntimeError("construct B200F0NPredictor(duration=True) to get the duration half")
         if self.training:
@@ -159,6 +163,8 @@ class B200F0NPredictor(nn.Module):
         if Cin != self.cfg.d_hid or tuple(s.shape) != (B, self.cfg.style_dim):
             raise ValueError("expected t_en [B,%d,L] and s [B,%d]; got %s %s" % (self.cfg.d_hid, self.cfg.style_dim,
                                                                               tuple(t_en.shape), tuple(s.shape)))
+        from .text_encoder import ragged_lengths
+        lens = ragged_lengths(input_lengths, mask, B, L, dev)
         prec = _lib.PREC[precision or self.precision]
         with torch.cuda.device(dev):
             if self._dirty or self._handle is None:
@@ -166,13 +172,14 @@ class B200F0NPredictor(nn.Module):
             x_, s_ = t_en.detach().float().contiguous(), s.detach().float().contiguous()
             need = _lib.check(lib.st2_dur_workspace_bytes(self._handle, B, L, prec), "st2_dur_workspace_bytes")
             if cuda_graph and not self._taps:
-                return self._graphs.run(("dur", B, L, prec, dev.index), (x_, s_),
+                ins = (x_, s_) if lens is None else (x_, s_, lens)
+                return self._graphs.run(("dur", B, L, prec, dev.index, lens is not None), ins,
                                         lambda: torch.empty(need, dtype=torch.uint8, device=dev),
-                                        lambda ins, ws: self._launch_dur(ins[0], ins[1], ws, B, L, prec))
+                                        lambda i, ws: self._launch_dur(i[0], i[1], i[2] if len(i) > 2 else None, ws, B, L, prec))
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            return self._launch_dur(x_, s_, self._workspace, B, L, prec)
+            return self._launch_dur(x_, s_, lens, self._workspace, B, L, prec)
 
     def last_launch_count(self) -> int:
         return int(_lib.load().st2_decoder_last_launch_count(self._handle)) if self._handle else 0

@@ -249,7 +249,9 @@ def test_text_encoder_batch_tensor_core_and_errors():
     assert np.abs(out[:2].cpu().numpy() - ref).max() <= 1e-4
     assert rel_l2(out.cpu().numpy(), o16.cpu().numpy()) <= 1e-2
     with pytest.raises(ValueError):
-        m(tok, torch.tensor([L] * (B - 1) + [L - 3]))                      # padded batch
+        m(tok, torch.tensor([L] * (B - 1) + [L + 3]))                      # longer than the batch
+    with pytest.raises(ValueError):
+        m(tok, torch.tensor([L] * (B - 1) + [L - 3]), torch.zeros(B, L, dtype=torch.bool))   # mask disagrees with the lengths
     with pytest.raises(IndexError):
         m(torch.full((1, 4), 178, dtype=torch.long).cuda())                # id out of range, like nn.Embedding
     with pytest.raises(_lib.St2Error):
@@ -290,6 +292,87 @@ def test_tokens_to_waveform_chain_runs_on_the_gpu():
     assert np.abs(out.cpu().numpy() - r_out).max() <= 5e-4
 
 
+# ---------------------------------------------------------------- padded (ragged) token batches
+def test_ragged_text_encoder_and_duration_reference_fixtures():
+    """The reference's modules on a padded batch (lengths 9, 6, 4; tests/golden/make_golden_ragged.py): masked_fill_ +
+    pack_padded_sequence semantics of models.py:258-285, :485-520, :426-439, eager and as a replayed graph."""
+    g = golden("text_ragged_B3_L9_w0_i5101.npz")
+    m = _text_encoder()
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    lengths = torch.from_numpy(g["lengths"]).long()
+    mask = torch.arange(9).unsqueeze(0) >= lengths.unsqueeze(1)
+    buf = m.set_tap("cnn.0", 3, 9, 512)
+    with torch.no_grad():
+        out = m(tok, lengths, mask)
+    m.clear_taps()
+    assert np.abs(G.cf(buf.cpu().numpy()) - g["tap:cnn.0"]).max() <= 2e-5
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= 1e-4
+    with torch.no_grad():
+        assert torch.equal(m(tok, lengths, cuda_graph=True), out)
+        for b, n in enumerate(g["lengths"]):
+            n = int(n)
+            assert not bool(out[b, :, n:].any())
+            assert np.abs(out[b, :, :n].cpu().numpy() - g["single%d" % b][0]).max() <= 1e-4
+            one = m(tok[b:b + 1, :n].contiguous())                  # the sentence alone, as inference.py runs it
+            assert float((one[0] - out[b, :, :n]).abs().max()) <= 1e-5
+
+    g = golden("dur_ragged_B3_L9_w0_i4101.npz")
+    p = _dur_predictor()
+    t_en, s = torch.from_numpy(g["t_en"]).cuda(), torch.from_numpy(g["s"]).cuda()
+    bufs = {k: p.set_tap(k, 3, 9, 512) for k in ("text_encoder.lstms.0", "lstm")}
+    with torch.no_grad():
+        d, dur = p.predict_duration(t_en, s, input_lengths=lengths)
+    p.clear_taps()
+    assert np.abs(bufs["text_encoder.lstms.0"].cpu().numpy() - g["tap:text_encoder.lstms.0"]).max() <= 2e-5
+    assert np.abs(bufs["lstm"].cpu().numpy() - g["tap:lstm"]).max() <= 2e-5
+    assert np.abs(d.cpu().numpy() - g["d"]).max() <= 1e-4 and np.abs(dur.cpu().numpy() - g["duration"]).max() <= 1e-4
+    with torch.no_grad():
+        dg, durg = p.predict_duration(t_en, s, input_lengths=lengths, mask=mask, cuda_graph=True)
+        assert torch.equal(dg, d) and torch.equal(durg, dur)
+        for b, n in enumerate(g["lengths"]):
+            n = int(n)
+            assert not bool(d[b, n:].any())
+            d1, dur1 = p.predict_duration(t_en[b:b + 1, :, :n].contiguous(), s[b:b + 1])
+            assert float((d1[0] - d[b, :n]).abs().max()) <= 1e-5 and float((dur1[0] - dur[b, :n]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("B,L", [(5, 33), (37, 64)])
+def test_ragged_batches_equal_one_sentence_at_a_time(B, L):
+    """Seeded ragged lengths (1 .. L, one utterance at L, one at 1): every utterance of the padded batch equals its own
+    unpadded call -- both LSTM cluster configurations (4 and 8 utterances per cluster, clusters whose utterances all end
+    early), fp32 and fp16 operands -- and the oracle on two of them."""
+    from oracle import predictor_np as PN
+    rng = np.random.RandomState(B * 100 + L)
+    lens = rng.randint(1, L + 1, size=B)
+    lens[0], lens[-1] = L, 1
+    if B > 8:
+        lens[8:16] = rng.randint(1, L // 3, size=8)             # a whole cluster that stops early
+    tok = synth.make_tokens(B, L, seed=5600 + B)
+    s = synth.make_duration_inputs(B, L, seed=4600 + B)["s"]
+    lengths = torch.from_numpy(lens).long()
+    te, pr = _text_encoder(), _dur_predictor()
+    with torch.no_grad():
+        t_en = te(tok.cuda(), lengths)
+        d, dur = pr.predict_duration(t_en, s.cuda(), input_lengths=lengths)
+        t16 = te(tok.cuda(), lengths, precision="fp16")
+        d16, dur16 = pr.predict_duration(t_en, s.cuda(), input_lengths=lengths, precision="fp16")
+        for b in range(B):
+            n = int(lens[b])
+            assert not bool(t_en[b, :, n:].any()) and not bool(d[b, n:].any()) and not bool(t16[b, :, n:].any())
+            one = te(tok[b:b + 1, :n].cuda().contiguous())
+            assert float((one[0] - t_en[b, :, :n]).abs().max()) <= 1e-5, b
+            d1, dur1 = pr.predict_duration(one, s[b:b + 1].cuda())
+            assert float((d1[0] - d[b, :n]).abs().max()) <= 2e-5 and float((dur1[0] - dur[b, :n]).abs().max()) <= 2e-4, b
+    assert rel_l2(t_en.cpu().numpy(), t16.cpu().numpy()) <= 1e-2 and rel_l2(d.cpu().numpy(), d16.cpu().numpy()) <= 1e-2
+    pick = [0, B - 1, B // 2]
+    r_t = PN.text_encoder({k: v.numpy() for k, v in synth.make_text_state_dict(seed=0).items()}, tok[pick].numpy(),
+                          lengths=lens[pick])
+    psd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0, duration=True).items()}
+    r_d, r_dur = PN.predict_duration(psd, r_t, s[pick].numpy(), lengths=lens[pick])
+    assert np.abs(t_en[pick].cpu().numpy() - r_t).max() <= 1e-4
+    assert np.abs(d[pick].cpu().numpy() - r_d).max() <= 2e-4 and np.abs(dur[pick].cpu().numpy() - r_dur).max() <= 2e-4
+
+
 # ---------------------------------------------------------------- sizes at the edges of the new modules
 @pytest.mark.parametrize("B,L", [(1, 1), (3, 400), (65, 5)])
 def test_text_and_duration_sizes_vs_oracle(B, L):
@@ -325,6 +408,8 @@ def test_cuda_graph_replay_of_text_encoder_and_predictor_matches_eager():
     tok = synth.make_tokens(1, 37, seed=5500).cuda()
     tok2 = synth.make_tokens(1, 37, seed=5501).cuda()
     te, pr = _text_encoder(), _dur_predictor()
+    te._graphs.clear()                      # the modules are shared with the tests above
+    pr._graphs.clear()
     s = synth.make_duration_inputs(1, 37, seed=4500)["s"].cuda()
     with torch.no_grad():
         for t in (tok, tok2, tok):

@@ -218,6 +218,34 @@ def test_text_encoder_oracle_matches_reference_fixtures():
             assert np.abs(PT.text_encoder(sdt, tok).numpy() - g["out"]).max() <= 5e-6
 
 
+def test_ragged_text_modules_match_reference_padded_batches():
+    """Padded batches (lengths 9, 6, 4) of TextEncoder.forward and of the duration half, as the reference's modules handle them
+    (masked_fill_ + pack_padded_sequence, models.py:258-285, :485-520, :426-439): fixtures of tests/golden/make_golden_ragged.py,
+    which also assert that the padded batch equals the one-sentence-at-a-time inference.py calls on the valid tokens."""
+    from oracle import predictor_np as P
+    g = golden("text_ragged_B3_L9_w0_i5101.npz")
+    sd = {k: v.numpy() for k, v in synth.make_text_state_dict(seed=0).items()}
+    lens = g["lengths"]
+    taps = {}
+    out = P.text_encoder(sd, g["tokens"], taps=taps, lengths=lens)
+    assert np.abs(out - g["out"]).max() <= 5e-6 and np.abs(taps["cnn.0"] - g["tap:cnn.0"]).max() <= 1e-5
+    for b, n in enumerate(lens):
+        assert np.abs(out[b, :, :n] - g["single%d" % b][0]).max() <= 1e-5
+        assert not out[b, :, n:].any()
+        # a padded utterance equals the oracle on that utterance alone
+        assert np.abs(P.text_encoder(sd, g["tokens"][b:b + 1, :n])[0] - out[b, :, :n]).max() <= 1e-6
+    g = golden("dur_ragged_B3_L9_w0_i4101.npz")
+    sd = {k: v.numpy() for k, v in synth.make_predictor_state_dict(seed=0, duration=True).items()}
+    taps = {}
+    d, dur = P.predict_duration(sd, g["t_en"], g["s"], taps=taps, lengths=g["lengths"])
+    assert np.abs(d - g["d"]).max() <= 2e-5 and np.abs(dur - g["duration"]).max() <= 2e-5
+    assert np.abs(taps["text_encoder.lstms.0"] - g["tap:text_encoder.lstms.0"]).max() <= 5e-6
+    assert np.abs(taps["lstm"] - g["tap:lstm"]).max() <= 1e-5
+    for b, n in enumerate(g["lengths"]):
+        assert np.abs(dur[b, :n] - g["single_dur%d" % b][0]).max() <= 2e-5
+        assert not d[b, n:].any()
+
+
 # ---------------------------------------------------------------- round-2 fixtures (tests/golden/make_golden_r2.py)
 def test_synth_plain_init_is_the_reference_init():
     """`init_weights` N(0, 0.01) (hifigan.py:37,47,318-319) never reaches the reference's forward: under the legacy weight_norm
