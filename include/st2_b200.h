@@ -173,7 +173,8 @@ ST2_API int st2_f0n_forward(st2_decoder* d, const float* en, const float* s, flo
 /* Duration half of the same predictor: replaces inference.py:242-245 --
  *   d = predictor.text_encoder(t_en, s, lengths, mask)        DurationEncoder.forward, models.py:485-520
  *   x, _ = predictor.lstm(d) ; duration = sigmoid(predictor.duration_proj(x)).sum(-1)
- * for a batch of equal-length utterances (no padding).  Available when the handle was also given the reference keys
+ * for a batch of equal-length utterances (st2_dur_forward_ragged below takes padded ones).  Available when the handle was also
+ * given the reference keys
  * "text_encoder.lstms.*", "lstm.*" and "duration_proj.linear_layer.*" before st2_decoder_finalize.
  *   t_en [B, d_hid, L], s [B, style_dim]  ->  d [B, L, d_hid+style_dim] (the reference's layout), duration [B, L]
  * (feed `duration` to st2_round_durations and `d`, transposed, to st2_length_regulate). */
@@ -204,6 +205,18 @@ ST2_API int st2_text_forward(st2_decoder* d, const int64_t* tokens, float* out, 
  * zero (models.py:279-283). */
 ST2_API int st2_text_forward_ragged(st2_decoder* d, const int64_t* tokens, const int32_t* lengths, float* out, int32_t B, int32_t L,
                     int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- Duration smoothing: replaces inference.py:248-255 (+ the mean returned at :272) ----
+ * Per utterance b, over its n_tokens[b] tokens (nullptr = L):
+ *   mu  = prev_d_mean[b] if it is non-zero else mean(duration_b);  sd = std(duration_b)          (unbiased, inference.py:248-251)
+ *   dur = duration * (1 - t) + (noise * sd + mu) * t                                             (inference.py:252)
+ *   dur[1:-2] <- mean + sign * 3 * 0.95 * std of that slice wherever |z-score| > 3               (inference.py:253, :134-148)
+ *   dur /= speed ;  mean_out[b] = mean(dur)                                                      (inference.py:255, :272)
+ * noise [B, L] is the caller's N(0, 1) tape standing in for torch.Tensor.normal_ (null allowed when t == 0); prev_d_mean [B] and
+ * mean_out [B] may be null.  Tokens beyond n_tokens[b] are written as 0.  All pointers are device memory; feed `out` to
+ * st2_round_durations. */
+ST2_API int st2_smooth_durations(const float* duration, const int32_t* n_tokens, const float* noise, const float* prev_d_mean,
+                        float t, float speed, float* out, float* mean_out, int32_t B, int32_t L, void* stream);
 
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 

@@ -454,6 +454,41 @@ def round_durations(duration: np.ndarray) -> np.ndarray:
     return np.maximum(np.rint(duration.astype(F32)), 1).astype(np.int64)
 
 
+def replace_outliers_zscore(x: np.ndarray, threshold: float = 3.0, factor: float = 0.95) -> np.ndarray:
+    """StyleTTS2.__replace_outliers_zscore (inference.py:134-148) on a 1-D fp32 slice: entries with |z| > threshold become
+    mean + sign * threshold * std * factor; std is torch's unbiased one (NaN for a single element: nothing is replaced)."""
+    x = x.astype(F32)
+    if x.size == 0:
+        return x
+    mean = F32(x.astype(np.float64).mean())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        std = F32(np.sqrt(((x.astype(np.float64) - np.float64(mean)) ** 2).sum() / (x.size - 1))) if x.size > 1 else F32(np.nan)
+        z = ((x - mean) / std).astype(F32)
+        mask = np.abs(z) > F32(threshold)
+        repl = (mean + np.sign(x - mean).astype(F32) * F32(F32(F32(threshold) * std) * F32(factor))).astype(F32)
+    out = x.copy()
+    out[mask] = repl[mask]
+    return out
+
+
+def smooth_durations(duration: np.ndarray, noise: Optional[np.ndarray], t: float = 0.1, speed: float = 1.0,
+                     prev_d_mean: float = 0.0):
+    """inference.py:248-255 for ONE sentence, duration [L] fp32, noise [L] the N(0,1) tape in place of normal_'s own draw
+    (dur_stats = noise * std + mean, what normal_(mean, std) computes): returns (duration for the rounding, its mean --
+    inference.py:272)."""
+    d = duration.astype(F32)
+    n = d.size
+    mean = F32(d.astype(np.float64).mean())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        std = F32(np.sqrt(((d.astype(np.float64) - np.float64(mean)) ** 2).sum() / (n - 1))) if n > 1 else F32(np.nan)
+    mu = F32(prev_d_mean) if prev_d_mean != 0 else mean                       # inference.py:248-251
+    stats = (noise.astype(F32) * std + mu).astype(F32) if noise is not None else np.full(n, mu, F32)
+    d = ((d * F32(1.0 - t)).astype(F32) + (stats * F32(t)).astype(F32)).astype(F32)      # inference.py:252
+    d[1:-2] = replace_outliers_zscore(d[1:-2])                                # inference.py:253
+    d = (d / F32(speed)).astype(F32)                                          # inference.py:255
+    return d, F32(d.astype(np.float64).mean())
+
+
 def alignment_matrix(pred_dur: np.ndarray) -> np.ndarray:
     """inference.py:258-262: one-hot [L,F], row i is 1 on [c_i, c_i + dur_i)."""
     L = pred_dur.shape[0]

@@ -43,6 +43,96 @@ int launch_round_durations(const float* duration, const int32_t* n_tokens, int32
     return ST2_OK;
 }
 
+// ---- duration smoothing (inference.py:248-255) ------------------------------------------------------------------------
+// Between the sigmoid-sum of the duration head and the rounding the reference (a) mixes every duration with a draw from
+// N(mean, std) of the sentence's own durations -- mean replaced by the previous split's mean duration when there is one -- with
+// weight t (inference.py:248-252), (b) replaces |z| > 3 outliers of duration[1:-2] by mean +- 3 * 0.95 * std of that slice
+// (inference.py:253, :134-148), (c) divides by the speed (inference.py:255) and returns the mean duration for the next split
+// (inference.py:272).  All statistics are per sentence, torch.std is the unbiased one.  One CTA per utterance; sums in fp64
+// with a fixed-order tree (deterministic), the element-wise arithmetic in fp32 with the reference's operation order (no FMA
+// contraction).  The normal draw comes from a caller-provided N(0, 1) tape z: dur_stats = z * std + mean (what
+// torch.Tensor.normal_(mean, std) computes from its own standard-normal draw).
+static constexpr int kSmThreads = 128;
+
+__device__ double smooth_block_sum(double v, double* red) {
+    __syncthreads();                                       // red may still be read from the previous reduction
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = kSmThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+// unbiased mean / std of v[lo, hi) (hi - lo >= 1; std is NaN for a single element, like torch)
+__device__ void smooth_mean_std(const float* v, int lo, int hi, double* red, float* mean_out, float* std_out) {
+    double s = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += kSmThreads) s += (double)v[i];
+    const double mean = smooth_block_sum(s, red) / (double)(hi - lo);
+    double q = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += kSmThreads) { const double dlt = (double)v[i] - mean; q += dlt * dlt; }
+    const double var = smooth_block_sum(q, red) / (double)(hi - lo - 1);      // n = 1: 0 / 0 = NaN
+    *mean_out = (float)mean;
+    *std_out = (float)sqrt(var);
+}
+
+__global__ void __launch_bounds__(kSmThreads)
+smooth_durations_kernel(const float* __restrict__ duration, const int32_t* __restrict__ n_tokens, const float* __restrict__ z,
+                        const float* __restrict__ prev_mean, float t, float speed, float* __restrict__ out,
+                        float* __restrict__ mean_out, int L) {
+    __shared__ double red[kSmThreads];
+    const int b = blockIdx.x;
+    const int n = n_tokens ? min(max(n_tokens[b], 0), L) : L;
+    const float* x = duration + (size_t)b * L;
+    float* y = out + (size_t)b * L;
+    for (int i = n + threadIdx.x; i < L; i += kSmThreads) y[i] = 0.f;          // padded tokens
+    if (n == 0) {
+        if (threadIdx.x == 0 && mean_out) mean_out[b] = 0.f;
+        return;
+    }
+    float mean, sd;
+    smooth_mean_std(x, 0, n, red, &mean, &sd);
+    const float prev = prev_mean ? prev_mean[b] : 0.f;
+    const float mu = prev != 0.f ? prev : mean;                                  // inference.py:248-251
+    const float c1 = (float)(1.0 - (double)t);                                   // Python computes 1 - t in double
+    for (int i = threadIdx.x; i < n; i += kSmThreads) {
+        const float stats = z ? __fadd_rn(__fmul_rn(z[(size_t)b * L + i], sd), mu) : mu;
+        y[i] = __fadd_rn(__fmul_rn(x[i], c1), __fmul_rn(stats, t));              // inference.py:252
+    }
+    __syncthreads();
+    if (n - 3 >= 1) {                                                            // duration[:, 1:-2], inference.py:253
+        float m2, sd2;
+        smooth_mean_std(y, 1, n - 2, red, &m2, &sd2);
+        const float repl = __fmul_rn(__fmul_rn(3.0f, sd2), 0.95f);               // threshold * std * factor, inference.py:143
+        for (int i = 1 + threadIdx.x; i < n - 2; i += kSmThreads) {
+            const float dlt = __fsub_rn(y[i], m2);
+            const float zz = __fdiv_rn(dlt, sd2);
+            if (fabsf(zz) > 3.0f) {                                              // NaN (single element): never
+                const float sg = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+                y[i] = __fadd_rn(m2, __fmul_rn(sg, repl));
+            }
+        }
+        __syncthreads();
+    }
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += kSmThreads) {
+        const float v = __fdiv_rn(y[i], speed);                                  // inference.py:255
+        y[i] = v;
+        s += (double)v;
+    }
+    const double tot = smooth_block_sum(s, red);
+    if (threadIdx.x == 0 && mean_out) mean_out[b] = (float)(tot / (double)n);    // inference.py:272
+}
+
+int launch_smooth_durations(const float* duration, const int32_t* n_tokens, const float* z, const float* prev_mean, float t,
+                            float speed, float* out, float* mean_out, int B, int L, cudaStream_t st) {
+    if (B <= 0 || L <= 0) return ST2_OK;
+    smooth_durations_kernel<<<B, kSmThreads, 0, st>>>(duration, n_tokens, z, prev_mean, t, speed, out, mean_out, L);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
 static constexpr int kLrThreads = 256;
 static constexpr int kLrTile = 128;      // frames per CTA
 

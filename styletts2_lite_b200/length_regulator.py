@@ -1,5 +1,6 @@
 """Duration -> frame length regulation (inference.py:257-268) on the GPU.
 
+    duration = smooth(duration, t, prev_d_mean) / speed   # st2_smooth_durations (inference.py:248-255)
     pred_dur = round(duration).clamp(min=1)          # st2_round_durations
     asr = t_en @ alignment ; en = d^T @ alignment    # st2_length_regulate (bit-exact gather)
 
@@ -34,6 +35,42 @@ def round_durations(duration: torch.Tensor, n_tokens: Optional[torch.Tensor] = N
         _lib.check(lib.st2_round_durations(_lib.ptr(duration), _lib.ptr(nt), _lib.ptr(dur), _lib.ptr(tot), B, L,
                                            _stream(duration.device)), "st2_round_durations")
     return dur, tot
+
+
+def smooth_durations(duration: torch.Tensor, noise: Optional[torch.Tensor] = None, t: float = 0.1, speed: float = 1.0,
+                     prev_d_mean=0.0, n_tokens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """inference.py:248-255 on the device, per utterance: mix with N(mean or prev_d_mean, std) draws (weight t), replace the
+    z-score outliers of duration[1:-2], divide by speed.  duration [B,L] fp32 (CUDA); noise [B,L] the N(0,1) tape that stands in
+    for `normal_` (drawn with torch.randn on the device when omitted and t > 0); prev_d_mean a float or a [B] tensor (0 = none).
+    Returns (smoothed duration [B,L], mean duration [B] -- inference.py:272, the next split's prev_d_mean)."""
+    if not duration.is_cuda:
+        raise _lib.St2Error("length regulator has no CPU path: inputs must be CUDA tensors")
+    speed = min(max(float(speed), 0.0001), 2.0)                   # inference.py:226
+    if not 0.0 <= float(t) <= 1.0:
+        raise ValueError("t must lie in [0, 1]")
+    lib = _lib.load()
+    dev = duration.device
+    duration = duration.detach().float().contiguous()
+    B, L = duration.shape
+    if noise is None and t > 0:
+        noise = torch.randn(B, L, device=dev, dtype=torch.float32)
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        if noise.shape != (B, L):
+            raise ValueError("noise must be [B,L]")
+    if isinstance(prev_d_mean, torch.Tensor):
+        prev = prev_d_mean.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if prev.numel() != B:
+            raise ValueError("prev_d_mean must have one entry per utterance")
+    else:
+        prev = None if float(prev_d_mean) == 0.0 else torch.full((B,), float(prev_d_mean), device=dev, dtype=torch.float32)
+    nt = None if n_tokens is None else n_tokens.to(device=dev, dtype=torch.int32).contiguous()
+    out = torch.empty_like(duration)
+    mean = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.st2_smooth_durations(_lib.ptr(duration), _lib.ptr(nt), _lib.ptr(noise), _lib.ptr(prev), float(t), speed,
+                                            _lib.ptr(out), _lib.ptr(mean), B, L, _stream(dev)), "st2_smooth_durations")
+    return out, mean
 
 
 def length_regulate(src: torch.Tensor, pred_dur: torch.Tensor, n_frames: int, channels_last: bool = False) -> torch.Tensor:

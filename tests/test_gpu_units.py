@@ -34,6 +34,41 @@ def test_length_regulator_golden_bit_exact():
     assert torch.equal(out_cl.cpu().transpose(1, 2), torch.from_numpy(g["asr"]))
 
 
+def test_duration_smoothing_reference_statements_and_ragged_batch():
+    """st2_smooth_durations against the reference statements of inference.py:248-257 (fixture smooth_cases.npz, one sentence per
+    case), then all cases as ONE padded batch with per-utterance n_tokens, previous means and tapes against the per-sentence
+    oracle; finally the rounded durations."""
+    g = golden("smooth_cases.npz")
+    K = int(g["n_cases"])
+    for k in range(K):
+        t, speed, prev = float(g["t_%d" % k]), float(g["speed_%d" % k]), float(g["prev_%d" % k])
+        out, mean = LR.smooth_durations(G.to_dev(g["duration_%d" % k]), G.to_dev(g["noise_%d" % k]), t, speed, prev)
+        ref = g["out_%d" % k]
+        assert np.abs(out.cpu().numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), k
+        assert abs(float(mean[0]) - float(g["mean_%d" % k])) <= 1e-5
+        pred, _ = LR.round_durations(out)
+        safe = np.abs(ref[0] - np.floor(ref[0]) - 0.5) > 1e-4
+        assert np.array_equal(pred.cpu().numpy()[0][safe], g["pred_%d" % k][safe]), k
+    # the cases that share (t, speed) as one padded batch
+    ks = [k for k in range(K) if float(g["t_%d" % k]) == np.float32(0.1) and float(g["speed_%d" % k]) == 1.0]
+    L = max(g["duration_%d" % k].shape[1] for k in ks)
+    dur = np.full((len(ks), L), 99.0, np.float32)                    # junk behind every utterance must not matter
+    z = np.zeros((len(ks), L), np.float32)
+    n_tok = np.array([g["duration_%d" % k].shape[1] for k in ks], np.int32)
+    prev = np.array([float(g["prev_%d" % k]) for k in ks], np.float32)
+    for i, k in enumerate(ks):
+        dur[i, :n_tok[i]] = g["duration_%d" % k][0]
+        z[i, :n_tok[i]] = g["noise_%d" % k][0]
+    out, mean = LR.smooth_durations(G.to_dev(dur), G.to_dev(z), 0.1, 1.0, torch.from_numpy(prev), torch.from_numpy(n_tok))
+    out = out.cpu().numpy()
+    for i, k in enumerate(ks):
+        ref, rmean = O.smooth_durations(g["duration_%d" % k][0], g["noise_%d" % k][0], 0.1, 1.0, float(prev[i]))
+        assert np.abs(out[i, :n_tok[i]] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), k
+        assert not out[i, n_tok[i]:].any() and abs(float(mean[i]) - rmean) <= 1e-5
+    with pytest.raises(Exception):
+        LR.smooth_durations(G.to_dev(dur), None, 1.5)                # t outside [0, 1]
+
+
 def test_length_regulator_ragged_empty_and_large():
     rng = np.random.default_rng(3)
     B, Cc, L = 5, 640, 300

@@ -218,6 +218,24 @@ def test_text_encoder_oracle_matches_reference_fixtures():
             assert np.abs(PT.text_encoder(sdt, tok).numpy() - g["out"]).max() <= 5e-6
 
 
+def test_duration_smoothing_oracle_matches_reference_statements():
+    """inference.py:248-257 lifted from the reference file and executed as is (tests/golden/make_golden_smooth.py): noise mix,
+    z-score outlier replacement on duration[1:-2], / speed, rounding -- sentence lengths 2 .. 200 incl. the empty / single-element
+    slices, a previous mean, t = 0."""
+    g = golden("smooth_cases.npz")
+    replaced = 0
+    for k in range(int(g["n_cases"])):
+        dur, z = g["duration_%d" % k][0], g["noise_%d" % k][0]
+        out, mean = O.smooth_durations(dur, z, float(g["t_%d" % k]), float(g["speed_%d" % k]), float(g["prev_%d" % k]))
+        ref = g["out_%d" % k][0]
+        assert np.abs(out - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), k
+        assert abs(mean - g["mean_%d" % k]) <= 1e-5
+        safe = np.abs(ref - np.floor(ref) - 0.5) > 1e-4              # away from rounding ties
+        assert np.array_equal(O.round_durations(out)[safe], g["pred_%d" % k].astype(np.int64)[safe]), k
+        replaced += int((np.abs(ref - dur / g["speed_%d" % k]) > 5.0).sum())
+    assert replaced >= 5                                             # the spikes of the fixture were really replaced
+
+
 def test_ragged_text_modules_match_reference_padded_batches():
     """Padded batches (lengths 9, 6, 4) of TextEncoder.forward and of the duration half, as the reference's modules handle them
     (masked_fill_ + pack_padded_sequence, models.py:258-285, :485-520, :426-439): fixtures of tests/golden/make_golden_ragged.py,

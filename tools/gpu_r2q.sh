@@ -1,4 +1,4 @@
 #!/bin/bash
-# ragged token batches: predictor / text-encoder GPU tests
+# full GPU suite (ragged token batches, duration smoothing included)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_predictor.py -q > gpurun_out/r2q_pred.log 2>&1; echo "predictor tests rc=$?"; tail -5 gpurun_out/r2q_pred.log
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2q_suite.log 2>&1; echo "gpu suite rc=$?"; tail -6 gpurun_out/r2q_suite.log
