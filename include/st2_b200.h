@@ -59,7 +59,7 @@ typedef enum {
  * constructor arguments Decoder actually uses (dim_in, style_dim; hifigan.py:417-422,
  * istftnet.py:661-667). */
 typedef struct {
-    int32_t variant;                 /* 0 = hifigan, 1 = istftnet */
+    int32_t variant;                 /* 0 = hifigan, 1 = istftnet, 4 = vocos (2 / 3 are the predictor / text-encoder handles) */
     int32_t dim_in;                  /* 512 */
     int32_t style_dim;               /* 128 */
     int32_t upsample_initial_channel;/* 512 */
@@ -69,8 +69,10 @@ typedef struct {
     int32_t n_kernels;               /* len(resblock_kernel_sizes) = 3 */
     int32_t resblock_kernel_sizes[3];
     int32_t resblock_dilations[3][3];
-    int32_t gen_istft_n_fft;         /* 20 (istftnet only) */
-    int32_t gen_istft_hop_size;      /* 5  (istftnet only) */
+    int32_t gen_istft_n_fft;         /* 20 (istftnet), 1200 (vocos) */
+    int32_t gen_istft_hop_size;      /* 5  (istftnet), 300 (vocos) */
+    int32_t intermediate_dim;        /* vocos only: 1536 (config_example.yaml:76) */
+    int32_t num_layers;              /* vocos only: 8 ConvNeXt blocks (config_example.yaml:77) */
 } st2_config;
 
 typedef struct st2_decoder st2_decoder;

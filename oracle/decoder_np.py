@@ -165,6 +165,9 @@ class Weights:
             return self._cache[name]
         if name + ".weight_g" in self.sd:
             w = fold_weight_norm(self.sd[name + ".weight_g"], self.sd[name + ".weight_v"])
+        elif name + ".parametrizations.weight.original0" in self.sd:      # parametrizations.weight_norm (vocos.py:10)
+            w = fold_weight_norm(self.sd[name + ".parametrizations.weight.original0"],
+                                 self.sd[name + ".parametrizations.weight.original1"])
         else:
             w = self.sd[name + ".weight"]
         self._cache[name] = w
@@ -198,7 +201,7 @@ def adain_resblk1d(W: Weights, name, x, s, upsample, taps=None, operand=None):
     sc = x
     if upsample:
         sc = np.repeat(sc, 2, axis=2)              # F.interpolate(scale_factor=2, 'nearest') hifigan.py:414
-    if (name + ".conv1x1.weight_v") in W.sd:
+    if (name + ".conv1x1.weight_v") in W.sd or (name + ".conv1x1.parametrizations.weight.original1") in W.sd:
         sc = conv1d(sc, W.w(name + ".conv1x1"), None, operand=operand)
     out = ((h + sc) / F32(math.sqrt(2))).astype(F32)
     if taps is not None:
@@ -420,6 +423,80 @@ def generator_istftnet(W: Weights, cfg, x, s, f0_curve, noise, taps=None, operan
     return stft_inverse(W, spec, phase, n_fft, hop)
 
 
+def gelu(x):
+    """nn.GELU() (vocos.py:48), the exact erf form."""
+    from scipy.special import erf
+    x64 = x.astype(F64)
+    return (0.5 * x64 * (1.0 + erf(x64 / math.sqrt(2.0)))).astype(F32)
+
+
+def convnext_block(W: Weights, name, x, s, operand=None, taps=None):
+    """ConvNeXtBlock.forward (vocos.py:57-69): depthwise Conv1d(k=7, pad 3) -> AdaIN1d -> Linear(dim, intermediate) -> GELU ->
+    Linear(intermediate, dim) -> gamma * x -> + residual.  x [B, dim, T]."""
+    B, C, T = x.shape
+    w, b = W.p(name + ".dwconv.weight"), W.p(name + ".dwconv.bias")
+    xp = np.zeros((B, C, T + 6), F32)
+    xp[:, :, 3:3 + T] = x
+    h = np.zeros((B, C, T), F32)
+    for k in range(7):
+        h += w[None, :, 0, k, None] * xp[:, :, k:k + T]
+    h = (h + b[None, :, None]).astype(F32)
+    if taps is not None:
+        taps[name + ".dwconv"] = h
+    h = adain(h, s, W.p(name + ".norm.fc.weight"), W.p(name + ".norm.fc.bias"))
+    h = h.transpose(0, 2, 1)                                                      # [B, T, C]
+    h = (round_operand(h, operand) @ round_operand(W.p(name + ".pwconv1.weight"), operand).T + W.p(name + ".pwconv1.bias")).astype(F32)
+    h = gelu(h)
+    h = (round_operand(h, operand) @ round_operand(W.p(name + ".pwconv2.weight"), operand).T + W.p(name + ".pwconv2.bias")).astype(F32)
+    h = (W.p(name + ".gamma") * h).astype(F32)
+    out = (x + h.transpose(0, 2, 1)).astype(F32)
+    if taps is not None:
+        taps[name] = out
+    return out
+
+
+def istft_same(W: Weights, spec, n_fft, hop):
+    """ISTFT.forward with padding='same' (vocos.py:195-232): irfft (norm 'backward') per frame, times the window, overlap-add
+    with stride hop, trim (win - hop) / 2 samples on both sides, divide by the overlap-added squared window.
+    spec complex [B, n_fft/2+1, T] -> [B, T*hop]."""
+    win = W.p("generator.stft.istft.window").astype(F32)
+    B, _, T = spec.shape
+    pad = (n_fft - hop) // 2
+    frames = (np.fft.irfft(spec.astype(np.complex128), n=n_fft, axis=1).astype(F32) * win[None, :, None]).astype(F32)
+    size = (T - 1) * hop + n_fft
+    y = np.zeros((B, size), F32)
+    env = np.zeros(size, F32)
+    wsq = (win * win).astype(F32)
+    for t in range(T):
+        y[:, t * hop:t * hop + n_fft] += frames[:, :, t]
+        env[t * hop:t * hop + n_fft] += wsq
+    assert (env[pad:size - pad] > 1e-11).all()                                    # vocos.py:229
+    return (y[:, pad:size - pad] / env[None, pad:size - pad]).astype(F32)
+
+
+def generator_vocos(W: Weights, cfg, x, s, taps=None, operand=None):
+    """Generator.forward + ISTFTHead.forward (vocos.py:159-164, :268-296).  x [B, dim, 2T] (the front half's output) ->
+    waveform [B, 1, 2T * hop]."""
+    for i in range(cfg.num_layers):
+        x = convnext_block(W, "generator.convnext.%d" % i, x, s, operand, taps)
+    h = x.transpose(0, 2, 1).astype(F64)                                          # final LayerNorm(dim, eps=1e-6), vocos.py:153
+    mean, var = h.mean(axis=2, keepdims=True), h.var(axis=2, keepdims=True)
+    h = ((h - mean) / np.sqrt(var + 1e-6)).astype(F32)
+    h = (h * W.p("generator.final_layer_norm.weight") + W.p("generator.final_layer_norm.bias")).astype(F32)
+    if taps is not None:
+        taps["generator.final_layer_norm"] = h
+    op = "fp16" if operand else None                                              # the head runs on fp16 operands in the 16-bit modes
+    o = (round_operand(h, op) @ round_operand(W.p("generator.stft.out.weight"), op).T + W.p("generator.stft.out.bias")).astype(F32)
+    o = o.transpose(0, 2, 1)                                                      # [B, n_fft + 2, T]
+    half = o.shape[1] // 2
+    mag = np.minimum(np.exp(o[:, :half]), F32(1e2)).astype(F32)                   # vocos.py:282-283
+    p = o[:, half:]
+    spec = (mag * np.cos(p)).astype(F32) + 1j * (mag * np.sin(p)).astype(F32)     # vocos.py:285-292
+    if taps is not None:
+        taps["generator.stft.out"] = o
+    return istft_same(W, spec, cfg.gen_istft_n_fft, cfg.gen_istft_hop_size)[:, None, :]
+
+
 def decoder_forward(sd: Dict[str, np.ndarray], cfg, asr, F0_curve, N, s, noise,
                     taps: Optional[dict] = None, operand: Optional[str] = None,
                     hp_groups: Optional[Dict[str, str]] = None, har_source=None):
@@ -442,6 +519,8 @@ def decoder_forward(sd: Dict[str, np.ndarray], cfg, asr, F0_curve, N, s, noise,
         x = adain_resblk1d(W, "decode.%d" % i, x, s, i == 3, taps, _operand_for("decode", operand, hp_groups))
     if taps is not None:
         taps["decode.out"] = x
+    if getattr(cfg, "is_vocos", False):
+        return generator_vocos(W, cfg, x, s, taps, operand)
     gen = generator_istftnet if cfg.is_istft else generator_hifigan
     return gen(W, cfg, x, s, F0_curve.astype(F32), noise, taps, operand, hp_groups, har_source)
 

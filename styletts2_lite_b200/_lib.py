@@ -30,12 +30,15 @@ class St2Config(C.Structure):
                 ("upsample_rates", C.c_int32 * 4), ("upsample_kernel_sizes", C.c_int32 * 4),
                 ("n_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 3),
                 ("resblock_dilations", (C.c_int32 * 3) * 3),
-                ("gen_istft_n_fft", C.c_int32), ("gen_istft_hop_size", C.c_int32)]
+                ("gen_istft_n_fft", C.c_int32), ("gen_istft_hop_size", C.c_int32),
+                ("intermediate_dim", C.c_int32), ("num_layers", C.c_int32)]
 
     @staticmethod
     def from_config(cfg: DecoderConfig) -> "St2Config":
         c = St2Config()
-        c.variant = 1 if cfg.is_istft else 0
+        c.variant = 4 if cfg.is_vocos else (1 if cfg.is_istft else 0)
+        c.intermediate_dim = cfg.intermediate_dim
+        c.num_layers = cfg.num_layers
         c.dim_in = cfg.dim_in
         c.style_dim = cfg.style_dim
         c.upsample_initial_channel = cfg.upsample_initial_channel

@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libst2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["decoder.cu", "predictor.cu", "api_units.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_source.cu",
-           "length_regulator.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "conv_pipe.cu", "conv_row.cu", "kernels_lstm.cu", "postprocess.cu"]
+           "length_regulator.cu", "vocos.cu", "conv_simt.cu", "conv_tc.cu", "conv_fused.cu", "conv_pipe.cu", "conv_row.cu", "kernels_lstm.cu", "postprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-I", INCLUDE]

@@ -24,7 +24,7 @@ HIDDEN_DIM = 512             # config_example.yaml:38
 
 @dataclass
 class DecoderConfig:
-    type: str = "hifigan"                       # 'hifigan' | 'istftnet'
+    type: str = "hifigan"                       # 'hifigan' | 'istftnet' | 'vocos'
     dim_in: int = HIDDEN_DIM
     style_dim: int = STYLE_DIM
     resblock_kernel_sizes: List[int] = field(default_factory=lambda: [3, 7, 11])
@@ -35,6 +35,18 @@ class DecoderConfig:
     upsample_kernel_sizes: List[int] = field(default_factory=lambda: [20, 10, 6, 4])
     gen_istft_n_fft: int = 20
     gen_istft_hop_size: int = 5
+    intermediate_dim: int = 1536                # vocos only (config_example.yaml:76-77)
+    num_layers: int = 8
+
+    @staticmethod
+    def vocos() -> "DecoderConfig":
+        """config_example.yaml:75-79: ConvNeXt backbone + ISTFTHead(n_fft 1200, hop 300) behind the shared front half."""
+        return DecoderConfig(type="vocos", upsample_rates=[], upsample_kernel_sizes=[], resblock_kernel_sizes=[],
+                             resblock_dilation_sizes=[], gen_istft_n_fft=1200, gen_istft_hop_size=300)
+
+    @property
+    def is_vocos(self) -> bool:
+        return self.type == "vocos"
 
     @staticmethod
     def hifigan() -> "DecoderConfig":
@@ -59,7 +71,7 @@ class DecoderConfig:
         p = 1
         for u in self.upsample_rates:
             p *= u
-        return p * (self.gen_istft_hop_size if self.is_istft else 1)
+        return p * (self.gen_istft_hop_size if (self.is_istft or self.is_vocos) else 1)
 
     @property
     def samples_per_frame(self) -> int:
@@ -92,12 +104,14 @@ class DecoderConfig:
         return k, u, u // 2 + u % 2, u % 2
 
 
-def _wn(specs, name, shape, bias=True):
-    """weight-normed conv: g has shape [shape[0],1,1] (dim=0 norm)."""
-    specs.append((name + ".weight_g", (shape[0], 1, 1), "g:" + name + ".weight_v"))
-    specs.append((name + ".weight_v", tuple(shape), "conv"))
+def _wn(specs, name, shape, bias=True, new_style=False):
+    """weight-normed conv: g has shape [shape[0],1,1] (dim=0 norm).  new_style: the keys of
+    torch.nn.utils.parametrizations.weight_norm (Modules/vocos.py:10): original0 = g, original1 = v."""
+    gk, vk = (".parametrizations.weight.original0", ".parametrizations.weight.original1") if new_style else (".weight_g", ".weight_v")
+    specs.append((name + gk, (shape[0], 1, 1), "g:" + name + vk))
+    specs.append((name + vk, tuple(shape), "conv"))
     if bias:
-        specs.append((name + ".bias", None, "bias:" + name + ".weight_v"))
+        specs.append((name + ".bias", None, "bias:" + name + vk))
 
 
 def _adain(specs, name, style_dim, c):
@@ -105,15 +119,15 @@ def _adain(specs, name, style_dim, c):
     specs.append((name + ".fc.bias", (2 * c,), "linear_bias:%d" % style_dim))
 
 
-def _adain_resblk1d(specs, name, cin, cout, style_dim, upsample):
-    _wn(specs, name + ".conv1", (cout, cin, 3))
-    _wn(specs, name + ".conv2", (cout, cout, 3))
+def _adain_resblk1d(specs, name, cin, cout, style_dim, upsample, new_style=False):
+    _wn(specs, name + ".conv1", (cout, cin, 3), new_style=new_style)
+    _wn(specs, name + ".conv2", (cout, cout, 3), new_style=new_style)
     _adain(specs, name + ".norm1", style_dim, cin)
     _adain(specs, name + ".norm2", style_dim, cout)
     if cin != cout:
-        _wn(specs, name + ".conv1x1", (cout, cin, 1), bias=False)
+        _wn(specs, name + ".conv1x1", (cout, cin, 1), bias=False, new_style=new_style)
     if upsample:
-        _wn(specs, name + ".pool", (cin, 1, 3))
+        _wn(specs, name + ".pool", (cin, 1, 3), new_style=new_style)
 
 
 def _adain_resblock1(specs, name, c, k, style_dim):
@@ -132,14 +146,18 @@ def param_specs(cfg: DecoderConfig):
     dim 0 for Conv1d, dim 1*groups for ConvTranspose1d)."""
     sd = cfg.style_dim
     specs = []
-    _adain_resblk1d(specs, "encode", cfg.dim_in + 2, 1024, sd, False)
+    ns = cfg.is_vocos                            # Modules/vocos.py uses the parametrizations weight_norm
+    _adain_resblk1d(specs, "encode", cfg.dim_in + 2, 1024, sd, False, ns)
     for i in range(3):
-        _adain_resblk1d(specs, "decode.%d" % i, 1024 + 2 + 64, 1024, sd, False)
-    _adain_resblk1d(specs, "decode.3", 1024 + 2 + 64, 512, sd, True)
-    _wn(specs, "F0_conv", (1, 1, 3))
-    _wn(specs, "N_conv", (1, 1, 3))
-    _wn(specs, "asr_res.0", (64, 512, 1))
+        _adain_resblk1d(specs, "decode.%d" % i, 1024 + 2 + 64, 1024, sd, False, ns)
+    _adain_resblk1d(specs, "decode.3", 1024 + 2 + 64, 512, sd, True, ns)
+    _wn(specs, "F0_conv", (1, 1, 3), new_style=ns)
+    _wn(specs, "N_conv", (1, 1, 3), new_style=ns)
+    _wn(specs, "asr_res.0", (64, 512, 1), new_style=ns)
     g = "generator"
+    if cfg.is_vocos:
+        _vocos_generator(specs, cfg)
+        return _resolve_bias_shapes(specs)
     specs.append((g + ".m_source.l_linear.weight", (1, HARMONICS), "linear"))
     specs.append((g + ".m_source.l_linear.bias", (1,), "linear_bias:%d" % HARMONICS))
     c0 = cfg.upsample_initial_channel
@@ -162,7 +180,31 @@ def param_specs(cfg: DecoderConfig):
     c_last = cfg.stage_channels(cfg.num_stages - 1)
     cpost = cfg.gen_istft_n_fft + 2 if cfg.is_istft else 1
     _wn(specs, g + ".conv_post", (cpost, c_last, 7))
-    # resolve bias shapes
+    return _resolve_bias_shapes(specs)
+
+
+def _vocos_generator(specs, cfg: DecoderConfig):
+    """Generator of Modules/vocos.py:103-162: num_layers ConvNeXtBlocks (:27-69: depthwise Conv1d k=7, AdaIN1d, Linear dim ->
+    intermediate, GELU, Linear back, layer scale gamma), final LayerNorm(dim, eps 1e-6), ISTFTHead.out = Linear(dim, n_fft + 2)."""
+    dim, sd = cfg.dim_in, cfg.style_dim
+    for i in range(cfg.num_layers):
+        n = "generator.convnext.%d" % i
+        specs.append((n + ".gamma", (dim,), "layer_scale:%g" % (1.0 / cfg.num_layers)))
+        specs.append((n + ".dwconv.weight", (dim, 1, 7), "trunc02"))
+        specs.append((n + ".dwconv.bias", (dim,), "small_bias"))
+        specs.append((n + ".norm.fc.weight", (2 * dim, sd), "trunc02"))
+        specs.append((n + ".norm.fc.bias", (2 * dim,), "small_bias"))
+        specs.append((n + ".pwconv1.weight", (cfg.intermediate_dim, dim), "trunc02"))
+        specs.append((n + ".pwconv1.bias", (cfg.intermediate_dim,), "small_bias"))
+        specs.append((n + ".pwconv2.weight", (dim, cfg.intermediate_dim), "trunc02"))
+        specs.append((n + ".pwconv2.bias", (dim,), "small_bias"))
+    specs.append(("generator.final_layer_norm.weight", (dim,), "gamma"))
+    specs.append(("generator.final_layer_norm.bias", (dim,), "beta"))
+    specs.append(("generator.stft.out.weight", (cfg.gen_istft_n_fft + 2, dim), "linear"))
+    specs.append(("generator.stft.out.bias", (cfg.gen_istft_n_fft + 2,), "linear_bias:%d" % dim))
+
+
+def _resolve_bias_shapes(specs):
     shapes = {n: s for n, s, _ in specs if s is not None}
     out = []
     for n, s, kind in specs:
@@ -181,7 +223,10 @@ def param_specs(cfg: DecoderConfig):
 
 
 def buffer_specs(cfg: DecoderConfig):
-    """CustomSTFT buffers registered by the istftnet Generator (istftnet.py:145-203)."""
+    """CustomSTFT buffers registered by the istftnet Generator (istftnet.py:145-203); the Hann window of the vocos ISTFT
+    (vocos.py:192-193)."""
+    if cfg.is_vocos:
+        return [("generator.stft.istft.window", (cfg.gen_istft_n_fft,))]
     if not cfg.is_istft:
         return []
     n, bins = cfg.gen_istft_n_fft, cfg.gen_istft_n_fft // 2 + 1

@@ -70,7 +70,7 @@ static inline int current_device_slot() {
 }
 int device_num_sms();                          // SM count of the current device (cached per device)
 
-enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2 };
+enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2, ACT_GELU = 3 };
 enum OutDtype { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 // kernel categories of the per-launch event profile (st2_decoder_get_profile)
 enum ProfCat {
@@ -149,7 +149,13 @@ int launch_concat_style(float* x, int ld, int C, const float* s, int S, int B, i
 int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, float* y, int ld_y, int B, int L, int C,
                           cudaStream_t st);
 int launch_layer_norm_lrelu(const float* x, const float* gamma, const float* beta, float slope, float* y, int B, int L, int C,
-                            cudaStream_t st);
+                            cudaStream_t st, float eps = 1e-5f);
+// Vocos generator pieces (vocos.cu; reference Modules/vocos.py)
+int launch_dwconv7(const float* x, const float* w7, const float* bias, float* y, int B, int T, int C, cudaStream_t st);
+int launch_scale_cols(float* w, float* bias, int rows, int ld, int cols, const float* scale, cudaStream_t st);
+int launch_vocos_basis(const float* window, float* basis, int n_fft, int k_pad, cudaStream_t st);
+int launch_vocos_spec(const float* o, int ld_o, void* a, int ld_a, int out_dtype, int64_t rows, int bins, cudaStream_t st);
+int launch_vocos_ola(const float* frames, const float* window, float* out, int B, int T, int n_fft, int hop, cudaStream_t st);
 int launch_embedding(const int64_t* tok, const float* table, float* y, int B, int L, int C, int n_symbols, cudaStream_t st);
 int launch_cl_to_cf(const float* x, float* y, int B, int L, int C, cudaStream_t st);
 int launch_duration_head(const float* x, const float* W, const float* bias, float* duration, int B, int L, int C, int nbins,

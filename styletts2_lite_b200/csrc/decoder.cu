@@ -17,7 +17,50 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-// Decoder weights (hifigan.py:416-443, istftnet.py:660-690)
+// Vocos generator weights (vocos.py:103-162: ConvNeXt blocks, final LayerNorm; :249-260: ISTFTHead.out and the ISTFT window)
+static void pack_vocos_generator(st2_decoder* d, Packer& P) {
+    const st2_config& c = d->cfg;
+    const int dim = c.dim_in, inter = c.intermediate_dim, N = c.gen_istft_n_fft;
+    for (int i = 0; i < c.num_layers; ++i) {
+        const std::string n = "generator.convnext." + std::to_string(i);
+        st2_decoder::ConvNeXtW& L = d->vx[i];
+        ConvW dw;                                                    // depthwise Conv1d weight [dim,1,7] -> [7][dim]
+        P.conv(dw, n + ".dwconv", 1, dim, 7, false, true, false);
+        L.dw_w = dw.w32; L.dw_b = dw.bias;
+        P.adain(L.norm, n + ".norm", dim);
+        P.linear(L.pw1, n + ".pwconv1.weight", n + ".pwconv1.bias", dim, inter);
+        const RawTensor* g = P.get(n + ".gamma");
+        if (!g || g->numel() != dim) {
+            if (P.err == ST2_OK) { set_error("%s.gamma must have %d elements", n.c_str(), dim); P.err = ST2_ERR_INVALID; }
+            return;
+        }
+        P.linear(L.pw2, n + ".pwconv2.weight", n + ".pwconv2.bias", inter, dim, g->ptr);     // gamma * (W x + b), vocos.py:63-64
+    }
+    d->vx_ln = (float*)P.dalloc((size_t)2 * dim * sizeof(float));
+    const float* lw = P.copy("generator.final_layer_norm.weight", dim);
+    const float* lb = P.copy("generator.final_layer_norm.bias", dim);
+    if (!d->vx_ln || !lw || !lb) return;
+    if (cudaMemcpyAsync(d->vx_ln, lw, (size_t)dim * sizeof(float), cudaMemcpyDeviceToDevice, P.st) != cudaSuccess ||
+        cudaMemcpyAsync(d->vx_ln + dim, lb, (size_t)dim * sizeof(float), cudaMemcpyDeviceToDevice, P.st) != cudaSuccess)
+        P.err = ST2_ERR_CUDA;
+    d->vx_kpad = round_up(N + 2, 128);                                // 1202 -> 1280: whole 256-column MMA tiles
+    P.linear(d->vx_out, "generator.stft.out.weight", "generator.stft.out.bias", dim, N + 2, nullptr, d->vx_kpad);
+    d->vx_window = P.copy("generator.stft.istft.window", N);
+    ConvW& bs = d->vx_basis;
+    bs.Cin = d->vx_kpad; bs.Cout = N; bs.k = 1; bs.transposed = false;
+    bs.w32 = (float*)P.dalloc((size_t)d->vx_kpad * N * sizeof(float));
+    if (!bs.w32 || !d->vx_window || P.err != ST2_OK) return;
+    if (launch_vocos_basis(d->vx_window, bs.w32, N, d->vx_kpad, P.st) != ST2_OK) P.err = ST2_ERR_CUDA;
+    if (d->tc_ok && N % 16 == 0) {
+        bs.cin_pad = d->vx_kpad; bs.cout_pad = N;
+        for (int dt = DT_BF16; dt <= DT_F16; ++dt) {
+            bs.w16[dt] = P.dalloc((size_t)d->vx_kpad * N * 2);
+            if (bs.w16[dt] && launch_pack_w16(bs.w32, bs.w16[dt], 1, d->vx_kpad, N, d->vx_kpad, N, dt, P.st) != ST2_OK) P.err = ST2_ERR_CUDA;
+        }
+    }
+}
+
+// Decoder weights (hifigan.py:416-443, istftnet.py:660-690; vocos.py:364-393)
 static void pack_decoder(st2_decoder* d, Packer& P) {
     const st2_config& c = d->cfg;
     const int dim_in = c.dim_in;
@@ -33,6 +76,10 @@ static void pack_decoder(st2_decoder* d, Packer& P) {
         d->n_w = u.w32; d->n_b = u.bias;
     }
     P.conv(d->asr_res, "asr_res.0", dim_in, 64, 1, false, true, true);
+    if (c.variant == 4) {
+        pack_vocos_generator(d, P);
+        return;
+    }
     d->lin_w = P.copy("generator.m_source.l_linear.weight", 9);
     d->lin_b = P.copy("generator.m_source.l_linear.bias", 1);
     const bool istft = c.variant == 1;
@@ -98,9 +145,55 @@ static int finalize_impl(st2_decoder* d, cudaStream_t st) {
     ST2_CUDA_CHECK(cudaGetLastError());
     d->num_params = 0;
     for (auto& kv : d->raw)
-        if (kv.first.find("generator.stft.") == std::string::npos) d->num_params += kv.second.numel();
+        if (c.variant == 4 ? kv.first != "generator.stft.istft.window" : kv.first.find("generator.stft.") == std::string::npos)
+            d->num_params += kv.second.numel();                       // registered buffers are not parameters
     d->finalized = true;
     return ST2_OK;
+}
+
+// Generator.forward + ISTFTHead.forward of the vocos variant (vocos.py:159-164, :268-296) on channels-last x [B][Tg][dim]
+static void vocos_generator(Exec& E, st2_decoder* d, float* x, float* out, int Tg) {
+    const st2_config& c = d->cfg;
+    const int B = E.B, C = c.dim_in, I = c.intermediate_dim, N = c.gen_istft_n_fft, KP = d->vx_kpad;
+    const int64_t rows = (int64_t)B * Tg;
+    float* xa = x;
+    float* xb = E.allocf(rows * C);
+    float* yd = E.allocf(rows * C);
+    float* hb = E.allocf(rows * I);
+    void* a16 = E.alloc(rows * C * 4);
+    void* g16 = E.alloc(rows * I * 4);
+    for (int i = 0; i < c.num_layers; ++i) {
+        const st2_decoder::ConvNeXtW& L = d->vx[i];
+        const std::string name = "generator.convnext." + std::to_string(i);
+        const int dt = E.fmt_for(name);
+        if (E.live()) E.chk(launch_dwconv7(xa, L.dw_w, L.dw_b, yd, B, Tg, C, E.st));            // vocos.py:59
+        E.prof(PC_MISC, 2.0 * rows * C * 7, 8.0 * rows * C);
+        E.tap(name + ".dwconv", yd, C, rows, C);
+        const bool tc1 = E.use_tc(L.pw1, dt), tc2 = E.use_tc(L.pw2, dt);
+        E.norm_act(yd, C, Tg, C, &L.norm, ACT_NONE, 0.f, nullptr, a16, C, tc1 ? dt : DT_F32);   // vocos.py:60 (AdaIN1d)
+        E.conv(L.pw1, a16, C, Tg, tc1 ? dt : DT_F32, hb, I, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0);   // vocos.py:62
+        E.norm_act(hb, I, Tg, I, nullptr, ACT_GELU, 0.f, nullptr, g16, I, tc2 ? dt : DT_F32);   // vocos.py:63
+        E.conv(L.pw2, g16, I, Tg, tc2 ? dt : DT_F32, xb, C, Tg, 1, 0, 1, xa, C, 0, 1.f, 0);     // vocos.py:64-69 (gamma folded, + residual)
+        std::swap(xa, xb);
+        E.tap(name, xa, C, rows, C);
+    }
+    if (E.live()) E.chk(launch_layer_norm_lrelu(xa, d->vx_ln, d->vx_ln + C, 1.0f, yd, B, Tg, C, E.st, 1e-6f));   // vocos.py:162 (eps 1e-6)
+    E.prof(PC_AFFINE_ACT, 0, 8.0 * rows * C);
+    E.tap("generator.final_layer_norm", yd, C, rows, C);
+    // ISTFTHead: the head GEMMs always take fp16 operands in the 16-bit modes (magnitudes up to 100 need the mantissa)
+    const int dth = E.prec != ST2_PREC_FP32 ? DT_F16 : DT_F32;
+    const bool tco = E.use_tc(d->vx_out, dth), tcb = E.use_tc(d->vx_basis, dth);
+    E.norm_act(yd, C, Tg, C, nullptr, ACT_NONE, 0.f, nullptr, a16, C, tco ? dth : DT_F32);
+    float* ob = E.allocf(rows * KP);
+    E.conv(d->vx_out, a16, C, Tg, tco ? dth : DT_F32, ob, KP, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0);   // vocos.py:280
+    E.tap("generator.stft.out", ob, KP, rows, N + 2);
+    void* sp = E.alloc(rows * KP * 4);
+    if (E.live()) E.chk(launch_vocos_spec(ob, KP, sp, KP, tcb ? dth : DT_F32, rows, N / 2 + 1, E.st));   // vocos.py:281-292
+    E.prof(PC_POST, 0, rows * KP * (4.0 + (tcb ? 2 : 4)));
+    float* fr = E.allocf(rows * N);
+    E.conv(d->vx_basis, sp, KP, Tg, tcb ? dth : DT_F32, fr, N, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0);     // irfft * window, vocos.py:214-215
+    if (E.live()) E.chk(launch_vocos_ola(fr, d->vx_window, out, B, Tg, N, c.gen_istft_hop_size, E.st));   // vocos.py:218-230
+    E.prof(PC_POST, 0, 4.0 * rows * N + 4.0 * rows * c.gen_istft_hop_size);
 }
 
 static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const float* nn, const float* s,
@@ -108,6 +201,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
                         int64_t ws_bytes, cudaStream_t st, bool dry, int64_t* peak_out) {
     const st2_config& c = d->cfg;
     const bool istft = c.variant == 1;
+    const bool vocos = c.variant == 4;
     Exec E{d, st, dry, prec, B, (char*)ws, ws_bytes};
     const int spf = d->spf();
     const int S = spf * T, L2 = 2 * T;
@@ -118,8 +212,8 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     float* H = E.allocf((int64_t)B * d->fc_rows);
     E.H = H;
     E.coef = E.allocf((int64_t)B * 2 * 2048);
-    float* frames = E.allocf((int64_t)B * L2 * 9);
-    float* har = E.allocf((int64_t)B * S);
+    float* frames = vocos ? nullptr : E.allocf((int64_t)B * L2 * 9);          // the vocos variant has no harmonic source
+    float* har = vocos ? nullptr : E.allocf((int64_t)B * S);
     float* x514 = E.allocf((int64_t)B * T * LD514);
     float* x1090 = E.allocf((int64_t)B * T * LD1090);
     const int C0 = c.upsample_initial_channel;
@@ -154,17 +248,19 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
                               1024 + 64, C1090, B, T, st));
         E.prof(PC_MISC, 2.0 * B * d->fc_rows * c.style_dim,
                4.0 * ((double)d->fc_rows * c.style_dim + 2.0 * B * c.dim_in * T + 4.0 * B * L2));
-        E.chk(launch_sinegen_frames(f0, frames, B, L2, up_scale, st));
-        E.chk(launch_har_source(f0, frames, noise, seed, d->seed_dev, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
-        // SineGen algorithmic bytes: read 4*B*2T (+ 36*B*S of noise when taped), write 4*B*S
-        E.prof(PC_SOURCE, 0, 4.0 * B * L2 + (noise ? 36.0 * B * S : 0.0) + 4.0 * B * S);
+        if (!vocos) {
+            E.chk(launch_sinegen_frames(f0, frames, B, L2, up_scale, st));
+            E.chk(launch_har_source(f0, frames, noise, seed, d->seed_dev, d->lin_w, d->lin_b, har, B, L2, up_scale, st));
+            // SineGen algorithmic bytes: read 4*B*2T (+ 36*B*S of noise when taped), write 4*B*S
+            E.prof(PC_SOURCE, 0, 4.0 * B * L2 + (noise ? 36.0 * B * S : 0.0) + 4.0 * B * S);
+        }
         if (istft) {
             E.chk(launch_stft_transform(har, d->stft_fr, d->stft_fi, har22, HLD, B, S, c.gen_istft_n_fft,
                                         c.gen_istft_hop_size, st));
             E.prof(PC_SOURCE, 0, 4.0 * B * S + 4.0 * B * har_frames * (c.gen_istft_n_fft + 2));
         }
     }
-    E.tap("har_source", har, 1, (int64_t)B * S, 1);
+    if (!vocos) E.tap("har_source", har, 1, (int64_t)B * S, 1);
     if (istft) E.tap("har", har22, HLD, (int64_t)B * har_frames, c.gen_istft_n_fft + 2);
 
     // ---- front half: encode, asr_res, decode[0..3] (hifigan.py:461-472)
@@ -185,6 +281,11 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     for (int i = 0; i < 3; ++i) E.resblk1d(d->decode[i], x1090, LD1090, T, x1090, LD1090);
     E.resblk1d(d->decode[3], x1090, LD1090, T, xg, C0);
     E.tap("decode.out", xg, C0, (int64_t)B * 2 * T, C0);
+    if (vocos) {
+        vocos_generator(E, d, xg, out, 2 * T);
+        if (peak_out) *peak_out = E.peak;
+        return E.err;
+    }
 
     // ---- generator (hifigan.py:328-345 / istftnet.py:552-573)
     const float* x = xg;
@@ -354,21 +455,7 @@ extern "C" {
 int st2_abi_version(void) { return ST2_ABI_VERSION; }
 const char* st2_last_error(void) { return st2::g_err; }
 
-int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
-    ST2_REQUIRE(cfg != nullptr && out != nullptr, "create: null argument");
-    ST2_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "create: variant must be 0 (hifigan) or 1 (istftnet)");
-    ST2_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= 4 && cfg->n_kernels == 3, "create: unsupported stage/kernel count");
-    ST2_REQUIRE(cfg->dim_in == 512 && cfg->style_dim >= 4 && cfg->style_dim <= 1024, "create: dim_in must be 512");
-    ST2_REQUIRE(cfg->upsample_initial_channel % 64 == 0 && (cfg->upsample_initial_channel >> cfg->n_stages) >= 4 &&
-                    ((cfg->upsample_initial_channel >> cfg->n_stages) % 4) == 0,
-                "create: unsupported upsample_initial_channel");
-    // the AdaIN coefficient buffer of a forward holds 2 x 2048 floats per utterance (Exec::coef)
-    ST2_REQUIRE(cfg->upsample_initial_channel <= 2048, "create: upsample_initial_channel must be <= 2048");
-    for (int i = 0; i < cfg->n_stages; ++i)
-        ST2_REQUIRE(cfg->upsample_rates[i] >= 1 && cfg->upsample_kernel_sizes[i] % cfg->upsample_rates[i] == 0,
-                    "create: upsample kernel must be a multiple of its rate");
-    if (cfg->variant == 1)
-        ST2_REQUIRE(cfg->gen_istft_n_fft == 20 && cfg->gen_istft_hop_size == 5, "create: iSTFT head supports n_fft=20, hop=5");
+static int create_handle(const st2_config* cfg, st2_decoder** out) {
     st2_decoder* d = new (std::nothrow) st2_decoder();
     ST2_REQUIRE(d != nullptr, "create: out of memory");
     d->cfg = *cfg;
@@ -379,6 +466,36 @@ int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
         d->tc_ok = (prop.major == 10);
     *out = d;
     return ST2_OK;
+}
+
+int st2_decoder_create(const st2_config* cfg, st2_decoder** out) {
+    ST2_REQUIRE(cfg != nullptr && out != nullptr, "create: null argument");
+    ST2_REQUIRE(cfg->variant == 0 || cfg->variant == 1 || cfg->variant == 4,
+                "create: variant must be 0 (hifigan), 1 (istftnet) or 4 (vocos)");
+    ST2_REQUIRE(cfg->dim_in == 512 && cfg->style_dim >= 4 && cfg->style_dim <= 1024, "create: dim_in must be 512");
+    if (cfg->variant == 4) {
+        // Modules/vocos.py:364-393: decode.3 ends at 512 channels = the generator's dim; ISTFT 'same' padding (vocos.py:203)
+        ST2_REQUIRE(cfg->upsample_initial_channel == 512 && cfg->n_stages == 0, "create: vocos has no upsampling stages");
+        ST2_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 16 && cfg->intermediate_dim >= 64 && cfg->intermediate_dim <= 2048 &&
+                        cfg->intermediate_dim % 64 == 0,
+                    "create: vocos needs 1..16 layers and an intermediate_dim that is a multiple of 64, at most 2048");
+        ST2_REQUIRE(cfg->gen_istft_hop_size >= 1 && cfg->gen_istft_n_fft % 16 == 0 && cfg->gen_istft_n_fft >= cfg->gen_istft_hop_size &&
+                        (cfg->gen_istft_n_fft - cfg->gen_istft_hop_size) % 2 == 0 && cfg->gen_istft_n_fft <= 4096,
+                    "create: vocos ISTFT needs n_fft a multiple of 16 (<= 4096), hop <= n_fft, n_fft - hop even");
+        return create_handle(cfg, out);
+    }
+    ST2_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= 4 && cfg->n_kernels == 3, "create: unsupported stage/kernel count");
+    ST2_REQUIRE(cfg->upsample_initial_channel % 64 == 0 && (cfg->upsample_initial_channel >> cfg->n_stages) >= 4 &&
+                    ((cfg->upsample_initial_channel >> cfg->n_stages) % 4) == 0,
+                "create: unsupported upsample_initial_channel");
+    // the AdaIN coefficient buffer of a forward holds 2 x 2048 floats per utterance (Exec::coef)
+    ST2_REQUIRE(cfg->upsample_initial_channel <= 2048, "create: upsample_initial_channel must be <= 2048");
+    for (int i = 0; i < cfg->n_stages; ++i)
+        ST2_REQUIRE(cfg->upsample_rates[i] >= 1 && cfg->upsample_kernel_sizes[i] % cfg->upsample_rates[i] == 0,
+                    "create: upsample kernel must be a multiple of its rate");
+    if (cfg->variant == 1)
+        ST2_REQUIRE(cfg->gen_istft_n_fft == 20 && cfg->gen_istft_hop_size == 5, "create: iSTFT head supports n_fft=20, hop=5");
+    return create_handle(cfg, out);
 }
 
 void st2_decoder_destroy(st2_decoder* d) {
@@ -413,7 +530,7 @@ int st2_decoder_finalize(st2_decoder* d, void* stream) {
 int64_t st2_decoder_num_params(const st2_decoder* d) { return d ? d->num_params : 0; }
 
 int64_t st2_decoder_workspace_bytes(const st2_decoder* d, int32_t B, int32_t T, int32_t precision) {
-    if (!d || !d->finalized || d->cfg.variant >= 2 || B <= 0 || T <= 0) {
+    if (!d || !d->finalized || d->cfg.variant == 2 || d->cfg.variant == 3 || B <= 0 || T <= 0) {
         st2::set_error("workspace_bytes: handle not finalized (or a predictor handle) or bad shape");
         return ST2_ERR_STATE;
     }
@@ -428,7 +545,7 @@ int st2_decoder_forward(st2_decoder* d, const float* asr, const float* f0, const
                         const float* noise, uint64_t seed, float* out, int32_t B, int32_t T, int32_t precision,
                         void* workspace, int64_t workspace_bytes, void* stream) {
     ST2_REQUIRE(d != nullptr, "forward: null handle");
-    if (!d->finalized || d->cfg.variant >= 2) {
+    if (!d->finalized || d->cfg.variant == 2 || d->cfg.variant == 3) {
         st2::set_error("forward: st2_decoder_finalize has not been called (or this is a predictor / text-encoder handle)");
         return ST2_ERR_STATE;
     }

@@ -278,7 +278,7 @@ __global__ void concat_style_kernel(float* __restrict__ x, int ld, int C, const 
 // h = gamma, h + ld_h = beta (per channel, shared by every row)
 template <int C, bool PLAIN>
 __global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ h, int ld_h, int h_off,
-                                      float* __restrict__ y, int ld_y, int64_t rows, int L, float slope) {
+                                      float* __restrict__ y, int ld_y, int64_t rows, int L, float slope, float eps) {
     constexpr int PER = C / 32;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -300,7 +300,7 @@ __global__ void ada_layer_norm_kernel(const float* __restrict__ x, const float* 
     for (int i = 0; i < PER; ++i) { const float dlt = v[i] - mean; sq = fmaf(dlt, dlt, sq); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * (1.f / C) + 1e-5f);
+    const float rstd = rsqrtf(sq * (1.f / C) + eps);
     const float* hb = PLAIN ? h : h + (row / L) * ld_h + h_off;
     const float* bb = PLAIN ? h + ld_h : hb + C;
     const float one = PLAIN ? 0.f : 1.f;
@@ -413,16 +413,16 @@ int launch_ada_layer_norm(const float* x, const float* h, int ld_h, int h_off, f
                           cudaStream_t st) {
     ST2_REQUIRE(C == 512 && ld_y % 4 == 0 && ld_h % 4 == 0 && h_off % 4 == 0, "ada_layer_norm: needs 512 channels (got %d)", C);
     const int64_t rows = (int64_t)B * L;
-    ada_layer_norm_kernel<512, false><<<cdiv(rows, 8), 256, 0, st>>>(x, h, ld_h, h_off, y, ld_y, rows, L, 0.f);
+    ada_layer_norm_kernel<512, false><<<cdiv(rows, 8), 256, 0, st>>>(x, h, ld_h, h_off, y, ld_y, rows, L, 0.f, 1e-5f);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
 
 int launch_layer_norm_lrelu(const float* x, const float* gamma, const float* beta, float slope, float* y, int B, int L, int C,
-                            cudaStream_t st) {
+                            cudaStream_t st, float eps) {
     ST2_REQUIRE(C == 512, "layer_norm: needs 512 channels (got %d)", C);
     const int64_t rows = (int64_t)B * L;
-    ada_layer_norm_kernel<512, true><<<cdiv(rows, 8), 256, 0, st>>>(x, gamma, (int)(beta - gamma), 0, y, C, rows, L, slope);
+    ada_layer_norm_kernel<512, true><<<cdiv(rows, 8), 256, 0, st>>>(x, gamma, (int)(beta - gamma), 0, y, C, rows, L, slope, eps);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

@@ -193,6 +193,7 @@ __device__ __forceinline__ float act_fn(float v, float p0, float p1) {
         float sn = FAST ? __sinf(p0 * v) : sinf(p0 * v);
         return fmaf(p1 * sn, sn, v);
     }
+    if (ACT == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));   // nn.GELU(), exact erf form (vocos.py:48)
     return v;
 }
 
@@ -255,7 +256,7 @@ affine_act_kernel(const float* __restrict__ x, int ld_x, const float* __restrict
                 o.y = act_fn<ACT, FAST>(o.y, al.y, ia.y);
                 o.z = act_fn<ACT, FAST>(o.z, al.z, ia.z);
                 o.w = act_fn<ACT, FAST>(o.w, al.w, ia.w);
-            } else if (ACT == ACT_LRELU) {
+            } else if (ACT == ACT_LRELU || ACT == ACT_GELU) {
                 o.x = act_fn<ACT, FAST>(o.x, slope, 0.f);
                 o.y = act_fn<ACT, FAST>(o.y, slope, 0.f);
                 o.z = act_fn<ACT, FAST>(o.z, slope, 0.f);
@@ -302,6 +303,7 @@ int launch_affine_act(const float* x, int ld_x, const float* coef, const float* 
     switch (act) {
         case ACT_NONE: return launch_affine_act_dt<ACT_NONE>(x, ld_x, coef, alpha, slope, y, ld_y, out_dtype, B, T, Cpad, st);
         case ACT_LRELU: return launch_affine_act_dt<ACT_LRELU>(x, ld_x, coef, alpha, slope, y, ld_y, out_dtype, B, T, Cpad, st);
+        case ACT_GELU: return launch_affine_act_dt<ACT_GELU>(x, ld_x, coef, alpha, slope, y, ld_y, out_dtype, B, T, Cpad, st);
         case ACT_SNAKE:
             ST2_REQUIRE(alpha != nullptr, "affine_act: snake needs alpha");
             return launch_affine_act_dt<ACT_SNAKE>(x, ld_x, coef, alpha, slope, y, ld_y, out_dtype, B, T, Cpad, st);

@@ -99,6 +99,15 @@ struct st2_decoder {
     float *stft_fr = nullptr, *stft_fi = nullptr, *stft_br = nullptr, *stft_bi = nullptr;
     std::map<std::string, Tap> taps;
 
+    // variant 4: Vocos generator (Modules/vocos.py:103-162, :235-296): ConvNeXt blocks, final LayerNorm, ISTFTHead
+    struct ConvNeXtW { float* dw_w = nullptr; float* dw_b = nullptr; AdaINRef norm; ConvW pw1, pw2; };
+    ConvNeXtW vx[16];
+    float* vx_ln = nullptr;                 // final_layer_norm weight[dim] | bias[dim]
+    ConvW vx_out;                           // ISTFTHead.out, columns padded to vx_kpad
+    ConvW vx_basis;                         // windowed inverse real DFT as a [vx_kpad, n_fft] matrix (vocos.cu)
+    float* vx_window = nullptr;             // generator.stft.istft.window [n_fft]
+    int vx_kpad = 0;
+
     // variant 2: the F0 / energy predictor ProsodyPredictor.F0Ntrain (models.py:407-419, :448-461); cfg.dim_in = d_hid
     LstmW shared;                           // models.py:407
     // duration half (row N2; packed only when the caller handed its weights over): DurationEncoder (models.py:468-483),
@@ -129,7 +138,7 @@ struct st2_decoder {
     int spf() const {    // samples per asr frame
         int p = 2;
         for (int i = 0; i < cfg.n_stages; ++i) p *= cfg.upsample_rates[i];
-        return p * (cfg.variant == 1 ? cfg.gen_istft_hop_size : 1);
+        return p * ((cfg.variant == 1 || cfg.variant == 4) ? cfg.gen_istft_hop_size : 1);
     }
     int stage_channels(int i) const { return cfg.upsample_initial_channel >> (i + 1); }
 };
@@ -184,8 +193,16 @@ struct Packer {
     }
     void conv(ConvW& c, const std::string& n, int Cin, int Cout, int k, bool transposed, bool bias, bool want16) {
         c.Cin = Cin; c.Cout = Cout; c.k = k; c.transposed = transposed;
+        // legacy weight_norm keys (hifigan.py / istftnet.py), the parametrizations ones of Modules/vocos.py:10, or a plain weight
         const RawTensor* g = get(n + ".weight_g", false);
-        const RawTensor* v = g ? get(n + ".weight_v") : get(n + ".weight");
+        const RawTensor* v = nullptr;
+        if (g) {
+            v = get(n + ".weight_v");
+        } else if ((g = get(n + ".parametrizations.weight.original0", false)) != nullptr) {
+            v = get(n + ".parametrizations.weight.original1");
+        } else {
+            v = get(n + ".weight");
+        }
         if (!v) return;
         const int d0 = transposed ? Cin : Cout, d1 = transposed ? Cout : Cin;
         if (v->shape.size() != 3 || v->shape[0] != d0 || v->shape[1] != d1 || v->shape[2] != k ||
@@ -211,8 +228,12 @@ struct Packer {
         }
     }
     // nn.Linear / nn.LSTM input matrix [Cout, Cin] as a 1x1 conv (packed [1][Cin][Cout] + 16-bit copies)
-    void linear(ConvW& c, const std::string& wname, const std::string& bname, int Cin, int Cout) {
-        c.Cin = Cin; c.Cout = Cout; c.k = 1; c.transposed = false;
+    // col_scale (optional, [Cout]): every output column and the bias are multiplied by it (a per-channel layer scale folded in);
+    // cout_pad > Cout: zero weight columns / zero bias entries up to cout_pad, which becomes the layer's Cout
+    void linear(ConvW& c, const std::string& wname, const std::string& bname, int Cin, int Cout, const float* col_scale = nullptr,
+                int cout_pad = 0) {
+        const int Cp = cout_pad > Cout ? cout_pad : Cout;
+        c.Cin = Cin; c.Cout = Cp; c.k = 1; c.transposed = false;
         const RawTensor* v = get(wname);
         if (!v) return;
         if (v->numel() != (int64_t)Cin * Cout || v->shape.empty() || v->shape[0] != Cout) {
@@ -220,15 +241,33 @@ struct Packer {
             err = ST2_ERR_INVALID;
             return;
         }
-        c.w32 = (float*)dalloc((size_t)Cin * Cout * sizeof(float));
+        c.w32 = (float*)dalloc((size_t)Cin * Cp * sizeof(float));
         if (!c.w32) return;
-        if (launch_fold_pack(nullptr, v->ptr, c.w32, Cout, Cin, 1, 0, st) != ST2_OK) err = ST2_ERR_CUDA;
-        if (!bname.empty()) c.bias = copy(bname, Cout);
-        if (d->tc_ok && Cin % 64 == 0 && Cout % 16 == 0) {
-            c.cin_pad = Cin; c.cout_pad = Cout;
+        if (Cp == Cout) {
+            if (launch_fold_pack(nullptr, v->ptr, c.w32, Cout, Cin, 1, 0, st) != ST2_OK) err = ST2_ERR_CUDA;
+        } else {
+            float* tmp = (float*)dalloc((size_t)Cin * Cout * sizeof(float));
+            if (!tmp) return;
+            if (launch_fold_pack(nullptr, v->ptr, tmp, Cout, Cin, 1, 0, st) != ST2_OK) err = ST2_ERR_CUDA;
+            if (cudaMemsetAsync(c.w32, 0, (size_t)Cin * Cp * sizeof(float), st) != cudaSuccess ||
+                cudaMemcpy2DAsync(c.w32, (size_t)Cp * sizeof(float), tmp, (size_t)Cout * sizeof(float), (size_t)Cout * sizeof(float),
+                                  Cin, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                err = ST2_ERR_CUDA;
+        }
+        if (!bname.empty()) {
+            const float* b = copy(bname, Cout);
+            c.bias = (float*)dalloc((size_t)Cp * sizeof(float));
+            if (!b || !c.bias) return;
+            if (cudaMemsetAsync(c.bias, 0, (size_t)Cp * sizeof(float), st) != cudaSuccess ||
+                cudaMemcpyAsync(c.bias, b, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                err = ST2_ERR_CUDA;
+        }
+        if (col_scale && launch_scale_cols(c.w32, c.bias, Cin, Cp, Cout, col_scale, st) != ST2_OK) err = ST2_ERR_CUDA;
+        if (d->tc_ok && Cin % 64 == 0 && Cp % 16 == 0) {
+            c.cin_pad = Cin; c.cout_pad = Cp;
             for (int dt = DT_BF16; dt <= DT_F16; ++dt) {
-                c.w16[dt] = dalloc((size_t)Cin * Cout * 2);
-                if (c.w16[dt] && launch_pack_w16(c.w32, c.w16[dt], 1, Cin, Cout, Cin, Cout, dt, st) != ST2_OK) err = ST2_ERR_CUDA;
+                c.w16[dt] = dalloc((size_t)Cin * Cp * 2);
+                if (c.w16[dt] && launch_pack_w16(c.w32, c.w16[dt], 1, Cin, Cp, Cin, Cp, dt, st) != ST2_OK) err = ST2_ERR_CUDA;
             }
         }
     }
@@ -329,7 +368,7 @@ struct Exec {
     int fmt_for(const std::string& name) const {
         if (prec == ST2_PREC_FP32) return DT_F32;
         if (prec == ST2_PREC_FP16) return DT_F16;
-        if (d->cfg.variant >= 2) return DT_F16;   // predictor / text encoder: 0.4 % of the decoder's FLOPs, its outputs steer the SineGen phase
+        if (d->cfg.variant == 2 || d->cfg.variant == 3) return DT_F16;   // predictor / text encoder: 0.4 % of the decoder's FLOPs, its outputs steer the SineGen phase
         // bf16 for the generator resblocks / ups (96 % of the FLOPs).  fp16 operands (same tensor
         // throughput) for generator.noise_res -- bf16 there alone costs ~9 dB of SNR -- and for the
         // front half (encode / decode / asr_res, K up to 3270), whose five chained blocks otherwise

@@ -36,7 +36,7 @@ def _register(root: nn.Module, name: str, tensor: torch.Tensor, buffer: bool = F
 
 
 class B200Decoder(nn.Module):
-    """Base of the two drop-in decoders.  `precision`: 'fp32' (SIMT, <=1e-4 of the CPU
+    """Base of the drop-in decoders (hifigan, istftnet, vocos).  `precision`: 'fp32' (SIMT, <=1e-4 of the CPU
     reference), 'bf16' (tcgen05, bf16 operands; generator.noise_res on fp16 operands) or
     'fp16' (tcgen05, fp16 operands)."""
 
@@ -48,9 +48,11 @@ class B200Decoder(nn.Module):
         self.cfg = cfg
         self.precision = precision
         for name, shape, kind in param_specs(cfg):
-            init = torch.ones(shape) if kind == "alpha" else torch.zeros(shape)
+            init = torch.ones(shape) if kind in ("alpha", "gamma") else torch.zeros(shape)
             _register(self, name, init)
-        if cfg.is_istft:
+        if cfg.is_vocos:
+            _register(self, "generator.stft.istft.window", torch.hann_window(cfg.gen_istft_n_fft), buffer=True)   # vocos.py:192-193
+        elif cfg.is_istft:
             bufs = stft_buffers(cfg)
             for name, _ in buffer_specs(cfg):
                 _register(self, name, bufs[name].clone(), buffer=True)

@@ -34,8 +34,11 @@ def _fan_in(shape):
 def make_state_dict(cfg: DecoderConfig, seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd = _draw(param_specs(cfg), g, perturb)
-    for name, shape in buffer_specs(cfg):
-        sd[name] = stft_buffers(cfg)[name]
+    if cfg.is_vocos:
+        sd["generator.stft.istft.window"] = torch.hann_window(cfg.gen_istft_n_fft)       # vocos.py:192 (periodic)
+    else:
+        for name, shape in buffer_specs(cfg):
+            sd[name] = stft_buffers(cfg)[name]
     return {k: v.float().contiguous() for k, v in sd.items()}
 
 
@@ -84,6 +87,14 @@ def _draw(specs, g, perturb: bool) -> Dict[str, torch.Tensor]:
                 sd[name] = 0.6 + 0.8 * torch.rand(shape, generator=g)
             else:
                 sd[name] = torch.ones(shape)
+        elif kind == "trunc02":                             # Generator._init_weights: trunc_normal_(std=0.02) (vocos.py:154-157)
+            w = torch.randn(shape, generator=g).clamp_(-2, 2) * 0.02
+            sd[name] = w * 3.0 if perturb else w                # the reference init is too small to exercise the blocks
+        elif kind == "small_bias":                          # constant_(bias, 0) in the reference init
+            sd[name] = 0.05 * torch.randn(shape, generator=g) if perturb else torch.zeros(shape)
+        elif kind.startswith("layer_scale:"):
+            v = float(kind.split(":")[1])
+            sd[name] = v * (0.5 + torch.rand(shape, generator=g)) if perturb else torch.full(shape, v)
         elif kind == "normal":                              # nn.Embedding init
             sd[name] = torch.randn(shape, generator=g)
         elif kind == "gamma":                               # LayerNorm scale: 1 in the reference init

@@ -493,3 +493,91 @@ def test_two_devices_in_one_process():
             outs.append(m(t["asr"], t["F0_curve"], t["N"], t["s"], seed=3).cpu())
         torch.cuda.synchronize(d)
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------- §8(f) N4: the Vocos decoder variant (Modules/vocos.py)
+def _vocos_inputs(B, T, seed, cfg):
+    return {k: v.numpy() for k, v in synth.make_inputs(B, T, seed, cfg, with_noise=False).items()}
+
+
+def _run_vocos(m, inp, precision="fp32"):
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        out = m(t["asr"], t["F0_curve"], t["N"], t["s"], precision=precision)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_vocos_small_fp32_golden_and_taps():
+    """Reference fixture of the unmodified Modules/vocos.py Decoder (tests/golden/make_golden_vocos.py): waveform <= 1e-4 and
+    the taps of the front half, the first / last ConvNeXt block, the final LayerNorm and ISTFTHead.out."""
+    cfg = DecoderConfig.vocos()
+    g = golden("vocos_B2_T6_w0_i1000.npz")
+    m = _decoder(cfg)
+    T = 6
+    shapes = {"decode.3": (2 * T, 512), "generator.convnext.0.dwconv": (2 * T, 512), "generator.convnext.0": (2 * T, 512),
+              "generator.convnext.7": (2 * T, 512), "generator.final_layer_norm": (2 * T, 512), "generator.stft.out": (2 * T, 1202)}
+    bufs = {n: m.set_tap(n, 2, rows, C_) for n, (rows, C_) in shapes.items()}
+    out = _run_vocos(m, _vocos_inputs(2, T, 1000, cfg))
+    m.clear_taps()
+    assert out.shape == (2, 1, 3600)
+    assert np.abs(G.cf(bufs["decode.3"].cpu().numpy()) - g["tap:decode.3"]).max() <= 1e-4
+    for n in ("generator.convnext.0", "generator.convnext.7"):
+        assert np.abs(G.cf(bufs[n].cpu().numpy()) - g["tap:" + n]).max() <= 1e-4, n
+    assert np.abs(bufs["generator.final_layer_norm"].cpu().numpy() - g["tap:generator.final_layer_norm"]).max() <= 1e-4
+    assert np.abs(bufs["generator.stft.out"].cpu().numpy() - g["tap:generator.stft.out"]).max() <= 1e-4
+    assert np.abs(out - g["out"]).max() <= 1e-4
+    # the oracle's depthwise conv (no reference hook sits between dwconv and norm)
+    taps = {}
+    sd = {k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()}
+    inp = _vocos_inputs(2, T, 1000, cfg)
+    O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], None, taps=taps)
+    assert np.abs(G.cf(bufs["generator.convnext.0.dwconv"].cpu().numpy()) - taps["generator.convnext.0.dwconv"]).max() <= 2e-5
+
+
+def test_vocos_3s_fp32_golden_and_tensor_core_paths():
+    cfg = DecoderConfig.vocos()
+    g = golden("vocos_B1_T120_w0_i1001.npz")
+    m = _decoder(cfg)
+    inp = _vocos_inputs(1, 120, 1001, cfg)
+    out = _run_vocos(m, inp)
+    assert out.shape == (1, 1, 72000) and np.abs(out - g["out"]).max() <= 1e-4
+    for prec in ("bf16", "fp16"):
+        o16 = _run_vocos(m, inp, prec)
+        assert snr_db(g["out"], o16) >= 40.0, (prec, snr_db(g["out"], o16))
+
+
+def test_vocos_batch_sizes_and_independence_vs_oracle():
+    """Odd frame counts (tiles that are not full), T = 3 (6 frames: barely longer than the 4-frame ISTFT overlap; at T = 2 the
+    front half's InstanceNorm over two samples amplifies fp32 rounding beyond any tolerance, on the CPU as well), a batch with
+    different styles: each utterance equals its own B = 1 call bit for bit, and the oracle on two of them."""
+    cfg = DecoderConfig.vocos()
+    m = _decoder(cfg)
+    sd = {k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()}
+    for B, T, seed in ((3, 37, 1010), (2, 3, 1011), (5, 203, 1012)):
+        inp = _vocos_inputs(B, T, seed, cfg)
+        out = _run_vocos(m, inp)
+        assert out.shape == (B, 1, 600 * T) and np.isfinite(out).all()
+        one = _run_vocos(m, {k: v[B - 1:B] for k, v in inp.items()})
+        assert np.array_equal(out[B - 1:B], one)
+        nb = 1 if T > 100 else 2
+        ref = O.decoder_forward(sd, cfg, inp["asr"][:nb], inp["F0_curve"][:nb], inp["N"][:nb], inp["s"][:nb], None)
+        assert np.abs(out[:nb] - ref).max() <= 1e-4, (B, T)
+
+
+def test_vocos_drop_in_constructor_and_graph_replay():
+    from styletts2_lite_b200 import vocos
+    m = vocos.Decoder(dim_in=512, style_dim=128, dim_out=80, intermediate_dim=1536, num_layers=8, gen_istft_n_fft=1200,
+                      gen_istft_hop_size=300, precision="bf16")
+    assert sum(p.numel() for p in m.parameters()) == 47_919_258 and len(m.state_dict()) == 149
+    cfg = DecoderConfig.vocos()
+    m.load_state_dict(synth.make_state_dict(cfg, 0, True))
+    m = m.to("cuda").eval()
+    inp = {k: v.cuda() for k, v in synth.make_inputs(2, 40, 1013, cfg, with_noise=False).items()}
+    with torch.no_grad():
+        a = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"])
+        b = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], cuda_graph=True)
+        c = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"], cuda_graph=True)
+    assert torch.equal(a, b) and torch.equal(b, c)
+    ref = _run_vocos(_decoder(cfg), {k: v.cpu().numpy() for k, v in inp.items()})
+    assert snr_db(ref, a.cpu().numpy()) >= 40.0

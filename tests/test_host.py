@@ -46,12 +46,18 @@ def test_create_validates_config_without_gpu(lib):
     assert lib.st2_decoder_create(C.byref(cc), C.byref(h)) == 0
     assert lib.st2_decoder_workspace_bytes(h, 1, 10, 0) == -2        # not finalized
     lib.st2_decoder_destroy(h)
+    cc = _lib.St2Config.from_config(DecoderConfig.vocos())               # the third decoder.type (Modules/vocos.py)
+    assert cc.variant == 4 and cc.num_layers == 8 and cc.intermediate_dim == 1536
+    assert lib.st2_decoder_create(C.byref(cc), C.byref(h)) == 0
+    lib.st2_decoder_destroy(h)
+    cc.gen_istft_hop_size = 301                                          # n_fft - hop must be even ('same' padding, vocos.py:203)
+    assert lib.st2_decoder_create(C.byref(cc), C.byref(h)) == -1
 
 
-@pytest.mark.parametrize("variant", ["hifigan", "istftnet"])
+@pytest.mark.parametrize("variant", ["hifigan", "istftnet", "vocos"])
 def test_state_dict_schema_matches_reference(variant):
     schema = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_schema.json")))[variant]
-    cfg = DecoderConfig.hifigan() if variant == "hifigan" else DecoderConfig.istftnet()
+    cfg = {"hifigan": DecoderConfig.hifigan, "istftnet": DecoderConfig.istftnet, "vocos": DecoderConfig.vocos}[variant]()
     mine = {n: list(s) for n, s, _ in param_specs(cfg)}
     mine.update({n: list(s) for n, s in buffer_specs(cfg)})
     assert mine == schema["state_dict"]
@@ -63,7 +69,13 @@ def test_state_dict_schema_matches_reference(variant):
     r = m.load_state_dict(sd)
     assert not r.missing_keys and not r.unexpected_keys
     # the reference's fallback strips a 7-char 'module.' prefix (inference.py:165-168): plain keys must load
-    assert torch.equal(m.state_dict()["generator.conv_post.weight_v"], sd["generator.conv_post.weight_v"])
+    key = "generator.stft.out.weight" if variant == "vocos" else "generator.conv_post.weight_v"
+    assert torch.equal(m.state_dict()[key], sd[key])
+    if variant == "vocos":
+        from styletts2_lite_b200.vocos import Decoder
+        m2 = Decoder(dim_in=512, style_dim=128, dim_out=80, intermediate_dim=1536, num_layers=8, gen_istft_n_fft=1200,
+                     gen_istft_hop_size=300)                             # models.py:555-562
+        assert set(m2.state_dict()) == set(schema["state_dict"]) and m2.cfg.samples_per_frame == 600
 
 
 def test_predictor_state_dict_schema_matches_reference():

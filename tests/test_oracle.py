@@ -218,6 +218,27 @@ def test_text_encoder_oracle_matches_reference_fixtures():
             assert np.abs(PT.text_encoder(sdt, tok).numpy() - g["out"]).max() <= 5e-6
 
 
+def test_vocos_oracle_matches_reference_fixtures():
+    """Vocos decoder variant (Modules/vocos.py:364-422; tests/golden/make_golden_vocos.py): ConvNeXt blocks, final LayerNorm,
+    ISTFTHead with 'same' padding -- output and taps of the small case, output of the 3 s case."""
+    cfg = DecoderConfig.vocos()
+    sd = {k: v.numpy() for k, v in synth.make_state_dict(cfg, 0, True).items()}
+    g = golden("vocos_B2_T6_w0_i1000.npz")
+    inp = {k: v.numpy() for k, v in synth.make_inputs(2, 6, 1000, cfg, with_noise=False).items()}
+    taps = {}
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], None, taps=taps)
+    assert out.shape == (2, 1, 3600) and np.abs(out - g["out"]).max() <= 2e-6
+    assert np.abs(taps["decode.3"] - g["tap:decode.3"]).max() <= 2e-5
+    for i in (0, 7):
+        assert np.abs(taps["generator.convnext.%d" % i] - g["tap:generator.convnext.%d" % i]).max() <= 2e-5
+    assert np.abs(taps["generator.final_layer_norm"] - g["tap:generator.final_layer_norm"]).max() <= 2e-5
+    assert np.abs(taps["generator.stft.out"].transpose(0, 2, 1) - g["tap:generator.stft.out"]).max() <= 2e-5
+    g = golden("vocos_B1_T120_w0_i1001.npz")
+    inp = {k: v.numpy() for k, v in synth.make_inputs(1, 120, 1001, cfg, with_noise=False).items()}
+    out = O.decoder_forward(sd, cfg, inp["asr"], inp["F0_curve"], inp["N"], inp["s"], None)
+    assert out.shape == (1, 1, 72000) and np.abs(out - g["out"]).max() <= 5e-6
+
+
 def test_duration_smoothing_oracle_matches_reference_statements():
     """inference.py:248-257 lifted from the reference file and executed as is (tests/golden/make_golden_smooth.py): noise mix,
     z-score outlier replacement on duration[1:-2], / speed, rounding -- sentence lengths 2 .. 200 incl. the empty / single-element
