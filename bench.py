@@ -256,6 +256,54 @@ def aux_cfg5(torch, dev, precision):
     return res
 
 
+def aux_vocos(torch, dev, precision, B, T):
+    """the Vocos decoder variant (Modules/vocos.py) at the headline shape, inputs resident; next to it the
+    unmodified reference module through PyTorch eager on the same GPU (fp32) when it is staged under baseline/_ref."""
+    from styletts2_lite_b200 import synth
+    from styletts2_lite_b200.config import DecoderConfig
+    from styletts2_lite_b200.decoder import B200Decoder
+    from oracle import stage_reference as SREF
+    cfg = DecoderConfig.vocos()
+    sd = synth.make_state_dict(cfg, 0, True)
+    m = B200Decoder(cfg, precision)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    inp = {k: v.to(dev) for k, v in synth.make_inputs(B, T, seed=1006, cfg=cfg, with_noise=False).items()}
+    out = [None]
+
+    def fwd(i):
+        with torch.no_grad():
+            out[0] = m(inp["asr"], inp["F0_curve"], inp["N"], inp["s"])
+    ms = _event_ms(torch, fwd, 3, 10)
+    secs = B * T * 600 / 24000.0
+    res = {"workload": "vocos Decoder.forward, %d utterances x %.0f s (T=%d), inputs resident" % (B, T * 600 / 24000.0, T),
+           "precision": precision, "ms": round(ms, 3), "audio_s_per_s": round(secs / (ms / 1e3), 1),
+           "launches": int(m.last_launch_count()),
+           "finite": tuple(out[0].shape) == (B, 1, 600 * T) and bool(torch.isfinite(out[0]).all())}
+    mine = out[0].float()
+    del m
+    torch.cuda.empty_cache()
+    try:
+        ref = SREF.build_reference(cfg, sd)
+    except Exception:  # noqa: BLE001
+        ref = None
+    if ref is not None:
+        ref = ref.to(dev)
+        ro = [None]
+
+        def rfwd(i):
+            with torch.no_grad():
+                ro[0] = ref(inp["asr"], inp["F0_curve"], inp["N"], inp["s"])
+        rms = _event_ms(torch, rfwd, 2, 5)
+        err = (ro[0].float() - mine)
+        snr = 10.0 * float(torch.log10(ro[0].float().pow(2).sum() / err.pow(2).sum().clamp_min(1e-30)))
+        res["eager_gpu_reference"] = {"kind": "reference", "precision": "fp32", "ms": round(rms, 3),
+                                      "audio_s_per_s": round(secs / (rms / 1e3), 1), "snr_db_of_this_library_vs_it": round(snr, 1)}
+        del ref
+        torch.cuda.empty_cache()
+    return res
+
+
 def aux_eager_gpu(torch, dev, variant, B, T):
     """The pre-existing GPU path: the reference decoder through PyTorch eager (cuDNN / ATen kernels) on the same GPU and shape,
     fp32 and bf16 autocast.  The unmodified reference modules when staged (baseline/_ref), else the torch port of them."""
@@ -566,6 +614,7 @@ def run_b200(a, rank, local_rank, world):
         del m
         torch.cuda.empty_cache()
         for key, fn in (("cfg5_istftnet_60s", lambda: aux_cfg5(torch, dev, a.precision)),
+                        ("vocos_n4", lambda: aux_vocos(torch, dev, a.precision, B, T)),
                         ("eager_gpu", lambda: aux_eager_gpu(torch, dev, a.variant, B, T))):
             try:
                 line[key] = fn()

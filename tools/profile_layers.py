@@ -19,7 +19,7 @@ ap.add_argument("--frames", type=int, default=200)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--variant", default="hifigan")
 a = ap.parse_args()
-cfg = DecoderConfig.hifigan() if a.variant == "hifigan" else DecoderConfig.istftnet()
+cfg = {"hifigan": DecoderConfig.hifigan, "istftnet": DecoderConfig.istftnet, "vocos": DecoderConfig.vocos}[a.variant]()
 m = B200Decoder(cfg, a.precision)
 m.load_state_dict(synth.make_state_dict(cfg, 0, True))
 m = m.cuda().eval()
