@@ -56,6 +56,7 @@ struct Tune {
     int verbose = 0, tc_halo = 0, lstm_bt = 0;
     int row_sub = 0, row_slot = 0, row_na = 0;                  // conv_row planner overrides for sweeps (0 = planner's choice)
     int no_xt16 = 0, no_run16 = 0, no_xu16 = 0, no_sum16 = 0;   // defaults of the per-handle storage options (st2_decoder_set_option)
+    int no_src16 = 0, no_out16 = 0;
 };
 const Tune& tune();
 int tune_set(const char* name, int value);    // ST2_OK, or ST2_ERR_INVALID for an unknown name
@@ -116,9 +117,9 @@ int launch_pool_dw16(const float* x, int ld_x, const float* w, const float* bias
                      int T, int Cpad, cudaStream_t st);
 int noise_conv_parts(int Tout);
 int launch_noise_conv(const float* har, const float* w, const float* bias, float* y, void* stats, int B, int S, int Tout,
-                      int C, int k, int stride, int pad, cudaStream_t st);
+                      int C, int k, int stride, int pad, cudaStream_t st, int y16 = 0);
 int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
-                        float* out, int B, int S, int C, int fast, cudaStream_t st);
+                        float* out, int B, int S, int C, int fast, cudaStream_t st, int x16 = 0);
 int launch_copy_dense(const float* src, int ld, float* dst, int64_t rows, int C, cudaStream_t st);
 int launch_half_to_float(const void* src, float* dst, int64_t n, cudaStream_t st);
 int launch_fold_pack(const float* g, const float* v, float* wp, int d0, int d1, int k, int transposed,
@@ -209,8 +210,10 @@ int launch_conv_fused(const ConvArgs& a, const float* coef, int coef_ld, int act
 bool conv_pipe_supported(const ConvArgs& a);
 int launch_conv_pipe(const ConvArgs& a, const float* coef, int coef_ld, int act, float slope, const float* alpha,
                      void* stats_out, cudaStream_t st);
+int launch_add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t st);
+// x_offset (optional, [C]): the tensor the coefficients will be applied to is stored as x - x_offset[c] (statistics are of x)
 int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld_h, int h_off, float* coef, int B, int T,
-                         int C, int Cpad, cudaStream_t st);
+                         int C, int Cpad, cudaStream_t st, const float* x_offset = nullptr);
 // 32 / 64-channel stride-1 Snake convs on fp16 stage-private tensors: row-per-thread epilogue, residual through the tensor
 // core, statistics per (CTA, utterance, epilogue warp) (conv_row.cu).  `desc` describes where the partials of an utterance
 // live; launch_adain_coef_row turns them into AdaIN coefficients.

@@ -95,6 +95,10 @@ static void pack_decoder(st2_decoder* d, Packer& P) {
         const int nc_cin = istft ? c.gen_istft_n_fft + 2 : 1;
         P.conv(d->noise_convs[i], "generator.noise_convs." + is, nc_cin, C, last ? 1 : 2 * sf, false, true, false);
         P.resblock1(d->noise_res[i], "generator.noise_res." + is, C, last ? 11 : 7, dil135);
+        d->noise_c2b[i] = (float*)P.dalloc((size_t)C * sizeof(float));
+        if (d->noise_c2b[i] && d->noise_res[i].c2[0].bias && d->noise_convs[i].bias && P.err == ST2_OK &&
+            launch_add_vec(d->noise_c2b[i], d->noise_res[i].c2[0].bias, d->noise_convs[i].bias, C, P.st) != ST2_OK)
+            P.err = ST2_ERR_CUDA;
         P.conv(d->ups[i], "generator.ups." + is, 2 * C, C, c.upsample_kernel_sizes[i], true, true, true);
         if (!istft) d->gen_alpha[i + 1] = P.copy("generator.alphas." + std::to_string(i + 1), C);
         for (int j = 0; j < c.n_kernels; ++j)
@@ -290,6 +294,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     // ---- generator (hifigan.py:328-345 / istftnet.py:552-573)
     const float* x = xg;
     int Tin = 2 * T;
+    int out16 = 0;                                          // the last stage's output is fp16
     for (int i = 0; i < c.n_stages; ++i) {
         const int64_t mark = E.off;
         const int C = d->stage_channels(i), Cin = 2 * C;
@@ -300,6 +305,10 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         const std::string is = std::to_string(i);
         // x_source = noise_res[i](noise_convs[i](har_source), s)
         float* nc = E.allocf((int64_t)B * Tout * C);
+        // noise_convs[i] output = block input of noise_res[i] (read as conv1 input and as the residual of its first iteration):
+        // stored as fp16 when every conv of the block takes it (option fp16_src; statistics still from the fp32 values)
+        void* nc16buf = E.alloc((int64_t)B * Tout * C * 2);
+        const int nc16 = (!istft && d->opt_src16 && E.resblock1_x16_ok(d->noise_res[i], Tout, 0)) ? 1 : 0;
         Exec::StatRef nc_stats{nullptr, 0, true};
         bool nc_have_stats = false;
         {
@@ -317,12 +326,13 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
                 nc_stats.ptr = stp;
                 nc_have_stats = true;
                 if (E.live()) {
-                    E.chk(launch_noise_conv(har, w.w32, w.bias, nc, stp, B, S, Tout, C, w.k, stride, pad, st));
-                    E.prof(PC_SOURCE, 2.0 * B * Tout * C * w.k, 4.0 * B * ((double)S + (double)Tout * C));
+                    E.chk(launch_noise_conv(har, w.w32, w.bias, nc16 ? (float*)nc16buf : nc, stp, B, S, Tout, C, w.k, stride, pad, st, nc16));
+                    E.prof(PC_SOURCE, 2.0 * B * Tout * C * w.k, 4.0 * B * (double)S + (nc16 ? 2.0 : 4.0) * B * (double)Tout * C);
                 }
             }
         }
-        E.resblock1(d->noise_res[i], nc, nc, Tout, nc, 1.f, 0, nc_have_stats ? &nc_stats : nullptr);
+        E.resblock1(d->noise_res[i], nc16 ? (const float*)nc16buf : nc, nc, Tout, nc, 1.f, 0, nc_have_stats ? &nc_stats : nullptr, nc16,
+                    0, nullptr, 0, nc16 ? d->noise_convs[i].bias : nullptr, nc16 ? d->noise_c2b[i] : nullptr);
         // x = ups[i](act(x)) + x_source
         const int dtu = E.fmt_for("generator.ups");
         const bool tcu = E.use_tc(d->ups[i], dtu);
@@ -362,12 +372,17 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
         int sum16 = c.n_kernels >= 2 ? 1 : 0;
         for (int j = 0; j < c.n_kernels && sum16; ++j)
             if (!E.resblock1_sum16_ok(d->resblocks[i * c.n_kernels + j], Tout, j == 0 ? 1 : (j + 1 == c.n_kernels ? 3 : 2), xu16)) sum16 = 0;
+        // the last stage's output is only read by conv_post's kernel: fp16 as well when the last block can write it (option fp16_out)
+        out16 = (last && !istft && sum16 && d->opt_out16 &&
+                 E.resblock1_sum16_ok(d->resblocks[i * c.n_kernels + c.n_kernels - 1], Tout, 3, xu16, 1)) ? 1 : 0;
         for (int j = 0; j < c.n_kernels; ++j) {
             const bool lastk = (j + 1 == c.n_kernels);
             E.resblock1(d->resblocks[i * c.n_kernels + j], xu, run, Tout, stage_out[i], lastk ? 1.f / (float)c.n_kernels : 1.f,
-                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr, xu16, sum16 ? (j == 0 ? 1 : (lastk ? 3 : 2)) : 0, sum16buf);
+                        j > 0 ? 1 : 0, fuse_u ? &xu_stats : nullptr, xu16, sum16 ? (j == 0 ? 1 : (lastk ? 3 : 2)) : 0, sum16buf,
+                        lastk ? out16 : 0);
         }
-        E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
+        if (out16) E.tap16("generator.stage" + is + ".out", stage_out[i], (int64_t)B * Tout * C);
+        else E.tap("generator.stage" + is + ".out", stage_out[i], C, (int64_t)B * Tout, C);
         x = stage_out[i];
         Tin = Tout;
         E.off = mark;
@@ -376,8 +391,8 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
     if (!istft) {
         if (E.live())
             E.chk(launch_post_hifigan(x, Cl, d->gen_alpha[c.n_stages], d->conv_post.w32, d->conv_post.bias, out, B, S, Cl,
-                                       prec != ST2_PREC_FP32 ? 1 : 0, st));
-        E.prof(PC_POST, 2.0 * B * S * Cl * 7, 4.0 * B * S * (Cl + 1));
+                                       prec != ST2_PREC_FP32 ? 1 : 0, st, out16));
+        E.prof(PC_POST, 2.0 * B * S * Cl * 7, (out16 ? 2.0 : 4.0) * B * S * Cl + 4.0 * B * S);
     } else {
         const int dt = E.fmt_for("generator.conv_post");
         const bool tc = E.use_tc(d->conv_post, dt);
@@ -412,7 +427,8 @@ const TuneField kTuneFields[] = {
     {"verbose", "ST2_PIPE_VERBOSE", &Tune::verbose, true}, {"tc_halo", "ST2_TC_HALO", &Tune::tc_halo, false},
     {"lstm_bt", "ST2_LSTM_BT", &Tune::lstm_bt, false}, {"no_xt16", "ST2_NO_XT16", &Tune::no_xt16, true},
     {"no_run16", "ST2_NO_RUN16", &Tune::no_run16, true}, {"no_xu16", "ST2_NO_XU16", &Tune::no_xu16, true},
-    {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}, {"row_sub", "ST2_ROW_SUB", &Tune::row_sub, false},
+    {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}, {"no_src16", "ST2_NO_SRC16", &Tune::no_src16, true},
+    {"no_out16", "ST2_NO_OUT16", &Tune::no_out16, true}, {"row_sub", "ST2_ROW_SUB", &Tune::row_sub, false},
     {"row_slot", "ST2_ROW_SLOT", &Tune::row_slot, false}, {"row_na", "ST2_ROW_NA", &Tune::row_na, false}};
 Tune& tune_storage() {
     static Tune t = [] {
@@ -574,7 +590,8 @@ int st2_decoder_set_tap(st2_decoder* d, const char* name, float* dst, int64_t ca
 int st2_decoder_set_option(st2_decoder* d, const char* name, int32_t value) {
     ST2_REQUIRE(d && name, "set_option: bad argument");
     struct { const char* n; int* v; } opts[] = {{"fp16_storage", &d->fp16_storage}, {"fp16_xt", &d->opt_xt16}, {"fp16_run", &d->opt_run16},
-                                                {"fp16_xu", &d->opt_xu16}, {"fp16_sum", &d->opt_sum16}};
+                                                {"fp16_xu", &d->opt_xu16}, {"fp16_sum", &d->opt_sum16},
+                                                {"fp16_src", &d->opt_src16}, {"fp16_out", &d->opt_out16}};
     for (auto& o : opts)
         if (strcmp(name, o.n) == 0) {
             *o.v = value ? 1 : 0;

@@ -170,7 +170,7 @@ int launch_pool_dw(const float* x, int ld_x, const float* w, const float* bias, 
 // (16-byte aligned rows, conflict-free 128-bit reads for consecutive rows); FAST selects sin.approx / approximate
 // reciprocal for the 16-bit precisions (the fp32 parity path keeps sinf).
 static constexpr int kPostTile = 256;
-template <bool FAST>
+template <bool FAST, bool X16>
 __global__ void __launch_bounds__(kPostTile)
 post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ alpha,
                     const float* __restrict__ w /*[7][C]*/, const float* __restrict__ bias,
@@ -188,7 +188,14 @@ post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restri
         int t = t0 + r - 3;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < S) {
-            v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * ld_x + c));
+            if (X16) {                                 // the last stage's output stored as fp16 (option fp16_out)
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(x) + ((size_t)b * S + t) * ld_x + c));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * ld_x + c));
+            }
             float4 al = *reinterpret_cast<const float4*>(alpha + c);
             if (FAST) {
                 float s0 = __sinf(al.x * v.x), s1 = __sinf(al.y * v.y), s2 = __sinf(al.z * v.z), s3 = __sinf(al.w * v.w);
@@ -223,16 +230,31 @@ post_hifigan_kernel(const float* __restrict__ x, int ld_x, const float* __restri
 }
 
 int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,
-                        float* out, int B, int S, int C, int fast, cudaStream_t st) {
+                        float* out, int B, int S, int C, int fast, cudaStream_t st, int x16) {
+    ST2_REQUIRE(!x16 || fast, "post_hifigan: fp16 input only on the 16-bit paths");
     ST2_REQUIRE(C % 4 == 0 && C <= 64 && ld_x % 4 == 0, "post_hifigan: C=%d ld=%d unsupported", C, ld_x);
     size_t smem = ((size_t)(kPostTile + 6) * (C + 4) + 7 * C) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(post_hifigan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(post_hifigan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(post_hifigan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(post_hifigan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(post_hifigan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     dim3 grid(cdiv(S, kPostTile), B);
-    if (fast) post_hifigan_kernel<true><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
-    else post_hifigan_kernel<false><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    if (x16) post_hifigan_kernel<true, true><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    else if (fast) post_hifigan_kernel<true, false><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    else post_hifigan_kernel<false, false><<<grid, kPostTile, smem, st>>>(x, ld_x, alpha, w, bias, out, S, C);
+    ST2_LAUNCH_CHECK();
+    return ST2_OK;
+}
+
+// ---- dst = a + b (pack time: a conv bias with the offset of a bias-free fp16 input folded in)
+__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = a[i] + b[i];
+}
+
+int launch_add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t st) {
+    add_vec_kernel<<<cdiv(n, 256), 256, 0, st>>>(dst, a, b, n);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
@@ -344,6 +366,12 @@ namespace st2 {
 // that follows (noise_res[i].adain1[0]).  HBM-bound on its output (4*C bytes per output step); weights and the
 // har segment of the tile live in shared memory.
 static constexpr int kNcTile = 256;     // output time steps per CTA (weights + har segment are staged once per tile)
+// Y16: y is stored as fp16 (the block input of noise_res[i], read twice by its first iteration) WITHOUT the bias: with one
+// input channel every output channel is bias[c] + w[.][c] * har, and a bias larger than the signal would eat the fp16 mantissa
+// that the InstanceNorm behind it then magnifies (measured 4e-2 relative L2 on noise_res.3 with the bias stored).  The consumers
+// add it back: the AdaIN coefficients get the offset (launch_adain_coef_f2) and the residual add of the first iteration has it
+// folded into that conv's bias (decoder.cu).  The statistics still come from the fp32 values with the bias.
+template <bool Y16>
 __global__ void __launch_bounds__(256)
 noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[k][C]*/, const float* __restrict__ bias,
                   float* __restrict__ y, float2* __restrict__ stats, int S, int Tout, int C, int k, int stride, int pad,
@@ -386,7 +414,13 @@ noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[
         for (int u = 0; u < 4; ++u) {
             const int ru = r + u * rpp, t = t0 + ru;
             if (ru >= kNcTile || t >= Tout) break;
-            *reinterpret_cast<float4*>(y + ((size_t)b * Tout + t) * C + q * 4) = acc[u];
+            if (Y16) {
+                const __half2 lo = __floats2half2_rn(acc[u].x - bv.x, acc[u].y - bv.y), hi = __floats2half2_rn(acc[u].z - bv.z, acc[u].w - bv.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + ((size_t)b * Tout + t) * C + q * 4) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            } else {
+                *reinterpret_cast<float4*>(y + ((size_t)b * Tout + t) * C + q * 4) = acc[u];
+            }
             s1[0] += acc[u].x; s1[1] += acc[u].y; s1[2] += acc[u].z; s1[3] += acc[u].w;
             s2[0] = fmaf(acc[u].x, acc[u].x, s2[0]); s2[1] = fmaf(acc[u].y, acc[u].y, s2[1]);
             s2[2] = fmaf(acc[u].z, acc[u].z, s2[2]); s2[3] = fmaf(acc[u].w, acc[u].w, s2[3]);
@@ -412,7 +446,7 @@ noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[
 int noise_conv_parts(int Tout) { return cdiv(Tout, kNcTile); }
 
 int launch_noise_conv(const float* har, const float* w, const float* bias, float* y, void* stats, int B, int S, int Tout,
-                      int C, int k, int stride, int pad, cudaStream_t st) {
+                      int C, int k, int stride, int pad, cudaStream_t st, int y16) {
     ST2_REQUIRE(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0 && bias != nullptr, "noise_conv: unsupported C=%d", C);
     const int ntile = cdiv(Tout, kNcTile);
     const int rpp = 256 / (C / 4);
@@ -420,11 +454,13 @@ int launch_noise_conv(const float* har, const float* w, const float* bias, float
     static size_t max_set[kMaxDevices] = {};     // per device (the attribute applies to the current device)
     size_t& ms = max_set[current_device_slot()];
     if (smem > 48 * 1024 && smem > ms) {
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ms = smem;
     }
     dim3 grid(ntile, B);
-    noise_conv_kernel<<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
+    if (y16) noise_conv_kernel<true><<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
+    else noise_conv_kernel<false><<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

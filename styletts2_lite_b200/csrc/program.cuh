@@ -82,9 +82,11 @@ struct st2_decoder {
     // ... and each of the four kinds alone ("fp16_xt", "fp16_run", "fp16_xu", "fp16_sum").  Defaults come
     // from the process-wide switches once, at create time.
     int opt_xt16 = 1, opt_run16 = 1, opt_xu16 = 1, opt_sum16 = 1;
+    int opt_src16 = 1, opt_out16 = 1;       // "fp16_src": noise_convs output (input of noise_res); "fp16_out": last stage's output
     void init_options() {
         const st2::Tune& t = st2::tune();
         opt_xt16 = !t.no_xt16; opt_run16 = !t.no_run16; opt_xu16 = !t.no_xu16; opt_sum16 = !t.no_sum16;
+        opt_src16 = !t.no_src16; opt_out16 = !t.no_out16;
     }
 
     ResBlk1dW encode, decode[4];
@@ -102,6 +104,7 @@ struct st2_decoder {
     // variant 4: Vocos generator (Modules/vocos.py:103-162, :235-296): ConvNeXt blocks, final LayerNorm, ISTFTHead
     struct ConvNeXtW { float* dw_w = nullptr; float* dw_b = nullptr; AdaINRef norm; ConvW pw1, pw2; };
     ConvNeXtW vx[16];
+    float* noise_c2b[4] = {nullptr, nullptr, nullptr, nullptr};   // noise_res[i].convs2.0.bias + noise_convs[i].bias (fp16_src path)
     float* vx_ln = nullptr;                 // final_layer_norm weight[dim] | bias[dim]
     ConvW vx_out;                           // ISTFTHead.out, columns padded to vx_kpad
     ConvW vx_basis;                         // windowed inverse real DFT as a [vx_kpad, n_fft] matrix (vocos.cu)
@@ -508,8 +511,14 @@ struct Exec {
     }
     // coef <- (1+gamma)*rstd, beta - mean*(1+gamma)*rstd  (n == nullptr: identity)
     static constexpr int kCoefMax = 2048;     // channels per utterance the coefficient buffer holds (allocated as B*2*2048)
-    void coef_from(const StatRef& sr, const AdaINRef* n, int T, int C, int Cpad) {
+    // x_offset: the tensor is stored as x - x_offset[c] (the bias-free fp16 noise source); only for float2 tile partials
+    void coef_from(const StatRef& sr, const AdaINRef* n, int T, int C, int Cpad, const float* x_offset = nullptr) {
         if (!live()) return;
+        if (x_offset != nullptr && (n == nullptr || !sr.f2 || sr.row)) {
+            set_error("coef_from: an input offset needs float2 tile partials");
+            err = ST2_ERR_STATE;
+            return;
+        }
         if (Cpad > kCoefMax) {
             set_error("coefficient buffer holds %d channels, layer needs %d", kCoefMax, Cpad);
             err = ST2_ERR_UNSUPPORTED;
@@ -520,7 +529,7 @@ struct Exec {
         else if (sr.row)
             chk(launch_adain_coef_row(sr.ptr, sr.rd, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
         else
-            chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st));
+            chk(launch_adain_coef_f2(sr.ptr, sr.nparts, H, d->fc_rows, n->h_off, coef, B, T, C, Cpad, st, x_offset));
         prof(PC_NORM_COEF, 0, 0);
         coef_ld = Cpad;
     }
@@ -643,13 +652,14 @@ struct Exec {
     // would resblock1 take its input tensor as fp16 (every conv of the block on the TMA pipeline kernel)?
     // would the last conv of this block write / accumulate the fp16 partial sum of the stage?
     //   mode 1: first block of a stage, writes the fp16 sum;  2: middle, fp16 sum in place;  3: last, fp16 sum -> fp32 stage output
-    bool resblock1_sum16_ok(const ResBlock1W& w, int T, int mode, int x16) {
+    // dest16 (mode 3 only): the last block writes the stage output as fp16 too
+    bool resblock1_sum16_ok(const ResBlock1W& w, int T, int mode, int x16, int dest16 = 0) {
         const int C = w.C, dt = fmt_for(w.name);
         if (!can_fuse(w.c1[0], dt, C, C, 1, 5) || !d->fp16_storage || !d->opt_xt16 || !d->opt_run16 || !d->opt_sum16) return false;
         for (int j = 0; j < 3; ++j) {        // every conv of the block on the pipeline kernel with the fp16 tensors it will see
             const int dil = w.dil[j], in16 = (j > 0 || x16) ? 1 : 0;
             if (!pipe_ok(w.c1[j], C, C, T, (w.k * dil - dil) / 2, dil, false, 0, dt, in16, 1) ||
-                !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, (j == 2 && mode > 1) ? 1 : 0, dt, 1, (j < 2 || mode < 3) ? 1 : 0, in16,
+                !pipe_ok(w.c2[j], C, C, T, (w.k - 1) / 2, 1, true, (j == 2 && mode > 1) ? 1 : 0, dt, 1, (j < 2 || mode < 3 || dest16) ? 1 : 0, in16,
                          (j == 2 && mode > 1) ? 1 : 0))
                 return false;
         }
@@ -668,7 +678,9 @@ struct Exec {
     }
     // sum16 (modes above) with sum16buf: the stage's partial sum lives in fp16 until the last block writes `dest`
     void resblock1(const ResBlock1W& w, const float* x_in, float* run, int T, float* dest, float scale, int accumulate,
-                   const StatRef* in_stats = nullptr, int x16 = 0, int sum16 = 0, void* sum16buf = nullptr) {
+                   const StatRef* in_stats = nullptr, int x16 = 0, int sum16 = 0, void* sum16buf = nullptr, int dest16 = 0,
+                   const float* x_offset = nullptr, const float* c2b0 = nullptr) {
+        // x_offset / c2b0: x_in is stored as x - x_offset[c]; c2b0 = c2[0].bias + x_offset puts it back in the residual add
         const int64_t mark = off;
         const int C = w.C;
         const int dt = fmt_for(w.name);
@@ -716,7 +728,7 @@ struct Exec {
             int cur16 = x16;
             for (int j = 0; j < 3; ++j) {
                 const int dil = w.dil[j];
-                coef_from(cur_st, &w.n1[j], T, C, C);
+                coef_from(cur_st, &w.n1[j], T, C, C, j == 0 ? x_offset : nullptr);
                 conv_fused(w.c1[j], cur, C, T, dt, ACT_SNAKE, 0.f, w.alpha1[j], xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr,
                            0, 0, 1.f, 0, st_xt, 0, 0, cur16, xt16);
                 if (!xt16) tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
@@ -724,12 +736,14 @@ struct Exec {
                 coef_from(produced(st_xt, nparts), &w.n2[j], T, C, C);
                 const bool last = (j == 2);
                 const bool s16 = last && sum16 != 0 && run16;                     // the caller asked resblock1_sum16_ok first
-                const int out16 = ((run16 && !last) || (s16 && sum16 < 3)) ? 1 : 0;
+                const int out16 = ((run16 && !last) || (s16 && (sum16 < 3 || dest16))) ? 1 : 0;
                 float* out = last ? ((s16 && sum16 < 3) ? (float*)sum16buf : dest) : (out16 ? (float*)r16buf : run);
-                conv_fused(w.c2[j], xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
+                ConvW c2 = w.c2[j];
+                if (j == 0 && x_offset != nullptr) c2.bias = const_cast<float*>(c2b0);
+                conv_fused(c2, xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
                            last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, out16, cur16,
                            (s16 && sum16 > 1) ? sum16buf : nullptr, (s16 && sum16 > 1) ? 1 : 0);
-                if (out16) tap16(w.name + ".iter" + std::to_string(j), out, (int64_t)B * T * C);
+                if (out16 && !(last && dest16)) tap16(w.name + ".iter" + std::to_string(j), out, (int64_t)B * T * C);
                 else if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
                 cur = out;
                 cur16 = out16;

@@ -237,9 +237,10 @@ def test_istftnet_small_tensor_core_snr(prec):
 
 
 def test_fp16_intra_block_tensor_costs_little():
-    """The fused resblocks keep four kinds of stage-private tensors in fp16 (conv1 output, the running
-    tensor between iterations, the stage input, the partial sum over the resblocks); option "fp16_storage" / "fp16_xt" = 0 turns
-    all of them off, "fp16_run" / "fp16_xu" / "fp16_sum" one kind each.
+    """The fused resblocks keep six kinds of stage-private tensors in fp16 (conv1 output, the running
+    tensor between iterations, the stage input, the partial sum over the resblocks, the noise_convs output that feeds noise_res,
+    the last stage's output that feeds conv_post); option "fp16_storage" / "fp16_xt" = 0 turns all of them off, "fp16_run" /
+    "fp16_xu" / "fp16_sum" / "fp16_src" / "fp16_out" one kind each.
     Against the fp32-stored variant the waveform differs by about as much as two bf16 runs with different rounding do
     (bound 45 dB) and the SNR against the reference stays within a few tenths of a dB (bar 40 dB)."""
     cfg = DecoderConfig.hifigan()
@@ -271,8 +272,8 @@ def test_fp16_intra_block_tensor_costs_little():
         assert np.array_equal(_run(m, inp, precision="bf16"), out32)
     finally:
         _lib.check(lib.st2_decoder_set_option(m._handle, b"fp16_xt", 1))
-    # ... and each of the other three alone changes the result (the path it guards really runs) within the same bound
-    for knob in (b"fp16_run", b"fp16_xu", b"fp16_sum"):
+    # ... and each of the other five alone changes the result (the path it guards really runs) within the same bound
+    for knob in (b"fp16_run", b"fp16_xu", b"fp16_sum", b"fp16_src", b"fp16_out"):
         _lib.check(lib.st2_decoder_set_option(m._handle, knob, 0))
         try:
             o = _run(m, inp, precision="bf16")
