@@ -469,6 +469,13 @@ struct Exec {
         a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
         a.y = y; a.ld_y = ld_y;
         a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
+        // a pointwise conv (k = 1: the Linear layers, LSTM input projections, shortcuts) has no halo: the B utterances are one
+        // dense [B*T] row range, so no 128-row tile is left partly empty at the end of every utterance (T = 400: 22 % of the tiles)
+        if (w.k == 1 && !w.transposed && stride == 1 && padding == 0 && out_row_shift == 0 && res_shift == 0 && !mirror &&
+            Tin == Tout && (int64_t)B * Tout < (int64_t)1 << 30) {
+            a.B = 1;
+            a.Tin = a.Tout = a.M = B * Tout;
+        }
         // algorithmic work: Conv1d 2*B*Tout*Cout*Cin*k ; ConvTranspose1d 2*B*Tin*Cin*Cout*k
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const bool tc = use_tc(w, dt);
