@@ -115,7 +115,7 @@ int launch_pool_dw(const float* x, int ld_x, const float* w, const float* bias, 
                    int T, int C, int Cpad, cudaStream_t st);
 int launch_pool_dw16(const float* x, int ld_x, const float* w, const float* bias, void* y, int ld_y, int out_dtype, int B,
                      int T, int Cpad, cudaStream_t st);
-int noise_conv_parts(int Tout);
+int noise_conv_parts(int Tout, int stride);
 int launch_noise_conv(const float* har, const float* w, const float* bias, float* y, void* stats, int B, int S, int Tout,
                       int C, int k, int stride, int pad, cudaStream_t st, int y16 = 0);
 int launch_post_hifigan(const float* x, int ld_x, const float* alpha, const float* w, const float* bias,

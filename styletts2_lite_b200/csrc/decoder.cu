@@ -321,7 +321,7 @@ static int forward_impl(st2_decoder* d, const float* asr, const float* f0, const
             } else {
                 // Conv1d(1 -> C) of the harmonic source: dedicated HBM-bound kernel that also emits the InstanceNorm
                 // partials of its output (consumed by noise_res[i].adain1[0])
-                nc_stats.nparts = noise_conv_parts(Tout);
+                nc_stats.nparts = noise_conv_parts(Tout, stride);
                 void* stp = E.alloc((int64_t)B * nc_stats.nparts * C * 8);
                 nc_stats.ptr = stp;
                 nc_have_stats = true;

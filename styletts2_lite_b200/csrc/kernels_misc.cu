@@ -365,13 +365,17 @@ namespace st2 {
 // harmonic source har[B][S] -> y[B][Tout][C] channels-last, plus per-tile (sum, sumsq) per channel for the AdaIN
 // that follows (noise_res[i].adain1[0]).  HBM-bound on its output (4*C bytes per output step); weights and the
 // har segment of the tile live in shared memory.
-static constexpr int kNcTile = 256;     // output time steps per CTA (weights + har segment are staged once per tile)
+// output time steps per CTA (weights + har segment are staged once per tile): 1024 for the small strides of the late stages
+// (the k = 1 conv of the last stage was bound by CTA turnover with 256: 30,000 CTAs of 16 KB of output each: 0.25 -> 0.15 ms;
+// stride 2: 0.23 -> 0.20 ms), 256 for the compute-heavy early stages (stride 6 measured slower with 1024; stride 30: 256 steps
+// already read 7,700 samples)
+static int nc_tile(int stride) { return stride <= 2 ? 1024 : 256; }
 // Y16: y is stored as fp16 (the block input of noise_res[i], read twice by its first iteration) WITHOUT the bias: with one
 // input channel every output channel is bias[c] + w[.][c] * har, and a bias larger than the signal would eat the fp16 mantissa
 // that the InstanceNorm behind it then magnifies (measured 4e-2 relative L2 on noise_res.3 with the bias stored).  The consumers
 // add it back: the AdaIN coefficients get the offset (launch_adain_coef_f2) and the residual add of the first iteration has it
 // folded into that conv's bias (decoder.cu).  The statistics still come from the fp32 values with the bias.
-template <bool Y16>
+template <bool Y16, int kNcTile>
 __global__ void __launch_bounds__(256)
 noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[k][C]*/, const float* __restrict__ bias,
                   float* __restrict__ y, float2* __restrict__ stats, int S, int Tout, int C, int k, int stride, int pad,
@@ -443,24 +447,29 @@ noise_conv_kernel(const float* __restrict__ har, const float* __restrict__ w /*[
     }
 }
 
-int noise_conv_parts(int Tout) { return cdiv(Tout, kNcTile); }
+int noise_conv_parts(int Tout, int stride) { return cdiv(Tout, nc_tile(stride)); }
 
 int launch_noise_conv(const float* har, const float* w, const float* bias, float* y, void* stats, int B, int S, int Tout,
                       int C, int k, int stride, int pad, cudaStream_t st, int y16) {
     ST2_REQUIRE(C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0 && bias != nullptr, "noise_conv: unsupported C=%d", C);
+    const int kNcTile = nc_tile(stride);
     const int ntile = cdiv(Tout, kNcTile);
     const int rpp = 256 / (C / 4);
     size_t smem = ((size_t)k * C + (kNcTile - 1) * stride + k + (size_t)rpp * C * 2) * sizeof(float);
     static size_t max_set[kMaxDevices] = {};     // per device (the attribute applies to the current device)
     size_t& ms = max_set[current_device_slot()];
     if (smem > 48 * 1024 && smem > ms) {
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ST2_CUDA_CHECK(cudaFuncSetAttribute(noise_conv_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ms = smem;
     }
     dim3 grid(ntile, B);
-    if (y16) noise_conv_kernel<true><<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
-    else noise_conv_kernel<false><<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile);
+#define ST2_NC_LAUNCH(Y16_, TILE_) noise_conv_kernel<Y16_, TILE_><<<grid, 256, smem, st>>>(har, w, bias, y, (float2*)stats, S, Tout, C, k, stride, pad, ntile)
+    if (kNcTile == 1024) { if (y16) ST2_NC_LAUNCH(true, 1024); else ST2_NC_LAUNCH(false, 1024); }
+    else { if (y16) ST2_NC_LAUNCH(true, 256); else ST2_NC_LAUNCH(false, 256); }
+#undef ST2_NC_LAUNCH
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }
