@@ -194,6 +194,8 @@ struct ConvArgs {
     int fmt16;                               // DT_BF16 / DT_F16 for the tensor-core path
     int x16in;                               // fused path: the input tensor x is 16-bit (fmt16) with pitch ld_x elements
     int y16out;                              // fused path: write y as fp16; statistics still from the fp32 values
+    int epi_gelu;                            // conv_tc only: y = GELU(conv + bias) stored in the 16-bit format fmt16 with pitch ld_y
+                                             // elements (the operand of the next pointwise conv); no residual / accumulate / scale
     int res16;                               // fused path (conv_pipe only): the residual tensor is fp16 with pitch ld_res elements
     const void* acc_src; int acc16;          // fused path (conv_pipe only): with accumulate, read the old values from acc_src (pitch
                                              // ld_y; fp16 when acc16) instead of y -- partial sums of a stage kept in fp16

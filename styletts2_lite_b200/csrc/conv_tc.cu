@@ -45,6 +45,7 @@ struct TcParams {
     // every tap reads it through a UMMA descriptor whose start address is shifted by whole 128-byte rows
     int halo_rows;               // 0 = off
     int halo_min;                // smallest time offset of any tap relative to m0
+    int epi_gelu;                // y = GELU(acc + bias) as 16-bit values (is_bf16 selects the format), pitch ld_y elements
 };
 
 __global__ void __launch_bounds__(TC_THREADS)
@@ -173,6 +174,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if (p.bias != nullptr && co + i < p.Cout) v[i] += __ldg(p.bias + co + i);
+            }
+            if (p.epi_gelu) {
+                // ConvNeXt MLP (vocos.py:62-63): the exact-erf GELU of the first Linear, written as the 16-bit operand of the second
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float g0 = 0.5f * v[2 * i] * (1.f + erff(v[2 * i] * 0.70710678118654752f));
+                    const float g1 = 0.5f * v[2 * i + 1] * (1.f + erff(v[2 * i + 1] * 0.70710678118654752f));
+                    if (p.is_bf16) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    } else {
+                        const __half2 h = __floats2half2_rn(g0, g1);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                }
+                uint16_t* yp16 = reinterpret_cast<uint16_t*>(p.y) + ((size_t)b * p.Tout + t) * p.ld_y + co;
+                if (full16) {
+                    *reinterpret_cast<uint4*>(yp16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(yp16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (co + i < p.Cout) yp16[i] = (uint16_t)(pk[i >> 1] >> ((i & 1) * 16));
+                }
+                continue;
             }
             const int nrep = (p.mirror && t == 2) ? 2 : 1;
             for (int rep = 0; rep < nrep; ++rep) {
@@ -442,6 +469,10 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     p.phases = a.phases; p.w_step = a.w_step; p.out_stride = a.out_stride; p.out_pad = a.out_pad;
     p.kchunks = a.w16_cin_pad / TC_KC;
     p.scale = a.scale; p.accumulate = a.accumulate; p.mirror = a.mirror; p.is_bf16 = is_bf16;
+    p.epi_gelu = a.epi_gelu;
+    ST2_REQUIRE(!a.epi_gelu || (a.res == nullptr && !a.accumulate && a.scale == 1.f && !a.mirror && a.ld_y % 8 == 0 &&
+                                (reinterpret_cast<uintptr_t>(a.y) & 15) == 0),
+                "conv_tc: the GELU epilogue takes no residual / accumulate / scale and needs a 16-byte aligned 16-bit output");
     // N tile: whole CoutPad up to 256, else the largest multiple-of-16 divisor <= 256
     int bn = a.w16_cout_pad;
     if (bn > 256) {

@@ -175,8 +175,13 @@ static void vocos_generator(Exec& E, st2_decoder* d, float* x, float* out, int T
         E.tap(name + ".dwconv", yd, C, rows, C);
         const bool tc1 = E.use_tc(L.pw1, dt), tc2 = E.use_tc(L.pw2, dt);
         E.norm_act(yd, C, Tg, C, &L.norm, ACT_NONE, 0.f, nullptr, a16, C, tc1 ? dt : DT_F32);   // vocos.py:60 (AdaIN1d)
-        E.conv(L.pw1, a16, C, Tg, tc1 ? dt : DT_F32, hb, I, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0);   // vocos.py:62
-        E.norm_act(hb, I, Tg, I, nullptr, ACT_GELU, 0.f, nullptr, g16, I, tc2 ? dt : DT_F32);   // vocos.py:63
+        if (tc1 && tc2) {
+            // 16-bit modes: GELU and the down-conversion in the first Linear's epilogue, no fp32 round trip of the 1536-wide tensor
+            E.conv(L.pw1, a16, C, Tg, dt, (float*)g16, I, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0, 0, 0, 1);   // vocos.py:62-63
+        } else {
+            E.conv(L.pw1, a16, C, Tg, tc1 ? dt : DT_F32, hb, I, Tg, 1, 0, 1, nullptr, 0, 0, 1.f, 0);   // vocos.py:62
+            E.norm_act(hb, I, Tg, I, nullptr, ACT_GELU, 0.f, nullptr, g16, I, tc2 ? dt : DT_F32);   // vocos.py:63
+        }
         E.conv(L.pw2, g16, I, Tg, tc2 ? dt : DT_F32, xb, C, Tg, 1, 0, 1, xa, C, 0, 1.f, 0);     // vocos.py:64-69 (gamma folded, + residual)
         std::swap(xa, xb);
         E.tap(name, xa, C, rows, C);

@@ -462,13 +462,19 @@ struct Exec {
     // Conv1d (stride 1 here except noise_convs) / ConvTranspose1d through the common ConvArgs contract
     void conv(const ConvW& w, const void* x, int ld_x, int Tin, int dt, float* y, int ld_y, int Tout, int stride,
               int padding, int dilation, const float* res, int ld_res, int res_shift, float scale, int accumulate,
-              int out_row_shift = 0, int mirror = 0) {
+              int out_row_shift = 0, int mirror = 0, int epi_gelu = 0) {
         if (!live()) return;
         ConvArgs a;
         if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
         a.res = res; a.ld_res = ld_res; a.res_shift = res_shift;
         a.y = y; a.ld_y = ld_y;
         a.scale = scale; a.accumulate = accumulate; a.mirror = mirror;
+        a.epi_gelu = epi_gelu;                   // tensor-core path only: y is the 16-bit GELU output (the caller checked use_tc)
+        if (epi_gelu && !use_tc(w, dt) && err == ST2_OK) {
+            set_error("conv: the GELU epilogue exists on the tensor-core path only");
+            err = ST2_ERR_STATE;
+            return;
+        }
         // a pointwise conv (k = 1: the Linear layers, LSTM input projections, shortcuts) has no halo: the B utterances are one
         // dense [B*T] row range, so no 128-row tile is left partly empty at the end of every utterance (T = 400: 22 % of the tiles)
         if (w.k == 1 && !w.transposed && stride == 1 && padding == 0 && out_row_shift == 0 && res_shift == 0 && !mirror &&
@@ -480,7 +486,7 @@ struct Exec {
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const bool tc = use_tc(w, dt);
         const double bytes = (double)B * ((double)w.Cin * Tin * (tc ? 2 : 4) +
-                                          (double)w.Cout * Tout * 4 * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) +
+                                          (double)w.Cout * Tout * (epi_gelu ? 2 : 4) * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) +
                              (double)w.k * w.Cin * w.Cout * (tc ? 2 : 4);
         if (tc) {
             a.x16 = x; a.ld_x16 = ld_x; a.w16 = w.w16[dt]; a.w16_cin_pad = w.cin_pad; a.w16_cout_pad = w.cout_pad;
