@@ -54,6 +54,7 @@ struct Tune {
     int pipe_xmax = 0, pipe_xmax16 = 0, pipe_nacc = 0, pipe_eg3_nores = 0, pipe_eg = 0;
     int pipe_nxg = 0, pipe_nrg = 0, pipe_na = 0, pipe_nx = 0, pipe_nr = 0;
     int verbose = 0, tc_halo = 0, lstm_bt = 0;
+    int no_row_inline_coef = 0;             // conv_row: always launch the coefficient kernel (A/B of the in-kernel coefficients)
     int row_sub = 0, row_slot = 0, row_na = 0;                  // conv_row planner overrides for sweeps (0 = planner's choice)
     int no_xt16 = 0, no_run16 = 0, no_xu16 = 0, no_sum16 = 0;   // defaults of the per-handle storage options (st2_decoder_set_option)
     int no_src16 = 0, no_out16 = 0;
@@ -220,11 +221,15 @@ int launch_adain_coef_f2(const void* partial, int nparts, const float* h, int ld
 // core, statistics per (CTA, utterance, epilogue warp) (conv_row.cu).  `desc` describes where the partials of an utterance
 // live; launch_adain_coef_row turns them into AdaIN coefficients.
 struct RowStatsDesc { int grid, J, nwarp, mmt, tq, tr, C; };
+// where a conv_row launch finds what it needs to compute the AdaIN coefficients of its input itself: the partials of the
+// conv_row launch that produced the input, the style rows (gamma | beta at h_off) and the row count the statistics are over
+struct RowCoefSrc { const void* partial; RowStatsDesc desc; const float* h; int ld_h; int h_off; int T; };
+bool conv_row_inline_coef_ok(const ConvArgs& a);
 bool conv_row_supported(const ConvArgs& a);                 // geometry, shared-memory plan and enough tiles to fill the grid
 bool conv_row_can_launch(const ConvArgs& a);                // geometry and plan only (unit tests force small problems through it)
 int64_t conv_row_stats_bytes(int B, int T, int C);
 int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, const float* alpha, void* stats_out,
-                    RowStatsDesc* desc, cudaStream_t st);
+                    RowStatsDesc* desc, cudaStream_t st, const RowCoefSrc* src = nullptr);
 int launch_adain_coef_row(const void* partial, const RowStatsDesc& d, const float* h, int ld_h, int h_off, float* coef, int B,
                           int T, int C, int Cpad, cudaStream_t st);
 

@@ -46,6 +46,9 @@ static constexpr int RW_X0 = 2;                          // first transform warp
 static constexpr int RW_NSEC = 5;                        // 128-row sections of an operand buffer: sub (<= 4) + the halo section
 static constexpr int RW_MAXGRID = 160;                   // statistics buffers are sized for at most this many CTAs
 
+// where the partials of an utterance live in the statistics buffer of a conv_row launch (see flush() and RowStatsDesc)
+struct RowStatsInfo { int grid, J, nwarp, mmt, tq, tr, C; };
+
 struct RowParams {
     // transform
     const float* coef; int coef_ld;
@@ -66,6 +69,9 @@ struct RowParams {
     // epilogue
     const float* bias; float scale;
     void* y; int ld_y;
+    // AdaIN coefficients computed in the kernel (cin_part != nullptr) from the partials of the conv_row launch that produced x,
+    // instead of read from `coef`: no coefficient launch between two convs of a resblock
+    const float2* cin_part; RowStatsInfo cin_si; const float* cin_h; int cin_ld_h, cin_h_off, cin_T;
     float2* stats;              // [grid][J][4 * NCH epilogue warps][32] (sum, sum of squares) or nullptr
 };
 
@@ -116,6 +122,43 @@ __device__ __forceinline__ float row_reduce_scatter32(float (&v)[32], int lane) 
     return v[0];
 }
 
+
+__device__ __forceinline__ int row_cta_start(const RowStatsInfo& s, int c) { return c * s.tq + (c < s.tr ? c : s.tr); }
+__device__ __forceinline__ int row_cta_of(const RowStatsInfo& s, int t) {
+    const int big = s.tr * (s.tq + 1);
+    return t < big ? t / (s.tq + 1) : s.tr + (t - big) / s.tq;
+}
+
+// AdaIN coefficients of (utterance b, channel c) from the per-(CTA, utterance, epilogue warp) partials a conv_row launch wrote
+// (layout: flush() of the kernel below): a = (1 + gamma) * rstd, b = beta - mean * a.  Sums in double, fixed order.
+__device__ __forceinline__ void row_coef_from_partials(const float2* __restrict__ partial, const RowStatsInfo& si,
+                                                       const float* __restrict__ h, int ld_h, int h_off, int T, int b, int c,
+                                                       float* a_out, float* b_out) {
+    const int C = si.C;
+    const int c_lo = row_cta_of(si, b * si.mmt), c_hi = row_cta_of(si, (b + 1) * si.mmt - 1);
+    const int chunk = c >> 5, col = c & 31;
+    const int per_cta = si.nwarp / (C >> 5);
+    double s = 0, ss = 0;
+    for (int cta = c_lo; cta <= c_hi; ++cta) {
+        const int j = b - row_cta_start(si, cta) / si.mmt;
+        const float2* pp = partial + (((size_t)cta * si.J + j) * si.nwarp + chunk * per_cta) * 32 + col;
+        float2 v[8];
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) v[wq] = wq < per_cta ? __ldg(pp + wq * 32) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) { s += (double)v[wq].x; ss += (double)v[wq].y; }
+    }
+    const double mean = s / (double)T;
+    double var = ss / (double)T - mean * mean;
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + 1e-5);
+    const double gamma = (double)h[(size_t)b * ld_h + h_off + c];
+    const double beta = (double)h[(size_t)b * ld_h + h_off + C + c];
+    const double ad = (1.0 + gamma) * rstd;
+    *a_out = (float)ad;
+    *b_out = (float)(beta - mean * ad);
+}
+
 template <bool BF16, bool X16, bool Y16, int NCH>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
@@ -142,7 +185,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     uint8_t* smem_x = smem_r + (size_t)p.nr * p.nres * rtile;            // lw x xd activation slots
     const int nxs = p.lw * p.xd;
     float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + C);
+    float* coef_s = bias_s + C;                                                  // [J][2][C] in-kernel AdaIN coefficients (<= 2 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(coef_s + (p.cin_part != nullptr ? p.J * 2 * C : 0));
     uint64_t* w_full = bars;                    // [1]
     uint64_t* a_full = bars + 1;                // [4 buffers][RW_NSEC sections of 128 operand rows]
     uint64_t* a_empty = a_full + 4 * RW_NSEC;   // [4][RW_NSEC]
@@ -216,6 +260,19 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
     pdl_trigger();
     pdl_wait();
+    if (p.cin_part != nullptr) {
+        // the AdaIN coefficients of this CTA's utterances, before the roles split (all 96 registers, nothing of the hot loops live):
+        // one (utterance, channel) per thread, ~24 partials each from L2
+        const int b_lo = m_lo / p.mmt, b_hi = (m_lo + m_n - 1) / p.mmt;
+        for (int idx = threadIdx.x; idx < (b_hi - b_lo + 1) * C; idx += blockDim.x) {
+            const int jj = idx / C, cc = idx - jj * C;
+            float av, bv;
+            row_coef_from_partials(p.cin_part, p.cin_si, p.cin_h, p.cin_ld_h, p.cin_h_off, p.cin_T, b_lo + jj, cc, &av, &bv);
+            coef_s[(jj * 2 + 0) * C + cc] = av;
+            coef_s[(jj * 2 + 1) * C + cc] = bv;
+        }
+        __syncthreads();
+    }
     // register split (the kernel launches with 96 per thread): the two epilogue warpgroups (warps 12-19) keep a whole 32-column
     // accumulator chunk plus 64 statistics registers, everybody else gives 16 back:  3 x 128 x 80 + 2 x 128 x 120 = 640 x 96
     // (each setmaxnreg dominates the code of its roles, so ptxas allocates the two regions with their own budgets)
@@ -373,11 +430,14 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             uint32_t xi = 0, xpar = 0;                              // ring cursor of the compute side
             int cached_b = -1;
             RXf cf;
+            const int cld = p.cin_part != nullptr ? C : p.coef_ld;
+            const float* cbase = p.cin_part != nullptr ? coef_s - (ptrdiff_t)(m_lo / p.mmt) * 2 * C : p.coef;
             while (mi < m_n) {
                 if (b != cached_b) {
-                    const float* ca = p.coef + (size_t)b * 2 * p.coef_ld;
-                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ca + c4));
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ca + p.coef_ld + c4));
+                    // utterance b: from the coefficient buffer, or from the table this CTA computed (generic loads either way)
+                    const float* ca = cbase + (ptrdiff_t)b * 2 * cld;
+                    const float4 a4 = *reinterpret_cast<const float4*>(ca + c4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(ca + cld + c4);
                     const float4 al = __ldg(reinterpret_cast<const float4*>(p.alpha + c4));
                     const float4 c = make_float4(__fdividef(0.5f, al.x), __fdividef(0.5f, al.y), __fdividef(0.5f, al.z), __fdividef(0.5f, al.w));
                     cf.a01 = make_float2(a4.x, a4.y); cf.a23 = make_float2(a4.z, a4.w);
@@ -528,14 +588,6 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 // ---------------------------------------------------------------- coefficients from the per-(CTA, utterance, warp) partials
 // grid (B), block 256: thread (c, slice) sums every `nsl`-th partial of channel c in double, then a fixed-order tree over the
 // slices.  The CTAs that hold partials of utterance b are those whose macro-tile range meets [b*mmt, (b+1)*mmt).
-struct RowStatsInfo { int grid, J, nwarp, mmt, tq, tr, C; };
-
-__device__ __forceinline__ int row_cta_start(const RowStatsInfo& s, int c) { return c * s.tq + (c < s.tr ? c : s.tr); }
-__device__ __forceinline__ int row_cta_of(const RowStatsInfo& s, int t) {
-    const int big = s.tr * (s.tq + 1);
-    return t < big ? t / (s.tq + 1) : s.tr + (t - big) / s.tq;
-}
-
 __global__ void __launch_bounds__(256)
 adain_coef_row_kernel(const float2* __restrict__ partial, const RowStatsInfo si, const float* __restrict__ h, int ld_h, int h_off,
                       float* __restrict__ coef, int T, int Cpad) {
@@ -698,14 +750,33 @@ int64_t conv_row_stats_bytes(int B, int T, int C) {
     return (int64_t)RW_MAXGRID * per_cta;
 }
 
+// can a launch of this geometry compute its AdaIN coefficients itself (RowCoefSrc)?  The table of its utterances must fit 2 KB
+bool conv_row_inline_coef_ok(const ConvArgs& a) {
+    if (!row_geometry_ok(a) || tune().no_row_inline_coef) return false;
+    RowParams p;
+    size_t smem;
+    int grid;
+    if (!row_plan(a, p, &smem, &grid)) return false;
+    return p.J * 2 * a.Cin * 4 <= 2048;
+}
+
 int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, const float* alpha, void* stats_out,
-                    RowStatsDesc* desc, cudaStream_t st) {
+                    RowStatsDesc* desc, cudaStream_t st, const RowCoefSrc* src) {
     RowParams p;
     size_t smem = 0;
     int grid = 0;
     ST2_REQUIRE(row_geometry_ok(a) && row_plan(a, p, &smem, &grid), "conv_row: unsupported geometry");
     ST2_REQUIRE(act == ACT_SNAKE && alpha != nullptr, "conv_row: only the Snake transform is built");
     p.coef = coef; p.coef_ld = coef_ld; p.alpha = alpha;
+    p.cin_part = nullptr;
+    if (src != nullptr) {
+        ST2_REQUIRE(src->partial != nullptr && src->h != nullptr && src->desc.C == a.Cin && p.J * 2 * a.Cin * 4 <= 2048,
+                    "conv_row: in-kernel coefficients need row partials of the same channel count and <= 2 KB of them per CTA");
+        p.cin_part = (const float2*)src->partial;
+        p.cin_si.grid = src->desc.grid; p.cin_si.J = src->desc.J; p.cin_si.nwarp = src->desc.nwarp; p.cin_si.mmt = src->desc.mmt;
+        p.cin_si.tq = src->desc.tq; p.cin_si.tr = src->desc.tr; p.cin_si.C = src->desc.C;
+        p.cin_h = src->h; p.cin_ld_h = src->ld_h; p.cin_h_off = src->h_off; p.cin_T = src->T;
+    }
     p.stats = (float2*)stats_out;
     const int C = a.Cin, nch = C / 32;
     const int is_bf16 = a.fmt16 == DT_BF16 ? 1 : 0;

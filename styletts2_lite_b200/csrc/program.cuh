@@ -589,7 +589,11 @@ struct Exec {
     void conv_fused(const ConvW& w, const float* x, int ld_x, int Tin, int dt, int act, float slope, const float* alpha,
                     float* y, int ld_y, int Tout, int stride, int padding, int dilation, const float* res, int ld_res,
                     int res_shift, float scale, int accumulate, void* stats_out, int out_row_shift = 0, int mirror = 0,
-                    int x16in = 0, int y16out = 0, int res16 = 0, const void* acc_src = nullptr, int acc16 = 0) {
+                    int x16in = 0, int y16out = 0, int res16 = 0, const void* acc_src = nullptr, int acc16 = 0,
+                    const StatRef* in_sr = nullptr, const AdaINRef* in_n = nullptr, const float* in_off = nullptr) {
+        // in_sr / in_n (/ in_off): the statistics and the AdaIN of this conv's input.  When both the producer of the statistics and
+        // this conv run on conv_row.cu the kernel computes its coefficients itself (no launch in between); otherwise the
+        // coefficient kernel is launched here, as coef_from() before the call would
         if (!live()) return;
         ConvArgs a;
         if (!fill_args(a, w, Tin, Tout, stride, padding, dilation, out_row_shift)) return;
@@ -600,8 +604,17 @@ struct Exec {
         a.x16in = x16in; a.y16out = y16out; a.res16 = res16; a.acc_src = acc_src; a.acc16 = acc16;
         // the 32 / 64-channel Snake convs on fp16 tensors run on the row-per-thread kernel (conv_row.cu); its statistics
         // partials have their own layout, recorded in last_rd for the coefficient kernel
-        last_row = act == ACT_SNAKE && !w.transposed && conv_row_supported(a);
-        if (last_row) chk(launch_conv_row(a, coef, coef_ld, act, alpha, stats_out, &last_rd, st));
+        const bool row = act == ACT_SNAKE && !w.transposed && conv_row_supported(a);
+        RowCoefSrc src{};
+        bool inline_coef = false;
+        if (in_sr != nullptr) {
+            inline_coef = row && in_n != nullptr && in_sr->f2 && in_sr->row && in_off == nullptr && conv_row_inline_coef_ok(a);
+            if (inline_coef) src = RowCoefSrc{in_sr->ptr, in_sr->rd, H, d->fc_rows, in_n->h_off, Tin};
+            else coef_from(*in_sr, in_n, Tin, w.Cin, w.Cin, in_off);
+            if (err != ST2_OK) return;
+        }
+        last_row = row;
+        if (row) chk(launch_conv_row(a, coef, coef_ld, act, alpha, stats_out, &last_rd, st, inline_coef ? &src : nullptr));
         else chk(launch_conv_fused(a, coef, coef_ld, act, slope, alpha, stats_out, st));
         const double flops = 2.0 * B * (w.transposed ? (double)Tin : (double)(Tout - out_row_shift)) * w.Cin * w.Cout * w.k;
         const double bytes = (double)B * ((double)w.Cin * Tin * (x16in ? 2 : 4) +
@@ -741,12 +754,12 @@ struct Exec {
             int cur16 = x16;
             for (int j = 0; j < 3; ++j) {
                 const int dil = w.dil[j];
-                coef_from(cur_st, &w.n1[j], T, C, C, j == 0 ? x_offset : nullptr);
+                const StatRef sr1 = cur_st;
                 conv_fused(w.c1[j], cur, C, T, dt, ACT_SNAKE, 0.f, w.alpha1[j], xt, C, T, 1, (w.k * dil - dil) / 2, dil, nullptr,
-                           0, 0, 1.f, 0, st_xt, 0, 0, cur16, xt16);
+                           0, 0, 1.f, 0, st_xt, 0, 0, cur16, xt16, 0, nullptr, 0, &sr1, &w.n1[j], j == 0 ? x_offset : nullptr);
                 if (!xt16) tap(w.name + ".convs1." + std::to_string(j), xt, C, (int64_t)B * T, C);
                 else tap16(w.name + ".convs1." + std::to_string(j), xt, (int64_t)B * T * C);
-                coef_from(produced(st_xt, nparts), &w.n2[j], T, C, C);
+                const StatRef sr2 = produced(st_xt, nparts);
                 const bool last = (j == 2);
                 const bool s16 = last && sum16 != 0 && run16;                     // the caller asked resblock1_sum16_ok first
                 const int out16 = ((run16 && !last) || (s16 && (sum16 < 3 || dest16))) ? 1 : 0;
@@ -755,7 +768,7 @@ struct Exec {
                 if (j == 0 && x_offset != nullptr) c2.bias = const_cast<float*>(c2b0);
                 conv_fused(c2, xt, C, T, dt, ACT_SNAKE, 0.f, w.alpha2[j], out, C, T, 1, (w.k - 1) / 2, 1, cur, C, 0,
                            last ? scale : 1.f, last ? accumulate : 0, last ? nullptr : st_run, 0, 0, xt16, out16, cur16,
-                           (s16 && sum16 > 1) ? sum16buf : nullptr, (s16 && sum16 > 1) ? 1 : 0);
+                           (s16 && sum16 > 1) ? sum16buf : nullptr, (s16 && sum16 > 1) ? 1 : 0, &sr2, &w.n2[j]);
                 if (out16 && !(last && dest16)) tap16(w.name + ".iter" + std::to_string(j), out, (int64_t)B * T * C);
                 else if (!last || (!accumulate && scale == 1.f)) tap(w.name + ".iter" + std::to_string(j), out, C, (int64_t)B * T, C);
                 cur = out;
