@@ -51,8 +51,9 @@ total = sum(a[1] for a in agg.values())
 n = sum(a[0] for a in agg.values())
 with open(os.path.join(out_dir, "%s_launch_summary.md" % tag), "w") as f:
     f.write("# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n" % tag)
-    f.write("`--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1400 -c 600`: "
-            "%d launches inside the timed steps, %.1f ms of kernel time.\n" % (n, total / 1000))
+    window = os.environ.get("NCU_WINDOW", "-s 1400 -c 600")          # the launch window the capture script used
+    f.write("`--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none %s`: "
+            "%d launches inside the timed steps, %.1f ms of kernel time.\n" % (window, n, total / 1000))
     f.write("Per-launch times under ncu are cold-cache and serialised: the SHARE column is what compares with bench.py's\n"
             "`roofline.kernels[*].share`; DRAM MB / launch is `dram__bytes_read.sum + dram__bytes_write.sum` averaged over the\n"
             "kernel's launches (compare with the algorithmic bytes of DESIGN.md section 4).\n\n"
