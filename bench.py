@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-chain", action="store_true", help="skip the auxiliary BASELINE configs[2] measurement (full_path_cfg3)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: --frames)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm")
+    ap.add_argument("--gather", default="p2p", choices=["direct", "p2p"],
+                    help="N > 1: NCCL send / recv on a side stream (default), or decode straight into rank 0's buffer over NVLink "
+                         "(symmetric memory; bit-identical, measured 1-2 %% slower per step at N = 2: the last kernel's stores go remote)")
     ap.add_argument("--no-aux", action="store_true", help="skip every auxiliary measurement (cfg3/cfg4/cfg5/eager_gpu)")
     return ap.parse_args()
 
@@ -73,9 +76,10 @@ def workload_config(a, n_gpus):
                       "bf16": "tcgen05 bf16 operands (generator.noise_res + front half on fp16 operands), fp32 accumulate"}[a.precision],
         "noise": "SineGen noise drawn on the device (Philox) inside the step",
         "l2": "L2 flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2",
-        "parallelism": ("replicas: utterances sharded per rank, no cross-rank math; every step's waveforms go point-to-point (NCCL) "
-                        "into one preallocated buffer on rank 0, on a side stream that overlaps the next forward; all transfers "
-                        "complete inside the timed region") if n_gpus > 1 else "single GPU",
+        "parallelism": ("replicas: utterances sharded per rank, no cross-rank math; every step's waveforms land in one preallocated "
+                        "buffer on rank 0 -- --gather direct: the decoder's last kernel stores there over NVLink (symmetric memory), "
+                        "--gather p2p (and the fallback): NCCL send / recv on a side stream that overlaps the next forward; all "
+                        "transfers complete inside the timed region") if n_gpus > 1 else "single GPU",
     }
 
 
@@ -351,7 +355,7 @@ def aux_eager_gpu(torch, dev, variant, B, T):
     return res
 
 
-def aux_cfg4(torch, dist, m, dev, rank, world, precision):
+def aux_cfg4(torch, dist, m, dev, rank, world, precision, direct=True):
     """BASELINE configs[3]: 1024 utterances x 10 s sharded over the ranks (parallel.shard_range), decoded in micro-batches of 32
     per rank, every micro-batch sent into its slice of ONE preallocated [1024,1,240000] buffer on rank 0 while the next one
     is being decoded (parallel.ShardedGather).  Timed on the device, max over ranks, second of two passes."""
@@ -359,7 +363,7 @@ def aux_cfg4(torch, dist, m, dev, rank, world, precision):
     from styletts2_lite_b200.parallel import ShardedGather
     N_UTT, T, MB = 1024, 400, 32
     S = 600 * T
-    g = ShardedGather(N_UTT, S, MB, dev)
+    g = ShardedGather(N_UTT, S, MB, dev, direct=direct)
     inp = {k: v.to(dev) for k, v in synth.make_inputs(MB, T, seed=1004 + rank, cfg=m.cfg, with_noise=False).items()}
     mine = g.my_micro_batches()
 
@@ -367,7 +371,8 @@ def aux_cfg4(torch, dist, m, dev, rank, world, precision):
         for j, (lo, hi) in enumerate(mine):
             n = hi - lo
             with torch.no_grad():
-                out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=seed0 + j, precision=precision)
+                out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=seed0 + j, precision=precision,
+                        out=g.target(j))
             g.submit(j, out)
         return g.finish()
     one_pass(100)                                    # warm-up pass (allocators, NCCL connections)
@@ -378,7 +383,8 @@ def aux_cfg4(torch, dist, m, dev, rank, world, precision):
     for j, (lo, hi) in enumerate(mine):
         n = hi - lo
         with torch.no_grad():
-            out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=5000 + j, precision=precision)
+            out = m(inp["asr"][:n], inp["F0_curve"][:n], inp["N"][:n], inp["s"][:n], seed=5000 + j, precision=precision,
+                    out=g.target(j))
         g.submit(j, out)
     e1.record()                                      # the last forward is issued; what follows is the exposed tail of the gather
     full = g.finish()
@@ -396,6 +402,8 @@ def aux_cfg4(torch, dist, m, dev, rank, world, precision):
             "ms": round(ms, 2), "audio_s_per_s": round(N_UTT * 10.0 / (ms / 1e3), 1),
             "gather_bytes_to_rank0": int((N_UTT - (g.spans[0][1] - g.spans[0][0])) * S * 4),
             "exposed_gather_tail_ms": round(tail_ms, 3), "finite": ok,
+            "gather": ("direct: the decoder's last kernel stores into rank 0's buffer (symmetric memory over NVLink)" if g.direct
+                       else "p2p: NCCL send / recv on a side stream"),
             "limiter": "rank 0 ingests (world-1)/world of 983 MB over its NVLink ports while it decodes its own shard; only the "
                        "tail after the last forward (exposed_gather_tail_ms) is not hidden"}
 
@@ -434,7 +442,7 @@ def run_b200(a, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # N > 1: one job = world x B utterances, one micro-batch per rank per step, straight into rank 0's preallocated buffer
-    gatherer = ShardedGather(B * world, S, B, dev) if world > 1 else None
+    gatherer = ShardedGather(B * world, S, B, dev, direct=(a.gather == "direct")) if world > 1 else None
     gather_calls = [0]
 
     def submit_gather(out):
@@ -445,7 +453,8 @@ def run_b200(a, rank, local_rank, world):
 
     def step_resident(i):
         with torch.no_grad():
-            out = m(res["asr"], res["F0_curve"], res["N"], res["s"], seed=1234 + i)
+            out = m(res["asr"], res["F0_curve"], res["N"], res["s"], seed=1234 + i,
+                    out=(gatherer.target(0) if gatherer is not None else None))
         if world > 1:
             submit_gather(out)
         return out
@@ -576,7 +585,7 @@ def run_b200(a, rank, local_rank, world):
     if world > 1 and not a.no_aux and a.precision != "fp32" and a.variant == "hifigan":
         # BASELINE configs[3] on every rank (a collective job); after the headline's timed regions
         try:
-            cfg4 = aux_cfg4(torch, dist, m, dev, rank, world, a.precision)
+            cfg4 = aux_cfg4(torch, dist, m, dev, rank, world, a.precision, direct=(a.gather == "direct"))
         except Exception as ex:  # noqa: BLE001
             cfg4 = {"error": str(ex)[:300]}
     if rank != 0:
@@ -595,6 +604,8 @@ def run_b200(a, rank, local_rank, world):
             "gpu_launches": int(launches * a.steps), "launches_per_step": int(launches),
             "clocks": clocks, "roofline": roof, "wall_s_timed_region": round(wall, 3),
             "per_step_ms": [round(x, 3) for x in per_step]}
+    if gatherer is not None:
+        line["config"]["gather_used"] = "direct (symmetric memory)" if gatherer.direct else "p2p (NCCL send / recv)"
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_reference_run(a.variant, a.cpu_frames or a.frames, 2, 1, batch=a.cpu_batch)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -184,7 +184,10 @@ class B200Decoder(nn.Module):
         return g["out"].clone()
 
     def forward(self, asr, F0_curve, N, s, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
-                precision: Optional[str] = None, cuda_graph: bool = False):
+                precision: Optional[str] = None, cuda_graph: bool = False, out: Optional[torch.Tensor] = None):
+        """`out` (optional): a contiguous fp32 [B,1,S] CUDA tensor the waveform is written into -- it may live on another GPU
+        of the box (peer memory, e.g. `parallel.ShardedGather.target()`): the last kernel of the forward then stores over NVLink
+        straight into the gathered buffer."""
         if self.training:
             raise RuntimeError("B200Decoder is inference-only (the reference's training-time F0/N smoothing, "
                                "hifigan.py:447-455, is out of scope); call .eval()")
@@ -212,13 +215,16 @@ class B200Decoder(nn.Module):
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # global torch RNG, like the reference
             # graph replay needs a launch sequence without host-side state: not with taps, a noise tape or the per-launch
             # event profile (its cudaEventRecord calls would be captured and later read back as garbage) -> eager
-            if cuda_graph and noise_ is None and not self._taps and not self._profiling:
+            if cuda_graph and noise_ is None and not self._taps and not self._profiling and out is None:
                 return self._forward_graph(asr_, f0_, n_, s_, seed, precision or self.precision)
             need = self._workspace_need(B, T, prec)
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            out = torch.empty(B, 1, S, dtype=torch.float32, device=dev)
+            if out is None:
+                out = torch.empty(B, 1, S, dtype=torch.float32, device=dev)
+            elif tuple(out.shape) != (B, 1, S) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float32 CUDA tensor of shape [%d,1,%d]" % (B, S))
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.st2_decoder_forward(self._handle, _lib.ptr(asr_), _lib.ptr(f0_), _lib.ptr(n_), _lib.ptr(s_),
                                                _lib.ptr(noise_), C.c_uint64(seed), _lib.ptr(out), B, T, prec,

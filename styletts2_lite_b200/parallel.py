@@ -8,6 +8,13 @@ NVLink on the GPU box, gloo in the CPU tests).
 sent straight into its slice of that buffer (point-to-point, no staging copies, no concatenation, no per-step allocation), and
 the transfers are issued on a side stream behind an event of the compute stream, so the gather of micro-batch k overlaps the
 forward of micro-batch k + 1.  `gather_waveforms` is the one-shot convenience form on top of the same buffer logic.
+
+`direct=True` (CUDA, one box): the buffer is symmetric memory (torch.distributed._symmetric_memory: every rank maps rank 0's
+allocation over NVLink / NVSwitch) and `target(j)` is the slice of it micro-batch j belongs to -- pass it as
+`decoder(..., out=g.target(j))` and the decoder's last kernel stores the waveform straight into rank 0's HBM: the gather is
+fused into the compute, there is no send / receive, no side stream and nothing to overlap.  A micro-batch that was not written
+in place is copied there device-to-device by `submit`.  Falls back to the point-to-point path when symmetric memory cannot be
+set up (CPU tensors, gloo, no peer access).
 """
 from __future__ import annotations
 
@@ -42,17 +49,50 @@ class ShardedGather:
     The buffer on `dst` is allocated once and reused by every job of the same shape (`reset()` starts the next one)."""
 
     def __init__(self, n_total: int, samples: int, micro_batch: int, device: torch.device, dst: int = 0,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, direct: bool = False):
         self.n_total, self.S, self.mb, self.dst = int(n_total), int(samples), max(1, int(micro_batch)), dst
         self.device = torch.device(device)
         self.on = _dist_on()
         self.world = dist.get_world_size() if self.on else 1
         self.rank = dist.get_rank() if self.on else 0
         self.spans = [shard_range(self.n_total, r, self.world) for r in range(self.world)]
-        self.full = torch.empty((self.n_total, 1, self.S), dtype=dtype, device=self.device) if self.rank == dst else None
+        self.direct = False
+        self._hdl = None
+        self._peer = None                      # dst's buffer as this rank sees it (direct mode)
+        if direct and self.on and self.device.type == "cuda":
+            self._setup_direct(dtype)
+        if self.direct:
+            self.full = self._peer if self.rank == dst else None
+        else:
+            self.full = (torch.empty((self.n_total, 1, self.S), dtype=dtype, device=self.device) if self.rank == dst else None)
         self.side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._works: List = []
         self._keep: List[torch.Tensor] = []
+
+    def _setup_direct(self, dtype: torch.dtype) -> None:
+        """Symmetric allocation of the gathered buffer (every rank allocates, only dst's copy is used) and the rendezvous that
+        maps dst's copy into this process.  All ranks must agree, so the outcome is reduced over the group."""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            with torch.cuda.device(self.device):
+                buf = symm.empty((self.n_total, 1, self.S), dtype=dtype, device=self.device)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                peer = buf if self.rank == self.dst else hdl.get_buffer(self.dst, (self.n_total, 1, self.S), dtype)
+        except Exception:  # noqa: BLE001  (no symmetric memory in this build / no peer access: use send / recv)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self._sym, self._hdl, self._peer, self.direct = buf, hdl, peer, True
+
+    def target(self, j: int) -> Optional[torch.Tensor]:
+        """Direct mode: the [hi - lo, 1, S] slice of dst's buffer that micro-batch j of THIS rank belongs to (peer memory on
+        every rank but dst) -- the `out=` of the decoder call.  None otherwise."""
+        if not self.direct:
+            return None
+        lo, hi = self.my_micro_batches()[j]
+        return self._peer[lo:hi]
 
     def micro_batches_of(self, rank: int) -> List[Tuple[int, int]]:
         a, b = self.spans[rank]
@@ -71,6 +111,11 @@ class ShardedGather:
         if tuple(wave.shape) != (hi - lo, 1, self.S):
             raise ValueError("micro-batch %d: expected %s, got %s" % (j, (hi - lo, 1, self.S), tuple(wave.shape)))
         wave = wave.contiguous()
+        if self.direct:
+            dst_view = self._peer[lo:hi]
+            if wave.data_ptr() != dst_view.data_ptr():          # not decoded in place: one device-to-device copy over NVLink
+                dst_view.copy_(wave, non_blocking=True)
+            return
 
         def issue():
             if self.rank == self.dst:
@@ -103,7 +148,7 @@ class ShardedGather:
 
     def drain_remote(self) -> None:
         """dst only: post the receives of micro-batches that other ranks have beyond dst's own count (ragged shards)."""
-        if not (self.on and self.rank == self.dst):
+        if self.direct or not (self.on and self.rank == self.dst):
             return
         mine = len(self.my_micro_batches())
         ops = []
@@ -119,6 +164,10 @@ class ShardedGather:
 
     def finish(self) -> Optional[torch.Tensor]:
         """Wait for every transfer issued so far (the current stream waits on the side stream); returns the buffer on dst."""
+        if self.direct:
+            # every rank's stores so far are ordered before the barrier on its stream; after it dst may read the buffer
+            self._hdl.barrier()
+            return self.full
         self.drain_remote()
         for w in self._works:
             w.wait()

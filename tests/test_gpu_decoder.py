@@ -303,6 +303,33 @@ def test_full_size_tensor_core_path_tracks_fp32_path(variant, B, T):
     assert snr >= 40.0
 
 
+def test_conv_row_inline_coefficients_match_the_coefficient_kernel():
+    """At sizes where the 32 / 64-channel resblocks run on conv_row.cu a launch fed by another conv_row launch computes its AdaIN
+    coefficients itself (39 fewer launches per forward).  Same partials, same fp64 arithmetic, another summation order than
+    adain_coef_row_kernel: against the build with the switch off the waveform must agree to rounding noise (>= 80 dB), the
+    launch count must really drop, and the path must be bit-reproducible."""
+    cfg = DecoderConfig.hifigan()
+    m = _decoder(cfg)
+    lib = _lib.load()
+    inp = synth.make_inputs(8, 400, seed=2400, cfg=cfg, with_noise=False)
+    t = {k: v.cuda() for k, v in inp.items()}
+
+    def run():
+        with torch.no_grad():
+            o = m(t["asr"], t["F0_curve"], t["N"], t["s"], seed=78, precision="bf16").float().cpu().numpy()
+        return o, m.last_launch_count()
+    a, na = run()
+    a2, _ = run()
+    _lib.check(lib.st2_set_tuning(b"no_row_inline_coef", 1))
+    try:
+        b, nb = run()
+    finally:
+        _lib.check(lib.st2_set_tuning(b"no_row_inline_coef", 0))
+    assert np.array_equal(a, a2)
+    assert nb - na >= 30, (na, nb)
+    assert snr_db(b, a) >= 80.0, snr_db(b, a)
+
+
 @pytest.mark.parametrize("variant", ["hifigan", "istftnet"])
 def test_cuda_graph_replay_matches_eager(variant):
     """forward(..., cuda_graph=True) captures the launches once per shape and replays them; the Philox seed is read from
