@@ -219,6 +219,12 @@ ST2_API int st2_text_forward_ragged(st2_decoder* d, const int64_t* tokens, const
  * st2_round_durations. */
 ST2_API int st2_smooth_durations(const float* duration, const int32_t* n_tokens, const float* noise, const float* prev_d_mean,
                         float t, float speed, float* out, float* mean_out, int32_t B, int32_t L, void* stream);
+/* The same for the B sentences of one text in order, as the loop of StyleTTS2.generate chains them (inference.py:312-313): sentence
+ * b takes the mean duration of sentence b - 1 (mean_out[b - 1]) as its prev_d_mean; prev_d_mean0 (device, 1 float, may be null = 0)
+ * seeds sentence 0. */
+ST2_API int st2_smooth_durations_chained(const float* duration, const int32_t* n_tokens, const float* noise,
+                        const float* prev_d_mean0, float t, float speed, float* out, float* mean_out, int32_t B, int32_t L,
+                        void* stream);
 
 /* ---- Length regulator: replaces inference.py:257-268 ---- */
 

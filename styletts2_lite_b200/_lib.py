@@ -95,6 +95,7 @@ SIGNATURES = {
     "st2_text_forward_ragged": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "st2_round_durations": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
     "st2_smooth_durations": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _I, _I, _P]),
+    "st2_smooth_durations_chained": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _I, _I, _P]),
     "st2_length_regulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "st2_sinegen_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "st2_har_source": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -22,6 +22,15 @@ int st2_smooth_durations(const float* duration, const int32_t* n_tokens, const f
     return launch_smooth_durations(duration, n_tokens, noise, prev_d_mean, t, speed, out, mean_out, B, L, (cudaStream_t)stream);
 }
 
+int st2_smooth_durations_chained(const float* duration, const int32_t* n_tokens, const float* noise, const float* prev_d_mean0, float t,
+                                 float speed, float* out, float* mean_out, int32_t B, int32_t L, void* stream) {
+    ST2_REQUIRE(duration && out && B >= 0 && L >= 0, "smooth_durations_chained: bad argument");
+    ST2_REQUIRE(t >= 0.f && t <= 1.f && speed > 0.f, "smooth_durations_chained: need 0 <= t <= 1 and speed > 0 (got %g, %g)",
+                (double)t, (double)speed);
+    ST2_REQUIRE(noise != nullptr || t == 0.f, "smooth_durations_chained: t > 0 needs the N(0,1) tape");
+    return launch_smooth_durations(duration, n_tokens, noise, prev_d_mean0, t, speed, out, mean_out, B, L, (cudaStream_t)stream, 1);
+}
+
 int st2_length_regulate(const float* src, const int32_t* dur, float* out, int32_t B, int32_t C, int32_t L,
                         int32_t F, int32_t channels_last, void* stream) {
     ST2_REQUIRE(B >= 0 && C >= 0 && L >= 0 && F >= 0, "length_regulate: negative size");

@@ -167,7 +167,7 @@ int launch_duration_head(const float* x, const float* W, const float* bias, floa
 int launch_round_durations(const float* duration, const int32_t* n_tokens, int32_t* dur, int32_t* total,
                            int B, int L, cudaStream_t st);
 int launch_smooth_durations(const float* duration, const int32_t* n_tokens, const float* z, const float* prev_mean, float t,
-                            float speed, float* out, float* mean_out, int B, int L, cudaStream_t st);
+                            float speed, float* out, float* mean_out, int B, int L, cudaStream_t st, int chain = 0);
 int launch_length_regulate(const float* src, const int32_t* dur, float* out, int B, int C, int L, int F,
                            int channels_last, cudaStream_t st);
 

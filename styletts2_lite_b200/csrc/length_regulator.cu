@@ -80,20 +80,23 @@ __device__ void smooth_mean_std(const float* v, int lo, int hi, double* red, flo
 __global__ void __launch_bounds__(kSmThreads)
 smooth_durations_kernel(const float* __restrict__ duration, const int32_t* __restrict__ n_tokens, const float* __restrict__ z,
                         const float* __restrict__ prev_mean, float t, float speed, float* __restrict__ out,
-                        float* __restrict__ mean_out, int L) {
+                        float* __restrict__ mean_out, int B, int L, int chain) {
+    // chain: one CTA walks the utterances in order and hands the mean duration of sentence b - 1 to sentence b as its previous mean
+    // (the loop of StyleTTS2.generate, inference.py:312-313); prev_mean[0] seeds the first one.  Otherwise one CTA per utterance.
     __shared__ double red[kSmThreads];
-    const int b = blockIdx.x;
+    float carried = (chain && prev_mean) ? prev_mean[0] : 0.f;
+    for (int b = chain ? 0 : (int)blockIdx.x; b < (chain ? B : (int)blockIdx.x + 1); ++b) {
     const int n = n_tokens ? min(max(n_tokens[b], 0), L) : L;
     const float* x = duration + (size_t)b * L;
     float* y = out + (size_t)b * L;
     for (int i = n + threadIdx.x; i < L; i += kSmThreads) y[i] = 0.f;          // padded tokens
     if (n == 0) {
         if (threadIdx.x == 0 && mean_out) mean_out[b] = 0.f;
-        return;
+        continue;
     }
     float mean, sd;
     smooth_mean_std(x, 0, n, red, &mean, &sd);
-    const float prev = prev_mean ? prev_mean[b] : 0.f;
+    const float prev = chain ? carried : (prev_mean ? prev_mean[b] : 0.f);
     const float mu = prev != 0.f ? prev : mean;                                  // inference.py:248-251
     const float c1 = (float)(1.0 - (double)t);                                   // Python computes 1 - t in double
     for (int i = threadIdx.x; i < n; i += kSmThreads) {
@@ -122,13 +125,16 @@ smooth_durations_kernel(const float* __restrict__ duration, const int32_t* __res
         s += (double)v;
     }
     const double tot = smooth_block_sum(s, red);
-    if (threadIdx.x == 0 && mean_out) mean_out[b] = (float)(tot / (double)n);    // inference.py:272
+    carried = (float)(tot / (double)n);                                          // inference.py:272 -> prev_d_mean of the next sentence
+    if (threadIdx.x == 0 && mean_out) mean_out[b] = carried;
+    __syncthreads();                                                             // y / red are reused by the next utterance
+    }
 }
 
 int launch_smooth_durations(const float* duration, const int32_t* n_tokens, const float* z, const float* prev_mean, float t,
-                            float speed, float* out, float* mean_out, int B, int L, cudaStream_t st) {
+                            float speed, float* out, float* mean_out, int B, int L, cudaStream_t st, int chain) {
     if (B <= 0 || L <= 0) return ST2_OK;
-    smooth_durations_kernel<<<B, kSmThreads, 0, st>>>(duration, n_tokens, z, prev_mean, t, speed, out, mean_out, L);
+    smooth_durations_kernel<<<chain ? 1 : B, kSmThreads, 0, st>>>(duration, n_tokens, z, prev_mean, t, speed, out, mean_out, B, L, chain);
     ST2_LAUNCH_CHECK();
     return ST2_OK;
 }

@@ -38,11 +38,13 @@ def round_durations(duration: torch.Tensor, n_tokens: Optional[torch.Tensor] = N
 
 
 def smooth_durations(duration: torch.Tensor, noise: Optional[torch.Tensor] = None, t: float = 0.1, speed: float = 1.0,
-                     prev_d_mean=0.0, n_tokens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                     prev_d_mean=0.0, n_tokens: Optional[torch.Tensor] = None, chained: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """inference.py:248-255 on the device, per utterance: mix with N(mean or prev_d_mean, std) draws (weight t), replace the
     z-score outliers of duration[1:-2], divide by speed.  duration [B,L] fp32 (CUDA); noise [B,L] the N(0,1) tape that stands in
     for `normal_` (drawn with torch.randn on the device when omitted and t > 0); prev_d_mean a float or a [B] tensor (0 = none).
-    Returns (smoothed duration [B,L], mean duration [B] -- inference.py:272, the next split's prev_d_mean)."""
+    Returns (smoothed duration [B,L], mean duration [B] -- inference.py:272, the next split's prev_d_mean).
+    chained=True: the B rows are the sentences of one text in order and sentence b takes the mean of sentence b - 1 as its previous
+    mean (the loop of StyleTTS2.generate, inference.py:312-313); prev_d_mean then seeds sentence 0 only."""
     if not duration.is_cuda:
         raise _lib.St2Error("length regulator has no CPU path: inputs must be CUDA tensors")
     speed = min(max(float(speed), 0.0001), 2.0)                   # inference.py:226
@@ -64,12 +66,13 @@ def smooth_durations(duration: torch.Tensor, noise: Optional[torch.Tensor] = Non
             raise ValueError("prev_d_mean must have one entry per utterance")
     else:
         prev = None if float(prev_d_mean) == 0.0 else torch.full((B,), float(prev_d_mean), device=dev, dtype=torch.float32)
+    fn = lib.st2_smooth_durations_chained if chained else lib.st2_smooth_durations
     nt = None if n_tokens is None else n_tokens.to(device=dev, dtype=torch.int32).contiguous()
     out = torch.empty_like(duration)
     mean = torch.empty(B, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.st2_smooth_durations(_lib.ptr(duration), _lib.ptr(nt), _lib.ptr(noise), _lib.ptr(prev), float(t), speed,
-                                            _lib.ptr(out), _lib.ptr(mean), B, L, _stream(dev)), "st2_smooth_durations")
+        _lib.check(fn(_lib.ptr(duration), _lib.ptr(nt), _lib.ptr(noise), _lib.ptr(prev), float(t), speed,
+                      _lib.ptr(out), _lib.ptr(mean), B, L, _stream(dev)), "st2_smooth_durations")
     return out, mean
 
 

@@ -609,3 +609,25 @@ def test_vocos_drop_in_constructor_and_graph_replay():
     assert torch.equal(a, b) and torch.equal(b, c)
     ref = _run_vocos(_decoder(cfg), {k: v.cpu().numpy() for k, v in inp.items()})
     assert snr_db(ref, a.cpu().numpy()) >= 40.0
+
+
+def test_vocos_other_head_geometry_vs_oracle():
+    """The reference constructor's own defaults for the ISTFT head (n_fft 1024, hop 256: Modules/vocos.py:366-368) with a smaller
+    backbone (2 blocks, intermediate 1024): 512 samples per asr frame, operand padding 1026 -> 1152, 4 frames per sample again."""
+    from styletts2_lite_b200 import vocos
+    m = vocos.Decoder(dim_in=512, style_dim=128, dim_out=80, intermediate_dim=1024, num_layers=2, gen_istft_n_fft=1024,
+                      gen_istft_hop_size=256)
+    cfg = m.cfg
+    assert cfg.samples_per_frame == 512
+    sdt = synth.make_state_dict(cfg, 3, True)
+    m.load_state_dict(sdt)
+    m = m.to("cuda").eval()
+    inp = synth.make_inputs(2, 9, 1020, cfg, with_noise=False)
+    with torch.no_grad():
+        out = m(inp["asr"].cuda(), inp["F0_curve"].cuda(), inp["N"].cuda(), inp["s"].cuda()).cpu().numpy()
+        o16 = m(inp["asr"].cuda(), inp["F0_curve"].cuda(), inp["N"].cuda(), inp["s"].cuda(), precision="fp16").cpu().numpy()
+    ref = O.decoder_forward({k: v.numpy() for k, v in sdt.items()}, cfg, inp["asr"].numpy(), inp["F0_curve"].numpy(),
+                            inp["N"].numpy(), inp["s"].numpy(), None)
+    assert out.shape == ref.shape == (2, 1, 512 * 9)
+    assert np.abs(out - ref).max() <= 1e-4
+    assert snr_db(ref, o16) >= 40.0

@@ -427,3 +427,73 @@ def test_cuda_graph_replay_of_text_encoder_and_predictor_matches_eager():
         e1 = te(tok)
         assert not torch.equal(e1, e) and torch.equal(te(tok, cuda_graph=True), e1)
         te.load_state_dict(synth.make_text_state_dict(seed=0))
+
+
+# ---------------------------------------------------------------- sentences of one text: StyleTTS2.generate on the device
+def test_chained_duration_smoothing_vs_sentence_loop_oracle():
+    """st2_smooth_durations_chained: sentence b takes the mean duration of sentence b - 1 as its previous mean (the loop of
+    StyleTTS2.generate, inference.py:312-313) -- against the per-sentence oracle chained on the host."""
+    from oracle import decoder_np as O
+    rng = np.random.RandomState(11)
+    lens = np.array([17, 5, 33, 2, 24], np.int32)
+    L = int(lens.max())
+    dur = np.full((len(lens), L), 7.0, np.float32)
+    z = rng.randn(len(lens), L).astype(np.float32)
+    for b, n in enumerate(lens):
+        dur[b, :n] = 1.0 + 6.0 * rng.rand(n)
+    dur[2, 5] = 60.0                                                 # an outlier that gets replaced
+    out, means = LR.smooth_durations(torch.from_numpy(dur).cuda(), torch.from_numpy(z).cuda(), t=0.2, speed=1.1, prev_d_mean=3.3,
+                                     n_tokens=torch.from_numpy(lens), chained=True)
+    out, means = out.cpu().numpy(), means.cpu().numpy()
+    prev = 3.3
+    for b, n in enumerate(lens):
+        ref, prev = O.smooth_durations(dur[b, :n], z[b, :n], 0.2, 1.1, float(prev))
+        assert np.abs(out[b, :n] - ref).max() <= 3e-6 * max(1.0, np.abs(ref).max()), b
+        assert abs(means[b] - prev) <= 1e-5 and not out[b, n:].any()
+
+
+def test_synthesizer_batches_what_the_reference_loops_over():
+    """pipeline.B200Synthesizer: the sentences of one text as ONE padded batch through TextEncoder / duration half / chained smoothing /
+    rounding, then per sentence through the length regulator, F0Ntrain and the Decoder -- against the reference's control flow
+    (inference.py:224-272, :303-319: one sentence at a time, prev_d_mean handed on) written out with the same modules at B = 1,
+    fp32, shared tapes.  Durations must agree as integers, waveforms to fp32 noise; generate() must be the device
+    post-processing of those waveforms, bit for bit."""
+    from styletts2_lite_b200.pipeline import B200Synthesizer
+    from oracle import postprocess_np as PPN
+    te, pr = _text_encoder(), _dur_predictor()
+    cfg = DecoderConfig.hifigan()
+    dec = B200Decoder(cfg, "fp32")
+    dec.load_state_dict(synth.make_state_dict(cfg, 0, True))
+    dec = dec.to("cuda").eval()
+    lens = [23, 9, 15]
+    sents = [synth.make_tokens(1, n, seed=5700 + n)[0] for n in lens]
+    s = synth.make_duration_inputs(1, 4, seed=4700)["s"].cuda()
+    L = max(lens)
+    z = torch.randn(len(lens), L, generator=torch.Generator().manual_seed(9)).cuda()
+    seeds = [41, 42, 43]
+    syn = B200Synthesizer(te, pr, dec, precision="fp32", cuda_graph=False)
+    waves, pred_dur, means = syn.infer_sentences(sents, s, speed=0.9, t=0.2, duration_noise=z, decoder_seeds=seeds)
+    prev = 0.0
+    with torch.no_grad():
+        for b, tok in enumerate(sents):                                # the reference loop
+            n = lens[b]
+            t_en = te(tok.unsqueeze(0).cuda())
+            d, duration = pr.predict_duration(t_en, s)
+            duration, mean = LR.smooth_durations(duration, z[b:b + 1, :n].contiguous(), t=0.2, speed=0.9, prev_d_mean=prev)
+            prev = float(mean[0])
+            pd, tot = LR.round_durations(duration)
+            dsm = duration[0].cpu().numpy()
+            safe = np.abs(dsm - np.floor(dsm) - 0.5) > 1e-3            # away from rounding ties the integer durations agree
+            assert np.array_equal(pd[0].cpu().numpy()[safe], pred_dur[b, :n].cpu().numpy()[safe]), b
+            if not np.array_equal(pd[0].cpu().numpy(), pred_dur[b, :n].cpu().numpy()):
+                continue                                               # a tie rounded the other way: frame counts differ
+            F = int(tot[0])
+            asr = LR.length_regulate(t_en, pd, F)
+            en = LR.length_regulate(d.transpose(1, 2).contiguous(), pd, F)
+            f0, nn_ = pr.F0Ntrain(en, s)
+            w = dec(asr, f0, nn_, s, seed=seeds[b]).reshape(-1)
+            assert w.shape == waves[b].shape and float((w - waves[b]).abs().max()) <= 2e-4, b
+            assert abs(prev - float(means[b])) <= 1e-4
+    r, pcm = syn.generate(sents, s, speed=0.9, stabilize=True, duration_noise=z, decoder_seeds=seeds)
+    ref_r, ref_pcm = PPN.postprocess([w.cpu().numpy() for w in waves])
+    assert np.array_equal(pcm.cpu().numpy(), ref_pcm) and np.array_equal(r.cpu().numpy(), ref_r)
