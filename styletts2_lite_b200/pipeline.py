@@ -6,8 +6,8 @@ scalar (the mean duration of sentence i - 1 steadies sentence i, inference.py:24
 padded batch through the TextEncoder, the duration half of the predictor (both with the reference's masking / packed-sequence
 semantics for padded batches), the chained duration smoothing and the rounding.  From there on the reference's modules have no
 length masking (the InstanceNorms of F0Ntrain and of the Decoder run over whatever frames they are given), so each sentence is
-regulated, sent through F0Ntrain and decoded with its own frame count, exactly as the reference does; graph replay keeps those
-B = 1 forwards cheap.  The waveforms are then trimmed / concatenated / padded / peak-normalised / quantised on the device
+regulated, sent through F0Ntrain and decoded with its own frame count, exactly as the reference does (optionally with graph
+replay for frame counts that repeat).  The waveforms are then trimmed / concatenated / padded / peak-normalised / quantised on the device
 (postprocess.assemble, inference.py:314-319 + Demo/infer.py:51-54).
 
 Every step is one of the C-ABI calls of include/st2_b200.h; there is no CPU path.
@@ -26,7 +26,9 @@ class B200Synthesizer:
     """text_encoder: B200TextEncoder, predictor: B200F0NPredictor(duration=True), decoder: B200Decoder (any variant); all on the
     same CUDA device, eval mode."""
 
-    def __init__(self, text_encoder, predictor, decoder, precision: Optional[str] = None, cuda_graph: bool = True):
+    def __init__(self, text_encoder, predictor, decoder, precision: Optional[str] = None, cuda_graph: bool = False):
+        """cuda_graph=True replays one captured graph per (frame count, precision) for the per-sentence forwards: worth it when
+        frame counts repeat (the caches hold 8 shapes each); free-running text rarely repeats them, so the default is eager."""
         self.text_encoder, self.predictor, self.decoder = text_encoder, predictor, decoder
         self.precision = precision
         self.cuda_graph = cuda_graph
