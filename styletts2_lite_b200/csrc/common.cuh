@@ -54,6 +54,7 @@ struct Tune {
     int pipe_xmax = 0, pipe_xmax16 = 0, pipe_nacc = 0, pipe_eg3_nores = 0, pipe_eg = 0;
     int pipe_nxg = 0, pipe_nrg = 0, pipe_na = 0, pipe_nx = 0, pipe_nr = 0;
     int verbose = 0, tc_halo = 0, lstm_bt = 0;
+    int no_row_bias_mma = 0;                // conv_row: bias added in the epilogue everywhere (A/B of the bias MMA)
     int no_row_inline_coef = 0;             // conv_row: always launch the coefficient kernel (A/B of the in-kernel coefficients)
     int row_sub = 0, row_slot = 0, row_na = 0;                  // conv_row planner overrides for sweeps (0 = planner's choice)
     int no_xt16 = 0, no_run16 = 0, no_xu16 = 0, no_sum16 = 0;   // defaults of the per-handle storage options (st2_decoder_set_option)

@@ -69,6 +69,10 @@ struct RowParams {
     // epilogue
     const float* bias; float scale;
     void* y; int ld_y;
+    // bias_mma (C = 32, scale == 1): the bias enters the accumulator through one extra tcgen05.mma -- D = ONES[128 x 16] x
+    // BIAS[16 x C] with bias_hi / bias_lo (an fp16 pair per channel) in rows k = 0, 1 -- instead of 8 shared-memory loads and 16
+    // packed FMAs per row in the epilogue, the busiest role of the 32-channel layers
+    int bias_mma;
     // AdaIN coefficients computed in the kernel (cin_part != nullptr) from the partials of the conv_row launch that produced x,
     // instead of read from `coef`: no coefficient launch between two convs of a resblock
     const float2* cin_part; RowStatsInfo cin_si; const float* cin_h; int cin_ld_h, cin_h_off, cin_T;
@@ -159,7 +163,7 @@ __device__ __forceinline__ void row_coef_from_partials(const float2* __restrict_
     *b_out = (float)(beta - mean * ad);
 }
 
-template <bool BF16, bool X16, bool Y16, int NCH>
+template <bool BF16, bool X16, bool Y16, int NCH, bool BM>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_xt, const __grid_constant__ CUtensorMap map_r,
@@ -181,7 +185,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     uint8_t* smem_a = smem;                                              // na x [a_rows][C] 16-bit, swizzled
     uint8_t* smem_w = smem_a + (size_t)p.na * p.a_bytes;                // ntaps x [C][C] resident taps
     uint8_t* smem_i = smem_w + (size_t)p.ntaps * btile;                  // fp16 identity [C][C]
-    uint8_t* smem_r = smem_i + btile;                                    // nr x nres x [128][C] fp16 residual tiles
+    uint8_t* smem_bt = smem_i + btile;                                   // bias_mma: fp16 bias tile [C][C] (k = 0, 1 used) + 512 B of ones
+    uint8_t* smem_r = smem_bt + (BM ? btile + 1024u : 0u);      // nr x nres x [128][C] fp16 residual tiles
     uint8_t* smem_x = smem_r + (size_t)p.nr * p.nres * rtile;            // lw x xd activation slots
     const int nxs = p.lw * p.xd;
     float* bias_s = reinterpret_cast<float*>(smem_x + (size_t)nxs * p.xslot);   // [C] bias * scale
@@ -245,6 +250,12 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     }
     // fp16 identity tile in the K-major swizzled B layout: element (n, k = n) of row n
     for (uint32_t i = threadIdx.x; i < btile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem_i)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (BM) {
+        for (uint32_t i = threadIdx.x; i < btile / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem_bt)[i] = make_uint4(0u, 0u, 0u, 0u);
+        // one 8-row group of fp16 ones: the A descriptor of the bias MMA has a zero group stride, all 16 row groups read these 512 B
+        for (uint32_t i = threadIdx.x; i < 512u / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem_bt + btile)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    }
     __syncthreads();
     if (threadIdx.x < C) {
         const uint32_t n = threadIdx.x;
@@ -252,6 +263,14 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         const uint32_t off = n * arow + (((n >> 3) ^ sw) << 4) + (n & 7u) * 2u;
         *reinterpret_cast<uint16_t*>(smem_i + off) = 0x3C00u;            // fp16 1.0
         bias_s[n] = (p.bias != nullptr ? p.bias[n] : 0.f) * p.scale;
+        if (BM) {
+            // row n of the K-major bias tile: (hi, lo) at k = 0, 1 -- 16-byte chunk 0 of the row, at its swizzled position
+            const float bv = bias_s[n];
+            const __half hi = __float2half_rn(bv);
+            const __half lo = __float2half_rn(bv - __half2float(hi));
+            const __half2 pr = __halves2half2(hi, lo);
+            *reinterpret_cast<uint32_t*>(smem_bt + n * arow + ((0u ^ sw) << 4)) = *reinterpret_cast<const uint32_t*>(&pr);
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -314,6 +333,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             const uint32_t a_buf_step = (uint32_t)p.a_bytes >> 4;
             const uint32_t w_lo0 = desc_lo(smem_u32(smem_w));
             const uint32_t i_lo = desc_lo(smem_u32(smem_i));
+            const uint32_t bt_lo = desc_lo(smem_u32(smem_bt)), ones_lo = desc_lo(smem_u32(smem_bt + btile));
             const uint32_t r_lo0 = desc_lo(smem_u32(smem_r));
             const uint32_t r_stage_step = ((uint32_t)p.nres * rtile) >> 4;
             const uint32_t row_step = (uint32_t)(p.tap_step * (int)(arow >> 4));
@@ -346,6 +366,11 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     mbar_wait(&acc_empty[acc], ((sc >> p.nacc_log2) & 1u) ^ 1u);
                     tc_fence_after();
                     uint32_t accum = 0;
+                    if (BM) {
+                        // A: the ones group, SBO = 0 (same swizzle mode as the other operands); B: the bias tile, k-step 0
+                        umma_f16_lohi2(d_tmem, ones_lo, (1u << 14) | (4u << 29), bt_lo, dhi, idesc_id, 0u);
+                        accum = 1u;
+                    }
                     if (p.nres) {
                         mbar_wait(&r_full[r_stage], r_par);
                         tc_fence_after();
@@ -528,6 +553,8 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
         };
+        // BM (a kernel variant): the accumulator already holds conv + bias and scale is 1, so a row goes from TMEM to the
+        // statistics and the store with no arithmetic of its own
         for (int mc = 0; mc < m_n; ++mc) {
             int m = mm * sub_rows + q * 32 + lane;                              // output row of this thread in sub-tile 0
             uint8_t* yrow = reinterpret_cast<uint8_t*>(p.y) + (((size_t)b * p.M + (size_t)m) * p.ld_y + ch * 32) * yes;
@@ -543,11 +570,16 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
                 if (m < p.M) {
                     float2 o[16];
+                    if (BM) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 bs = lds128(bias_u32 + (uint32_t)(i * 16));
-                        o[2 * i] = ffma2(make_float2(v[4 * i], v[4 * i + 1]), sc2, make_float2(bs.x, bs.y));
-                        o[2 * i + 1] = ffma2(make_float2(v[4 * i + 2], v[4 * i + 3]), sc2, make_float2(bs.z, bs.w));
+                        for (int i = 0; i < 16; ++i) o[i] = make_float2(v[2 * i], v[2 * i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bs = lds128(bias_u32 + (uint32_t)(i * 16));
+                            o[2 * i] = ffma2(make_float2(v[4 * i], v[4 * i + 1]), sc2, make_float2(bs.x, bs.y));
+                            o[2 * i + 1] = ffma2(make_float2(v[4 * i + 2], v[4 * i + 3]), sc2, make_float2(bs.z, bs.w));
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -665,10 +697,13 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
     p.nacc = nch == 1 ? 8 : 4;
     p.nacc_log2 = nch == 1 ? 3 : 2;
     p.tmem_cols = 256;
+    // the bias through the tensor core: 32-channel layers with scale 1 (every conv of a resblock but the last of a stage); the
+    // 64-channel layers run 8 epilogue warps and have no shared memory to spare for an 8 KB bias tile
+    p.bias_mma = (nch == 1 && a.bias != nullptr && a.scale == 1.f && !tune().no_row_bias_mma) ? 1 : 0;
     const int ntw = 18 - 4 * nch;
     const int xes = a.x16in ? 2 : 4;
     const int brows = nch == 1 ? 32 : 16;                  // rows per transform batch
-    const int64_t budget = 224 * 1024;
+    const int64_t budget = 224 * 1024 + (p.bias_mma ? 2048 : 0);      // + 1 KB of alignment slack = 227 KB at most
     bool ok = false;
     // 4 KB activation blocks (two transform batches per barrier round trip: 2 KB blocks measured 0.36 vs 0.30 ms on the
     // 64-channel k = 3 layer) with the largest macro tile that fits (the halo is transformed once per macro tile), then the
@@ -690,7 +725,7 @@ static bool row_plan(const ConvArgs& a, RowParams& p, size_t* smem_out, int* gri
             for (int na = (tune().row_na >= 2 && tune().row_na <= 4 ? tune().row_na : (sub == 1 ? 3 : 2)); na >= 2 && !ok; --na) {
             if (tune().row_na && na != tune().row_na) continue;
             const int lw_max = na * nblk < ntw ? na * nblk : ntw;
-            const int64_t fixed = na * a_bytes + (int64_t)a.ntaps * btile + btile + 4096;
+            const int64_t fixed = na * a_bytes + (int64_t)a.ntaps * btile + btile + 4096 + (p.bias_mma ? btile + 1024 : 0);
             const int nr_max = p.nres ? 4 : 0, nr_min = p.nres ? 2 : 0;
             // as many transform warps as have a ring (at least 10; 7 for the smallest macro tile) with the deepest rings that fit
             for (int lw = lw_max; lw >= (lw_max < 10 ? lw_max : (sub == 1 ? 7 : 10)) && !ok; --lw) {
@@ -814,18 +849,19 @@ int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, 
     ST2_REQUIRE(stats_out == nullptr || (int64_t)grid * p.J * (4 * nch) * 32 * 8 <= conv_row_stats_bytes(a.B, a.Tout, C),
                 "conv_row: statistics buffer too small");
     // the opt-in to > 48 KB of dynamic shared memory is per device: once per (device, variant)
-    static bool attr_done[kMaxDevices][16] = {};
+    static bool attr_done[kMaxDevices][32] = {};
     const int dev = current_device_slot();
-#define ROW_LAUNCH(BF, X, Y, N)                                                                                                  \
+#define ROW_LAUNCH(BF, X, Y, N, M)                                                                                               \
     do {                                                                                                                         \
-        bool& done = attr_done[dev][(BF ? 8 : 0) + (X ? 4 : 0) + (Y ? 2 : 0) + (N - 1)];                                         \
+        bool& done = attr_done[dev][(M ? 16 : 0) + (BF ? 8 : 0) + (X ? 4 : 0) + (Y ? 2 : 0) + (N - 1)];                          \
         if (!done) {                                                                                                             \
-            ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_row_kernel<BF, X, Y, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            ST2_CUDA_CHECK(cudaFuncSetAttribute(conv_row_kernel<BF, X, Y, N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             done = true;                                                                                                         \
         }                                                                                                                        \
-        conv_row_kernel<BF, X, Y, N><<<grid, RW_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);                     \
+        conv_row_kernel<BF, X, Y, N, M><<<grid, RW_THREADS, smem, st>>>(map_b, map_x, map_xt, map_r, map_o, p);                  \
     } while (0)
-#define ROW_LAUNCH_Y(BF, X, N) do { if (a.y16out) ROW_LAUNCH(BF, X, true, N); else ROW_LAUNCH(BF, X, false, N); } while (0)
+#define ROW_LAUNCH_M(BF, X, Y, N) do { if (N == 1 && p.bias_mma) ROW_LAUNCH(BF, X, Y, N, (N == 1)); else ROW_LAUNCH(BF, X, Y, N, false); } while (0)
+#define ROW_LAUNCH_Y(BF, X, N) do { if (a.y16out) ROW_LAUNCH_M(BF, X, true, N); else ROW_LAUNCH_M(BF, X, false, N); } while (0)
     const bool bf = is_bf16 != 0, x16 = a.x16in != 0;
     if (nch == 1) {
         if (bf) { if (x16) ROW_LAUNCH_Y(true, true, 1); else ROW_LAUNCH_Y(true, false, 1); }
@@ -835,6 +871,7 @@ int launch_conv_row(const ConvArgs& a, const float* coef, int coef_ld, int act, 
         else { if (x16) ROW_LAUNCH_Y(false, true, 2); else ROW_LAUNCH_Y(false, false, 2); }
     }
 #undef ROW_LAUNCH_Y
+#undef ROW_LAUNCH_M
 #undef ROW_LAUNCH
     ST2_LAUNCH_CHECK();
     return ST2_OK;

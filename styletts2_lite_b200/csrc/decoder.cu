@@ -430,7 +430,7 @@ const TuneField kTuneFields[] = {
     {"pipe_nrg", "ST2_PIPE_NRG", &Tune::pipe_nrg, false}, {"pipe_na", "ST2_PIPE_NA", &Tune::pipe_na, false},
     {"pipe_nx", "ST2_PIPE_NX", &Tune::pipe_nx, false}, {"pipe_nr", "ST2_PIPE_NR", &Tune::pipe_nr, false},
     {"verbose", "ST2_PIPE_VERBOSE", &Tune::verbose, true}, {"tc_halo", "ST2_TC_HALO", &Tune::tc_halo, false},
-    {"no_row_inline_coef", "ST2_NO_ROW_INLINE_COEF", &Tune::no_row_inline_coef, true},
+    {"no_row_bias_mma", "ST2_NO_ROW_BIAS_MMA", &Tune::no_row_bias_mma, true}, {"no_row_inline_coef", "ST2_NO_ROW_INLINE_COEF", &Tune::no_row_inline_coef, true},
     {"lstm_bt", "ST2_LSTM_BT", &Tune::lstm_bt, false}, {"no_xt16", "ST2_NO_XT16", &Tune::no_xt16, true},
     {"no_run16", "ST2_NO_RUN16", &Tune::no_run16, true}, {"no_xu16", "ST2_NO_XU16", &Tune::no_xu16, true},
     {"no_sum16", "ST2_NO_SUM16", &Tune::no_sum16, true}, {"no_src16", "ST2_NO_SRC16", &Tune::no_src16, true},

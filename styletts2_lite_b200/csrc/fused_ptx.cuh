@@ -39,6 +39,18 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
         : "memory");
 }
+// the same with a descriptor hi word per operand (operands of different layouts / strides)
+__device__ __forceinline__ void umma_f16_lohi2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+        : "memory");
+}
 // hi word of the K-major SWIZZLE_128B descriptor: SBO = 1024 B (>>4) | version 1 @ bit 46 | layout 2 @ bit 61
 static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
