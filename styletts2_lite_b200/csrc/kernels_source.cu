@@ -104,9 +104,11 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
     float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1]
     float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
     u1 = fminf(fmaxf(u1, 1e-12f), 1.0f);
-    float r = sqrtf(-2.0f * logf(u1));
+    // hardware log2 / sincos: the draw is this library's own (the reference's randn cannot be reproduced anyway), its argument
+    // range is (0, 1] / [0, 2 pi), and the accurate library versions made this the heaviest part of the kernel
+    float r = sqrtf(-2.0f * __logf(u1));
     float s, c;
-    sincosf(6.2831853071795864f * u2, &s, &c);
+    __sincosf(6.2831853071795864f * u2, &s, &c);
     z0 = r * c;
     z1 = r * s;
 }
